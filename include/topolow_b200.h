@@ -1,0 +1,192 @@
+/* include/topolow_b200.h
+ *
+ * C ABI of libtopolow_b200.so: the B200 (sm_100a) drop-in for topolow's native
+ * hot path.  Plain pointers and sizes only.  Citations are relative to the
+ * reference tree (/root/reference).
+ *
+ * What each entry point replaces:
+ *
+ *   topolow_optimize_layout_exact()   the body behind the .Call symbol
+ *       _topolow_optimize_layout_exact_cpp (src/RcppExports.cpp:16-39, arity 16,
+ *       registered at :41-49), i.e. optimize_layout_exact_cpp
+ *       (src/optimization.cpp:108-126): same 16 arguments in the same order and
+ *       meaning, R objects flattened to (pointer, size); same five results
+ *       (src/optimization.cpp:375-381).
+ *   topolow_fit()                     the same call in struct form, plus the
+ *       B200 extensions (mode, precision, seed, explicit pair order, trace).
+ *   topolow_fit_batch()               the fork-parallel fan-out of independent
+ *       fits: parallel::mclapply over parameter samples / folds
+ *       (R/adaptive_sampling.R:645-672, :1301-1320, :2670-2693).  One call, many
+ *       fits, per-job status instead of exceptions (:2657-2666).
+ *   topolow_plan_*()                  device-resident form of one fit for callers
+ *       that keep inputs in HBM and step the loop themselves (bench, sharded map).
+ *   topolow_est_distances()           as.matrix(stats::dist(positions)), R/core.R:474.
+ *   topolow_holdout_errors()          the OutSampleError reduction of
+ *       error_calculator_comparison (R/error_metrics.R:95-114) as consumed by
+ *       likelihood_function (R/adaptive_sampling.R:2639-2647).
+ *
+ * Error behaviour mirrors Rcpp::stop (src/optimization.cpp:131,359-361): status
+ * TOPOLOW_ERR_TOO_FEW_POINTS / TOPOLOW_ERR_NONFINITE carry the reference's two
+ * messages in result->message; the R shim turns them into Rf_error.
+ * No CPU fallback exists: without a usable CUDA device every compute entry
+ * returns TOPOLOW_ERR_CUDA.
+ */
+#ifndef TOPOLOW_B200_H
+#define TOPOLOW_B200_H
+
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define TOPOLOW_API __attribute__((visibility("default")))
+#else
+#define TOPOLOW_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+  TOPOLOW_OK = 0,
+  TOPOLOW_ERR_BAD_ARG = 1,        /* message says which */
+  TOPOLOW_ERR_NONFINITE = 2,      /* "Numerical instability at iteration %d. Reduce k0 or c_repulsion." */
+  TOPOLOW_ERR_CUDA = 3,           /* CUDA runtime / no device; message holds cudaGetErrorString */
+  TOPOLOW_ERR_TOO_FEW_POINTS = 4, /* "Need at least 2 points for embedding" */
+  TOPOLOW_ERR_INTERRUPTED = 5     /* interrupt callback returned non-zero */
+};
+
+/* mode */
+enum {
+  TOPOLOW_MODE_COLOURED = 0, /* production: hierarchical tournament of matchings (every pair once
+                                per iteration, updates within a matching commute) */
+  TOPOLOW_MODE_REPLAY = 1    /* FP64, consumes a given / seeded std::mt19937 pair permutation and
+                                executes it by dependency levels: exactly the sequential loop */
+};
+/* precision (coloured mode) */
+enum {
+  TOPOLOW_PREC_F32 = 0,      /* FP32 FMA forces and positions, FP64 error sums and controller */
+  TOPOLOW_PREC_F64_EXACT = 1 /* IEEE double, one rounding per reference operation (bit-comparable
+                                with the CPU loop run on the same pair order) */
+};
+
+typedef struct {
+  int64_t n;                        /* points (rows of initial_positions) */
+  int32_t ndim;                     /* columns of initial_positions */
+  int64_t n_edges;                  /* measured upper-triangle pairs (R/core.R:383-402) */
+  const int32_t* edge_i;            /* 0-based */
+  const int32_t* edge_j;            /* 0-based, edge_i[e] != edge_j[e] */
+  const double* edge_dist;          /* target distance */
+  const int32_t* edge_thresh;       /* 0 exact, +1 '>' , -1 '<'  (R/core.R:346,358-359) */
+  const int32_t* degrees;           /* rowSums(!is.na), diagonal included (R/core.R:340-341) */
+  const double* initial_positions;  /* n x ndim, column-major like an R matrix */
+} topolow_problem;
+
+typedef struct {
+  int32_t n_iter;                   /* mapping_max_iter */
+  double k0;
+  double cooling_rate;
+  double c_repulsion;
+  double relative_epsilon;
+  int32_t convergence_window;       /* convergence_counter */
+  int32_t convergence_check_freq;   /* < 1 means 10 (src/optimization.cpp:181) */
+  int32_t verbose;                  /* print "Iter a/b, MAE=..., k=..." lines to stderr */
+  /* ---- B200 extensions (all-zero = production defaults) ---- */
+  int32_t mode;                     /* TOPOLOW_MODE_* */
+  int32_t precision;                /* TOPOLOW_PREC_* */
+  uint64_t seed;                    /* schedule seed (coloured) / std::mt19937 seed (replay) */
+  const int32_t* pair_order;        /* replay only, optional: [n_iter][pairs_per_iter][2]; i<0 = skip */
+  int64_t pairs_per_iter;
+  int32_t device;                   /* CUDA device ordinal */
+  int32_t max_ctas;                 /* 0 = all SMs; cap on the persistent grid (tests / sharing) */
+} topolow_params;
+
+typedef struct {
+  double* positions;                /* caller-allocated n x ndim, column-major; best state */
+  int32_t converged;
+  int32_t iterations;               /* best_iter (src/optimization.cpp:378) */
+  double final_mae;                 /* best_mae */
+  double final_k;                   /* best_k */
+  int32_t status;                   /* TOPOLOW_* */
+  int32_t fail_iter;                /* iteration for TOPOLOW_ERR_NONFINITE */
+  int32_t iterations_run;           /* iterations actually executed */
+  int64_t pair_updates;             /* pair visits executed */
+  double device_ms;                 /* CUDA-event time of the optimisation kernels */
+  double* trace_mae;                /* optional, length n_iter; NaN where no check ran */
+  char message[256];
+} topolow_result;
+
+/* Polled between device chunks (R_CheckUserInterrupt equivalent); non-zero aborts. */
+typedef int (*topolow_interrupt_fn)(void* user);
+
+/* ---- single fit ------------------------------------------------------- */
+TOPOLOW_API int topolow_fit(const topolow_problem* problem, const topolow_params* params, topolow_result* result);
+
+TOPOLOW_API int topolow_fit_interruptible(const topolow_problem* problem, const topolow_params* params,
+                              topolow_result* result, topolow_interrupt_fn poll, void* user);
+
+/* The reference's 16 arguments, flattened.  dissimilarity_matrix and
+ * threshold_matrix (n x n, column-major, Inf = unmeasured) may be NULL: they
+ * are redundant with the edge list (both come from the same upper triangle,
+ * R/core.R:383-402,429-436) and are only validated when given. */
+TOPOLOW_API int topolow_optimize_layout_exact(
+    const double* initial_positions, int32_t n, int32_t ndim, const double* dissimilarity_matrix,
+    const int32_t* threshold_matrix, const int32_t* degrees, const int32_t* edge_i,
+    const int32_t* edge_j, const double* edge_dist, const int32_t* edge_thresh, int64_t n_edges,
+    int32_t n_iter, double k0, double cooling_rate, double c_repulsion, double relative_epsilon,
+    int32_t convergence_window, int32_t convergence_check_freq, int32_t verbose,
+    double* positions_out, int32_t* converged_out, int32_t* iterations_out, double* final_mae_out,
+    double* final_k_out, char* message, int32_t message_len);
+
+/* ---- batch of independent fits ----------------------------------------- */
+/* Jobs run concurrently on `device` (params[j].device is ignored); results[j].status is
+ * per job and the call itself only fails for argument / CUDA set-up errors. */
+TOPOLOW_API int topolow_fit_batch(int32_t n_jobs, const topolow_problem* problems, const topolow_params* params,
+                      topolow_result* results, int32_t device);
+
+/* ---- device-resident plan ----------------------------------------------- */
+typedef struct topolow_plan topolow_plan;
+
+TOPOLOW_API int topolow_plan_create(const topolow_problem* problem, const topolow_params* params,
+                        topolow_plan** plan_out, char* message, int32_t message_len);
+/* Run up to n_iters further iterations (stops early on convergence).  `stream`
+ * is a cudaStream_t (NULL = the plan's own).  ms_out = CUDA-event time on that stream. */
+TOPOLOW_API int topolow_plan_run(topolow_plan* plan, int32_t n_iters, void* stream, double* ms_out);
+TOPOLOW_API int topolow_plan_result(topolow_plan* plan, topolow_result* result);
+/* Geometry of the schedule: fills up to `cap` int64 values
+ * {tiles, super_blocks, warps_per_cta, ctas, tasks_per_cta, rounds, pairs_per_iter, smem_bytes}. */
+TOPOLOW_API int topolow_plan_info(const topolow_plan* plan, int64_t* out, int32_t cap);
+TOPOLOW_API void topolow_plan_destroy(topolow_plan* plan);
+
+/* The sequential pair order that is equivalent to iteration `iter` of a coloured-mode plan
+ * (host-side walk of the same schedule functions the kernel executes).  out = [pairs][2]
+ * original point ids; returns the number of pairs written (n(n-1)/2) or <0 on error. */
+TOPOLOW_API int64_t topolow_plan_enumerate(const topolow_plan* plan, int32_t iter, int32_t* out, int64_t cap_pairs);
+
+/* The same walk without a device or a plan: geometry and relabelling are pure functions of
+ * (n, ndim, precision, sm_count, max_ctas, seed).  out may be NULL (geometry only). */
+TOPOLOW_API int64_t topolow_schedule_enumerate(int64_t n, int32_t ndim, int32_t precision, int32_t sm_count,
+                                   int32_t max_ctas, uint64_t seed, int32_t iter, int32_t* out,
+                                   int64_t cap_pairs, int64_t* geometry_out);
+
+/* ---- post-processing kernels --------------------------------------------- */
+/* est_distances[n x n] (column-major == row-major, symmetric) from positions[n x ndim col-major]. */
+TOPOLOW_API int topolow_est_distances(const double* positions, int64_t n, int32_t ndim, double* est_distances,
+                          int32_t device);
+/* sum |truth - ||x_i - x_j||| and count over held-out cells (cell_i, cell_j may repeat a pair in
+ * both orientations, as the flattened R matrices do). */
+TOPOLOW_API int topolow_holdout_errors(const double* positions, int64_t n, int32_t ndim, int64_t n_cells,
+                           const int32_t* cell_i, const int32_t* cell_j, const double* truth,
+                           double* sum_abs_out, int64_t* count_out, int32_t device);
+
+/* ---- measurement helpers --------------------------------------------------- */
+/* which: 0 FFMA (FP32 flop/s), 1 packed fma.f32x2, 2 DFMA, 3 SHFL (warp-instr/s), 4 MUFU.RSQ,
+ * 5 device copy (bytes/s read+write).  value_out in the unit named. */
+TOPOLOW_API int topolow_microbench(int32_t which, int32_t device, double* value_out);
+TOPOLOW_API int topolow_device_info(int32_t device, int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor,
+                        int64_t* global_mem);
+TOPOLOW_API const char* topolow_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TOPOLOW_B200_H */

@@ -1,0 +1,119 @@
+// topolow_b200/csrc/common.cuh - shared device/host helpers.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cfloat>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <stdexcept>
+#include <string>
+
+#define TL_HD __host__ __device__ __forceinline__
+#define TL_D __device__ __forceinline__
+
+namespace tl {
+
+struct CudaError : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+
+inline void cuda_check(cudaError_t e, const char* what, const char* file, int line) {
+  if (e != cudaSuccess) {
+    char buf[512];
+    std::snprintf(buf, sizeof buf, "CUDA error: %s (%s) at %s:%d", cudaGetErrorString(e), what, file, line);
+    throw CudaError(buf);
+  }
+}
+#define TL_CUDA(x) ::tl::cuda_check((x), #x, __FILE__, __LINE__)
+
+// ---------------------------------------------------------------------------
+// Convergence controller.  One instance per fit lives in device memory and is
+// advanced by one thread; the host reads it back between launches.
+// Follows src/optimization.cpp:168-181 (state), :289 (cooling), :294-357
+// (three-way classification), :368-374 (restore).
+// ---------------------------------------------------------------------------
+struct FitParams {
+  int n_iter;
+  double k0, cooling_rate, c_repulsion, relative_epsilon;
+  int convergence_window, convergence_check_freq;
+};
+
+struct FitState {
+  double k;              // current spring constant
+  double best_mae;       // DBL_MAX until the first check
+  double best_k;
+  double last_error;     // MAE of the latest check
+  int best_iter;
+  int worsening_count;
+  int converge_count;
+  int converged;         // plateau or worsening exit taken
+  int stop;              // loop must not run further iterations (converged or failed)
+  int iter;              // iterations completed so far
+  int snapshot;          // set by controller_check when best_* was updated by this check
+  int status;            // 0 ok, 2 non-finite
+  int fail_iter;
+  int pad;
+  unsigned long long pair_updates;
+};
+
+TL_HD void state_init(FitState& s, const FitParams& p) {
+  s.k = p.k0;
+  s.best_mae = DBL_MAX;
+  s.best_k = p.k0;
+  s.last_error = 0.0;
+  s.best_iter = 0;
+  s.worsening_count = 0;
+  s.converge_count = 0;
+  s.converged = 0;
+  s.stop = 0;
+  s.iter = 0;
+  s.snapshot = 0;
+  s.status = 0;
+  s.fail_iter = 0;
+  s.pad = 0;
+  s.pair_updates = 0ULL;
+}
+
+TL_HD bool is_check_iter(int iter /*0-based, just completed*/, const FitParams& p) {
+  int freq = p.convergence_check_freq < 1 ? 10 : p.convergence_check_freq;
+  return ((iter + 1) % freq == 0) || (iter == p.n_iter - 1);
+}
+
+// `iter` is the 0-based iteration that just finished; s.k already cooled.
+// Sets s.snapshot when the caller must copy positions -> best positions.
+TL_HD void controller_check(FitState& s, const FitParams& p, int iter, double total, long long count) {
+  const double current_error = (count > 0) ? total / (double)count : 0.0;
+  s.last_error = current_error;
+  s.snapshot = 0;
+  const double improvement_threshold = s.best_mae * (1.0 - p.relative_epsilon);
+  const double worsening_threshold = s.best_mae * (1.0 + p.relative_epsilon);
+  if (current_error < improvement_threshold) {
+    s.best_mae = current_error; s.best_k = s.k; s.best_iter = iter + 1; s.snapshot = 1;
+    s.worsening_count = 0; s.converge_count = 0;
+  } else if (current_error <= worsening_threshold) {
+    if (current_error < s.best_mae) {
+      s.best_mae = current_error; s.best_k = s.k; s.best_iter = iter + 1; s.snapshot = 1;
+    }
+    s.worsening_count = 0;
+    s.converge_count++;
+    if (s.converge_count >= p.convergence_window) { s.converged = 1; s.stop = 1; }
+  } else {
+    s.converge_count = 0;
+    s.worsening_count++;
+    if (s.worsening_count >= p.convergence_window) { s.converged = 1; s.stop = 1; }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Small stateless integer mixing used by the schedule (host == device).
+// ---------------------------------------------------------------------------
+TL_HD uint64_t mix64(uint64_t x) {
+  x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ULL;
+  x ^= x >> 27; x *= 0x94d049bb133111ebULL;
+  x ^= x >> 31;
+  return x;
+}
+
+}  // namespace tl

@@ -1,0 +1,610 @@
+// topolow_b200/csrc/plan.cu
+//
+// Host driver of the production (coloured) mode and the C ABI declared in
+// include/topolow_b200.h.  Builds the device image of one fit (relabelled positions, masses,
+// bucketed edge records), picks the schedule geometry, launches the persistent kernel in
+// chunks of iterations and assembles the five results of
+// optimize_layout_exact_cpp (src/optimization.cpp:375-381).
+#include <algorithm>
+#include <cstring>
+#include <memory>
+#include <random>
+#include <vector>
+
+#include "../../include/topolow_b200.h"
+#include "replay.h"
+#include "tilepass_launch.h"
+
+using namespace tl;
+
+struct topolow_plan {
+  int device = 0;
+  int precision = 0;
+  int64_t n = 0, E = 0;
+  int D = 0;
+  Geometry geo{};
+  FitParams prm{};
+  std::vector<int32_t> point_of_slot;  // -1 = phantom
+  std::vector<int32_t> slot_of_point;
+  // device
+  void* pos = nullptr; void* best = nullptr; void* dp1 = nullptr;
+  EdgeRec* edges = nullptr; uint32_t* bucket_off = nullptr;
+  FitState* state = nullptr; double* partials = nullptr; unsigned* barrier = nullptr; double* trace = nullptr;
+  volatile int* h_flag = nullptr; int* d_flag = nullptr;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int chunk_iters = 1;
+  double total_ms = 0.0;
+  size_t smem = 0;
+
+  ~topolow_plan() {
+    cudaFree(pos); cudaFree(best); cudaFree(dp1); cudaFree(edges); cudaFree(bucket_off);
+    cudaFree(state); cudaFree(partials); cudaFree(barrier); cudaFree(trace);
+    if (h_flag) cudaFreeHost((void*)h_flag);
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
+    if (stream) cudaStreamDestroy(stream);
+  }
+};
+
+namespace {
+
+struct BadArg : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+
+void set_msg(char* dst, int len, const char* src) {
+  if (dst && len > 0) std::snprintf(dst, len, "%s", src);
+}
+
+void validate(const topolow_problem& pb, const topolow_params& pr) {
+  if (pb.n < 2) throw BadArg("Need at least 2 points for embedding");
+  if (pb.ndim < 1) throw BadArg("ndim must be a positive integer");
+  if (pr.n_iter < 0) throw BadArg("mapping_max_iter must be a positive integer");
+  if (!pb.initial_positions || !pb.degrees) throw BadArg("initial_positions and degrees are required");
+  if (pb.n_edges > 0 && (!pb.edge_i || !pb.edge_j || !pb.edge_dist || !pb.edge_thresh))
+    throw BadArg("edge arrays are required when n_edges > 0");
+  if (pb.n_edges < 0 || pb.n_edges >= (1ll << 32)) throw BadArg("n_edges out of range");
+  for (int64_t e = 0; e < pb.n_edges; ++e) {
+    const int64_t a = pb.edge_i[e], b = pb.edge_j[e];
+    if (a < 0 || b < 0 || a >= pb.n || b >= pb.n || a == b) throw BadArg("edge index out of range");
+    const int t = pb.edge_thresh[e];
+    if (t < -1 || t > 1) throw BadArg("edge_thresh must be -1, 0 or 1");
+  }
+}
+
+// Fisher-Yates with splitmix64: identical on every host.
+std::vector<int32_t> random_permutation(int64_t n, uint64_t seed) {
+  std::vector<int32_t> p(n);
+  for (int64_t i = 0; i < n; ++i) p[i] = (int32_t)i;
+  uint64_t s = mix64(seed ^ 0x51ab5eedULL);
+  for (int64_t i = n - 1; i > 0; --i) {
+    s += 0x9e3779b97f4a7c15ULL;
+    const uint64_t r = mix64(s) % (uint64_t)(i + 1);
+    std::swap(p[i], p[r]);
+  }
+  return p;
+}
+
+Geometry choose_geometry(int64_t n, int D, int precision, int sms, int max_ctas, uint64_t seed) {
+  Geometry g{};
+  g.n = (int)n; g.D = D; g.seed = seed;
+  g.T = (int)((n + kTile - 1) / kTile);
+  const size_t rs = precision == TOPOLOW_PREC_F64_EXACT ? sizeof(double) : sizeof(float);
+  int wmax = precision == TOPOLOW_PREC_F64_EXACT ? ExactF64::kMaxWarps : FastF32::kMaxWarps;
+  while (wmax > 1 && tile_smem_bytes(D, wmax, rs) > 200 * 1024) --wmax;
+  const int ctas = std::max(1, max_ctas > 0 ? std::min(max_ctas, sms) : sms);
+  const int T = g.T;
+  if (T <= 2 * wmax || ctas == 1) {
+    // one CTA: no inter-CTA barrier at all
+    g.G = 1;
+    g.m = (T + 2 * wmax - 1) / (2 * wmax);
+    if (g.m < 1) g.m = 1;
+    g.W = std::max(1, (T + 2 * g.m - 1) / (2 * g.m));
+  } else if (T < 2 * ctas * 4) {
+    // latency-bound regime: 4 warps per CTA, as many CTAs as there is work
+    g.W = 4; g.m = 1;
+    g.G = (T + 2 * g.W - 1) / (2 * g.W);
+  } else {
+    g.G = ctas;
+    g.m = (T + 2 * g.G * wmax - 1) / (2 * g.G * wmax);
+    g.W = (T + 2 * g.G * g.m - 1) / (2 * g.G * g.m);
+  }
+  g.S = 2 * g.G * g.m;
+  return g;
+}
+
+int64_t enumerate_schedule(const Geometry& g, const std::vector<int32_t>& pos, int iter, int32_t* out,
+                           int64_t cap_pairs) {
+  int64_t np = 0;
+  bool overflow = false;
+  auto emit = [&](int slot_a, int slot_b) {
+    const int pa = pos[slot_a], pb = pos[slot_b];
+    if (pa < 0 || pb < 0) return;
+    if (np >= cap_pairs) { overflow = true; return; }
+    out[2 * np] = pa; out[2 * np + 1] = pb; ++np;
+  };
+  auto ring = [&](int tA, int tB) {
+    if (tA < 0 || tB < 0) return;
+    const RingParams rp = ring_params(g, iter, tA, tB);
+    for (int i = 0; i < 32; ++i)
+      for (int a = 0; a < 32; ++a) emit(tA * 32 + a, tB * 32 + ring_b(rp, a, i));
+  };
+  auto intra = [&](int t) {
+    if (t < 0) return;
+    const XorParams xp = xor_params(g, iter, t);
+    for (int i = 0; i < 31; ++i) {
+      const int x = xor_at(xp, i);
+      for (int a = 0; a < 32; ++a) if (a < (a ^ x)) emit(t * 32 + a, t * 32 + (a ^ x));
+    }
+  };
+  const int W = g.W;
+  for (int r = 0; r < g.S - 1; ++r) {
+    const int rr = round_at(g, iter, r);
+    for (int q = 0; q < g.S / 2; ++q) {
+      int X, Y;
+      circle_pair(g.S, rr, q, X, Y);
+      const int rot = cross_rot(g, iter, X, Y);
+      for (int v = 0; v < W; ++v)
+        for (int w = 0; w < W; ++w)
+          ring(tile_at(g, iter, X * W + w), tile_at(g, iter, Y * W + (w + v + rot) % W));
+    }
+  }
+  for (int q = 0; q < g.S / 2; ++q) {
+    const int Mt = diag_subrounds(W), rot = diag_rot(g, iter, q);
+    for (int u = 0; u < Mt; ++u)
+      for (int w = 0; w < W; ++w) {
+        int sb, ia, ib;
+        if (diag_pair(W, u, rot, w, sb, ia, ib))
+          ring(tile_at(g, iter, (2 * q + sb) * W + ia), tile_at(g, iter, (2 * q + sb) * W + ib));
+      }
+    for (int w = 0; w < W; ++w) intra(tile_at(g, iter, (2 * q) * W + w));
+    for (int w = 0; w < W; ++w) intra(tile_at(g, iter, (2 * q + 1) * W + w));
+  }
+  return overflow ? -2 : np;
+}
+
+template <class real>
+void upload_points(topolow_plan& pl, const topolow_problem& pb) {
+  const size_t slots = (size_t)pl.geo.T * kTile;
+  std::vector<real> hp(slots * pl.D, (real)0), hd(slots, (real)0);
+  for (int64_t i = 0; i < pl.n; ++i) {
+    const size_t s = pl.slot_of_point[i];
+    for (int d = 0; d < pl.D; ++d) hp[s * pl.D + d] = (real)pb.initial_positions[(size_t)d * pl.n + i];
+    hd[s] = (real)((double)pb.degrees[i] + 1.0);
+  }
+  TL_CUDA(cudaMalloc(&pl.pos, hp.size() * sizeof(real)));
+  TL_CUDA(cudaMalloc(&pl.best, hp.size() * sizeof(real)));
+  TL_CUDA(cudaMalloc(&pl.dp1, hd.size() * sizeof(real)));
+  TL_CUDA(cudaMemcpy(pl.pos, hp.data(), hp.size() * sizeof(real), cudaMemcpyHostToDevice));
+  TL_CUDA(cudaMemcpy(pl.best, hp.data(), hp.size() * sizeof(real), cudaMemcpyHostToDevice));
+  TL_CUDA(cudaMemcpy(pl.dp1, hd.data(), hd.size() * sizeof(real), cudaMemcpyHostToDevice));
+}
+
+void upload_edges(topolow_plan& pl, const topolow_problem& pb) {
+  const int T = pl.geo.T;
+  const size_t nkeys = (size_t)T * T;
+  std::vector<uint32_t> off(nkeys + 1, 0);
+  std::vector<EdgeRec> recs(pl.E);
+  std::vector<uint64_t> keys(pl.E);
+  for (int64_t e = 0; e < pl.E; ++e) {
+    uint32_t sa = (uint32_t)pl.slot_of_point[pb.edge_i[e]], sb = (uint32_t)pl.slot_of_point[pb.edge_j[e]];
+    if (sa > sb) std::swap(sa, sb);  // lower slot first => lower (or equal) tile first
+    keys[e] = (uint64_t)(sa >> 5) * T + (sb >> 5);
+    off[keys[e] + 1]++;
+  }
+  for (size_t k = 0; k < nkeys; ++k) off[k + 1] += off[k];
+  std::vector<uint32_t> cur(off.begin(), off.end() - 1);
+  for (int64_t e = 0; e < pl.E; ++e) {  // stable: input order kept inside a bucket
+    uint32_t sa = (uint32_t)pl.slot_of_point[pb.edge_i[e]], sb = (uint32_t)pl.slot_of_point[pb.edge_j[e]];
+    if (sa > sb) std::swap(sa, sb);
+    const int t = pb.edge_thresh[e];
+    EdgeRec r;
+    r.target = pb.edge_dist[e];
+    r.slot_lo = sa;
+    r.slot_hi_type = sb | ((uint32_t)(t == 1 ? 1 : (t == -1 ? 2 : 0)) << 30);
+    recs[cur[keys[e]]++] = r;
+  }
+  TL_CUDA(cudaMalloc(&pl.edges, std::max<size_t>(recs.size(), 1) * sizeof(EdgeRec)));
+  TL_CUDA(cudaMalloc(&pl.bucket_off, off.size() * sizeof(uint32_t)));
+  if (!recs.empty()) TL_CUDA(cudaMemcpy(pl.edges, recs.data(), recs.size() * sizeof(EdgeRec), cudaMemcpyHostToDevice));
+  TL_CUDA(cudaMemcpy(pl.bucket_off, off.data(), off.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+}
+
+std::unique_ptr<topolow_plan> make_plan(const topolow_problem& pb, const topolow_params& pr) {
+  validate(pb, pr);
+  if (pb.ndim > kMaxDim) throw BadArg("ndim > 16 is not built into libtopolow_b200 (coloured mode)");
+  if (pb.n > (1ll << 29)) throw BadArg("n too large");
+  auto pl = std::make_unique<topolow_plan>();
+  pl->device = pr.device;
+  TL_CUDA(cudaSetDevice(pr.device));
+  int sms = 0;
+  TL_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, pr.device));
+  pl->precision = pr.precision;
+  pl->n = pb.n; pl->E = pb.n_edges; pl->D = pb.ndim;
+  pl->prm = FitParams{pr.n_iter, pr.k0, pr.cooling_rate, pr.c_repulsion, pr.relative_epsilon,
+                      pr.convergence_window, pr.convergence_check_freq};
+  pl->geo = choose_geometry(pb.n, pb.ndim, pr.precision, sms, pr.max_ctas, pr.seed);
+  const Geometry& g = pl->geo;
+  if (g.G > 1) {
+    const int fit = pr.precision == TOPOLOW_PREC_F64_EXACT ? max_coresident_f64(g.D, g.W) : max_coresident_f32(g.D, g.W);
+    if (fit < g.G) throw BadArg("schedule does not fit the device (co-resident CTAs)");
+  }
+  pl->smem = tile_smem_bytes(g.D, g.W, pr.precision == TOPOLOW_PREC_F64_EXACT ? 8 : 4);
+
+  // random relabelling of points into slots; phantom slots pad the last tile
+  pl->slot_of_point = random_permutation(pb.n, pr.seed);
+  pl->point_of_slot.assign((size_t)g.T * kTile, -1);
+  for (int64_t i = 0; i < pb.n; ++i) pl->point_of_slot[pl->slot_of_point[i]] = (int32_t)i;
+
+  if (pr.precision == TOPOLOW_PREC_F64_EXACT) upload_points<double>(*pl, pb);
+  else upload_points<float>(*pl, pb);
+  upload_edges(*pl, pb);
+
+  FitState st; state_init(st, pl->prm);
+  TL_CUDA(cudaMalloc(&pl->state, sizeof(FitState)));
+  TL_CUDA(cudaMemcpy(pl->state, &st, sizeof st, cudaMemcpyHostToDevice));
+  TL_CUDA(cudaMalloc(&pl->partials, sizeof(double) * 4 * g.G));
+  TL_CUDA(cudaMemset(pl->partials, 0, sizeof(double) * 4 * g.G));
+  TL_CUDA(cudaMalloc(&pl->barrier, 2 * sizeof(unsigned)));
+  TL_CUDA(cudaMemset(pl->barrier, 0, 2 * sizeof(unsigned)));
+  const int ntr = std::max(pr.n_iter, 1);
+  std::vector<double> nanv(ntr, NAN);
+  TL_CUDA(cudaMalloc(&pl->trace, sizeof(double) * ntr));
+  TL_CUDA(cudaMemcpy(pl->trace, nanv.data(), sizeof(double) * ntr, cudaMemcpyHostToDevice));
+  TL_CUDA(cudaHostAlloc((void**)&pl->h_flag, 2 * sizeof(int), cudaHostAllocMapped));
+  pl->h_flag[0] = 0; pl->h_flag[1] = 0;
+  TL_CUDA(cudaHostGetDevicePointer((void**)&pl->d_flag, (void*)pl->h_flag, 0));
+  TL_CUDA(cudaStreamCreate(&pl->stream));
+  TL_CUDA(cudaEventCreate(&pl->ev0));
+  TL_CUDA(cudaEventCreate(&pl->ev1));
+
+  // iterations per launch: aim at ~50 ms of device time, at most 50 iterations (the reference
+  // polls for a user interrupt every 50 iterations, src/optimization.cpp:364)
+  const double pairs = 0.5 * (double)pb.n * (double)(pb.n - 1);
+  const double est_ms = pairs / 1.0e8 + 0.03;
+  pl->chunk_iters = (int)std::max(1.0, std::min(50.0, 50.0 / est_ms));
+  return pl;
+}
+
+void launch_chunk(topolow_plan& pl, int n_iters, cudaStream_t stream) {
+  const unsigned long long ppi = (unsigned long long)pl.n * (unsigned long long)(pl.n - 1) / 2ull;
+  if (pl.precision == TOPOLOW_PREC_F64_EXACT) {
+    TileDev<double> dv{(double*)pl.pos, (double*)pl.best, (const double*)pl.dp1, pl.edges, pl.bucket_off, pl.state,
+                       pl.partials, pl.barrier, pl.trace, (long long)pl.E, ppi};
+    launch_tile_f64(dv, pl.geo, pl.prm, n_iters, pl.d_flag, stream);
+  } else {
+    TileDev<float> dv{(float*)pl.pos, (float*)pl.best, (const float*)pl.dp1, pl.edges, pl.bucket_off, pl.state,
+                      pl.partials, pl.barrier, pl.trace, (long long)pl.E, ppi};
+    launch_tile_f32(dv, pl.geo, pl.prm, n_iters, pl.d_flag, stream);
+  }
+}
+
+// Runs up to n_iters iterations; returns device milliseconds.
+double run_plan(topolow_plan& pl, int n_iters, cudaStream_t stream_in, topolow_interrupt_fn poll, void* user,
+                bool* interrupted) {
+  TL_CUDA(cudaSetDevice(pl.device));
+  cudaStream_t s = stream_in ? stream_in : pl.stream;
+  TL_CUDA(cudaEventRecord(pl.ev0, s));
+  int left = n_iters;
+  while (left > 0) {
+    if (pl.h_flag[0]) break;
+    if (poll && poll(user)) { if (interrupted) *interrupted = true; break; }
+    const int c = std::min(left, pl.chunk_iters);
+    launch_chunk(pl, c, s);
+    left -= c;
+    if (poll) TL_CUDA(cudaStreamSynchronize(s));  // interruptible runs stay one chunk deep
+  }
+  TL_CUDA(cudaEventRecord(pl.ev1, s));
+  TL_CUDA(cudaEventSynchronize(pl.ev1));
+  float ms = 0.f;
+  TL_CUDA(cudaEventElapsedTime(&ms, pl.ev0, pl.ev1));
+  pl.total_ms += ms;
+  return ms;
+}
+
+template <class real>
+void download_best(const topolow_plan& pl, double* out) {
+  const size_t slots = (size_t)pl.geo.T * kTile;
+  std::vector<real> hp(slots * pl.D);
+  TL_CUDA(cudaMemcpy(hp.data(), pl.best, hp.size() * sizeof(real), cudaMemcpyDeviceToHost));
+  for (int64_t i = 0; i < pl.n; ++i) {
+    const size_t s = pl.slot_of_point[i];
+    for (int d = 0; d < pl.D; ++d) out[(size_t)d * pl.n + i] = (double)hp[s * pl.D + d];
+  }
+}
+
+void fill_result(topolow_plan& pl, topolow_result& res, bool interrupted) {
+  TL_CUDA(cudaSetDevice(pl.device));
+  FitState st;
+  TL_CUDA(cudaMemcpy(&st, pl.state, sizeof st, cudaMemcpyDeviceToHost));
+  if (res.positions) {
+    if (pl.precision == TOPOLOW_PREC_F64_EXACT) download_best<double>(pl, res.positions);
+    else download_best<float>(pl, res.positions);
+  }
+  res.converged = st.converged;
+  res.iterations = st.best_iter;   // src/optimization.cpp:368-381: always the best snapshot
+  res.final_mae = st.best_mae;
+  res.final_k = st.best_k;
+  res.iterations_run = st.iter;
+  res.pair_updates = (int64_t)st.pair_updates;
+  res.device_ms = pl.total_ms;
+  res.fail_iter = st.fail_iter;
+  res.status = TOPOLOW_OK;
+  res.message[0] = 0;
+  if (st.status == 2) {
+    res.status = TOPOLOW_ERR_NONFINITE;
+    std::snprintf(res.message, sizeof res.message,
+                  "Numerical instability at iteration %d. Reduce k0 or c_repulsion.", st.fail_iter);
+  } else if (interrupted) {
+    res.status = TOPOLOW_ERR_INTERRUPTED;
+    std::snprintf(res.message, sizeof res.message, "interrupted");
+  }
+  if (res.trace_mae && pl.prm.n_iter > 0)
+    TL_CUDA(cudaMemcpy(res.trace_mae, pl.trace, sizeof(double) * pl.prm.n_iter, cudaMemcpyDeviceToHost));
+}
+
+void print_trace(const topolow_params& pr, const double* trace, int iters_run) {
+  // the reference's verbose lines (src/optimization.cpp:298-301), replayed from the device trace
+  for (int it = 0; it < iters_run; ++it) {
+    if (std::isnan(trace[it])) continue;
+    if ((it + 1) % 10 == 0 || it == pr.n_iter - 1)
+      std::fprintf(stderr, "Iter %d/%d, MAE=%g, k=%g\n", it + 1, pr.n_iter, trace[it],
+                   pr.k0 * std::pow(1.0 - pr.cooling_rate, it + 1));
+  }
+}
+
+int fit_impl(const topolow_problem* pb, const topolow_params* pr, topolow_result* res, topolow_interrupt_fn poll,
+             void* user) {
+  if (!pb || !pr || !res) return TOPOLOW_ERR_BAD_ARG;
+  res->message[0] = 0;
+  res->status = TOPOLOW_OK;
+  try {
+    if (pb->n < 2) {
+      res->status = TOPOLOW_ERR_TOO_FEW_POINTS;
+      set_msg(res->message, sizeof res->message, "Need at least 2 points for embedding");
+      return res->status;
+    }
+    if (!res->positions) throw BadArg("result->positions must be caller-allocated");
+    std::vector<double> tmp_trace;
+    double* user_trace = res->trace_mae;
+    if (pr->verbose && !res->trace_mae) { tmp_trace.assign(std::max(pr->n_iter, 1), NAN); res->trace_mae = tmp_trace.data(); }
+    if (pr->mode == TOPOLOW_MODE_REPLAY) {
+      validate(*pb, *pr);
+      if (pb->n > replay_max_n()) throw BadArg("replay mode supports n <= 8192");
+      if (pr->pair_order && pr->pairs_per_iter <= 0) throw BadArg("pairs_per_iter must be > 0 with pair_order");
+      TL_CUDA(cudaSetDevice(pr->device));
+      run_replay(*pb, *pr, *res, poll, user);
+      if (res->status == TOPOLOW_ERR_NONFINITE)
+        std::snprintf(res->message, sizeof res->message,
+                      "Numerical instability at iteration %d. Reduce k0 or c_repulsion.", res->fail_iter);
+    } else {
+      auto pl = make_plan(*pb, *pr);
+      bool interrupted = false;
+      run_plan(*pl, pr->n_iter, nullptr, poll, user, &interrupted);
+      fill_result(*pl, *res, interrupted);
+    }
+    if (pr->verbose && res->trace_mae) print_trace(*pr, res->trace_mae, res->iterations_run);
+    res->trace_mae = user_trace;
+    return res->status;
+  } catch (const BadArg& e) {
+    res->status = TOPOLOW_ERR_BAD_ARG;
+    set_msg(res->message, sizeof res->message, e.what());
+  } catch (const std::invalid_argument& e) {
+    res->status = TOPOLOW_ERR_BAD_ARG;
+    set_msg(res->message, sizeof res->message, e.what());
+  } catch (const CudaError& e) {
+    res->status = TOPOLOW_ERR_CUDA;
+    set_msg(res->message, sizeof res->message, e.what());
+    cudaGetLastError();
+  } catch (const std::exception& e) {
+    res->status = TOPOLOW_ERR_BAD_ARG;
+    set_msg(res->message, sizeof res->message, e.what());
+  }
+  return res->status;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* topolow_version(void) { return "topolow_b200 0.1 (sm_100a)"; }
+
+int topolow_device_info(int32_t device, int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor, int64_t* global_mem) {
+  cudaDeviceProp p;
+  if (cudaGetDeviceProperties(&p, device) != cudaSuccess) { cudaGetLastError(); return TOPOLOW_ERR_CUDA; }
+  if (sm_count) *sm_count = p.multiProcessorCount;
+  if (cc_major) *cc_major = p.major;
+  if (cc_minor) *cc_minor = p.minor;
+  if (global_mem) *global_mem = (int64_t)p.totalGlobalMem;
+  return TOPOLOW_OK;
+}
+
+int topolow_fit(const topolow_problem* problem, const topolow_params* params, topolow_result* result) {
+  return fit_impl(problem, params, result, nullptr, nullptr);
+}
+
+int topolow_fit_interruptible(const topolow_problem* problem, const topolow_params* params, topolow_result* result,
+                              topolow_interrupt_fn poll, void* user) {
+  return fit_impl(problem, params, result, poll, user);
+}
+
+int topolow_optimize_layout_exact(const double* initial_positions, int32_t n, int32_t ndim,
+                                  const double* dissimilarity_matrix, const int32_t* threshold_matrix,
+                                  const int32_t* degrees, const int32_t* edge_i, const int32_t* edge_j,
+                                  const double* edge_dist, const int32_t* edge_thresh, int64_t n_edges, int32_t n_iter,
+                                  double k0, double cooling_rate, double c_repulsion, double relative_epsilon,
+                                  int32_t convergence_window, int32_t convergence_check_freq, int32_t verbose,
+                                  double* positions_out, int32_t* converged_out, int32_t* iterations_out,
+                                  double* final_mae_out, double* final_k_out, char* message, int32_t message_len) {
+  // The dense matrices repeat the edge list (R/core.R:383-402 vs :429-436); when given, check it.
+  if (dissimilarity_matrix) {
+    for (int64_t e = 0; e < n_edges; ++e) {
+      const int64_t a = std::min(edge_i[e], edge_j[e]), b = std::max(edge_i[e], edge_j[e]);
+      if (a < 0 || b >= n) break;  // reported by validate()
+      if (dissimilarity_matrix[a + b * (int64_t)n] != edge_dist[e] ||
+          (threshold_matrix && threshold_matrix[a + b * (int64_t)n] != edge_thresh[e])) {
+        set_msg(message, message_len, "dissimilarity_matrix / threshold_matrix disagree with the edge list");
+        return TOPOLOW_ERR_BAD_ARG;
+      }
+    }
+  }
+  topolow_problem pb{};
+  pb.n = n; pb.ndim = ndim; pb.n_edges = n_edges; pb.edge_i = edge_i; pb.edge_j = edge_j; pb.edge_dist = edge_dist;
+  pb.edge_thresh = edge_thresh; pb.degrees = degrees; pb.initial_positions = initial_positions;
+  topolow_params pr{};
+  pr.n_iter = n_iter; pr.k0 = k0; pr.cooling_rate = cooling_rate; pr.c_repulsion = c_repulsion;
+  pr.relative_epsilon = relative_epsilon; pr.convergence_window = convergence_window;
+  pr.convergence_check_freq = convergence_check_freq; pr.verbose = verbose;
+  topolow_result rs{};
+  rs.positions = positions_out;
+  const int rc = topolow_fit(&pb, &pr, &rs);
+  if (converged_out) *converged_out = rs.converged;
+  if (iterations_out) *iterations_out = rs.iterations;
+  if (final_mae_out) *final_mae_out = rs.final_mae;
+  if (final_k_out) *final_k_out = rs.final_k;
+  set_msg(message, message_len, rs.message);
+  return rc;
+}
+
+int topolow_fit_batch(int32_t n_jobs, const topolow_problem* problems, const topolow_params* params,
+                      topolow_result* results, int32_t device) {
+  if (n_jobs < 0 || (n_jobs > 0 && (!problems || !params || !results))) return TOPOLOW_ERR_BAD_ARG;
+  // Independent fits: every job gets its own plan and stream; chunks of all jobs are issued
+  // round-robin so that the device always has several fits in flight.
+  std::vector<std::unique_ptr<topolow_plan>> plans(n_jobs);
+  std::vector<int> left(n_jobs, 0);
+  for (int j = 0; j < n_jobs; ++j) {
+    topolow_result& r = results[j];
+    r.status = TOPOLOW_OK; r.message[0] = 0;
+    try {
+      if (problems[j].n < 2) {
+        r.status = TOPOLOW_ERR_TOO_FEW_POINTS;
+        set_msg(r.message, sizeof r.message, "Need at least 2 points for embedding");
+        continue;
+      }
+      if (!r.positions) throw BadArg("result->positions must be caller-allocated");
+      if (params[j].mode != TOPOLOW_MODE_COLOURED) throw BadArg("batch supports the coloured mode only");
+      topolow_params pr = params[j];
+      pr.device = device;
+      plans[j] = make_plan(problems[j], pr);
+      left[j] = pr.n_iter;
+    } catch (const CudaError& e) {
+      r.status = TOPOLOW_ERR_CUDA; set_msg(r.message, sizeof r.message, e.what()); cudaGetLastError();
+    } catch (const std::exception& e) {
+      r.status = TOPOLOW_ERR_BAD_ARG; set_msg(r.message, sizeof r.message, e.what());
+    }
+  }
+  try {
+    bool any = true;
+    for (int j = 0; j < n_jobs; ++j) if (plans[j]) TL_CUDA(cudaEventRecord(plans[j]->ev0, plans[j]->stream));
+    while (any) {
+      any = false;
+      for (int j = 0; j < n_jobs; ++j) {
+        if (!plans[j] || left[j] <= 0 || plans[j]->h_flag[0]) continue;
+        const int c = std::min(left[j], plans[j]->chunk_iters);
+        launch_chunk(*plans[j], c, plans[j]->stream);
+        left[j] -= c;
+        any = true;
+      }
+    }
+    for (int j = 0; j < n_jobs; ++j) {
+      if (!plans[j]) continue;
+      TL_CUDA(cudaEventRecord(plans[j]->ev1, plans[j]->stream));
+      TL_CUDA(cudaEventSynchronize(plans[j]->ev1));
+      float ms = 0.f;
+      TL_CUDA(cudaEventElapsedTime(&ms, plans[j]->ev0, plans[j]->ev1));
+      plans[j]->total_ms = ms;
+      fill_result(*plans[j], results[j], false);
+    }
+  } catch (const CudaError& e) {
+    for (int j = 0; j < n_jobs; ++j)
+      if (plans[j]) { results[j].status = TOPOLOW_ERR_CUDA; set_msg(results[j].message, sizeof results[j].message, e.what()); }
+    cudaGetLastError();
+    return TOPOLOW_ERR_CUDA;
+  }
+  return TOPOLOW_OK;
+}
+
+int topolow_plan_create(const topolow_problem* problem, const topolow_params* params, topolow_plan** plan_out,
+                        char* message, int32_t message_len) {
+  if (!problem || !params || !plan_out) return TOPOLOW_ERR_BAD_ARG;
+  *plan_out = nullptr;
+  try {
+    if (params->mode != TOPOLOW_MODE_COLOURED) throw BadArg("plans exist for the coloured mode only");
+    *plan_out = make_plan(*problem, *params).release();
+    return TOPOLOW_OK;
+  } catch (const CudaError& e) {
+    set_msg(message, message_len, e.what()); cudaGetLastError();
+    return TOPOLOW_ERR_CUDA;
+  } catch (const std::exception& e) {
+    set_msg(message, message_len, e.what());
+    return problem->n < 2 ? TOPOLOW_ERR_TOO_FEW_POINTS : TOPOLOW_ERR_BAD_ARG;
+  }
+}
+
+int topolow_plan_run(topolow_plan* plan, int32_t n_iters, void* stream, double* ms_out) {
+  if (!plan) return TOPOLOW_ERR_BAD_ARG;
+  try {
+    const double ms = run_plan(*plan, n_iters, (cudaStream_t)stream, nullptr, nullptr, nullptr);
+    if (ms_out) *ms_out = ms;
+    return TOPOLOW_OK;
+  } catch (const CudaError&) {
+    cudaGetLastError();
+    return TOPOLOW_ERR_CUDA;
+  } catch (const std::exception&) {
+    return TOPOLOW_ERR_BAD_ARG;
+  }
+}
+
+int topolow_plan_result(topolow_plan* plan, topolow_result* result) {
+  if (!plan || !result) return TOPOLOW_ERR_BAD_ARG;
+  try {
+    fill_result(*plan, *result, false);
+    return result->status;
+  } catch (const CudaError& e) {
+    result->status = TOPOLOW_ERR_CUDA; set_msg(result->message, sizeof result->message, e.what()); cudaGetLastError();
+    return TOPOLOW_ERR_CUDA;
+  }
+}
+
+int topolow_plan_info(const topolow_plan* plan, int64_t* out, int32_t cap) {
+  if (!plan || !out) return TOPOLOW_ERR_BAD_ARG;
+  const Geometry& g = plan->geo;
+  const int64_t v[8] = {g.T, g.S, g.W, g.G, g.m, g.S, (int64_t)plan->n * (plan->n - 1) / 2, (int64_t)plan->smem};
+  for (int i = 0; i < cap && i < 8; ++i) out[i] = v[i];
+  return TOPOLOW_OK;
+}
+
+void topolow_plan_destroy(topolow_plan* plan) { delete plan; }
+
+// Host walk of the schedule the kernel executes (same functions, same loop nest).
+int64_t topolow_plan_enumerate(const topolow_plan* plan, int32_t iter, int32_t* out, int64_t cap_pairs) {
+  if (!plan || !out) return -1;
+  return enumerate_schedule(plan->geo, plan->point_of_slot, iter, out, cap_pairs);
+}
+
+// The same walk without a device: geometry + relabelling are pure functions of
+// (n, ndim, precision, sm_count, max_ctas, seed).  geometry_out (optional, 8 values) as in
+// topolow_plan_info.
+int64_t topolow_schedule_enumerate(int64_t n, int32_t ndim, int32_t precision, int32_t sm_count, int32_t max_ctas,
+                                   uint64_t seed, int32_t iter, int32_t* out, int64_t cap_pairs,
+                                   int64_t* geometry_out) {
+  if (n < 2 || ndim < 1 || ndim > kMaxDim || sm_count < 1) return -1;
+  const Geometry g = choose_geometry(n, ndim, precision, sm_count, max_ctas, seed);
+  if (geometry_out) {
+    const int64_t v[8] = {g.T, g.S, g.W, g.G, g.m, g.S, n * (n - 1) / 2,
+                          (int64_t)tile_smem_bytes(g.D, g.W, precision == TOPOLOW_PREC_F64_EXACT ? 8 : 4)};
+    for (int i = 0; i < 8; ++i) geometry_out[i] = v[i];
+  }
+  if (!out) return 0;
+  const std::vector<int32_t> sop = random_permutation(n, seed);
+  std::vector<int32_t> pos((size_t)g.T * kTile, -1);
+  for (int64_t i = 0; i < n; ++i) pos[sop[i]] = (int32_t)i;
+  return enumerate_schedule(g, pos, iter, out, cap_pairs);
+}
+
+}  // extern "C"

@@ -1,0 +1,142 @@
+// topolow_b200/csrc/schedule.h
+//
+// The coloured-parallel schedule, as pure integer functions shared by the CUDA kernel
+// (tilepass.cu) and the host enumerator (topolow_plan_enumerate).  It replaces
+// std::shuffle(all_pairs) of src/optimization.cpp:196 by a structured permutation of the same
+// N(N-1)/2 pairs: every unordered pair is visited exactly once per iteration, and pairs that
+// run concurrently never share a point, so the whole iteration equals ONE sequential order of
+// the reference's Gauss-Seidel loop (src/optimization.cpp:199-282) - the order
+// topolow_plan_enumerate() writes out.
+//
+// Hierarchy (point -> tile of 32 -> super-block of W tiles -> S = 2*G*m super-blocks):
+//   level 2  round-robin tournament over super-blocks (circle method): S-1 cross rounds of
+//            S/2 disjoint super-block pairs (one CTA task each) + 1 diagonal round; a barrier
+//            across the G CTAs of the fit separates rounds.
+//   level 1  inside a cross task (X,Y): W sub-rounds, warp w takes tile X[w] x tile Y[(w+v)%W];
+//            inside a diagonal task: circle method over the W tiles of each super-block, then
+//            every tile against itself; __syncthreads() separates sub-rounds.
+//   level 0  tile x tile: 32 steps of a systolic ring - lane a keeps point A[a] in registers,
+//            the B points rotate through the lanes by an odd stride g, so step i pairs lane a
+//            with B[(a + s0 + g*i) mod 32]: a perfect matching per step.
+//            tile x itself: 31 XOR steps, lane a meets lane a^x.
+// Randomisation per iteration (stateless hashes of (seed, iter)): the tile -> super-block
+// placement, the order of the rounds, the sub-round rotation and the ring's (s0, g).
+#pragma once
+
+#include "common.cuh"
+
+namespace tl {
+
+constexpr int kTile = 32;
+
+struct Geometry {
+  int n;        // real points
+  int T;        // tiles = ceil(n / 32)
+  int W;        // tiles per super-block == warps per CTA
+  int G;        // CTAs cooperating on the fit
+  int m;        // tasks per CTA per round
+  int S;        // super-blocks = 2*G*m
+  int D;        // dimensions
+  uint64_t seed;
+};
+
+// ---- stateless permutation of [0, size): 4-round Feistel + cycle walking ------------------
+TL_HD uint32_t feistel_perm(uint32_t x, uint32_t size, uint64_t key) {
+  if (size <= 1) return 0;
+  int half = 1;
+  while ((1u << (2 * half)) < size) ++half;
+  const uint32_t mask = (1u << half) - 1u;
+  do {
+    uint32_t l = x >> half, r = x & mask;
+#pragma unroll
+    for (int round = 0; round < 4; ++round) {
+      const uint32_t f = (uint32_t)(mix64(((uint64_t)r << 8) + (uint64_t)round + key) & mask);
+      const uint32_t nl = r;
+      r = l ^ f;
+      l = nl;
+    }
+    x = (l << half) | r;
+  } while (x >= size);
+  return x;
+}
+
+TL_HD uint64_t iter_key(const Geometry& g, int iter, uint32_t salt) {
+  return mix64(g.seed ^ mix64(((uint64_t)(uint32_t)iter << 32) | salt));
+}
+
+// Tile held by tile-slot `slot` (super-block slot/W, position slot%W) in this iteration, or -1.
+TL_HD int tile_at(const Geometry& g, int iter, int slot) {
+  const uint32_t t = feistel_perm((uint32_t)slot, (uint32_t)(g.S * g.W), iter_key(g, iter, 1));
+  return (int)t < g.T ? (int)t : -1;
+}
+
+// The r-th cross round executed in this iteration (a permutation of [0, S-1)).
+TL_HD int round_at(const Geometry& g, int iter, int r) {
+  return (int)feistel_perm((uint32_t)r, (uint32_t)(g.S - 1), iter_key(g, iter, 2));
+}
+
+// Circle method: the q-th pair (q in [0, S/2)) of round rr in a tournament of S (even) teams.
+TL_HD void circle_pair(int S, int rr, int q, int& x, int& y) {
+  const int M = S - 1;
+  if (q == 0) { x = M; y = rr; }
+  else { x = (rr + q) % M; y = (rr - q + M) % M; }
+}
+
+struct RingParams { int s0, g, ginv; };
+// Ring offset / stride for tile pair (ta, tb) (actual tile ids, order-insensitive).
+TL_HD RingParams ring_params(const Geometry& geo, int iter, int ta, int tb) {
+  const int lo = ta < tb ? ta : tb, hi = ta < tb ? tb : ta;
+  const uint64_t h = mix64(iter_key(geo, iter, 3) ^ (((uint64_t)(uint32_t)lo << 32) | (uint32_t)hi));
+  RingParams p;
+  p.s0 = (int)(h & 31);
+  p.g = (int)((h >> 5) & 15) * 2 + 1;
+  p.ginv = (p.g * (2 - p.g * p.g)) & 31;  // Newton step: g*g == 1 (mod 8) so this is g^-1 (mod 32)
+  return p;
+}
+// B index that lane `a` holds at ring step i.
+TL_HD int ring_b(const RingParams& p, int a, int i) { return (a + p.s0 + p.g * i) & 31; }
+// Step at which lane a meets B index b.
+TL_HD int ring_step(const RingParams& p, int a, int b) { return (p.ginv * (b - a - p.s0)) & 31; }
+
+struct XorParams { int s0, g; };
+TL_HD XorParams xor_params(const Geometry& geo, int iter, int t) {
+  const uint64_t h = mix64(iter_key(geo, iter, 4) ^ (uint64_t)(uint32_t)t);
+  XorParams p;
+  p.s0 = (int)(h % 31);
+  p.g = (int)((h >> 8) % 30) + 1;  // 1..30, coprime with 31
+  return p;
+}
+// XOR distance used at intra-tile step i (i in [0,31)): a permutation of 1..31.
+TL_HD int xor_at(const XorParams& p, int i) { return (p.s0 + p.g * i) % 31 + 1; }
+
+// Sub-round rotation of a cross task.
+TL_HD int cross_rot(const Geometry& geo, int iter, int x, int y) {
+  const int lo = x < y ? x : y, hi = x < y ? y : x;
+  return (int)(mix64(iter_key(geo, iter, 5) ^ (((uint64_t)(uint32_t)lo << 32) | (uint32_t)hi)) % (uint32_t)geo.W);
+}
+// Diagonal task: number of tile-level sub-rounds inside one super-block, and the pair a warp
+// takes.  Returns false when warp `w` idles in sub-round u.  sb_sel: 0 -> first super-block of
+// the task, 1 -> second.  (ia, ib) are tile positions inside that super-block.
+TL_HD int diag_subrounds(int W) { return W <= 1 ? 0 : (W + (W & 1)) - 1; }
+TL_HD bool diag_pair(int W, int u, int rot, int w, int& sb_sel, int& ia, int& ib) {
+  const int Wp = W + (W & 1), Mt = Wp - 1;
+  const int uu = (u + rot) % Mt;
+  int z;
+  if ((W & 1) == 0) {
+    const int h = W / 2;
+    sb_sel = w / h; z = w % h;
+    if (sb_sel > 1) return false;
+  } else {
+    const int h = (W - 1) / 2;
+    if (h == 0 || w >= 2 * h) return false;
+    sb_sel = w / h; z = w % h + 1;  // z == 0 would be the bye against the dummy tile
+  }
+  circle_pair(Wp, uu, z, ia, ib);
+  return ia < W && ib < W;
+}
+TL_HD int diag_rot(const Geometry& geo, int iter, int q) {
+  const int Mt = diag_subrounds(geo.W);
+  return Mt > 0 ? (int)(mix64(iter_key(geo, iter, 6) ^ (uint64_t)(uint32_t)q) % (uint32_t)Mt) : 0;
+}
+
+}  // namespace tl

@@ -1,0 +1,552 @@
+// topolow_b200/csrc/tilepass.cuh
+//
+// PRODUCTION KERNEL (TOPOLOW_MODE_COLOURED): one persistent kernel runs whole iterations of
+// the reference's pair loop (src/optimization.cpp:193-366) - all N(N-1)/2 pair updates, the
+// cooling step (:289), the edge MAE (:54-81, :294-296), the three-way convergence controller
+// with best-state snapshot (:303-357) and the finite check (:359-361) - with no host
+// round-trip.  The pair order is the structured permutation defined in schedule.h.
+//
+// Data layout in HBM
+//   pos / best : [slot][D] reals (AoS; slot = position of a point after the initial random
+//                relabelling, 32 consecutive slots = one tile, padded with phantom slots)
+//   dp1        : [slot] (degree + 1), 0 marks a phantom slot
+//   edges      : 16-byte records {double target; u32 slot_lo; u32 slot_hi | type << 30},
+//                counting-sorted by (tile_lo, tile_hi); bucket_off[tile_lo * T + tile_hi]
+// On chip
+//   the 2W tiles of a CTA task sit in shared memory as [k][33] (dimension-major, padded);
+//   during a tile x tile pass lane a holds its A point and the travelling B point in
+//   registers, B moves with warp shuffles; measured pairs of the tile pair are scattered
+//   into a per-warp 32x32 target table + three 32-bit lane masks before the pass.
+#pragma once
+
+#include "schedule.h"
+
+namespace tl {
+
+struct __align__(16) EdgeRec {
+  double target;
+  uint32_t slot_lo;        // slot in the lower-numbered tile (or lower slot when same tile)
+  uint32_t slot_hi_type;   // slot in the other tile | type << 30   (0 exact, 1 '>', 2 '<')
+};
+
+template <class real>
+struct TileDev {
+  real* pos;
+  real* best;
+  const real* dp1;
+  const EdgeRec* edges;
+  const uint32_t* bucket_off;
+  FitState* state;
+  double* partials;      // [G][4]: error sum, count, non-finite flag, unused
+  unsigned* barrier;     // [2]: arrivals, generation
+  double* trace;         // [n_iter] or null
+  long long n_edges;
+  unsigned long long pairs_per_iter;
+};
+
+// ---------------------------------------------------------------------------------------
+// Math policies.  `mass` is what travels with a point besides its coordinates.
+// ---------------------------------------------------------------------------------------
+struct FastF32 {
+  typedef float real;
+  static constexpr int kMaxWarps = 16;
+  static constexpr int kMass = 2;  // {1/(deg+1), 1/(4(deg+1)+k)}; both 0 for a phantom
+  struct Ctx { float two_k, c_half, k; };
+  static TL_D Ctx make_ctx(double k, double c_rep) {
+    Ctx c; c.two_k = (float)(2.0 * k); c.c_half = (float)(0.5 * c_rep); c.k = (float)k; return c;
+  }
+  static TL_D void make_mass(real dp1, const Ctx& c, real* mass) {
+    const bool ok = dp1 > 0.f;
+    mass[0] = ok ? __fdividef(1.0f, dp1) : 0.f;
+    mass[1] = ok ? __fdividef(1.0f, fmaf(4.0f, dp1, c.k)) : 0.f;
+  }
+  static TL_D bool valid(const real* mass) { return mass[0] > 0.f; }
+
+  // Scalars of one pair visit (src/optimization.cpp:207-281): returns the factors with which
+  // delta is applied to each endpoint.
+  template <int D>
+  static TL_D void factors(const real (&delta)[D], const real* mA, const real* mB, bool meas, real target,
+                           int type, const Ctx& c, real& fA, real& fB) {
+    real s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int k = 0; k < D; k += 2) {
+      s0 = fmaf(delta[k], delta[k], s0);
+      if (k + 1 < D) s1 = fmaf(delta[k + 1], delta[k + 1], s1);
+    }
+    const real d2 = s0 + s1;
+    const real dist = d2 * rsqrtf(fmaxf(d2, 1e-35f));
+    const real ids = __fdividef(1.0f, dist + 0.01f);
+    const real rep = c.c_half * ids * ids * ids;            // c / (2 ds^3)
+    const real spr = c.two_k * (target - dist) * ids;       // 2k (t - d) / ds
+    const bool spring = meas && (type == 0 || (type > 0 ? dist < target : dist > target));
+    const bool ok = valid(mA) && valid(mB);
+    fA = ok ? (spring ? spr * mA[1] : rep * mA[0]) : 0.f;
+    fB = ok ? (spring ? spr * mB[1] : rep * mB[0]) : 0.f;
+  }
+  template <int D>
+  static TL_D void pair(real (&A)[D], real (&B)[D], const real* mA, const real* mB, bool meas, real target,
+                        int type, const Ctx& c) {
+    real delta[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) delta[k] = B[k] - A[k];
+    real fA, fB;
+    factors<D>(delta, mA, mB, meas, target, type, c, fA, fB);
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+      A[k] = fmaf(-delta[k], fA, A[k]);
+      B[k] = fmaf(delta[k], fB, B[k]);
+    }
+  }
+  // Both lanes of an intra-tile pair run this, each moving only itself.
+  template <int D>
+  static TL_D void pair_self(real (&self)[D], const real (&other)[D], const real* ms, const real* mo, bool meas,
+                             real target, int type, const Ctx& c) {
+    real delta[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) delta[k] = other[k] - self[k];
+    real fS, fO;
+    factors<D>(delta, ms, mo, meas, target, type, c, fS, fO);
+#pragma unroll
+    for (int k = 0; k < D; ++k) self[k] = fmaf(-delta[k], fS, self[k]);
+  }
+};
+
+// IEEE double, one rounding per reference operation, no FMA contraction: bit-comparable with
+// the CPU loop executed on the order topolow_plan_enumerate() reports.
+struct ExactF64 {
+  typedef double real;
+  static constexpr int kMaxWarps = 8;  // 255 registers per thread: the divisions need them
+  static constexpr int kMass = 1;  // deg + 1 (0 = phantom)
+  struct Ctx { double k, c_rep; };
+  static TL_D Ctx make_ctx(double k, double c_rep) { Ctx c; c.k = k; c.c_rep = c_rep; return c; }
+  static TL_D void make_mass(real dp1, const Ctx&, real* mass) { mass[0] = dp1; }
+  static TL_D bool valid(const real* mass) { return mass[0] > 0.0; }
+
+  template <int D>
+  static TL_D void scalars(const real (&delta)[D], bool meas, real target, int type, const Ctx& c, bool& spring,
+                           real& factor) {
+    real dist_sq = 0.0;
+#pragma unroll
+    for (int k = 0; k < D; ++k) dist_sq = __dadd_rn(dist_sq, __dmul_rn(delta[k], delta[k]));
+    const real dist = __dsqrt_rn(dist_sq);
+    const real ds = __dadd_rn(dist, 0.01);
+    spring = meas && (type == 0 || (type > 0 ? dist < target : dist > target));
+    if (spring) factor = __ddiv_rn(__dmul_rn(__dmul_rn(2.0, c.k), __dsub_rn(target, dist)), ds);
+    else factor = __ddiv_rn(c.c_rep, __dmul_rn(__dmul_rn(__dmul_rn(2.0, ds), ds), ds));
+  }
+  static TL_D real norm(bool spring, real dp1, const Ctx& c) {
+    return spring ? __dadd_rn(__dmul_rn(4.0, dp1), c.k) : dp1;
+  }
+  template <int D>
+  static TL_D void pair(real (&A)[D], real (&B)[D], const real* mA, const real* mB, bool meas, real target,
+                        int type, const Ctx& c) {
+    if (!(valid(mA) && valid(mB))) return;
+    real delta[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) delta[k] = __dsub_rn(B[k], A[k]);
+    bool spring; real factor;
+    scalars<D>(delta, meas, target, type, c, spring, factor);
+    const real nA = norm(spring, mA[0], c), nB = norm(spring, mB[0], c);
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+      const real force = __dmul_rn(delta[k], factor);
+      A[k] = __dsub_rn(A[k], __ddiv_rn(force, nA));
+      B[k] = __dadd_rn(B[k], __ddiv_rn(force, nB));
+    }
+  }
+  template <int D>
+  static TL_D void pair_self(real (&self)[D], const real (&other)[D], const real* ms, const real* mo, bool meas,
+                             real target, int type, const Ctx& c) {
+    if (!(valid(ms) && valid(mo))) return;
+    real delta[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) delta[k] = __dsub_rn(other[k], self[k]);
+    bool spring; real factor;
+    scalars<D>(delta, meas, target, type, c, spring, factor);
+    const real nS = norm(spring, ms[0], c);
+#pragma unroll
+    for (int k = 0; k < D; ++k) self[k] = __dsub_rn(self[k], __ddiv_rn(__dmul_rn(delta[k], factor), nS));
+  }
+};
+
+// ---------------------------------------------------------------------------------------
+// Device helpers
+// ---------------------------------------------------------------------------------------
+TL_D unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// FitState moves between CTAs through L2 (never a stale L1 line).
+static_assert(sizeof(FitState) % 8 == 0, "FitState is copied as 64-bit words");
+TL_D void load_state(FitState& dst, const FitState* src) {
+  unsigned long long* d = reinterpret_cast<unsigned long long*>(&dst);
+  const unsigned long long* s = reinterpret_cast<const unsigned long long*>(src);
+  for (int i = 0; i < (int)(sizeof(FitState) / 8); ++i) d[i] = __ldcg(s + i);
+}
+TL_D void store_state(FitState* dst, const FitState& src) {
+  unsigned long long* d = reinterpret_cast<unsigned long long*>(dst);
+  const unsigned long long* s = reinterpret_cast<const unsigned long long*>(&src);
+  for (int i = 0; i < (int)(sizeof(FitState) / 8); ++i) __stcg(d + i, s[i]);
+}
+
+// Barrier across the G CTAs of one fit (all co-resident: cooperative launch).
+TL_D void gang_barrier(unsigned* bar, int G, unsigned& gen) {
+  __syncthreads();
+  if (G > 1) {
+    if (threadIdx.x == 0) {
+      __threadfence();
+      const unsigned arrived = atomicAdd(&bar[0], 1u);
+      if (arrived == (unsigned)G - 1u) {
+        atomicExch(&bar[0], 0u);
+        __threadfence();
+        atomicAdd(&bar[1], 1u);
+      } else {
+        while (ld_acquire_u32(&bar[1]) == gen) { __nanosleep(20); }
+      }
+      __threadfence();
+    }
+    gen++;
+    __syncthreads();
+  }
+}
+
+template <int D>
+struct TileShape {
+  static constexpr int kStride = 33;                  // padded row of one dimension
+  static constexpr int kReals = (D + 1) * kStride;    // D coordinate rows + the dp1 row
+};
+
+// global AoS tile -> shared [k][33]
+template <int D, class real>
+TL_D void load_tile(real* s, const real* gpos, const real* gdp1, int tile, int lane) {
+  if (tile < 0) {
+#pragma unroll
+    for (int k = 0; k <= D; ++k) s[k * 33 + lane] = (real)0;
+    return;
+  }
+  const real* base = gpos + (size_t)tile * (kTile * D);
+#pragma unroll
+  for (int j = 0; j < D; ++j) {
+    const int e = lane + 32 * j;
+    s[(e % D) * 33 + (e / D)] = __ldcg(base + e);
+  }
+  s[D * 33 + lane] = gdp1[(size_t)tile * kTile + lane];
+}
+template <int D, class real>
+TL_D void store_tile(const real* s, real* gpos, int tile, int lane) {
+  if (tile < 0) return;
+  real* base = gpos + (size_t)tile * (kTile * D);
+#pragma unroll
+  for (int j = 0; j < D; ++j) {
+    const int e = lane + 32 * j;
+    __stcg(base + e, s[(e % D) * 33 + (e / D)]);
+  }
+}
+
+template <class real>
+struct WarpTable {
+  real* tgt;        // [32 steps][32 lanes]
+  uint32_t* mask;   // [3][32]: measured, '>' , '<'
+};
+
+// Scatter the measured pairs of bucket (lo,hi) into the warp's table.  `swap` = the A side is
+// the higher-numbered tile.  Ring passes index by (step, lane), intra passes by (xor, lane).
+template <class real>
+TL_D void fill_table_ring(const WarpTable<real>& tb, const EdgeRec* edges, uint32_t beg, uint32_t end, bool swap,
+                          const RingParams& rp, int lane) {
+  for (uint32_t e = beg + lane; e < end; e += 32) {
+    const EdgeRec r = edges[e];
+    const int lo = r.slot_lo & 31, hi = r.slot_hi_type & 31;
+    const int ty = r.slot_hi_type >> 30;
+    const int a = swap ? hi : lo, b = swap ? lo : hi;
+    const int i = ring_step(rp, a, b);
+    tb.tgt[i * 32 + a] = (real)r.target;
+    atomicOr(&tb.mask[a], 1u << i);
+    if (ty == 1) atomicOr(&tb.mask[32 + a], 1u << i);
+    if (ty == 2) atomicOr(&tb.mask[64 + a], 1u << i);
+  }
+}
+template <class real>
+TL_D void fill_table_xor(const WarpTable<real>& tb, const EdgeRec* edges, uint32_t beg, uint32_t end, int lane) {
+  for (uint32_t e = beg + lane; e < end; e += 32) {
+    const EdgeRec r = edges[e];
+    const int a = r.slot_lo & 31, b = r.slot_hi_type & 31;
+    const int ty = r.slot_hi_type >> 30;
+    const int x = a ^ b;
+    tb.tgt[x * 32 + a] = (real)r.target;
+    tb.tgt[x * 32 + b] = (real)r.target;
+    atomicOr(&tb.mask[a], 1u << x);
+    atomicOr(&tb.mask[b], 1u << x);
+    if (ty == 1) { atomicOr(&tb.mask[32 + a], 1u << x); atomicOr(&tb.mask[32 + b], 1u << x); }
+    if (ty == 2) { atomicOr(&tb.mask[64 + a], 1u << x); atomicOr(&tb.mask[64 + b], 1u << x); }
+  }
+}
+
+// tile A x tile B, 32 ring steps.  sA / sB are the shared-memory tiles.
+template <int D, class M>
+TL_D void ring_pass(typename M::real* sA, typename M::real* sB, int tA, int tB, const WarpTable<typename M::real>& tb,
+                    const TileDev<typename M::real>& dv, const Geometry& geo, int iter, const typename M::Ctx& ctx,
+                    int lane) {
+  typedef typename M::real real;
+  const unsigned full = 0xffffffffu;
+  const RingParams rp = ring_params(geo, iter, tA, tB);
+  const int lo = tA < tB ? tA : tB, hi = tA < tB ? tB : tA;
+  const size_t key = (size_t)lo * geo.T + hi;
+  const uint32_t beg = dv.bucket_off[key], end = dv.bucket_off[key + 1];
+  uint32_t m_meas = 0, m_gt = 0, m_lt = 0;
+  if (beg != end) {  // warp-uniform
+    tb.mask[lane] = 0; tb.mask[32 + lane] = 0; tb.mask[64 + lane] = 0;
+    __syncwarp();
+    fill_table_ring<real>(tb, dv.edges, beg, end, tA > tB, rp, lane);
+    __syncwarp();
+    m_meas = tb.mask[lane]; m_gt = tb.mask[32 + lane]; m_lt = tb.mask[64 + lane];
+  }
+  real A[D], B[D], mA[M::kMass], mB[M::kMass];
+  const int b0 = (lane + rp.s0) & 31;
+#pragma unroll
+  for (int k = 0; k < D; ++k) { A[k] = sA[k * 33 + lane]; B[k] = sB[k * 33 + b0]; }
+  M::make_mass(sA[D * 33 + lane], ctx, mA);
+  M::make_mass(sB[D * 33 + b0], ctx, mB);
+  const int src = (lane + rp.g) & 31;
+#pragma unroll 1
+  for (int i = 0; i < 32; ++i) {
+    const bool meas = (m_meas >> i) & 1u;
+    real target = (real)0;
+    int type = 0;
+    if (meas) {
+      target = tb.tgt[i * 32 + lane];
+      type = (int)((m_gt >> i) & 1u) - (int)((m_lt >> i) & 1u);
+    }
+    M::template pair<D>(A, B, mA, mB, meas, target, type, ctx);
+    if (i < 31) {
+#pragma unroll
+      for (int k = 0; k < D; ++k) B[k] = __shfl_sync(full, B[k], src);
+#pragma unroll
+      for (int k = 0; k < M::kMass; ++k) mB[k] = __shfl_sync(full, mB[k], src);
+    }
+  }
+  const int bf = (lane + rp.s0 + 31 * rp.g) & 31;
+#pragma unroll
+  for (int k = 0; k < D; ++k) { sA[k * 33 + lane] = A[k]; sB[k * 33 + bf] = B[k]; }
+}
+
+// tile x itself, 31 XOR steps; every lane moves only its own point.
+template <int D, class M>
+TL_D void intra_pass(typename M::real* sT, int t, const WarpTable<typename M::real>& tb,
+                     const TileDev<typename M::real>& dv, const Geometry& geo, int iter,
+                     const typename M::Ctx& ctx, int lane) {
+  typedef typename M::real real;
+  const unsigned full = 0xffffffffu;
+  const size_t key = (size_t)t * geo.T + t;
+  const uint32_t beg = dv.bucket_off[key], end = dv.bucket_off[key + 1];
+  uint32_t m_meas = 0, m_gt = 0, m_lt = 0;
+  if (beg != end) {
+    tb.mask[lane] = 0; tb.mask[32 + lane] = 0; tb.mask[64 + lane] = 0;
+    __syncwarp();
+    fill_table_xor<real>(tb, dv.edges, beg, end, lane);
+    __syncwarp();
+    m_meas = tb.mask[lane]; m_gt = tb.mask[32 + lane]; m_lt = tb.mask[64 + lane];
+  }
+  real S[D], O[D], mS[M::kMass], mO[M::kMass];
+#pragma unroll
+  for (int k = 0; k < D; ++k) S[k] = sT[k * 33 + lane];
+  M::make_mass(sT[D * 33 + lane], ctx, mS);
+  const XorParams xp = xor_params(geo, iter, t);
+#pragma unroll 1
+  for (int i = 0; i < 31; ++i) {
+    const int x = xor_at(xp, i);
+#pragma unroll
+    for (int k = 0; k < D; ++k) O[k] = __shfl_xor_sync(full, S[k], x);
+#pragma unroll
+    for (int k = 0; k < M::kMass; ++k) mO[k] = __shfl_xor_sync(full, mS[k], x);
+    const bool meas = (m_meas >> x) & 1u;
+    real target = (real)0;
+    int type = 0;
+    if (meas) {
+      target = tb.tgt[x * 32 + lane];
+      type = (int)((m_gt >> x) & 1u) - (int)((m_lt >> x) & 1u);
+    }
+    M::template pair_self<D>(S, O, mS, mO, meas, target, type, ctx);
+  }
+#pragma unroll
+  for (int k = 0; k < D; ++k) sT[k * 33 + lane] = S[k];
+}
+
+// Deterministic CTA reduction of (sum, count, flag); result valid in thread 0.
+TL_D void block_reduce3(double& a, double& b, double& c, double* scratch /* [3*32] */) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_down_sync(full, a, o);
+    b += __shfl_down_sync(full, b, o);
+    c += __shfl_down_sync(full, c, o);
+  }
+  if (lane == 0) { scratch[warp] = a; scratch[32 + warp] = b; scratch[64 + warp] = c; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    a = 0; b = 0; c = 0;
+    for (int w = 0; w < nw; ++w) { a += scratch[w]; b += scratch[32 + w]; c += scratch[64 + w]; }
+  }
+  __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------
+// The persistent kernel: up to n_iters iterations of one fit, G CTAs of W warps.
+// ---------------------------------------------------------------------------------------
+template <int D, class M>
+__global__ void __launch_bounds__(M::kMaxWarps * 32, 1)
+tile_kernel(TileDev<typename M::real> dv, Geometry geo, FitParams prm, int n_iters, volatile int* host_flag) {
+  typedef typename M::real real;
+  constexpr int TS = TileShape<D>::kReals;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ FitState st;
+  __shared__ double red_scratch[96];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int W = geo.W, cta = blockIdx.x;
+  real* s_tiles = reinterpret_cast<real*>(smem_raw);
+  real* s_tgt = s_tiles + (size_t)2 * W * TS;
+  uint32_t* s_mask = reinterpret_cast<uint32_t*>(s_tgt + (size_t)W * 1024);
+  int* s_tid = reinterpret_cast<int*>(s_mask + W * 96);
+  const WarpTable<real> tb{s_tgt + warp * 1024, s_mask + warp * 96};
+
+  unsigned gen = 0;
+  if (tid == 0) load_state(st, dv.state);
+  if (geo.G > 1) gen = ld_acquire_u32(&dv.barrier[1]);
+  __syncthreads();
+
+  for (int it = 0; it < n_iters; ++it) {
+    if (st.stop) break;
+    const int iter = st.iter;
+    const typename M::Ctx ctx = M::make_ctx(st.k, prm.c_repulsion);
+
+    // ---------------- cross rounds ----------------
+    for (int r = 0; r < geo.S - 1; ++r) {
+      const int rr = round_at(geo, iter, r);
+      for (int tt = 0; tt < geo.m; ++tt) {
+        int X, Y;
+        circle_pair(geo.S, rr, cta * geo.m + tt, X, Y);
+        const int tX = tile_at(geo, iter, X * W + warp), tY = tile_at(geo, iter, Y * W + warp);
+        if (lane == 0) { s_tid[warp] = tX; s_tid[W + warp] = tY; }
+        load_tile<D, real>(s_tiles + (size_t)warp * TS, dv.pos, dv.dp1, tX, lane);
+        load_tile<D, real>(s_tiles + (size_t)(W + warp) * TS, dv.pos, dv.dp1, tY, lane);
+        __syncthreads();
+        const int rot = cross_rot(geo, iter, X, Y);
+        for (int v = 0; v < W; ++v) {
+          const int bw = (warp + v + rot) % W;
+          const int tA = s_tid[warp], tB = s_tid[W + bw];
+          if (tA >= 0 && tB >= 0)
+            ring_pass<D, M>(s_tiles + (size_t)warp * TS, s_tiles + (size_t)(W + bw) * TS, tA, tB, tb, dv, geo, iter,
+                            ctx, lane);
+          __syncthreads();
+        }
+        store_tile<D, real>(s_tiles + (size_t)warp * TS, dv.pos, tX, lane);
+        store_tile<D, real>(s_tiles + (size_t)(W + warp) * TS, dv.pos, tY, lane);
+        __syncwarp();
+      }
+      gang_barrier(dv.barrier, geo.G, gen);
+    }
+
+    // ---------------- diagonal round ----------------
+    for (int tt = 0; tt < geo.m; ++tt) {
+      const int q = cta * geo.m + tt;
+      const int tX = tile_at(geo, iter, (2 * q) * W + warp), tY = tile_at(geo, iter, (2 * q + 1) * W + warp);
+      if (lane == 0) { s_tid[warp] = tX; s_tid[W + warp] = tY; }
+      load_tile<D, real>(s_tiles + (size_t)warp * TS, dv.pos, dv.dp1, tX, lane);
+      load_tile<D, real>(s_tiles + (size_t)(W + warp) * TS, dv.pos, dv.dp1, tY, lane);
+      __syncthreads();
+      const int Mt = diag_subrounds(W), rot = diag_rot(geo, iter, q);
+      for (int u = 0; u < Mt; ++u) {
+        int sb, ia, ib;
+        if (diag_pair(W, u, rot, warp, sb, ia, ib)) {
+          const int tA = s_tid[sb * W + ia], tB = s_tid[sb * W + ib];
+          if (tA >= 0 && tB >= 0)
+            ring_pass<D, M>(s_tiles + (size_t)(sb * W + ia) * TS, s_tiles + (size_t)(sb * W + ib) * TS, tA, tB, tb, dv,
+                            geo, iter, ctx, lane);
+        }
+        __syncthreads();
+      }
+      if (tX >= 0) intra_pass<D, M>(s_tiles + (size_t)warp * TS, tX, tb, dv, geo, iter, ctx, lane);
+      if (tY >= 0) intra_pass<D, M>(s_tiles + (size_t)(W + warp) * TS, tY, tb, dv, geo, iter, ctx, lane);
+      store_tile<D, real>(s_tiles + (size_t)warp * TS, dv.pos, tX, lane);
+      store_tile<D, real>(s_tiles + (size_t)(W + warp) * TS, dv.pos, tY, lane);
+      __syncwarp();
+    }
+    gang_barrier(dv.barrier, geo.G, gen);
+
+    // ---------------- end of iteration: cooling, MAE, controller, finite check ----------------
+    const bool check = is_check_iter(iter, prm);
+    const bool fin = ((iter + 1) % 10 == 0);
+    if (tid == 0) {
+      st.k = st.k * (1.0 - prm.cooling_rate);
+      st.pair_updates += dv.pairs_per_iter;
+    }
+    if (check || fin) {
+      double e_sum = 0.0, e_cnt = 0.0, bad = 0.0;
+      if (check) {
+        for (long long e = (long long)cta * blockDim.x + tid; e < dv.n_edges; e += (long long)geo.G * blockDim.x) {
+          const EdgeRec rec = dv.edges[e];
+          const real* pa = dv.pos + (size_t)rec.slot_lo * D;
+          const real* pb = dv.pos + (size_t)(rec.slot_hi_type & 0x3fffffffu) * D;
+          const int ty = rec.slot_hi_type >> 30;
+          double ss = 0.0;
+#pragma unroll
+          for (int k = 0; k < D; ++k) {
+            const double df = (double)__ldcg(pb + k) - (double)__ldcg(pa + k);
+            ss = __dadd_rn(ss, __dmul_rn(df, df));
+          }
+          const double dist = __dsqrt_rn(ss);
+          const bool contributes = (ty == 0) || (ty == 1 && dist < rec.target) || (ty == 2 && dist > rec.target);
+          if (contributes) { e_sum += fabs(rec.target - dist); e_cnt += 1.0; }
+        }
+      }
+      if (fin) {
+        const size_t total = (size_t)geo.T * kTile * D;
+        for (size_t x = (size_t)cta * blockDim.x + tid; x < total; x += (size_t)geo.G * blockDim.x)
+          if (!isfinite((double)__ldcg(dv.pos + x))) bad = 1.0;
+      }
+      block_reduce3(e_sum, e_cnt, bad, red_scratch);
+      if (tid == 0) {
+        double* p = dv.partials + (size_t)cta * 4;
+        __stcg(p, e_sum); __stcg(p + 1, e_cnt); __stcg(p + 2, bad);
+      }
+      gang_barrier(dv.barrier, geo.G, gen);
+      if (cta == 0 && tid == 0) {
+        double s = 0.0, c = 0.0, b = 0.0;
+        for (int g = 0; g < geo.G; ++g) {
+          const double* p = dv.partials + (size_t)g * 4;
+          s += __ldcg(p); c += __ldcg(p + 1); b += __ldcg(p + 2);
+        }
+        st.snapshot = 0;
+        if (check) {
+          controller_check(st, prm, iter, s, (long long)c);
+          if (dv.trace) dv.trace[iter] = st.last_error;
+        }
+        if (!st.stop && fin && b > 0.0) { st.status = 2; st.fail_iter = iter + 1; st.stop = 1; }
+        st.iter = iter + 1;
+        store_state(dv.state, st);
+      }
+      gang_barrier(dv.barrier, geo.G, gen);
+      if (cta != 0 && tid == 0) load_state(st, dv.state);
+      __syncthreads();
+      if (st.snapshot) {
+        const size_t total = (size_t)geo.T * kTile * D;
+        for (size_t x = (size_t)cta * blockDim.x + tid; x < total; x += (size_t)geo.G * blockDim.x)
+          dv.best[x] = __ldcg(dv.pos + x);
+        gang_barrier(dv.barrier, geo.G, gen);
+      }
+    } else {
+      if (tid == 0) st.iter = iter + 1;
+      __syncthreads();
+    }
+  }
+  if (cta == 0 && tid == 0) {
+    store_state(dv.state, st);
+    if (host_flag) { host_flag[1] = st.iter; __threadfence_system(); host_flag[0] = st.stop; }
+  }
+}
+
+}  // namespace tl
