@@ -272,10 +272,10 @@ class Plan:
         return result_dict(res, out, tr)
 
     def info(self):
-        v = (C.c_int64 * 8)()
-        self._L.topolow_plan_info(self._h, v, 8)
+        v = (C.c_int64 * 10)()
+        self._L.topolow_plan_info(self._h, v, 10)
         keys = ["tiles", "super_blocks", "warps_per_cta", "ctas", "tasks_per_cta", "rounds", "pairs_per_iter",
-                "smem_bytes"]
+                "smem_bytes", "iters_per_launch", "launches"]
         return dict(zip(keys, [int(x) for x in v]))
 
     def enumerate(self, it):

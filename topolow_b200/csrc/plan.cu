@@ -34,6 +34,7 @@ struct topolow_plan {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int chunk_iters = 1;
+  int64_t launches = 0;
   double total_ms = 0.0;
   size_t smem = 0;
 
@@ -273,10 +274,12 @@ void launch_chunk(topolow_plan& pl, int n_iters, cudaStream_t stream) {
     TileDev<double> dv{(double*)pl.pos, (double*)pl.best, (const double*)pl.dp1, pl.edges, pl.bucket_off, pl.state,
                        pl.partials, pl.barrier, pl.trace, (long long)pl.E, ppi};
     launch_tile_f64(dv, pl.geo, pl.prm, n_iters, pl.d_flag, stream);
+    pl.launches++;
   } else {
     TileDev<float> dv{(float*)pl.pos, (float*)pl.best, (const float*)pl.dp1, pl.edges, pl.bucket_off, pl.state,
                       pl.partials, pl.barrier, pl.trace, (long long)pl.E, ppi};
     launch_tile_f32(dv, pl.geo, pl.prm, n_iters, pl.d_flag, stream);
+    pl.launches++;
   }
 }
 
@@ -574,8 +577,9 @@ int topolow_plan_result(topolow_plan* plan, topolow_result* result) {
 int topolow_plan_info(const topolow_plan* plan, int64_t* out, int32_t cap) {
   if (!plan || !out) return TOPOLOW_ERR_BAD_ARG;
   const Geometry& g = plan->geo;
-  const int64_t v[8] = {g.T, g.S, g.W, g.G, g.m, g.S, (int64_t)plan->n * (plan->n - 1) / 2, (int64_t)plan->smem};
-  for (int i = 0; i < cap && i < 8; ++i) out[i] = v[i];
+  const int64_t v[10] = {g.T, g.S, g.W, g.G, g.m, g.S, (int64_t)plan->n * (plan->n - 1) / 2, (int64_t)plan->smem,
+                         plan->chunk_iters, plan->launches};
+  for (int i = 0; i < cap && i < 10; ++i) out[i] = v[i];
   return TOPOLOW_OK;
 }
 
