@@ -166,9 +166,9 @@ int64_t enumerate_schedule(const Geometry& g, const std::vector<int32_t>& pos, i
 }
 
 template <class real>
-void upload_points(topolow_plan& pl, const topolow_problem& pb) {
+void upload_points(topolow_plan& pl, const topolow_problem& pb, real phantom_coord) {
   const size_t slots = (size_t)pl.geo.T * kTile;
-  std::vector<real> hp(slots * pl.D, (real)0), hd(slots, (real)0);
+  std::vector<real> hp(slots * pl.D, phantom_coord), hd(slots, (real)0);
   for (int64_t i = 0; i < pl.n; ++i) {
     const size_t s = pl.slot_of_point[i];
     for (int d = 0; d < pl.D; ++d) hp[s * pl.D + d] = (real)pb.initial_positions[(size_t)d * pl.n + i];
@@ -238,8 +238,8 @@ std::unique_ptr<topolow_plan> make_plan(const topolow_problem& pb, const topolow
   pl->point_of_slot.assign((size_t)g.T * kTile, -1);
   for (int64_t i = 0; i < pb.n; ++i) pl->point_of_slot[pl->slot_of_point[i]] = (int32_t)i;
 
-  if (pr.precision == TOPOLOW_PREC_F64_EXACT) upload_points<double>(*pl, pb);
-  else upload_points<float>(*pl, pb);
+  if (pr.precision == TOPOLOW_PREC_F64_EXACT) upload_points<double>(*pl, pb, ExactF64::kPhantomCoord);
+  else upload_points<float>(*pl, pb, FastF32::kPhantomCoord);
   upload_edges(*pl, pb);
 
   FitState st; state_init(st, pl->prm);

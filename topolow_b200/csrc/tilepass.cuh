@@ -45,69 +45,147 @@ struct TileDev {
 };
 
 // ---------------------------------------------------------------------------------------
-// Math policies.  `mass` is what travels with a point besides its coordinates.
+// Math policies.  A policy owns the register image of a point (`Point<D>`: coordinates + the
+// mass terms that travel with it) and the arithmetic of one pair visit.
 // ---------------------------------------------------------------------------------------
+
+// Two FP32 values in one 64-bit register: sm_100 has 2-wide FP32 FMA/ADD/MUL (SASS FFMA2 ...),
+// which halves the instruction count of the coordinate loops.
+typedef float2 f32x2;
+TL_D f32x2 pk2(float lo, float hi) { return make_float2(lo, hi); }
+TL_D void upk2(f32x2 v, float& lo, float& hi) { lo = v.x; hi = v.y; }
+TL_D f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { return __ffma2_rn(a, b, c); }
+TL_D f32x2 mul2(f32x2 a, f32x2 b) { return __fmul2_rn(a, b); }
+TL_D f32x2 add2(f32x2 a, f32x2 b) { return __fadd2_rn(a, b); }
+TL_D float rsqrt_fast(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+TL_D float rcp_fast(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+
+// FP32 production arithmetic.  A phantom slot (padding of the last tile) has zero mass and sits
+// at kPhantomCoord in every dimension: against a real point 1/ds^3 flushes to zero, against
+// another phantom the zero mass cancels the force, so no validity predicate is needed.
 struct FastF32 {
   typedef float real;
   static constexpr int kMaxWarps = 16;
-  static constexpr int kMass = 2;  // {1/(deg+1), 1/(4(deg+1)+k)}; both 0 for a phantom
+  static constexpr float kPhantomCoord = 1.0e18f;
   struct Ctx { float two_k, c_half, k; };
   static TL_D Ctx make_ctx(double k, double c_rep) {
     Ctx c; c.two_k = (float)(2.0 * k); c.c_half = (float)(0.5 * c_rep); c.k = (float)k; return c;
   }
-  static TL_D void make_mass(real dp1, const Ctx& c, real* mass) {
-    const bool ok = dp1 > 0.f;
-    mass[0] = ok ? __fdividef(1.0f, dp1) : 0.f;
-    mass[1] = ok ? __fdividef(1.0f, fmaf(4.0f, dp1, c.k)) : 0.f;
-  }
-  static TL_D bool valid(const real* mass) { return mass[0] > 0.f; }
-
-  // Scalars of one pair visit (src/optimization.cpp:207-281): returns the factors with which
-  // delta is applied to each endpoint.
   template <int D>
-  static TL_D void factors(const real (&delta)[D], const real* mA, const real* mB, bool meas, real target,
-                           int type, const Ctx& c, real& fA, real& fB) {
-    real s0 = 0.f, s1 = 0.f;
+  struct Point {
+    static constexpr int H = (D + 1) / 2;
+    f32x2 c[H];       // coordinates, two per register (odd D: the last high half is 0)
+    float rdeg;       // 1 / (deg + 1)          (0 for a phantom)
+    float rnorm;      // 1 / (4 (deg + 1) + k)  (0 for a phantom)
+    TL_D void load(const float* s, int idx, const Ctx& ctx) {
 #pragma unroll
-    for (int k = 0; k < D; k += 2) {
-      s0 = fmaf(delta[k], delta[k], s0);
-      if (k + 1 < D) s1 = fmaf(delta[k + 1], delta[k + 1], s1);
+      for (int j = 0; j < H; ++j)
+        c[j] = pk2(s[(2 * j) * 33 + idx], (2 * j + 1 < D) ? s[(2 * j + 1) * 33 + idx] : 0.f);
+      const float dp1 = s[D * 33 + idx];
+      const bool ok = dp1 > 0.f;
+      rdeg = ok ? rcp_fast(dp1) : 0.f;
+      rnorm = ok ? rcp_fast(fmaf(4.0f, dp1, ctx.k)) : 0.f;
     }
-    const real d2 = s0 + s1;
-    const real dist = d2 * rsqrtf(fmaxf(d2, 1e-35f));
-    const real ids = __fdividef(1.0f, dist + 0.01f);
-    const real rep = c.c_half * ids * ids * ids;            // c / (2 ds^3)
-    const real spr = c.two_k * (target - dist) * ids;       // 2k (t - d) / ds
-    const bool spring = meas && (type == 0 || (type > 0 ? dist < target : dist > target));
-    const bool ok = valid(mA) && valid(mB);
-    fA = ok ? (spring ? spr * mA[1] : rep * mA[0]) : 0.f;
-    fB = ok ? (spring ? spr * mB[1] : rep * mB[0]) : 0.f;
+    TL_D void store(float* s, int idx) const {
+#pragma unroll
+      for (int j = 0; j < H; ++j) {
+        float lo, hi;
+        upk2(c[j], lo, hi);
+        s[(2 * j) * 33 + idx] = lo;
+        if (2 * j + 1 < D) s[(2 * j + 1) * 33 + idx] = hi;
+      }
+    }
+    TL_D void shfl_from(int src) {
+      const unsigned full = 0xffffffffu;
+#pragma unroll
+      for (int j = 0; j < H; ++j) {
+        float lo, hi;
+        upk2(c[j], lo, hi);
+        lo = __shfl_sync(full, lo, src);
+        if (2 * j + 1 < D) hi = __shfl_sync(full, hi, src);
+        c[j] = pk2(lo, hi);
+      }
+      rdeg = __shfl_sync(full, rdeg, src);
+      rnorm = __shfl_sync(full, rnorm, src);
+    }
+    TL_D void shfl_xor_of(const Point& o, int x) {
+      const unsigned full = 0xffffffffu;
+#pragma unroll
+      for (int j = 0; j < H; ++j) {
+        float lo, hi;
+        upk2(o.c[j], lo, hi);
+        lo = __shfl_xor_sync(full, lo, x);
+        if (2 * j + 1 < D) hi = __shfl_xor_sync(full, hi, x);
+        c[j] = pk2(lo, hi);
+      }
+      rdeg = __shfl_xor_sync(full, o.rdeg, x);
+      rnorm = __shfl_xor_sync(full, o.rnorm, x);
+    }
+  };
+
+  // delta = B - A, and the scalar with which it is applied to each endpoint
+  // (src/optimization.cpp:207-281 with reciprocals hoisted out of the coordinate loop).
+  template <int D>
+  static TL_D void force(const Point<D>& A, const Point<D>& B, f32x2 (&delta)[Point<D>::H], bool meas,
+                         const float* tgt_cell, uint32_t gt_bit, uint32_t lt_bit, const Ctx& c, float& fA, float& fB) {
+    constexpr int H = Point<D>::H;
+    const f32x2 neg1 = pk2(-1.0f, -1.0f);
+#pragma unroll
+    for (int j = 0; j < H; ++j) delta[j] = fma2(A.c[j], neg1, B.c[j]);
+    f32x2 acc0 = mul2(delta[0], delta[0]);
+    f32x2 acc1 = pk2(0.f, 0.f);
+    if (H > 1) acc1 = mul2(delta[1], delta[1]);
+#pragma unroll
+    for (int j = 2; j < H; ++j) {
+      if (j & 1) acc1 = fma2(delta[j], delta[j], acc1);
+      else acc0 = fma2(delta[j], delta[j], acc0);
+    }
+    if (H > 1) acc0 = add2(acc0, acc1);
+    float lo, hi;
+    upk2(acc0, lo, hi);
+    const float d2 = lo + hi;
+    const float dist = d2 * rsqrt_fast(fmaxf(d2, 1e-35f));
+    const float ids = rcp_fast(dist + 0.01f);
+    float f = c.c_half * ids * ids * ids;   // repulsion: c / (2 ds^3)
+    float wA = A.rdeg, wB = B.rdeg;
+    if (__any_sync(0xffffffffu, meas)) {    // warp-uniform: most steps of a sparse map skip this
+      if (meas) {
+        const float target = *tgt_cell;
+        const bool spring = (gt_bit | lt_bit) == 0u ? true : (gt_bit ? dist < target : dist > target);
+        if (spring) {
+          f = c.two_k * (target - dist) * ids;   // spring: 2k (t - d) / ds
+          wA = A.rnorm; wB = B.rnorm;
+        }
+      }
+    }
+    fA = f * wA;
+    fB = f * wB;
   }
   template <int D>
-  static TL_D void pair(real (&A)[D], real (&B)[D], const real* mA, const real* mB, bool meas, real target,
-                        int type, const Ctx& c) {
-    real delta[D];
+  static TL_D void pair(Point<D>& A, Point<D>& B, bool meas, const float* tgt_cell, uint32_t gt_bit, uint32_t lt_bit,
+                        const Ctx& c) {
+    constexpr int H = Point<D>::H;
+    f32x2 delta[H];
+    float fA, fB;
+    force<D>(A, B, delta, meas, tgt_cell, gt_bit, lt_bit, c, fA, fB);
+    const f32x2 nA = pk2(-fA, -fA), pB = pk2(fB, fB);
 #pragma unroll
-    for (int k = 0; k < D; ++k) delta[k] = B[k] - A[k];
-    real fA, fB;
-    factors<D>(delta, mA, mB, meas, target, type, c, fA, fB);
-#pragma unroll
-    for (int k = 0; k < D; ++k) {
-      A[k] = fmaf(-delta[k], fA, A[k]);
-      B[k] = fmaf(delta[k], fB, B[k]);
+    for (int j = 0; j < H; ++j) {
+      A.c[j] = fma2(delta[j], nA, A.c[j]);
+      B.c[j] = fma2(delta[j], pB, B.c[j]);
     }
   }
   // Both lanes of an intra-tile pair run this, each moving only itself.
   template <int D>
-  static TL_D void pair_self(real (&self)[D], const real (&other)[D], const real* ms, const real* mo, bool meas,
-                             real target, int type, const Ctx& c) {
-    real delta[D];
+  static TL_D void pair_self(Point<D>& S, const Point<D>& O, bool meas, const float* tgt_cell, uint32_t gt_bit,
+                             uint32_t lt_bit, const Ctx& c) {
+    constexpr int H = Point<D>::H;
+    f32x2 delta[H];
+    float fS, fO;
+    force<D>(S, O, delta, meas, tgt_cell, gt_bit, lt_bit, c, fS, fO);
+    const f32x2 nS = pk2(-fS, -fS);
 #pragma unroll
-    for (int k = 0; k < D; ++k) delta[k] = other[k] - self[k];
-    real fS, fO;
-    factors<D>(delta, ms, mo, meas, target, type, c, fS, fO);
-#pragma unroll
-    for (int k = 0; k < D; ++k) self[k] = fmaf(-delta[k], fS, self[k]);
+    for (int j = 0; j < H; ++j) S.c[j] = fma2(delta[j], nS, S.c[j]);
   }
 };
 
@@ -116,56 +194,82 @@ struct FastF32 {
 struct ExactF64 {
   typedef double real;
   static constexpr int kMaxWarps = 8;  // 255 registers per thread: the divisions need them
-  static constexpr int kMass = 1;  // deg + 1 (0 = phantom)
+  static constexpr double kPhantomCoord = 0.0;
   struct Ctx { double k, c_rep; };
   static TL_D Ctx make_ctx(double k, double c_rep) { Ctx c; c.k = k; c.c_rep = c_rep; return c; }
-  static TL_D void make_mass(real dp1, const Ctx&, real* mass) { mass[0] = dp1; }
-  static TL_D bool valid(const real* mass) { return mass[0] > 0.0; }
-
   template <int D>
-  static TL_D void scalars(const real (&delta)[D], bool meas, real target, int type, const Ctx& c, bool& spring,
-                           real& factor) {
-    real dist_sq = 0.0;
+  struct Point {
+    double c[D];
+    double dp1;   // deg + 1, 0 = phantom
+    TL_D void load(const double* s, int idx, const Ctx&) {
+#pragma unroll
+      for (int k = 0; k < D; ++k) c[k] = s[k * 33 + idx];
+      dp1 = s[D * 33 + idx];
+    }
+    TL_D void store(double* s, int idx) const {
+#pragma unroll
+      for (int k = 0; k < D; ++k) s[k * 33 + idx] = c[k];
+    }
+    TL_D void shfl_from(int src) {
+#pragma unroll
+      for (int k = 0; k < D; ++k) c[k] = __shfl_sync(0xffffffffu, c[k], src);
+      dp1 = __shfl_sync(0xffffffffu, dp1, src);
+    }
+    TL_D void shfl_xor_of(const Point& o, int x) {
+#pragma unroll
+      for (int k = 0; k < D; ++k) c[k] = __shfl_xor_sync(0xffffffffu, o.c[k], x);
+      dp1 = __shfl_xor_sync(0xffffffffu, o.dp1, x);
+    }
+  };
+  template <int D>
+  static TL_D void scalars(const double (&delta)[D], bool meas, const double* tgt_cell, uint32_t gt_bit,
+                           uint32_t lt_bit, const Ctx& c, bool& spring, double& factor) {
+    double dist_sq = 0.0;
 #pragma unroll
     for (int k = 0; k < D; ++k) dist_sq = __dadd_rn(dist_sq, __dmul_rn(delta[k], delta[k]));
-    const real dist = __dsqrt_rn(dist_sq);
-    const real ds = __dadd_rn(dist, 0.01);
-    spring = meas && (type == 0 || (type > 0 ? dist < target : dist > target));
+    const double dist = __dsqrt_rn(dist_sq);
+    const double ds = __dadd_rn(dist, 0.01);
+    spring = false;
+    double target = 0.0;
+    if (meas) {
+      target = *tgt_cell;
+      spring = (gt_bit | lt_bit) == 0u ? true : (gt_bit ? dist < target : dist > target);
+    }
     if (spring) factor = __ddiv_rn(__dmul_rn(__dmul_rn(2.0, c.k), __dsub_rn(target, dist)), ds);
     else factor = __ddiv_rn(c.c_rep, __dmul_rn(__dmul_rn(__dmul_rn(2.0, ds), ds), ds));
   }
-  static TL_D real norm(bool spring, real dp1, const Ctx& c) {
+  static TL_D double norm(bool spring, double dp1, const Ctx& c) {
     return spring ? __dadd_rn(__dmul_rn(4.0, dp1), c.k) : dp1;
   }
   template <int D>
-  static TL_D void pair(real (&A)[D], real (&B)[D], const real* mA, const real* mB, bool meas, real target,
-                        int type, const Ctx& c) {
-    if (!(valid(mA) && valid(mB))) return;
-    real delta[D];
+  static TL_D void pair(Point<D>& A, Point<D>& B, bool meas, const double* tgt_cell, uint32_t gt_bit, uint32_t lt_bit,
+                        const Ctx& c) {
+    if (!(A.dp1 > 0.0 && B.dp1 > 0.0)) return;
+    double delta[D];
 #pragma unroll
-    for (int k = 0; k < D; ++k) delta[k] = __dsub_rn(B[k], A[k]);
-    bool spring; real factor;
-    scalars<D>(delta, meas, target, type, c, spring, factor);
-    const real nA = norm(spring, mA[0], c), nB = norm(spring, mB[0], c);
+    for (int k = 0; k < D; ++k) delta[k] = __dsub_rn(B.c[k], A.c[k]);
+    bool spring; double factor;
+    scalars<D>(delta, meas, tgt_cell, gt_bit, lt_bit, c, spring, factor);
+    const double nA = norm(spring, A.dp1, c), nB = norm(spring, B.dp1, c);
 #pragma unroll
     for (int k = 0; k < D; ++k) {
-      const real force = __dmul_rn(delta[k], factor);
-      A[k] = __dsub_rn(A[k], __ddiv_rn(force, nA));
-      B[k] = __dadd_rn(B[k], __ddiv_rn(force, nB));
+      const double force = __dmul_rn(delta[k], factor);
+      A.c[k] = __dsub_rn(A.c[k], __ddiv_rn(force, nA));
+      B.c[k] = __dadd_rn(B.c[k], __ddiv_rn(force, nB));
     }
   }
   template <int D>
-  static TL_D void pair_self(real (&self)[D], const real (&other)[D], const real* ms, const real* mo, bool meas,
-                             real target, int type, const Ctx& c) {
-    if (!(valid(ms) && valid(mo))) return;
-    real delta[D];
+  static TL_D void pair_self(Point<D>& S, const Point<D>& O, bool meas, const double* tgt_cell, uint32_t gt_bit,
+                             uint32_t lt_bit, const Ctx& c) {
+    if (!(S.dp1 > 0.0 && O.dp1 > 0.0)) return;
+    double delta[D];
 #pragma unroll
-    for (int k = 0; k < D; ++k) delta[k] = __dsub_rn(other[k], self[k]);
-    bool spring; real factor;
-    scalars<D>(delta, meas, target, type, c, spring, factor);
-    const real nS = norm(spring, ms[0], c);
+    for (int k = 0; k < D; ++k) delta[k] = __dsub_rn(O.c[k], S.c[k]);
+    bool spring; double factor;
+    scalars<D>(delta, meas, tgt_cell, gt_bit, lt_bit, c, spring, factor);
+    const double nS = norm(spring, S.dp1, c);
 #pragma unroll
-    for (int k = 0; k < D; ++k) self[k] = __dsub_rn(self[k], __ddiv_rn(__dmul_rn(delta[k], factor), nS));
+    for (int k = 0; k < D; ++k) S.c[k] = __dsub_rn(S.c[k], __ddiv_rn(__dmul_rn(delta[k], factor), nS));
   }
 };
 
@@ -290,7 +394,6 @@ TL_D void ring_pass(typename M::real* sA, typename M::real* sB, int tA, int tB, 
                     const TileDev<typename M::real>& dv, const Geometry& geo, int iter, const typename M::Ctx& ctx,
                     int lane) {
   typedef typename M::real real;
-  const unsigned full = 0xffffffffu;
   const RingParams rp = ring_params(geo, iter, tA, tB);
   const int lo = tA < tB ? tA : tB, hi = tA < tB ? tB : tA;
   const size_t key = (size_t)lo * geo.T + hi;
@@ -303,33 +406,21 @@ TL_D void ring_pass(typename M::real* sA, typename M::real* sB, int tA, int tB, 
     __syncwarp();
     m_meas = tb.mask[lane]; m_gt = tb.mask[32 + lane]; m_lt = tb.mask[64 + lane];
   }
-  real A[D], B[D], mA[M::kMass], mB[M::kMass];
-  const int b0 = (lane + rp.s0) & 31;
-#pragma unroll
-  for (int k = 0; k < D; ++k) { A[k] = sA[k * 33 + lane]; B[k] = sB[k * 33 + b0]; }
-  M::make_mass(sA[D * 33 + lane], ctx, mA);
-  M::make_mass(sB[D * 33 + b0], ctx, mB);
+  typename M::template Point<D> A, B;
+  A.load(sA, lane, ctx);
+  B.load(sB, (lane + rp.s0) & 31, ctx);
   const int src = (lane + rp.g) & 31;
+  const real* cell = tb.tgt + lane;
 #pragma unroll 1
-  for (int i = 0; i < 32; ++i) {
-    const bool meas = (m_meas >> i) & 1u;
-    real target = (real)0;
-    int type = 0;
-    if (meas) {
-      target = tb.tgt[i * 32 + lane];
-      type = (int)((m_gt >> i) & 1u) - (int)((m_lt >> i) & 1u);
-    }
-    M::template pair<D>(A, B, mA, mB, meas, target, type, ctx);
-    if (i < 31) {
-#pragma unroll
-      for (int k = 0; k < D; ++k) B[k] = __shfl_sync(full, B[k], src);
-#pragma unroll
-      for (int k = 0; k < M::kMass; ++k) mB[k] = __shfl_sync(full, mB[k], src);
-    }
+  for (int i = 0; i < 31; ++i) {
+    M::template pair<D>(A, B, (m_meas & 1u) != 0u, cell, m_gt & 1u, m_lt & 1u, ctx);
+    B.shfl_from(src);
+    m_meas >>= 1; m_gt >>= 1; m_lt >>= 1;
+    cell += 32;
   }
-  const int bf = (lane + rp.s0 + 31 * rp.g) & 31;
-#pragma unroll
-  for (int k = 0; k < D; ++k) { sA[k * 33 + lane] = A[k]; sB[k * 33 + bf] = B[k]; }
+  M::template pair<D>(A, B, (m_meas & 1u) != 0u, cell, m_gt & 1u, m_lt & 1u, ctx);
+  A.store(sA, lane);
+  B.store(sB, (lane + rp.s0 + 31 * rp.g) & 31);
 }
 
 // tile x itself, 31 XOR steps; every lane moves only its own point.
@@ -338,7 +429,6 @@ TL_D void intra_pass(typename M::real* sT, int t, const WarpTable<typename M::re
                      const TileDev<typename M::real>& dv, const Geometry& geo, int iter,
                      const typename M::Ctx& ctx, int lane) {
   typedef typename M::real real;
-  const unsigned full = 0xffffffffu;
   const size_t key = (size_t)t * geo.T + t;
   const uint32_t beg = dv.bucket_off[key], end = dv.bucket_off[key + 1];
   uint32_t m_meas = 0, m_gt = 0, m_lt = 0;
@@ -349,29 +439,17 @@ TL_D void intra_pass(typename M::real* sT, int t, const WarpTable<typename M::re
     __syncwarp();
     m_meas = tb.mask[lane]; m_gt = tb.mask[32 + lane]; m_lt = tb.mask[64 + lane];
   }
-  real S[D], O[D], mS[M::kMass], mO[M::kMass];
-#pragma unroll
-  for (int k = 0; k < D; ++k) S[k] = sT[k * 33 + lane];
-  M::make_mass(sT[D * 33 + lane], ctx, mS);
+  typename M::template Point<D> S, O;
+  S.load(sT, lane, ctx);
   const XorParams xp = xor_params(geo, iter, t);
 #pragma unroll 1
   for (int i = 0; i < 31; ++i) {
     const int x = xor_at(xp, i);
-#pragma unroll
-    for (int k = 0; k < D; ++k) O[k] = __shfl_xor_sync(full, S[k], x);
-#pragma unroll
-    for (int k = 0; k < M::kMass; ++k) mO[k] = __shfl_xor_sync(full, mS[k], x);
-    const bool meas = (m_meas >> x) & 1u;
-    real target = (real)0;
-    int type = 0;
-    if (meas) {
-      target = tb.tgt[x * 32 + lane];
-      type = (int)((m_gt >> x) & 1u) - (int)((m_lt >> x) & 1u);
-    }
-    M::template pair_self<D>(S, O, mS, mO, meas, target, type, ctx);
+    O.shfl_xor_of(S, x);
+    M::template pair_self<D>(S, O, ((m_meas >> x) & 1u) != 0u, tb.tgt + x * 32 + lane, (m_gt >> x) & 1u,
+                             (m_lt >> x) & 1u, ctx);
   }
-#pragma unroll
-  for (int k = 0; k < D; ++k) sT[k * 33 + lane] = S[k];
+  S.store(sT, lane);
 }
 
 // Deterministic CTA reduction of (sum, count, flag); result valid in thread 0.
