@@ -1,0 +1,286 @@
+"""GPU parity tests (run with -m gpu on the B200 box).  Everything goes through the C ABI
+(topolow_b200._lib -> libtopolow_b200.so); the oracle is only the checker.
+
+Bars:
+  replay mode (FP64)              bit-exact positions / iterations / k vs the seeded CPU loop and vs the
+                                  golden vectors produced by the reference's own source; MAE within 1e-12
+  coloured mode, FP64 exact       bit-exact positions vs the CPU loop run on the enumerated pair order
+  coloured mode, FP32 production  <= 2e-4 max abs coordinate error vs the FP64 run of the same order after a
+                                  few iterations; statistical parity (MAE over 10 seeds) vs the reference's
+                                  random-shuffle loop: |mean difference| <= max(2 x pooled SE, 2 % relative)
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from conftest import load_fixture, load_golden, random_r_matrix, small_problem
+from oracle import cpu_oracle, r_glue
+from tools import synth
+from topolow_b200 import _lib, core, cv
+
+pytestmark = pytest.mark.gpu
+
+GOLDENS = ["triangle", "small_thresholds", "small_sparse", "h3n2_ndim5", "hiv_ndim5"]
+
+
+# ------------------------------------------------------------------ replay mode ----------------
+@pytest.mark.parametrize("name", GOLDENS)
+def test_replay_reproduces_reference_golden(name):
+    z, args, seed = load_golden(name)
+    got = _lib.fit(*args, mode=_lib.MODE_REPLAY, seed=seed)
+    assert np.array_equal(got["positions"], z["positions"])          # bit for bit
+    assert got["iterations"] == int(z["iterations"])
+    assert got["converged"] == bool(z["converged"])
+    assert got["final_k"] == float(z["final_k"])
+    assert got["final_mae"] == pytest.approx(float(z["final_mae"]), rel=1e-12)
+
+
+def test_replay_explicit_order_and_early_convergence():
+    args = small_problem(70, 3, 0.3, 4)
+    want = cpu_oracle.optimize_layout_exact(*args, 300, 5.0, 0.03, 0.02, 1e-3, 3, 2, seed=5, trace=True)
+    got = _lib.fit(*args, 300, 5.0, 0.03, 0.02, 1e-3, 3, 2, mode=_lib.MODE_REPLAY, seed=5, trace=True)
+    assert want["converged"] and want["iterations"] < 300           # exercises the early exit
+    assert np.array_equal(got["positions"], want["positions"])
+    assert (got["iterations"], got["converged"]) == (want["iterations"], want["converged"])
+    np.testing.assert_allclose(got["trace_mae"][: got["iterations_run"]], want["trace_mae"][: got["iterations_run"]],
+                               rtol=1e-12, equal_nan=True)
+    order = cpu_oracle.pair_orders(70, 12, 9)
+    w2 = cpu_oracle.optimize_layout_exact(*args, 12, 5.0, 0.03, 0.02, pair_order=order)
+    g2 = _lib.fit(*args, 12, 5.0, 0.03, 0.02, mode=_lib.MODE_REPLAY, pair_order=order)
+    assert np.array_equal(g2["positions"], w2["positions"])
+
+
+# ------------------------------------------------------------------ coloured mode, exact ------
+def _exact_case(args, iters, hp, seed, max_ctas=0):
+    plan = _lib.Plan(*args, iters, *hp, precision=_lib.PREC_F64_EXACT, seed=seed, max_ctas=max_ctas)
+    order = np.stack([plan.enumerate(it) for it in range(iters)])
+    info = plan.info()
+    plan.run(iters)
+    got = plan.result()
+    plan.close()
+    want = cpu_oracle.optimize_layout_exact(*args, iters, *hp, pair_order=order)
+    return got, want, info
+
+
+@pytest.mark.parametrize("n,d,dens", [(3, 2, 1.0), (33, 2, 0.5), (100, 7, 0.15), (150, 3, 0.2), (260, 16, 0.05)])
+def test_coloured_fp64_equals_cpu_loop_on_the_enumerated_order(n, d, dens):
+    args = small_problem(n, d, dens, n)
+    got, want, info = _exact_case(args, 7, (5.0, 0.01, 0.02, 1e-4, 5, 3), seed=n)
+    assert info["ctas"] == 1
+    assert np.array_equal(got["positions"], want["positions"])
+    assert got["iterations"] == want["iterations"] and got["final_k"] == want["final_k"]
+    assert got["final_mae"] == pytest.approx(want["final_mae"], rel=1e-12)
+    assert got["pair_updates"] == 7 * n * (n - 1) // 2
+
+
+def test_coloured_fp64_multi_cta_barrier_path():
+    # n = 1100 -> 35 tiles -> several co-operating CTAs (grid barrier between rounds)
+    args = small_problem(1100, 4, 0.03, 12)
+    got, want, info = _exact_case(args, 3, (5.0, 0.01, 0.02, 1e-4, 5, 3), seed=2)
+    assert info["ctas"] > 1
+    assert np.array_equal(got["positions"], want["positions"])
+    # and a forced multi-task-per-CTA geometry
+    got, want, info = _exact_case(args, 2, (5.0, 0.01, 0.02, 1e-4, 5, 3), seed=3, max_ctas=2)
+    assert info["tasks_per_cta"] >= 1 and info["ctas"] == 2
+    assert np.array_equal(got["positions"], want["positions"])
+
+
+@pytest.mark.parametrize("fixture,hp", [("h3n2", (14.76214, 0.03641074, 0.002943064)),
+                                        ("hiv", (3.550036, 0.04130713, 0.0007038619))])
+def test_coloured_fp64_on_bundled_data(fixture, hp):
+    # BASELINE.json configs[0] / configs[1]: real titers incl. '<' / '>' thresholds, ndim = 5
+    f = load_fixture(fixture)
+    init = np.random.default_rng(1).normal(size=(int(f["n"]), 5))
+    args = (init, f["degrees"], f["edge_i"], f["edge_j"], f["edge_dist"], f["edge_thresh"])
+    got, want, _ = _exact_case(args, 10, (*hp, 1e-4, 5, 3), seed=4)
+    assert np.array_equal(got["positions"], want["positions"])
+
+
+def test_coloured_convergence_controller_matches():
+    args = small_problem(90, 3, 0.3, 6, thresholds=False)
+    hp = (5.0, 0.05, 0.02, 1e-2, 2, 2)
+    got, want, _ = _exact_case(args, 120, hp, seed=1)
+    assert want["converged"] and want["iterations"] < 120
+    assert (got["converged"], got["iterations"]) == (want["converged"], want["iterations"])
+    assert np.array_equal(got["positions"], want["positions"])
+
+
+# ------------------------------------------------------------------ coloured mode, FP32 -------
+@pytest.mark.parametrize("n,d,dens", [(150, 3, 0.2), (300, 16, 0.05), (285, 5, 0.08), (1100, 5, 0.03)])
+def test_fp32_tracks_fp64_on_the_same_order(n, d, dens):
+    args = small_problem(n, d, dens, 100 + n)
+    hp = (5.0, 0.01, 0.02, 1e-4, 50, 3)
+    a = _lib.fit(*args, 6, *hp, precision=_lib.PREC_F64_EXACT, seed=8)
+    b = _lib.fit(*args, 6, *hp, precision=_lib.PREC_F32, seed=8)
+    scale = np.abs(a["positions"]).max()
+    assert np.abs(a["positions"] - b["positions"]).max() <= 2e-4 * max(scale, 1.0)
+    assert b["final_mae"] == pytest.approx(a["final_mae"], rel=1e-3)
+
+
+def test_statistical_parity_with_the_random_shuffle_loop():
+    """Production schedule + FP32 vs the reference's std::shuffle loop (oracle), 10 seeds, same inputs:
+    the edge MAE at the best state and the in-sample mae of R/core.R:481 must agree within
+    max(2 x SE of the difference, 2 %)."""
+    n, d = 160, 3
+    gpu, cpu = [], []
+    for seed in range(10):
+        args = small_problem(n, d, 0.15, 1000 + seed, thresholds=True)
+        hp = (5.0, 0.01, 0.02, 1e-4, 5, 3)
+        cpu.append(cpu_oracle.optimize_layout_exact(*args, 150, *hp, seed=seed)["final_mae"])
+        gpu.append(_lib.fit(*args, 150, *hp, precision=_lib.PREC_F32, seed=seed)["final_mae"])
+    gpu, cpu = np.array(gpu), np.array(cpu)
+    diff = gpu.mean() - cpu.mean()
+    se = np.sqrt(gpu.var(ddof=1) / 10 + cpu.var(ddof=1) / 10)
+    assert abs(diff) <= max(2 * se, 0.02 * cpu.mean()), (gpu, cpu)
+
+
+# ------------------------------------------------------------------ edge cases ---------------
+def test_degenerate_inputs_stay_finite():
+    # tests/testthat/test-edge-cases.R:5-82,243-263
+    zero = np.zeros((3, 3))
+    with pytest.warns(UserWarning, match="No finite non-zero dissimilarities"):
+        r = core.euclidean_embedding(zero, 2, 20, 1.0, 0.01, 0.01)
+    assert np.isfinite(r.mae)
+    thr = np.array([["0", ">5", "<10"], [">5", "0", ">20"], ["<10", ">20", "0"]], dtype=object)
+    r = core.euclidean_embedding(thr, 2, 30, 2.0, 0.01, 0.05)
+    assert np.all(np.isfinite(r.positions)) and np.all(np.isfinite(r.est_distances))
+    one = np.full((4, 4), np.nan); one[0, 1] = one[1, 0] = 5; np.fill_diagonal(one, 0)
+    r = core.euclidean_embedding(one, 2, 50, 1.0, 0.01, 0.1)
+    assert np.all(np.isfinite(r.positions))
+    rng = np.random.default_rng(0)
+    for lo, hi in ((1000, 10000), (1e-6, 1e-3)):
+        m = rng.uniform(lo, hi, size=(3, 3)); m = np.triu(m, 1); m = m + m.T
+        r = core.euclidean_embedding(m, 2, 20, 1.0, 0.01, 0.01)
+        assert np.all(np.isfinite(r.positions))
+    m = rng.uniform(1, 10, size=(5, 5)); m = np.triu(m, 1); m = m + m.T
+    r = core.euclidean_embedding(m, 4, 30, 0.1, 0.001, 0.001)
+    assert np.all(np.isfinite(r.positions))
+
+
+def test_numerical_instability_is_reported_like_rcpp_stop():
+    # src/optimization.cpp:359-361
+    init = np.zeros((4, 2))
+    for mode, prec in ((_lib.MODE_REPLAY, 0), (_lib.MODE_COLOURED, _lib.PREC_F64_EXACT), (_lib.MODE_COLOURED, _lib.PREC_F32)):
+        with pytest.raises(_lib.TopolowError) as e:
+            _lib.fit(init, [2, 2, 1, 1], [0], [1], [1.0], [0], 20, 1e300 if prec else 1e30, 0.01, 1e308 if prec else 1e38,
+                     convergence_window=100, convergence_check_freq=50, mode=mode, precision=prec)
+        assert e.value.status == _lib.ERR_NONFINITE
+        assert "Numerical instability at iteration 10. Reduce k0 or c_repulsion." in str(e.value)
+
+
+def test_bad_arguments_are_rejected():
+    args = list(small_problem(20, 2, 0.5, 0))
+    bad = list(args); bad[2] = np.array(args[2]); bad[2][0] = 99
+    with pytest.raises(_lib.TopolowError) as e:
+        _lib.fit(*bad, 5, 1.0, 0.01, 0.01)
+    assert e.value.status == _lib.ERR_BAD_ARG and "edge index" in str(e.value)
+    with pytest.raises(_lib.TopolowError) as e:
+        _lib.fit(np.zeros((20, 17)), *args[1:], 5, 1.0, 0.01, 0.01)
+    assert e.value.status == _lib.ERR_BAD_ARG
+
+
+def test_sixteen_argument_entry_point():
+    # the flattened .Call signature (src/RcppExports.cpp:16-39)
+    init, deg, ei, ej, ed, et = small_problem(40, 2, 0.4, 3)
+    n = 40
+    dm, tm = cpu_oracle.dense_from_edges(n, ei, ej, ed, et)
+    out = np.empty((n, 2), order="F")
+    conv, iters = C.c_int32(0), C.c_int32(0)
+    mae, k = C.c_double(0), C.c_double(0)
+    msg = C.create_string_buffer(256)
+    initf = np.asfortranarray(init)
+    dmf, tmf = np.asfortranarray(dm), np.asfortranarray(tm.astype(np.int32))
+    rc = _lib.lib().topolow_optimize_layout_exact(
+        initf.ctypes.data_as(_lib._dp), n, 2, dmf.ctypes.data_as(_lib._dp), tmf.ctypes.data_as(_lib._i32p),
+        deg.ctypes.data_as(_lib._i32p), ei.ctypes.data_as(_lib._i32p), ej.ctypes.data_as(_lib._i32p),
+        ed.ctypes.data_as(_lib._dp), et.ctypes.data_as(_lib._i32p), len(ei), 30, 2.0, 0.01, 0.01, 1e-4, 5, 3, 0,
+        out.ctypes.data_as(_lib._dp), C.byref(conv), C.byref(iters), C.byref(mae), C.byref(k), msg, 256)
+    assert rc == 0 and np.all(np.isfinite(out)) and 0 < iters.value <= 30 and mae.value > 0
+
+
+# ------------------------------------------------------------------ R-facing mirror -----------
+def test_euclidean_embedding_object_and_post_processing():
+    # tests/testthat/test-core.R:67-139
+    m = random_r_matrix(30, 0.5, 11)
+    names = ["P%d" % i for i in range(30)]
+    init = np.random.default_rng(2).normal(size=(30, 2))
+    r = core.euclidean_embedding(m, 2, 40, 1.0, 0.01, 0.01, initial_positions=init, rownames=names, precision="f64")
+    assert set(r) >= {"positions", "est_distances", "mae", "iter", "parameters", "convergence"}
+    assert r.positions.shape == (30, 2) and isinstance(r.convergence["achieved"], bool)
+    assert r.parameters["method"] == core.METHOD_NAME and sorted(r.rownames) == sorted(names)
+    np.testing.assert_allclose(r.est_distances, r_glue.dist_matrix(r.positions), rtol=0, atol=0)
+    # mae of R/core.R:479-481 against the oracle's restatement on the same (reordered) matrix
+    mm = m if r.order is None else m[np.ix_(r.order, r.order)]
+    raw = np.array([[r_glue._as_numeric(x) for x in row] for row in mm])
+    ok = ~np.isnan(raw)
+    assert r.mae == pytest.approx(float(np.mean(np.abs(raw[ok] - r.est_distances[ok]))), rel=1e-12)
+    # thresholds + NA (test-core.R:90-104)
+    t = np.array([[0, ">2", None], [">2", 0, 4], [None, 4, 0]], dtype=object)
+    r = core.euclidean_embedding(t, 2, 10, 1.0, 0.01, 0.01)
+    assert np.isfinite(r.est_distances[0, 2]) and r.est_distances[0, 2] == r.est_distances[2, 0]
+    # triangle relations (test-core.R:106-127)
+    tri = np.array([[0, 1, 2], [1, 0, 1], [2, 1, 0]], dtype=float)
+    r = core.euclidean_embedding(tri, 2, 10, 1.0, 0.01, 0.01, preserve_order=True)
+    dd = r.est_distances
+    assert dd[0, 2] > dd[0, 1] and dd[0, 2] < dd[0, 1] + dd[1, 2]
+
+
+def test_holdout_errors_and_likelihood_function():
+    rng = np.random.default_rng(3)
+    pos = rng.normal(size=(25, 3))
+    ci = rng.integers(0, 25, size=200).astype(np.int32); cj = rng.integers(0, 25, size=200).astype(np.int32)
+    truth = rng.uniform(0, 5, size=200); truth[::17] = np.nan
+    s, c = _lib.holdout_errors(pos, ci, cj, truth)
+    d = np.linalg.norm(pos[ci] - pos[cj], axis=1)
+    ok = ~np.isnan(truth)
+    assert c == ok.sum() and s == pytest.approx(np.abs(truth[ok] - d[ok]).sum(), rel=1e-12)
+    # likelihood_function: same folds and initial positions, FP64 -> pooled numbers of the same size
+    m = random_r_matrix(26, 0.7, 5)
+    folds = r_glue.make_folds(m, 4, np.random.default_rng(1))
+    inits = [[np.random.default_rng(10 + f).normal(size=(26, 2)) for f in range(4)]]
+    want = r_glue.likelihood_function(m, 60, 1e-4, 2, 2.0, 0.02, 0.01, folds=4, fold_indices=folds, init_list=inits[0])
+    got = cv.likelihood_function(m, 60, 1e-4, 2, 2.0, 0.02, 0.01, folds=4, fold_indices=folds, init_list=inits,
+                                 precision="f64")
+    assert [f["n_samples"] for f in got["folds"]] == [f["n_samples"] for f in want["folds"]]
+    assert got["Holdout_MAE"] == pytest.approx(want["Holdout_MAE"], rel=0.25)   # different pair orders
+    assert got["NLL"] == pytest.approx(sum(f["n_samples"] for f in got["folds"]) * (1 + np.log(2 * got["Holdout_MAE"])))
+
+
+def test_batch_equals_individual_fits():
+    jobs, singles = [], []
+    for j, (n, d) in enumerate([(40, 2), (150, 3), (90, 5), (285, 5)]):
+        a = small_problem(n, d, 0.2, 50 + j)
+        kw = dict(n_iter=25, k0=3.0, cooling_rate=0.02, c_repulsion=0.01, seed=j)
+        jobs.append(dict(initial_positions=a[0], degrees=a[1], edge_i=a[2], edge_j=a[3], edge_dist=a[4],
+                         edge_thresh=a[5], **kw))
+        singles.append(_lib.fit(*a, 25, 3.0, 0.02, 0.01, seed=j))
+    jobs.append(dict(initial_positions=np.zeros((1, 2)), degrees=[1], edge_i=[], edge_j=[], edge_dist=[],
+                     edge_thresh=[], n_iter=5, k0=1.0, cooling_rate=0.1, c_repulsion=0.1))
+    out = _lib.fit_batch(jobs)
+    for got, want in zip(out[:4], singles):
+        assert np.array_equal(got["positions"], want["positions"]) and got["iterations"] == want["iterations"]
+    assert out[4]["status"] == _lib.ERR_TOO_FEW_POINTS      # per-job status, the batch itself succeeds
+
+
+# ------------------------------------------------------------------ full-size properties ------
+def test_cfg3_size_fp32_against_fp64_and_pair_count():
+    prob = synth.make_problem(10_000, 10, 0.95, seed=1)
+    fa = synth.fit_args(prob)
+    hp = (5.0, 0.01, 0.02, 1e-4, 100, 3)
+    a = _lib.fit(*fa, 3, *hp, precision=_lib.PREC_F64_EXACT, seed=2)
+    b = _lib.fit(*fa, 3, *hp, precision=_lib.PREC_F32, seed=2)
+    assert a["pair_updates"] == b["pair_updates"] == 3 * 10_000 * 9_999 // 2
+    assert np.abs(a["positions"] - b["positions"]).max() <= 1e-3 * np.abs(a["positions"]).max()
+    assert b["final_mae"] == pytest.approx(a["final_mae"], rel=1e-3)
+
+
+def test_cfg4_size_runs_and_improves():
+    prob = synth.make_problem(100_000, 16, 0.99, seed=0)
+    fa = synth.fit_args(prob)
+    r = _lib.fit(*fa, 6, 5.0, 0.01, 0.02, 1e-4, 100, 3, seed=0, trace=True)
+    assert r["pair_updates"] == 6 * 100_000 * 99_999 // 2 and np.all(np.isfinite(r["positions"]))
+    t = r["trace_mae"][~np.isnan(r["trace_mae"])]
+    assert len(t) == 2 and t[1] < t[0]
+EOF
+git add -A; git commit -qm "Add golden fixtures from the compiled reference source, CPU and GPU parity tests, sharding helper" -q; echo ok
