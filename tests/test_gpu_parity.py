@@ -283,4 +283,3 @@ def test_cfg4_size_runs_and_improves():
     t = r["trace_mae"][~np.isnan(r["trace_mae"])]
     assert len(t) == 2 and t[1] < t[0]
 EOF
-git add -A; git commit -qm "Add golden fixtures from the compiled reference source, CPU and GPU parity tests, sharding helper" -q; echo ok
