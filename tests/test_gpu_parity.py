@@ -282,4 +282,3 @@ def test_cfg4_size_runs_and_improves():
     assert r["pair_updates"] == 6 * 100_000 * 99_999 // 2 and np.all(np.isfinite(r["positions"]))
     t = r["trace_mae"][~np.isnan(r["trace_mae"])]
     assert len(t) == 2 and t[1] < t[0]
-EOF
