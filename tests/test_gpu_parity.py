@@ -161,9 +161,10 @@ def test_degenerate_inputs_stay_finite():
 def test_numerical_instability_is_reported_like_rcpp_stop():
     # src/optimization.cpp:359-361
     init = np.zeros((4, 2))
-    for mode, prec in ((_lib.MODE_REPLAY, 0), (_lib.MODE_COLOURED, _lib.PREC_F64_EXACT), (_lib.MODE_COLOURED, _lib.PREC_F32)):
+    for mode, prec, big in ((_lib.MODE_REPLAY, 0, True), (_lib.MODE_COLOURED, _lib.PREC_F64_EXACT, True),
+                            (_lib.MODE_COLOURED, _lib.PREC_F32, False)):
         with pytest.raises(_lib.TopolowError) as e:
-            _lib.fit(init, [2, 2, 1, 1], [0], [1], [1.0], [0], 20, 1e300 if prec else 1e30, 0.01, 1e308 if prec else 1e38,
+            _lib.fit(init, [2, 2, 1, 1], [0], [1], [1.0], [0], 20, 1e300 if big else 1e30, 0.01, 1e308 if big else 1e38,
                      convergence_window=100, convergence_check_freq=50, mode=mode, precision=prec)
         assert e.value.status == _lib.ERR_NONFINITE
         assert "Numerical instability at iteration 10. Reduce k0 or c_repulsion." in str(e.value)
