@@ -49,6 +49,15 @@ struct TileDev {
 // mass terms that travel with it) and the arithmetic of one pair visit.
 // ---------------------------------------------------------------------------------------
 
+// What a lane knows about the measured pairs of the current tile pair: bit i of `meas` = my pair at
+// step (or xor distance) i is measured, `gt` / `lt` its threshold kind, `any` = OR of `meas` over the
+// warp (uniform), col[i * 32] = its target.
+template <class real>
+struct EdgeView {
+  const real* col;
+  uint32_t any, meas, gt, lt;
+};
+
 // Two FP32 values in one 64-bit register: sm_100 has 2-wide FP32 FMA/ADD/MUL (SASS FFMA2 ...),
 // which halves the instruction count of the coordinate loops.
 typedef float2 f32x2;
@@ -126,8 +135,8 @@ struct FastF32 {
   // delta = B - A, and the scalar with which it is applied to each endpoint
   // (src/optimization.cpp:207-281 with reciprocals hoisted out of the coordinate loop).
   template <int D>
-  static TL_D void force(const Point<D>& A, const Point<D>& B, f32x2 (&delta)[Point<D>::H], bool meas,
-                         const float* tgt_cell, uint32_t gt_bit, uint32_t lt_bit, const Ctx& c, float& fA, float& fB) {
+  static TL_D void force(const Point<D>& A, const Point<D>& B, f32x2 (&delta)[Point<D>::H], const EdgeView<float>& ev,
+                         int idx, const Ctx& c, float& fA, float& fB) {
     constexpr int H = Point<D>::H;
     const f32x2 neg1 = pk2(-1.0f, -1.0f);
 #pragma unroll
@@ -148,10 +157,11 @@ struct FastF32 {
     const float ids = rcp_fast(dist + 0.01f);
     float f = c.c_half * ids * ids * ids;   // repulsion: c / (2 ds^3)
     float wA = A.rdeg, wB = B.rdeg;
-    if (__any_sync(0xffffffffu, meas)) {    // warp-uniform: most steps of a sparse map skip this
-      if (meas) {
-        const float target = *tgt_cell;
-        const bool spring = (gt_bit | lt_bit) == 0u ? true : (gt_bit ? dist < target : dist > target);
+    const uint32_t bit = 1u << idx;
+    if (ev.any & bit) {                     // warp-uniform: most steps of a sparse map skip this
+      if (ev.meas & bit) {
+        const float target = ev.col[idx * 32];
+        const bool spring = ((ev.gt | ev.lt) & bit) == 0u ? true : ((ev.gt & bit) ? dist < target : dist > target);
         if (spring) {
           f = c.two_k * (target - dist) * ids;   // spring: 2k (t - d) / ds
           wA = A.rnorm; wB = B.rnorm;
@@ -162,12 +172,11 @@ struct FastF32 {
     fB = f * wB;
   }
   template <int D>
-  static TL_D void pair(Point<D>& A, Point<D>& B, bool meas, const float* tgt_cell, uint32_t gt_bit, uint32_t lt_bit,
-                        const Ctx& c) {
+  static TL_D void pair(Point<D>& A, Point<D>& B, const EdgeView<float>& ev, int idx, const Ctx& c) {
     constexpr int H = Point<D>::H;
     f32x2 delta[H];
     float fA, fB;
-    force<D>(A, B, delta, meas, tgt_cell, gt_bit, lt_bit, c, fA, fB);
+    force<D>(A, B, delta, ev, idx, c, fA, fB);
     const f32x2 nA = pk2(-fA, -fA), pB = pk2(fB, fB);
 #pragma unroll
     for (int j = 0; j < H; ++j) {
@@ -177,12 +186,11 @@ struct FastF32 {
   }
   // Both lanes of an intra-tile pair run this, each moving only itself.
   template <int D>
-  static TL_D void pair_self(Point<D>& S, const Point<D>& O, bool meas, const float* tgt_cell, uint32_t gt_bit,
-                             uint32_t lt_bit, const Ctx& c) {
+  static TL_D void pair_self(Point<D>& S, const Point<D>& O, const EdgeView<float>& ev, int idx, const Ctx& c) {
     constexpr int H = Point<D>::H;
     f32x2 delta[H];
     float fS, fO;
-    force<D>(S, O, delta, meas, tgt_cell, gt_bit, lt_bit, c, fS, fO);
+    force<D>(S, O, delta, ev, idx, c, fS, fO);
     const f32x2 nS = pk2(-fS, -fS);
 #pragma unroll
     for (int j = 0; j < H; ++j) S.c[j] = fma2(delta[j], nS, S.c[j]);
@@ -222,8 +230,8 @@ struct ExactF64 {
     }
   };
   template <int D>
-  static TL_D void scalars(const double (&delta)[D], bool meas, const double* tgt_cell, uint32_t gt_bit,
-                           uint32_t lt_bit, const Ctx& c, bool& spring, double& factor) {
+  static TL_D void scalars(const double (&delta)[D], const EdgeView<double>& ev, int idx, const Ctx& c, bool& spring,
+                           double& factor) {
     double dist_sq = 0.0;
 #pragma unroll
     for (int k = 0; k < D; ++k) dist_sq = __dadd_rn(dist_sq, __dmul_rn(delta[k], delta[k]));
@@ -231,9 +239,10 @@ struct ExactF64 {
     const double ds = __dadd_rn(dist, 0.01);
     spring = false;
     double target = 0.0;
-    if (meas) {
-      target = *tgt_cell;
-      spring = (gt_bit | lt_bit) == 0u ? true : (gt_bit ? dist < target : dist > target);
+    const uint32_t bit = 1u << idx;
+    if (ev.meas & bit) {
+      target = ev.col[idx * 32];
+      spring = ((ev.gt | ev.lt) & bit) == 0u ? true : ((ev.gt & bit) ? dist < target : dist > target);
     }
     if (spring) factor = __ddiv_rn(__dmul_rn(__dmul_rn(2.0, c.k), __dsub_rn(target, dist)), ds);
     else factor = __ddiv_rn(c.c_rep, __dmul_rn(__dmul_rn(__dmul_rn(2.0, ds), ds), ds));
@@ -242,14 +251,13 @@ struct ExactF64 {
     return spring ? __dadd_rn(__dmul_rn(4.0, dp1), c.k) : dp1;
   }
   template <int D>
-  static TL_D void pair(Point<D>& A, Point<D>& B, bool meas, const double* tgt_cell, uint32_t gt_bit, uint32_t lt_bit,
-                        const Ctx& c) {
+  static TL_D void pair(Point<D>& A, Point<D>& B, const EdgeView<double>& ev, int idx, const Ctx& c) {
     if (!(A.dp1 > 0.0 && B.dp1 > 0.0)) return;
     double delta[D];
 #pragma unroll
     for (int k = 0; k < D; ++k) delta[k] = __dsub_rn(B.c[k], A.c[k]);
     bool spring; double factor;
-    scalars<D>(delta, meas, tgt_cell, gt_bit, lt_bit, c, spring, factor);
+    scalars<D>(delta, ev, idx, c, spring, factor);
     const double nA = norm(spring, A.dp1, c), nB = norm(spring, B.dp1, c);
 #pragma unroll
     for (int k = 0; k < D; ++k) {
@@ -259,14 +267,13 @@ struct ExactF64 {
     }
   }
   template <int D>
-  static TL_D void pair_self(Point<D>& S, const Point<D>& O, bool meas, const double* tgt_cell, uint32_t gt_bit,
-                             uint32_t lt_bit, const Ctx& c) {
+  static TL_D void pair_self(Point<D>& S, const Point<D>& O, const EdgeView<double>& ev, int idx, const Ctx& c) {
     if (!(S.dp1 > 0.0 && O.dp1 > 0.0)) return;
     double delta[D];
 #pragma unroll
     for (int k = 0; k < D; ++k) delta[k] = __dsub_rn(O.c[k], S.c[k]);
     bool spring; double factor;
-    scalars<D>(delta, meas, tgt_cell, gt_bit, lt_bit, c, spring, factor);
+    scalars<D>(delta, ev, idx, c, spring, factor);
     const double nS = norm(spring, S.dp1, c);
 #pragma unroll
     for (int k = 0; k < D; ++k) S.c[k] = __dsub_rn(S.c[k], __ddiv_rn(__dmul_rn(delta[k], factor), nS));
@@ -388,57 +395,74 @@ TL_D void fill_table_xor(const WarpTable<real>& tb, const EdgeRec* edges, uint32
   }
 }
 
-// tile A x tile B, 32 ring steps.  sA / sB are the shared-memory tiles.
+TL_D void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// Bucket range of tile pair (ta, tb) and an L2 prefetch of its edge records (issued one task ahead
+// of use: the edge stream is far larger than L2, the per-pass loads must not go to DRAM).
+TL_D uint2 bucket_range(const uint32_t* bucket_off, const EdgeRec* edges, int T, int ta, int tb) {
+  const int lo = ta < tb ? ta : tb, hi = ta < tb ? tb : ta;
+  const size_t key = (size_t)lo * T + hi;
+  uint2 r;
+  r.x = bucket_off[key];
+  r.y = bucket_off[key + 1];
+  const char* p = reinterpret_cast<const char*>(edges + r.x);
+  const char* e = reinterpret_cast<const char*>(edges + r.y);
+  for (int i = 0; i < 8 && p < e; ++i, p += 128) prefetch_l2(p);
+  return r;
+}
+
+template <class real>
+TL_D EdgeView<real> make_view(const WarpTable<real>& tb, int lane, bool filled) {
+  EdgeView<real> ev;
+  ev.col = tb.tgt + lane;
+  ev.meas = filled ? tb.mask[lane] : 0u;
+  ev.gt = filled ? tb.mask[32 + lane] : 0u;
+  ev.lt = filled ? tb.mask[64 + lane] : 0u;
+  ev.any = __reduce_or_sync(0xffffffffu, ev.meas);
+  return ev;
+}
+
+// tile A x tile B, 32 ring steps.  sA / sB are the shared-memory tiles, [beg, end) the bucket.
 template <int D, class M>
-TL_D void ring_pass(typename M::real* sA, typename M::real* sB, int tA, int tB, const WarpTable<typename M::real>& tb,
-                    const TileDev<typename M::real>& dv, const Geometry& geo, int iter, const typename M::Ctx& ctx,
-                    int lane) {
+TL_D void ring_pass(typename M::real* sA, typename M::real* sB, int tA, int tB, uint32_t beg, uint32_t end,
+                    const WarpTable<typename M::real>& tb, const TileDev<typename M::real>& dv, const Geometry& geo,
+                    int iter, const typename M::Ctx& ctx, int lane) {
   typedef typename M::real real;
   const RingParams rp = ring_params(geo, iter, tA, tB);
-  const int lo = tA < tB ? tA : tB, hi = tA < tB ? tB : tA;
-  const size_t key = (size_t)lo * geo.T + hi;
-  const uint32_t beg = dv.bucket_off[key], end = dv.bucket_off[key + 1];
-  uint32_t m_meas = 0, m_gt = 0, m_lt = 0;
   if (beg != end) {  // warp-uniform
     tb.mask[lane] = 0; tb.mask[32 + lane] = 0; tb.mask[64 + lane] = 0;
     __syncwarp();
     fill_table_ring<real>(tb, dv.edges, beg, end, tA > tB, rp, lane);
     __syncwarp();
-    m_meas = tb.mask[lane]; m_gt = tb.mask[32 + lane]; m_lt = tb.mask[64 + lane];
   }
+  const EdgeView<real> ev = make_view<real>(tb, lane, beg != end);
   typename M::template Point<D> A, B;
   A.load(sA, lane, ctx);
   B.load(sB, (lane + rp.s0) & 31, ctx);
   const int src = (lane + rp.g) & 31;
-  const real* cell = tb.tgt + lane;
 #pragma unroll 1
   for (int i = 0; i < 31; ++i) {
-    M::template pair<D>(A, B, (m_meas & 1u) != 0u, cell, m_gt & 1u, m_lt & 1u, ctx);
+    M::template pair<D>(A, B, ev, i, ctx);
     B.shfl_from(src);
-    m_meas >>= 1; m_gt >>= 1; m_lt >>= 1;
-    cell += 32;
   }
-  M::template pair<D>(A, B, (m_meas & 1u) != 0u, cell, m_gt & 1u, m_lt & 1u, ctx);
+  M::template pair<D>(A, B, ev, 31, ctx);
   A.store(sA, lane);
   B.store(sB, (lane + rp.s0 + 31 * rp.g) & 31);
 }
 
 // tile x itself, 31 XOR steps; every lane moves only its own point.
 template <int D, class M>
-TL_D void intra_pass(typename M::real* sT, int t, const WarpTable<typename M::real>& tb,
+TL_D void intra_pass(typename M::real* sT, int t, uint32_t beg, uint32_t end, const WarpTable<typename M::real>& tb,
                      const TileDev<typename M::real>& dv, const Geometry& geo, int iter,
                      const typename M::Ctx& ctx, int lane) {
   typedef typename M::real real;
-  const size_t key = (size_t)t * geo.T + t;
-  const uint32_t beg = dv.bucket_off[key], end = dv.bucket_off[key + 1];
-  uint32_t m_meas = 0, m_gt = 0, m_lt = 0;
   if (beg != end) {
     tb.mask[lane] = 0; tb.mask[32 + lane] = 0; tb.mask[64 + lane] = 0;
     __syncwarp();
     fill_table_xor<real>(tb, dv.edges, beg, end, lane);
     __syncwarp();
-    m_meas = tb.mask[lane]; m_gt = tb.mask[32 + lane]; m_lt = tb.mask[64 + lane];
   }
+  const EdgeView<real> ev = make_view<real>(tb, lane, beg != end);
   typename M::template Point<D> S, O;
   S.load(sT, lane, ctx);
   const XorParams xp = xor_params(geo, iter, t);
@@ -446,8 +470,7 @@ TL_D void intra_pass(typename M::real* sT, int t, const WarpTable<typename M::re
   for (int i = 0; i < 31; ++i) {
     const int x = xor_at(xp, i);
     O.shfl_xor_of(S, x);
-    M::template pair_self<D>(S, O, ((m_meas >> x) & 1u) != 0u, tb.tgt + x * 32 + lane, (m_gt >> x) & 1u,
-                             (m_lt >> x) & 1u, ctx);
+    M::template pair_self<D>(S, O, ev, x, ctx);
   }
   S.store(sT, lane);
 }
@@ -513,12 +536,19 @@ tile_kernel(TileDev<typename M::real> dv, Geometry geo, FitParams prm, int n_ite
         load_tile<D, real>(s_tiles + (size_t)(W + warp) * TS, dv.pos, dv.dp1, tY, lane);
         __syncthreads();
         const int rot = cross_rot(geo, iter, X, Y);
+        // lane v fetches the bucket range of this warp's sub-round v and prefetches its records
+        uint2 my_rng = make_uint2(0u, 0u);
+        if (lane < W) {
+          const int tA = s_tid[warp], tB = s_tid[W + (warp + lane + rot) % W];
+          if (tA >= 0 && tB >= 0) my_rng = bucket_range(dv.bucket_off, dv.edges, geo.T, tA, tB);
+        }
         for (int v = 0; v < W; ++v) {
           const int bw = (warp + v + rot) % W;
           const int tA = s_tid[warp], tB = s_tid[W + bw];
+          const uint32_t beg = __shfl_sync(0xffffffffu, my_rng.x, v), end = __shfl_sync(0xffffffffu, my_rng.y, v);
           if (tA >= 0 && tB >= 0)
-            ring_pass<D, M>(s_tiles + (size_t)warp * TS, s_tiles + (size_t)(W + bw) * TS, tA, tB, tb, dv, geo, iter,
-                            ctx, lane);
+            ring_pass<D, M>(s_tiles + (size_t)warp * TS, s_tiles + (size_t)(W + bw) * TS, tA, tB, beg, end, tb, dv,
+                            geo, iter, ctx, lane);
           __syncthreads();
         }
         store_tile<D, real>(s_tiles + (size_t)warp * TS, dv.pos, tX, lane);
@@ -537,18 +567,34 @@ tile_kernel(TileDev<typename M::real> dv, Geometry geo, FitParams prm, int n_ite
       load_tile<D, real>(s_tiles + (size_t)(W + warp) * TS, dv.pos, dv.dp1, tY, lane);
       __syncthreads();
       const int Mt = diag_subrounds(W), rot = diag_rot(geo, iter, q);
+      // lanes 0..Mt-1: bucket of this warp's tile pair in sub-round `lane`; lanes 16, 17: own tiles
+      uint2 my_rng = make_uint2(0u, 0u);
+      {
+        int ta = -1, tb2 = -1;
+        if (lane < Mt) {
+          int sb, ia, ib;
+          if (diag_pair(W, lane, rot, warp, sb, ia, ib)) { ta = s_tid[sb * W + ia]; tb2 = s_tid[sb * W + ib]; }
+        } else if (lane == 16) { ta = tb2 = tX; }
+        else if (lane == 17) { ta = tb2 = tY; }
+        if (ta >= 0 && tb2 >= 0) my_rng = bucket_range(dv.bucket_off, dv.edges, geo.T, ta, tb2);
+      }
       for (int u = 0; u < Mt; ++u) {
         int sb, ia, ib;
+        const uint32_t beg = __shfl_sync(0xffffffffu, my_rng.x, u), end = __shfl_sync(0xffffffffu, my_rng.y, u);
         if (diag_pair(W, u, rot, warp, sb, ia, ib)) {
           const int tA = s_tid[sb * W + ia], tB = s_tid[sb * W + ib];
           if (tA >= 0 && tB >= 0)
-            ring_pass<D, M>(s_tiles + (size_t)(sb * W + ia) * TS, s_tiles + (size_t)(sb * W + ib) * TS, tA, tB, tb, dv,
-                            geo, iter, ctx, lane);
+            ring_pass<D, M>(s_tiles + (size_t)(sb * W + ia) * TS, s_tiles + (size_t)(sb * W + ib) * TS, tA, tB, beg, end,
+                            tb, dv, geo, iter, ctx, lane);
         }
         __syncthreads();
       }
-      if (tX >= 0) intra_pass<D, M>(s_tiles + (size_t)warp * TS, tX, tb, dv, geo, iter, ctx, lane);
-      if (tY >= 0) intra_pass<D, M>(s_tiles + (size_t)(W + warp) * TS, tY, tb, dv, geo, iter, ctx, lane);
+      {
+        const uint32_t bx = __shfl_sync(0xffffffffu, my_rng.x, 16), ex = __shfl_sync(0xffffffffu, my_rng.y, 16);
+        const uint32_t by = __shfl_sync(0xffffffffu, my_rng.x, 17), ey = __shfl_sync(0xffffffffu, my_rng.y, 17);
+        if (tX >= 0) intra_pass<D, M>(s_tiles + (size_t)warp * TS, tX, bx, ex, tb, dv, geo, iter, ctx, lane);
+        if (tY >= 0) intra_pass<D, M>(s_tiles + (size_t)(W + warp) * TS, tY, by, ey, tb, dv, geo, iter, ctx, lane);
+      }
       store_tile<D, real>(s_tiles + (size_t)warp * TS, dv.pos, tX, lane);
       store_tile<D, real>(s_tiles + (size_t)(W + warp) * TS, dv.pos, tY, lane);
       __syncwarp();
