@@ -138,6 +138,8 @@ struct FastF32 {
   static TL_D void force(const Point<D>& A, const Point<D>& B, f32x2 (&delta)[Point<D>::H], const EdgeView<float>& ev,
                          int idx, const Ctx& c, float& fA, float& fB) {
     constexpr int H = Point<D>::H;
+    const uint32_t bit = 1u << idx;
+    const float target = ev.col[idx * 32];   // issued first: its latency hides behind the distance
     const f32x2 neg1 = pk2(-1.0f, -1.0f);
 #pragma unroll
     for (int j = 0; j < H; ++j) delta[j] = fma2(A.c[j], neg1, B.c[j]);
@@ -155,19 +157,16 @@ struct FastF32 {
     const float d2 = lo + hi;
     const float dist = d2 * rsqrt_fast(fmaxf(d2, 1e-35f));
     const float ids = rcp_fast(dist + 0.01f);
-    float f = c.c_half * ids * ids * ids;   // repulsion: c / (2 ds^3)
-    float wA = A.rdeg, wB = B.rdeg;
-    const uint32_t bit = 1u << idx;
-    if (ev.any & bit) {                     // warp-uniform: most steps of a sparse map skip this
-      if (ev.meas & bit) {
-        const float target = ev.col[idx * 32];
-        const bool spring = ((ev.gt | ev.lt) & bit) == 0u ? true : ((ev.gt & bit) ? dist < target : dist > target);
-        if (spring) {
-          f = c.two_k * (target - dist) * ids;   // spring: 2k (t - d) / ds
-          wA = A.rnorm; wB = B.rnorm;
-        }
-      }
-    }
+    // Branch-free choice between repulsion c / (2 ds^3) and spring 2k (t - d) / ds: the target cell is
+    // read unconditionally (stale / garbage when the pair is not measured, discarded by the selects).
+    // ('>' threshold: spring iff dist < target; '<': iff dist > target; exact: always) - bitwise on
+    // purpose: && / ?: would be compiled into divergent branches.
+    const uint32_t below = dist < target ? bit : 0u, above = dist > target ? bit : 0u;
+    const bool spring = (ev.meas & ((ev.gt & below) | (ev.lt & above) | ~(ev.gt | ev.lt)) & bit) != 0u;
+    const float rep = c.c_half * ids * ids;
+    const float spr = c.two_k * (target - dist);
+    const float f = (spring ? spr : rep) * ids;
+    const float wA = spring ? A.rnorm : A.rdeg, wB = spring ? B.rnorm : B.rdeg;
     fA = f * wA;
     fB = f * wB;
   }
@@ -440,7 +439,7 @@ TL_D void ring_pass(typename M::real* sA, typename M::real* sB, int tA, int tB, 
   A.load(sA, lane, ctx);
   B.load(sB, (lane + rp.s0) & 31, ctx);
   const int src = (lane + rp.g) & 31;
-#pragma unroll 1
+#pragma unroll 2
   for (int i = 0; i < 31; ++i) {
     M::template pair<D>(A, B, ev, i, ctx);
     B.shfl_from(src);
