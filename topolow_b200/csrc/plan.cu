@@ -107,9 +107,15 @@ Geometry choose_geometry(int64_t n, int D, int precision, int sms, int max_ctas,
     g.W = 4; g.m = 1;
     g.G = (T + 2 * g.W - 1) / (2 * g.W);
   } else {
-    g.G = ctas;
-    g.m = (T + 2 * g.G * wmax - 1) / (2 * g.G * wmax);
-    g.W = (T + 2 * g.G * g.m - 1) / (2 * g.G * g.m);
+    // every SM busy; among CTA counts close to that pick the one with the fewest sub-round units
+    // (2 G m rounds x m W sub-rounds): it wastes the fewest tile slots on padding.
+    long best = -1;
+    for (int G = ctas; G >= std::max(1, (ctas * 7) / 8); --G) {
+      const int m = (T + 2 * G * wmax - 1) / (2 * G * wmax);
+      const int W = (T + 2 * G * m - 1) / (2 * G * m);
+      const long units = 2L * G * m * m * W;
+      if (best < 0 || units * 100 < best * 99) { best = units; g.G = G; g.m = m; g.W = W; }  // >1 % better only
+    }
   }
   g.S = 2 * g.G * g.m;
   return g;

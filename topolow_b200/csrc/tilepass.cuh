@@ -301,6 +301,22 @@ TL_D void store_state(FitState* dst, const FitState& src) {
   for (int i = 0; i < (int)(sizeof(FitState) / 8); ++i) __stcg(d + i, s[i]);
 }
 
+// Hand-off flags in shared memory (one per travelling tile).
+TL_D void wait_flag(volatile int* flag, int want, int lane) {
+  if (lane == 0) {
+    while (*flag < want) { }
+    __threadfence_block();
+  }
+  __syncwarp();
+}
+TL_D void post_flag(volatile int* flag, int value, int lane) {
+  __syncwarp();
+  if (lane == 0) {
+    __threadfence_block();
+    *flag = value;
+  }
+}
+
 // Barrier across the G CTAs of one fit (all co-resident: cooperative launch).
 TL_D void gang_barrier(unsigned* bar, int G, unsigned& gen) {
   __syncthreads();
@@ -511,6 +527,7 @@ tile_kernel(TileDev<typename M::real> dv, Geometry geo, FitParams prm, int n_ite
   real* s_tgt = s_tiles + (size_t)2 * W * TS;
   uint32_t* s_mask = reinterpret_cast<uint32_t*>(s_tgt + (size_t)W * 1024);
   int* s_tid = reinterpret_cast<int*>(s_mask + W * 96);
+  int* s_flag = s_tid + 2 * W;
   const WarpTable<real> tb{s_tgt + warp * 1024, s_mask + warp * 96};
 
   unsigned gen = 0;
@@ -530,7 +547,7 @@ tile_kernel(TileDev<typename M::real> dv, Geometry geo, FitParams prm, int n_ite
         int X, Y;
         circle_pair(geo.S, rr, cta * geo.m + tt, X, Y);
         const int tX = tile_at(geo, iter, X * W + warp), tY = tile_at(geo, iter, Y * W + warp);
-        if (lane == 0) { s_tid[warp] = tX; s_tid[W + warp] = tY; }
+        if (lane == 0) { s_tid[warp] = tX; s_tid[W + warp] = tY; s_flag[warp] = 0; }
         load_tile<D, real>(s_tiles + (size_t)warp * TS, dv.pos, dv.dp1, tX, lane);
         load_tile<D, real>(s_tiles + (size_t)(W + warp) * TS, dv.pos, dv.dp1, tY, lane);
         __syncthreads();
@@ -541,15 +558,20 @@ tile_kernel(TileDev<typename M::real> dv, Geometry geo, FitParams prm, int n_ite
           const int tA = s_tid[warp], tB = s_tid[W + (warp + lane + rot) % W];
           if (tA >= 0 && tB >= 0) my_rng = bucket_range(dv.bucket_off, dv.edges, geo.T, tA, tB);
         }
+        // Sub-rounds without a CTA barrier: tile Y[b] is handed from warp to warp.  s_flag[b] counts
+        // the passes completed on Y[b]; the pass of sub-round v needs exactly v of them (the one
+        // before it ran on warp + 1), so the waits form chains that end at sub-round 0.
         for (int v = 0; v < W; ++v) {
           const int bw = (warp + v + rot) % W;
           const int tA = s_tid[warp], tB = s_tid[W + bw];
           const uint32_t beg = __shfl_sync(0xffffffffu, my_rng.x, v), end = __shfl_sync(0xffffffffu, my_rng.y, v);
+          wait_flag(s_flag + bw, v, lane);
           if (tA >= 0 && tB >= 0)
             ring_pass<D, M>(s_tiles + (size_t)warp * TS, s_tiles + (size_t)(W + bw) * TS, tA, tB, beg, end, tb, dv,
                             geo, iter, ctx, lane);
-          __syncthreads();
+          post_flag(s_flag + bw, v + 1, lane);
         }
+        wait_flag(s_flag + warp, W, lane);   // every pass on Y[warp] is done: this warp writes it back
         store_tile<D, real>(s_tiles + (size_t)warp * TS, dv.pos, tX, lane);
         store_tile<D, real>(s_tiles + (size_t)(W + warp) * TS, dv.pos, tY, lane);
         __syncwarp();
