@@ -102,9 +102,9 @@ Geometry choose_geometry(int64_t n, int D, int precision, int sms, int max_ctas,
     g.m = (T + 2 * wmax - 1) / (2 * wmax);
     if (g.m < 1) g.m = 1;
     g.W = std::max(1, (T + 2 * g.m - 1) / (2 * g.m));
-  } else if (T < 2 * ctas * 4) {
+  } else if (T < 2 * ctas * std::min(4, wmax)) {
     // latency-bound regime: 4 warps per CTA, as many CTAs as there is work
-    g.W = 4; g.m = 1;
+    g.W = std::min(4, wmax); g.m = 1;
     g.G = (T + 2 * g.W - 1) / (2 * g.W);
   } else {
     // every SM busy; among CTA counts close to that pick the one with the fewest sub-round units
@@ -134,15 +134,33 @@ int64_t enumerate_schedule(const Geometry& g, const std::vector<int32_t>& pos, i
   auto ring = [&](int tA, int tB) {
     if (tA < 0 || tB < 0) return;
     const RingParams rp = ring_params(g, iter, tA, tB);
-    for (int i = 0; i < 32; ++i)
-      for (int a = 0; a < 32; ++a) emit(tA * 32 + a, tB * 32 + ring_b(rp, a, i));
+    for (int i = 0; i < 32; ++i) {
+      for (int a = 0; a < 32; ++a) {
+        const int b = ring_b(rp, a, i);
+        emit(tA * kTile + a, tB * kTile + b);
+        emit(tA * kTile + a + 32, tB * kTile + b + 32);
+      }
+      for (int a = 0; a < 32; ++a) {
+        const int b = ring_b(rp, a, i);
+        emit(tA * kTile + a, tB * kTile + b + 32);
+        emit(tA * kTile + a + 32, tB * kTile + b);
+      }
+    }
   };
   auto intra = [&](int t) {
     if (t < 0) return;
     const XorParams xp = xor_params(g, iter, t);
+    for (int a = 0; a < 32; ++a) emit(t * kTile + a, t * kTile + a + 32);
     for (int i = 0; i < 31; ++i) {
       const int x = xor_at(xp, i);
-      for (int a = 0; a < 32; ++a) if (a < (a ^ x)) emit(t * 32 + a, t * 32 + (a ^ x));
+      for (int a = 0; a < 32; ++a) if (a < (a ^ x)) {
+        emit(t * kTile + a, t * kTile + (a ^ x));
+        emit(t * kTile + a + 32, t * kTile + (a ^ x) + 32);
+      }
+      for (int a = 0; a < 32; ++a) if (a < (a ^ x)) {
+        emit(t * kTile + a, t * kTile + (a ^ x) + 32);
+        emit(t * kTile + a + 32, t * kTile + (a ^ x));
+      }
     }
   };
   const int W = g.W;
@@ -197,7 +215,7 @@ void upload_edges(topolow_plan& pl, const topolow_problem& pb) {
   for (int64_t e = 0; e < pl.E; ++e) {
     uint32_t sa = (uint32_t)pl.slot_of_point[pb.edge_i[e]], sb = (uint32_t)pl.slot_of_point[pb.edge_j[e]];
     if (sa > sb) std::swap(sa, sb);  // lower slot first => lower (or equal) tile first
-    keys[e] = (uint64_t)(sa >> 5) * T + (sb >> 5);
+    keys[e] = (uint64_t)(sa / kTile) * T + (sb / kTile);
     off[keys[e] + 1]++;
   }
   for (size_t k = 0; k < nkeys; ++k) off[k + 1] += off[k];

@@ -8,17 +8,19 @@
 // the reference's Gauss-Seidel loop (src/optimization.cpp:199-282) - the order
 // topolow_plan_enumerate() writes out.
 //
-// Hierarchy (point -> tile of 32 -> super-block of W tiles -> S = 2*G*m super-blocks):
+// Hierarchy (point -> tile of 64 -> super-block of W tiles -> S = 2*G*m super-blocks):
 //   level 2  round-robin tournament over super-blocks (circle method): S-1 cross rounds of
 //            S/2 disjoint super-block pairs (one CTA task each) + 1 diagonal round; a barrier
 //            across the G CTAs of the fit separates rounds.
 //   level 1  inside a cross task (X,Y): W sub-rounds, warp w takes tile X[w] x tile Y[(w+v)%W];
 //            inside a diagonal task: circle method over the W tiles of each super-block, then
 //            every tile against itself; __syncthreads() separates sub-rounds.
-//   level 0  tile x tile: 32 steps of a systolic ring - lane a keeps point A[a] in registers,
-//            the B points rotate through the lanes by an odd stride g, so step i pairs lane a
-//            with B[(a + s0 + g*i) mod 32]: a perfect matching per step.
-//            tile x itself: 31 XOR steps, lane a meets lane a^x.
+//   level 0  tile x tile (64 x 64): 32 steps of a systolic ring - lane a keeps A[a], A[a+32] in
+//            registers, the B points travel through the lanes in pairs (B[b], B[b+32]) by an odd
+//            stride g, b = (a + s0 + g*i) mod 32; a step is two perfect matchings one after the
+//            other: {(A[a],B[b]), (A[a+32],B[b+32])} then {(A[a],B[b+32]), (A[a+32],B[b])}.
+//            tile x itself: the 32 pairs (a, a+32), then 31 XOR steps in which lane a meets lane
+//            a^x, again as two matchings per step.
 // Randomisation per iteration (stateless hashes of (seed, iter)): the tile -> super-block
 // placement, the order of the rounds, the sub-round rotation and the ring's (s0, g).
 #pragma once
@@ -27,7 +29,7 @@
 
 namespace tl {
 
-constexpr int kTile = 32;
+constexpr int kTile = 64;   // points per tile: every lane of a warp holds two
 
 struct Geometry {
   int n;        // real points

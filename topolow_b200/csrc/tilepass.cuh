@@ -8,15 +8,16 @@
 //
 // Data layout in HBM
 //   pos / best : [slot][D] reals (AoS; slot = position of a point after the initial random
-//                relabelling, 32 consecutive slots = one tile, padded with phantom slots)
+//                relabelling, 64 consecutive slots = one tile, padded with phantom slots)
 //   dp1        : [slot] (degree + 1), 0 marks a phantom slot
 //   edges      : 16-byte records {double target; u32 slot_lo; u32 slot_hi | type << 30},
 //                counting-sorted by (tile_lo, tile_hi); bucket_off[tile_lo * T + tile_hi]
 // On chip
-//   the 2W tiles of a CTA task sit in shared memory as [k][33] (dimension-major, padded);
-//   during a tile x tile pass lane a holds its A point and the travelling B point in
-//   registers, B moves with warp shuffles; measured pairs of the tile pair are scattered
-//   into a per-warp 32x32 target table + three 32-bit lane masks before the pass.
+//   the 2W tiles of a CTA task sit in shared memory as [k][65] (dimension-major, padded);
+//   during a tile x tile pass lane a holds two A points (slots a, a+32) and two travelling B
+//   points in registers - four pair updates per ring step, two of them independent at a time -
+//   and the B points move with warp shuffles; measured pairs of the tile pair are scattered
+//   into a per-warp 4 x 32 x 32 target table + twelve 32-bit lane masks before the pass.
 #pragma once
 
 #include "schedule.h"
@@ -49,14 +50,15 @@ struct TileDev {
 // mass terms that travel with it) and the arithmetic of one pair visit.
 // ---------------------------------------------------------------------------------------
 
-// What a lane knows about the measured pairs of the current tile pair: bit i of `meas` = my pair at
-// step (or xor distance) i is measured, `gt` / `lt` its threshold kind, `any` = OR of `meas` over the
-// warp (uniform), col[i * 32] = its target.
+// One pair visit's measurement: `meas` / `gt` / `lt` are zero or non-zero words (the lane's mask
+// ANDed with the step bit), `target` is only meaningful when meas != 0.
 template <class real>
-struct EdgeView {
-  const real* col;
-  uint32_t any, meas, gt, lt;
+struct Cell {
+  real target;
+  uint32_t meas, gt, lt;
 };
+
+constexpr int kRow = 65;   // shared-memory row of one dimension: 64 slots + 1 pad
 
 // Two FP32 values in one 64-bit register: sm_100 has 2-wide FP32 FMA/ADD/MUL (SASS FFMA2 ...),
 // which halves the instruction count of the coordinate loops.
@@ -74,7 +76,7 @@ TL_D float rcp_fast(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(
 // another phantom the zero mass cancels the force, so no validity predicate is needed.
 struct FastF32 {
   typedef float real;
-  static constexpr int kMaxWarps = 16;
+  static constexpr int kMaxWarps = 8;   // 256 threads: up to 255 registers for the 4 resident points
   static constexpr float kPhantomCoord = 1.0e18f;
   struct Ctx { float two_k, c_half, k; };
   static TL_D Ctx make_ctx(double k, double c_rep) {
@@ -89,8 +91,8 @@ struct FastF32 {
     TL_D void load(const float* s, int idx, const Ctx& ctx) {
 #pragma unroll
       for (int j = 0; j < H; ++j)
-        c[j] = pk2(s[(2 * j) * 33 + idx], (2 * j + 1 < D) ? s[(2 * j + 1) * 33 + idx] : 0.f);
-      const float dp1 = s[D * 33 + idx];
+        c[j] = pk2(s[(2 * j) * kRow + idx], (2 * j + 1 < D) ? s[(2 * j + 1) * kRow + idx] : 0.f);
+      const float dp1 = s[D * kRow + idx];
       const bool ok = dp1 > 0.f;
       rdeg = ok ? rcp_fast(dp1) : 0.f;
       rnorm = ok ? rcp_fast(fmaf(4.0f, dp1, ctx.k)) : 0.f;
@@ -100,8 +102,8 @@ struct FastF32 {
       for (int j = 0; j < H; ++j) {
         float lo, hi;
         upk2(c[j], lo, hi);
-        s[(2 * j) * 33 + idx] = lo;
-        if (2 * j + 1 < D) s[(2 * j + 1) * 33 + idx] = hi;
+        s[(2 * j) * kRow + idx] = lo;
+        if (2 * j + 1 < D) s[(2 * j + 1) * kRow + idx] = hi;
       }
     }
     TL_D void shfl_from(int src) {
@@ -135,11 +137,10 @@ struct FastF32 {
   // delta = B - A, and the scalar with which it is applied to each endpoint
   // (src/optimization.cpp:207-281 with reciprocals hoisted out of the coordinate loop).
   template <int D>
-  static TL_D void force(const Point<D>& A, const Point<D>& B, f32x2 (&delta)[Point<D>::H], const EdgeView<float>& ev,
-                         int idx, const Ctx& c, float& fA, float& fB) {
+  static TL_D void force(const Point<D>& A, const Point<D>& B, f32x2 (&delta)[Point<D>::H], const Cell<float>& cell,
+                         const Ctx& c, float& fA, float& fB) {
     constexpr int H = Point<D>::H;
-    const uint32_t bit = 1u << idx;
-    const float target = ev.col[idx * 32];   // issued first: its latency hides behind the distance
+    const float target = cell.target;
     const f32x2 neg1 = pk2(-1.0f, -1.0f);
 #pragma unroll
     for (int j = 0; j < H; ++j) delta[j] = fma2(A.c[j], neg1, B.c[j]);
@@ -161,8 +162,8 @@ struct FastF32 {
     // read unconditionally (stale / garbage when the pair is not measured, discarded by the selects).
     // ('>' threshold: spring iff dist < target; '<': iff dist > target; exact: always) - bitwise on
     // purpose: && / ?: would be compiled into divergent branches.
-    const uint32_t below = dist < target ? bit : 0u, above = dist > target ? bit : 0u;
-    const bool spring = (ev.meas & ((ev.gt & below) | (ev.lt & above) | ~(ev.gt | ev.lt)) & bit) != 0u;
+    const uint32_t below = dist < target ? ~0u : 0u, above = dist > target ? ~0u : 0u;
+    const bool spring = (cell.meas & ((cell.gt & below) | (cell.lt & above) | ~(cell.gt | cell.lt))) != 0u;
     const float rep = c.c_half * ids * ids;
     const float spr = c.two_k * (target - dist);
     const float f = (spring ? spr : rep) * ids;
@@ -171,11 +172,11 @@ struct FastF32 {
     fB = f * wB;
   }
   template <int D>
-  static TL_D void pair(Point<D>& A, Point<D>& B, const EdgeView<float>& ev, int idx, const Ctx& c) {
+  static TL_D void pair(Point<D>& A, Point<D>& B, const Cell<float>& cell, const Ctx& c) {
     constexpr int H = Point<D>::H;
     f32x2 delta[H];
     float fA, fB;
-    force<D>(A, B, delta, ev, idx, c, fA, fB);
+    force<D>(A, B, delta, cell, c, fA, fB);
     const f32x2 nA = pk2(-fA, -fA), pB = pk2(fB, fB);
 #pragma unroll
     for (int j = 0; j < H; ++j) {
@@ -185,11 +186,11 @@ struct FastF32 {
   }
   // Both lanes of an intra-tile pair run this, each moving only itself.
   template <int D>
-  static TL_D void pair_self(Point<D>& S, const Point<D>& O, const EdgeView<float>& ev, int idx, const Ctx& c) {
+  static TL_D void pair_self(Point<D>& S, const Point<D>& O, const Cell<float>& cell, const Ctx& c) {
     constexpr int H = Point<D>::H;
     f32x2 delta[H];
     float fS, fO;
-    force<D>(S, O, delta, ev, idx, c, fS, fO);
+    force<D>(S, O, delta, cell, c, fS, fO);
     const f32x2 nS = pk2(-fS, -fS);
 #pragma unroll
     for (int j = 0; j < H; ++j) S.c[j] = fma2(delta[j], nS, S.c[j]);
@@ -200,7 +201,7 @@ struct FastF32 {
 // the CPU loop executed on the order topolow_plan_enumerate() reports.
 struct ExactF64 {
   typedef double real;
-  static constexpr int kMaxWarps = 8;  // 255 registers per thread: the divisions need them
+  static constexpr int kMaxWarps = 4;  // shared memory: 4 x 32 x 32 doubles of targets per warp
   static constexpr double kPhantomCoord = 0.0;
   struct Ctx { double k, c_rep; };
   static TL_D Ctx make_ctx(double k, double c_rep) { Ctx c; c.k = k; c.c_rep = c_rep; return c; }
@@ -210,12 +211,12 @@ struct ExactF64 {
     double dp1;   // deg + 1, 0 = phantom
     TL_D void load(const double* s, int idx, const Ctx&) {
 #pragma unroll
-      for (int k = 0; k < D; ++k) c[k] = s[k * 33 + idx];
-      dp1 = s[D * 33 + idx];
+      for (int k = 0; k < D; ++k) c[k] = s[k * kRow + idx];
+      dp1 = s[D * kRow + idx];
     }
     TL_D void store(double* s, int idx) const {
 #pragma unroll
-      for (int k = 0; k < D; ++k) s[k * 33 + idx] = c[k];
+      for (int k = 0; k < D; ++k) s[k * kRow + idx] = c[k];
     }
     TL_D void shfl_from(int src) {
 #pragma unroll
@@ -229,7 +230,7 @@ struct ExactF64 {
     }
   };
   template <int D>
-  static TL_D void scalars(const double (&delta)[D], const EdgeView<double>& ev, int idx, const Ctx& c, bool& spring,
+  static TL_D void scalars(const double (&delta)[D], const Cell<double>& cell, const Ctx& c, bool& spring,
                            double& factor) {
     double dist_sq = 0.0;
 #pragma unroll
@@ -238,10 +239,9 @@ struct ExactF64 {
     const double ds = __dadd_rn(dist, 0.01);
     spring = false;
     double target = 0.0;
-    const uint32_t bit = 1u << idx;
-    if (ev.meas & bit) {
-      target = ev.col[idx * 32];
-      spring = ((ev.gt | ev.lt) & bit) == 0u ? true : ((ev.gt & bit) ? dist < target : dist > target);
+    if (cell.meas) {
+      target = cell.target;
+      spring = (cell.gt | cell.lt) == 0u ? true : (cell.gt ? dist < target : dist > target);
     }
     if (spring) factor = __ddiv_rn(__dmul_rn(__dmul_rn(2.0, c.k), __dsub_rn(target, dist)), ds);
     else factor = __ddiv_rn(c.c_rep, __dmul_rn(__dmul_rn(__dmul_rn(2.0, ds), ds), ds));
@@ -250,13 +250,13 @@ struct ExactF64 {
     return spring ? __dadd_rn(__dmul_rn(4.0, dp1), c.k) : dp1;
   }
   template <int D>
-  static TL_D void pair(Point<D>& A, Point<D>& B, const EdgeView<double>& ev, int idx, const Ctx& c) {
+  static TL_D void pair(Point<D>& A, Point<D>& B, const Cell<double>& cell, const Ctx& c) {
     if (!(A.dp1 > 0.0 && B.dp1 > 0.0)) return;
     double delta[D];
 #pragma unroll
     for (int k = 0; k < D; ++k) delta[k] = __dsub_rn(B.c[k], A.c[k]);
     bool spring; double factor;
-    scalars<D>(delta, ev, idx, c, spring, factor);
+    scalars<D>(delta, cell, c, spring, factor);
     const double nA = norm(spring, A.dp1, c), nB = norm(spring, B.dp1, c);
 #pragma unroll
     for (int k = 0; k < D; ++k) {
@@ -266,13 +266,13 @@ struct ExactF64 {
     }
   }
   template <int D>
-  static TL_D void pair_self(Point<D>& S, const Point<D>& O, const EdgeView<double>& ev, int idx, const Ctx& c) {
+  static TL_D void pair_self(Point<D>& S, const Point<D>& O, const Cell<double>& cell, const Ctx& c) {
     if (!(S.dp1 > 0.0 && O.dp1 > 0.0)) return;
     double delta[D];
 #pragma unroll
     for (int k = 0; k < D; ++k) delta[k] = __dsub_rn(O.c[k], S.c[k]);
     bool spring; double factor;
-    scalars<D>(delta, ev, idx, c, spring, factor);
+    scalars<D>(delta, cell, c, spring, factor);
     const double nS = norm(spring, S.dp1, c);
 #pragma unroll
     for (int k = 0; k < D; ++k) S.c[k] = __dsub_rn(S.c[k], __ddiv_rn(__dmul_rn(delta[k], factor), nS));
@@ -340,73 +340,116 @@ TL_D void gang_barrier(unsigned* bar, int G, unsigned& gen) {
 
 template <int D>
 struct TileShape {
-  static constexpr int kStride = 33;                  // padded row of one dimension
-  static constexpr int kReals = (D + 1) * kStride;    // D coordinate rows + the dp1 row
+  static constexpr int kReals = (D + 1) * kRow;    // D coordinate rows + the dp1 row, 64 slots each
 };
 
-// global AoS tile -> shared [k][33]
+// global AoS tile -> shared [k][65]
 template <int D, class real>
 TL_D void load_tile(real* s, const real* gpos, const real* gdp1, int tile, int lane) {
   if (tile < 0) {
 #pragma unroll
-    for (int k = 0; k <= D; ++k) s[k * 33 + lane] = (real)0;
+    for (int k = 0; k <= D; ++k) { s[k * kRow + lane] = (real)0; s[k * kRow + lane + 32] = (real)0; }
     return;
   }
   const real* base = gpos + (size_t)tile * (kTile * D);
 #pragma unroll
-  for (int j = 0; j < D; ++j) {
+  for (int j = 0; j < 2 * D; ++j) {
     const int e = lane + 32 * j;
-    s[(e % D) * 33 + (e / D)] = __ldcg(base + e);
+    s[(e % D) * kRow + (e / D)] = __ldcg(base + e);
   }
-  s[D * 33 + lane] = gdp1[(size_t)tile * kTile + lane];
+  s[D * kRow + lane] = gdp1[(size_t)tile * kTile + lane];
+  s[D * kRow + lane + 32] = gdp1[(size_t)tile * kTile + lane + 32];
 }
 template <int D, class real>
 TL_D void store_tile(const real* s, real* gpos, int tile, int lane) {
   if (tile < 0) return;
   real* base = gpos + (size_t)tile * (kTile * D);
 #pragma unroll
-  for (int j = 0; j < D; ++j) {
+  for (int j = 0; j < 2 * D; ++j) {
     const int e = lane + 32 * j;
-    __stcg(base + e, s[(e % D) * 33 + (e / D)]);
+    __stcg(base + e, s[(e % D) * kRow + (e / D)]);
   }
 }
 
+// Per-warp table of the measured pairs of one tile pair.  Combination c = 2 * (A half) + (B half)
+// (half 0 = slots 0..31, half 1 = slots 32..63): tgt[c][step][lane], mask[c][kind][lane] with
+// kind 0 = measured, 1 = '>', 2 = '<'.
+constexpr int kTableReals = 4 * 32 * 32;
+constexpr int kTableMasks = 4 * 3 * 32;
 template <class real>
 struct WarpTable {
-  real* tgt;        // [32 steps][32 lanes]
-  uint32_t* mask;   // [3][32]: measured, '>' , '<'
+  real* tgt;
+  uint32_t* mask;
+};
+struct LaneMasks {
+  uint32_t meas[4], gt[4], lt[4];
 };
 
-// Scatter the measured pairs of bucket (lo,hi) into the warp's table.  `swap` = the A side is
-// the higher-numbered tile.  Ring passes index by (step, lane), intra passes by (xor, lane).
+template <class real>
+TL_D void table_clear(const WarpTable<real>& tb, int lane) {
+#pragma unroll
+  for (int j = 0; j < 12; ++j) tb.mask[j * 32 + lane] = 0u;
+  __syncwarp();
+}
+template <class real>
+TL_D void table_put(const WarpTable<real>& tb, int c, int idx, int lane_of, real target, int ty) {
+  tb.tgt[(c * 32 + idx) * 32 + lane_of] = target;
+  atomicOr(&tb.mask[(c * 3 + 0) * 32 + lane_of], 1u << idx);
+  if (ty == 1) atomicOr(&tb.mask[(c * 3 + 1) * 32 + lane_of], 1u << idx);
+  if (ty == 2) atomicOr(&tb.mask[(c * 3 + 2) * 32 + lane_of], 1u << idx);
+}
+template <class real>
+TL_D LaneMasks table_masks(const WarpTable<real>& tb, int lane, bool filled) {
+  LaneMasks m;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    m.meas[c] = filled ? tb.mask[(c * 3 + 0) * 32 + lane] : 0u;
+    m.gt[c] = filled ? tb.mask[(c * 3 + 1) * 32 + lane] : 0u;
+    m.lt[c] = filled ? tb.mask[(c * 3 + 2) * 32 + lane] : 0u;
+  }
+  return m;
+}
+template <class real>
+TL_D Cell<real> table_cell(const WarpTable<real>& tb, const LaneMasks& m, int c, int idx, int lane) {
+  Cell<real> cell;
+  const uint32_t bit = 1u << idx;
+  cell.target = tb.tgt[(c * 32 + idx) * 32 + lane];   // garbage when not measured: discarded by the policy
+  cell.meas = m.meas[c] & bit;
+  cell.gt = m.gt[c] & bit;
+  cell.lt = m.lt[c] & bit;
+  return cell;
+}
+
+// Scatter the measured pairs of bucket (lo, hi) into the warp's table.  `swap` = the A side is the
+// higher-numbered tile.  Ring passes index by (combination, ring step, A lane).
 template <class real>
 TL_D void fill_table_ring(const WarpTable<real>& tb, const EdgeRec* edges, uint32_t beg, uint32_t end, bool swap,
                           const RingParams& rp, int lane) {
   for (uint32_t e = beg + lane; e < end; e += 32) {
     const EdgeRec r = edges[e];
-    const int lo = r.slot_lo & 31, hi = r.slot_hi_type & 31;
+    const int lo = r.slot_lo & 63, hi = r.slot_hi_type & 63;
     const int ty = r.slot_hi_type >> 30;
     const int a = swap ? hi : lo, b = swap ? lo : hi;
-    const int i = ring_step(rp, a, b);
-    tb.tgt[i * 32 + a] = (real)r.target;
-    atomicOr(&tb.mask[a], 1u << i);
-    if (ty == 1) atomicOr(&tb.mask[32 + a], 1u << i);
-    if (ty == 2) atomicOr(&tb.mask[64 + a], 1u << i);
+    const int la = a & 31, lb = b & 31;
+    table_put<real>(tb, 2 * (a >> 5) + (b >> 5), ring_step(rp, la, lb), la, (real)r.target, ty);
   }
 }
+// Intra passes index by (combination seen from the lane, xor distance, lane); the pair of a lane's
+// own two slots sits at combination 1, index 0 (xor distance 0 never occurs otherwise).
 template <class real>
 TL_D void fill_table_xor(const WarpTable<real>& tb, const EdgeRec* edges, uint32_t beg, uint32_t end, int lane) {
   for (uint32_t e = beg + lane; e < end; e += 32) {
     const EdgeRec r = edges[e];
-    const int a = r.slot_lo & 31, b = r.slot_hi_type & 31;
+    const int u = r.slot_lo & 63, v = r.slot_hi_type & 63;
     const int ty = r.slot_hi_type >> 30;
-    const int x = a ^ b;
-    tb.tgt[x * 32 + a] = (real)r.target;
-    tb.tgt[x * 32 + b] = (real)r.target;
-    atomicOr(&tb.mask[a], 1u << x);
-    atomicOr(&tb.mask[b], 1u << x);
-    if (ty == 1) { atomicOr(&tb.mask[32 + a], 1u << x); atomicOr(&tb.mask[32 + b], 1u << x); }
-    if (ty == 2) { atomicOr(&tb.mask[64 + a], 1u << x); atomicOr(&tb.mask[64 + b], 1u << x); }
+    const int lu = u & 31, lv = v & 31, pu = u >> 5, pv = v >> 5;
+    const int x = lu ^ lv;
+    if (x == 0) {
+      table_put<real>(tb, 1, 0, lu, (real)r.target, ty);
+    } else {
+      table_put<real>(tb, 2 * pu + pv, x, lu, (real)r.target, ty);
+      table_put<real>(tb, 2 * pv + pu, x, lv, (real)r.target, ty);
+    }
   }
 }
 
@@ -422,22 +465,13 @@ TL_D uint2 bucket_range(const uint32_t* bucket_off, const EdgeRec* edges, int T,
   r.y = bucket_off[key + 1];
   const char* p = reinterpret_cast<const char*>(edges + r.x);
   const char* e = reinterpret_cast<const char*>(edges + r.y);
-  for (int i = 0; i < 8 && p < e; ++i, p += 128) prefetch_l2(p);
+  for (int i = 0; i < 16 && p < e; ++i, p += 128) prefetch_l2(p);
   return r;
 }
 
-template <class real>
-TL_D EdgeView<real> make_view(const WarpTable<real>& tb, int lane, bool filled) {
-  EdgeView<real> ev;
-  ev.col = tb.tgt + lane;
-  ev.meas = filled ? tb.mask[lane] : 0u;
-  ev.gt = filled ? tb.mask[32 + lane] : 0u;
-  ev.lt = filled ? tb.mask[64 + lane] : 0u;
-  ev.any = __reduce_or_sync(0xffffffffu, ev.meas);
-  return ev;
-}
-
-// tile A x tile B, 32 ring steps.  sA / sB are the shared-memory tiles, [beg, end) the bucket.
+// tile A x tile B (64 x 64 pairs), 32 ring steps of 4 pair visits per lane.  Lane a keeps
+// A0 = A[a], A1 = A[a+32]; the travelling pair B0 = B[b], B1 = B[b+32] with b = ring_b(a, i).
+// Step i: (A0,B0) and (A1,B1) - independent, they interleave - then (A0,B1) and (A1,B0).
 template <int D, class M>
 TL_D void ring_pass(typename M::real* sA, typename M::real* sB, int tA, int tB, uint32_t beg, uint32_t end,
                     const WarpTable<typename M::real>& tb, const TileDev<typename M::real>& dv, const Geometry& geo,
@@ -445,49 +479,57 @@ TL_D void ring_pass(typename M::real* sA, typename M::real* sB, int tA, int tB, 
   typedef typename M::real real;
   const RingParams rp = ring_params(geo, iter, tA, tB);
   if (beg != end) {  // warp-uniform
-    tb.mask[lane] = 0; tb.mask[32 + lane] = 0; tb.mask[64 + lane] = 0;
-    __syncwarp();
+    table_clear<real>(tb, lane);
     fill_table_ring<real>(tb, dv.edges, beg, end, tA > tB, rp, lane);
     __syncwarp();
   }
-  const EdgeView<real> ev = make_view<real>(tb, lane, beg != end);
-  typename M::template Point<D> A, B;
-  A.load(sA, lane, ctx);
-  B.load(sB, (lane + rp.s0) & 31, ctx);
+  const LaneMasks m = table_masks<real>(tb, lane, beg != end);
+  typename M::template Point<D> A0, A1, B0, B1;
+  const int b0 = (lane + rp.s0) & 31;
+  A0.load(sA, lane, ctx); A1.load(sA, lane + 32, ctx);
+  B0.load(sB, b0, ctx); B1.load(sB, b0 + 32, ctx);
   const int src = (lane + rp.g) & 31;
-#pragma unroll 2
-  for (int i = 0; i < 31; ++i) {
-    M::template pair<D>(A, B, ev, i, ctx);
-    B.shfl_from(src);
+#pragma unroll 1
+  for (int i = 0; i < 32; ++i) {
+    M::template pair<D>(A0, B0, table_cell<real>(tb, m, 0, i, lane), ctx);
+    M::template pair<D>(A1, B1, table_cell<real>(tb, m, 3, i, lane), ctx);
+    M::template pair<D>(A0, B1, table_cell<real>(tb, m, 1, i, lane), ctx);
+    M::template pair<D>(A1, B0, table_cell<real>(tb, m, 2, i, lane), ctx);
+    if (i < 31) { B0.shfl_from(src); B1.shfl_from(src); }
   }
-  M::template pair<D>(A, B, ev, 31, ctx);
-  A.store(sA, lane);
-  B.store(sB, (lane + rp.s0 + 31 * rp.g) & 31);
+  const int bf = (lane + rp.s0 + 31 * rp.g) & 31;
+  A0.store(sA, lane); A1.store(sA, lane + 32);
+  B0.store(sB, bf); B1.store(sB, bf + 32);
 }
 
-// tile x itself, 31 XOR steps; every lane moves only its own point.
+// tile x itself (64 points).  Lane a owns S0 = slot a and S1 = slot a+32: first that pair, then 31
+// XOR steps against lane a^x: (S0,O0) and (S1,O1) computed two-sided on local copies of the partner's
+// points (the partner computes the same values), then (S0,O1) and (S1,O0) moving only the lane's own.
 template <int D, class M>
 TL_D void intra_pass(typename M::real* sT, int t, uint32_t beg, uint32_t end, const WarpTable<typename M::real>& tb,
                      const TileDev<typename M::real>& dv, const Geometry& geo, int iter,
                      const typename M::Ctx& ctx, int lane) {
   typedef typename M::real real;
   if (beg != end) {
-    tb.mask[lane] = 0; tb.mask[32 + lane] = 0; tb.mask[64 + lane] = 0;
-    __syncwarp();
+    table_clear<real>(tb, lane);
     fill_table_xor<real>(tb, dv.edges, beg, end, lane);
     __syncwarp();
   }
-  const EdgeView<real> ev = make_view<real>(tb, lane, beg != end);
-  typename M::template Point<D> S, O;
-  S.load(sT, lane, ctx);
+  const LaneMasks m = table_masks<real>(tb, lane, beg != end);
+  typename M::template Point<D> S0, S1, O0, O1;
+  S0.load(sT, lane, ctx); S1.load(sT, lane + 32, ctx);
+  M::template pair<D>(S0, S1, table_cell<real>(tb, m, 1, 0, lane), ctx);
   const XorParams xp = xor_params(geo, iter, t);
 #pragma unroll 1
   for (int i = 0; i < 31; ++i) {
     const int x = xor_at(xp, i);
-    O.shfl_xor_of(S, x);
-    M::template pair_self<D>(S, O, ev, x, ctx);
+    O0.shfl_xor_of(S0, x); O1.shfl_xor_of(S1, x);
+    M::template pair<D>(S0, O0, table_cell<real>(tb, m, 0, x, lane), ctx);
+    M::template pair<D>(S1, O1, table_cell<real>(tb, m, 3, x, lane), ctx);
+    M::template pair_self<D>(S0, O1, table_cell<real>(tb, m, 1, x, lane), ctx);
+    M::template pair_self<D>(S1, O0, table_cell<real>(tb, m, 2, x, lane), ctx);
   }
-  S.store(sT, lane);
+  S0.store(sT, lane); S1.store(sT, lane + 32);
 }
 
 // Deterministic CTA reduction of (sum, count, flag); result valid in thread 0.
@@ -525,10 +567,10 @@ tile_kernel(TileDev<typename M::real> dv, Geometry geo, FitParams prm, int n_ite
   const int W = geo.W, cta = blockIdx.x;
   real* s_tiles = reinterpret_cast<real*>(smem_raw);
   real* s_tgt = s_tiles + (size_t)2 * W * TS;
-  uint32_t* s_mask = reinterpret_cast<uint32_t*>(s_tgt + (size_t)W * 1024);
-  int* s_tid = reinterpret_cast<int*>(s_mask + W * 96);
+  uint32_t* s_mask = reinterpret_cast<uint32_t*>(s_tgt + (size_t)W * kTableReals);
+  int* s_tid = reinterpret_cast<int*>(s_mask + W * kTableMasks);
   int* s_flag = s_tid + 2 * W;
-  const WarpTable<real> tb{s_tgt + warp * 1024, s_mask + warp * 96};
+  const WarpTable<real> tb{s_tgt + (size_t)warp * kTableReals, s_mask + warp * kTableMasks};
 
   unsigned gen = 0;
   if (tid == 0) load_state(st, dv.state);

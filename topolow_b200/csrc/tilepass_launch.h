@@ -8,8 +8,8 @@ constexpr int kMaxDim = 16;
 
 // Dynamic shared memory of one CTA: 2W tiles + W (target table + masks) + 2W tile ids + W flags.
 inline size_t tile_smem_bytes(int D, int W, size_t real_size) {
-  const size_t tile = (size_t)(D + 1) * 33 * real_size;
-  return 2 * W * tile + (size_t)W * (1024 * real_size + 96 * 4) + (size_t)3 * W * 4;
+  const size_t tile = (size_t)(D + 1) * kRow * real_size;
+  return 2 * W * tile + (size_t)W * (kTableReals * real_size + kTableMasks * 4) + (size_t)3 * W * 4;
 }
 
 // Launch `n_iters` iterations (cooperative when geo.G > 1).  Throws CudaError.
