@@ -301,36 +301,38 @@ TL_D void store_state(FitState* dst, const FitState& src) {
   for (int i = 0; i < (int)(sizeof(FitState) / 8); ++i) __stcg(d + i, s[i]);
 }
 
-// Hand-off flags in shared memory (one per travelling tile).
-TL_D void wait_flag(volatile int* flag, int want, int lane) {
-  if (lane == 0) {
-    while (*flag < want) { }
-    __threadfence_block();
-  }
+// Hand-off flags in shared memory (one per travelling tile).  Every lane polls the same word (one
+// broadcast load), so the warp leaves the loop together: a single-lane spin would leave the warp
+// diverged and every later shuffle would take the slow divergent path.
+TL_D void wait_flag(volatile int* flag, int want) {
+  while (*flag < want) { }
+  __threadfence_block();
   __syncwarp();
 }
 TL_D void post_flag(volatile int* flag, int value, int lane) {
   __syncwarp();
-  if (lane == 0) {
-    __threadfence_block();
-    *flag = value;
-  }
+  __threadfence_block();
+  if (lane == 0) *flag = value;
 }
 
-// Barrier across the G CTAs of one fit (all co-resident: cooperative launch).
+// Barrier across the G CTAs of one fit (all co-resident: cooperative launch).  Warp 0 arrives with
+// one lane and then polls the generation word with all its lanes (uniform exit).
 TL_D void gang_barrier(unsigned* bar, int G, unsigned& gen) {
   __syncthreads();
   if (G > 1) {
-    if (threadIdx.x == 0) {
-      __threadfence();
-      const unsigned arrived = atomicAdd(&bar[0], 1u);
-      if (arrived == (unsigned)G - 1u) {
-        atomicExch(&bar[0], 0u);
+    if (threadIdx.x < 32) {
+      unsigned last = 0u;
+      if (threadIdx.x == 0) {
         __threadfence();
-        atomicAdd(&bar[1], 1u);
-      } else {
-        while (ld_acquire_u32(&bar[1]) == gen) { __nanosleep(20); }
+        last = (atomicAdd(&bar[0], 1u) == (unsigned)G - 1u) ? 1u : 0u;
+        if (last) {
+          atomicExch(&bar[0], 0u);
+          __threadfence();
+          atomicAdd(&bar[1], 1u);
+        }
       }
+      __syncwarp();
+      while (ld_acquire_u32(&bar[1]) == gen) { __nanosleep(20); }
       __threadfence();
     }
     gen++;
@@ -607,13 +609,13 @@ tile_kernel(TileDev<typename M::real> dv, Geometry geo, FitParams prm, int n_ite
           const int bw = (warp + v + rot) % W;
           const int tA = s_tid[warp], tB = s_tid[W + bw];
           const uint32_t beg = __shfl_sync(0xffffffffu, my_rng.x, v), end = __shfl_sync(0xffffffffu, my_rng.y, v);
-          wait_flag(s_flag + bw, v, lane);
+          wait_flag(s_flag + bw, v);
           if (tA >= 0 && tB >= 0)
             ring_pass<D, M>(s_tiles + (size_t)warp * TS, s_tiles + (size_t)(W + bw) * TS, tA, tB, beg, end, tb, dv,
                             geo, iter, ctx, lane);
           post_flag(s_flag + bw, v + 1, lane);
         }
-        wait_flag(s_flag + warp, W, lane);   // every pass on Y[warp] is done: this warp writes it back
+        wait_flag(s_flag + warp, W);   // every pass on Y[warp] is done: this warp writes it back
         store_tile<D, real>(s_tiles + (size_t)warp * TS, dv.pos, tX, lane);
         store_tile<D, real>(s_tiles + (size_t)(W + warp) * TS, dv.pos, tY, lane);
         __syncwarp();
