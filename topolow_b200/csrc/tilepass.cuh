@@ -184,6 +184,46 @@ struct FastF32 {
       B.c[j] = fma2(delta[j], pB, B.c[j]);
     }
   }
+  // Two independent pair visits written in lock-step so that their dependency chains (distance ->
+  // rsqrt -> rcp -> factors) overlap: (P, Q) and (R, S) share no point.
+  template <int D, bool kSelfOnly>
+  static TL_D void pair2(Point<D>& P, Point<D>& Q, const Cell<float>& c0, Point<D>& R, Point<D>& S, const Cell<float>& c1,
+                         const Ctx& c) {
+    constexpr int H = Point<D>::H;
+    const f32x2 neg1 = pk2(-1.0f, -1.0f);
+    f32x2 d0[H], d1[H];
+#pragma unroll
+    for (int j = 0; j < H; ++j) { d0[j] = fma2(P.c[j], neg1, Q.c[j]); d1[j] = fma2(R.c[j], neg1, S.c[j]); }
+    f32x2 a0 = mul2(d0[0], d0[0]), a1 = mul2(d1[0], d1[0]);
+    f32x2 b0 = pk2(0.f, 0.f), b1 = pk2(0.f, 0.f);
+    if (H > 1) { b0 = mul2(d0[1], d0[1]); b1 = mul2(d1[1], d1[1]); }
+#pragma unroll
+    for (int j = 2; j < H; ++j) {
+      if (j & 1) { b0 = fma2(d0[j], d0[j], b0); b1 = fma2(d1[j], d1[j], b1); }
+      else { a0 = fma2(d0[j], d0[j], a0); a1 = fma2(d1[j], d1[j], a1); }
+    }
+    if (H > 1) { a0 = add2(a0, b0); a1 = add2(a1, b1); }
+    const float s0 = a0.x + a0.y, s1 = a1.x + a1.y;
+    const float r0 = rsqrt_fast(fmaxf(s0, 1e-35f)), r1 = rsqrt_fast(fmaxf(s1, 1e-35f));
+    const float dist0 = s0 * r0, dist1 = s1 * r1;
+    const float i0 = rcp_fast(dist0 + 0.01f), i1 = rcp_fast(dist1 + 0.01f);
+    const uint32_t bl0 = dist0 < c0.target ? ~0u : 0u, ab0 = dist0 > c0.target ? ~0u : 0u;
+    const uint32_t bl1 = dist1 < c1.target ? ~0u : 0u, ab1 = dist1 > c1.target ? ~0u : 0u;
+    const bool sp0 = (c0.meas & ((c0.gt & bl0) | (c0.lt & ab0) | ~(c0.gt | c0.lt))) != 0u;
+    const bool sp1 = (c1.meas & ((c1.gt & bl1) | (c1.lt & ab1) | ~(c1.gt | c1.lt))) != 0u;
+    const float f0 = (sp0 ? c.two_k * (c0.target - dist0) : c.c_half * i0 * i0) * i0;
+    const float f1 = (sp1 ? c.two_k * (c1.target - dist1) : c.c_half * i1 * i1) * i1;
+    const float fP = f0 * (sp0 ? P.rnorm : P.rdeg), fR = f1 * (sp1 ? R.rnorm : R.rdeg);
+    const f32x2 nP = pk2(-fP, -fP), nR = pk2(-fR, -fR);
+#pragma unroll
+    for (int j = 0; j < H; ++j) { P.c[j] = fma2(d0[j], nP, P.c[j]); R.c[j] = fma2(d1[j], nR, R.c[j]); }
+    if (!kSelfOnly) {
+      const float fQ = f0 * (sp0 ? Q.rnorm : Q.rdeg), fS = f1 * (sp1 ? S.rnorm : S.rdeg);
+      const f32x2 pQ = pk2(fQ, fQ), pS = pk2(fS, fS);
+#pragma unroll
+      for (int j = 0; j < H; ++j) { Q.c[j] = fma2(d0[j], pQ, Q.c[j]); S.c[j] = fma2(d1[j], pS, S.c[j]); }
+    }
+  }
   // Both lanes of an intra-tile pair run this, each moving only itself.
   template <int D>
   static TL_D void pair_self(Point<D>& S, const Point<D>& O, const Cell<float>& cell, const Ctx& c) {
@@ -264,6 +304,12 @@ struct ExactF64 {
       A.c[k] = __dsub_rn(A.c[k], __ddiv_rn(force, nA));
       B.c[k] = __dadd_rn(B.c[k], __ddiv_rn(force, nB));
     }
+  }
+  template <int D, bool kSelfOnly>
+  static TL_D void pair2(Point<D>& P, Point<D>& Q, const Cell<double>& c0, Point<D>& R, Point<D>& S,
+                         const Cell<double>& c1, const Ctx& c) {
+    if (kSelfOnly) { pair_self<D>(P, Q, c0, c); pair_self<D>(R, S, c1, c); }
+    else { pair<D>(P, Q, c0, c); pair<D>(R, S, c1, c); }
   }
   template <int D>
   static TL_D void pair_self(Point<D>& S, const Point<D>& O, const Cell<double>& cell, const Ctx& c) {
@@ -493,10 +539,8 @@ TL_D void ring_pass(typename M::real* sA, typename M::real* sB, int tA, int tB, 
   const int src = (lane + rp.g) & 31;
 #pragma unroll 1
   for (int i = 0; i < 32; ++i) {
-    M::template pair<D>(A0, B0, table_cell<real>(tb, m, 0, i, lane), ctx);
-    M::template pair<D>(A1, B1, table_cell<real>(tb, m, 3, i, lane), ctx);
-    M::template pair<D>(A0, B1, table_cell<real>(tb, m, 1, i, lane), ctx);
-    M::template pair<D>(A1, B0, table_cell<real>(tb, m, 2, i, lane), ctx);
+    M::template pair2<D, false>(A0, B0, table_cell<real>(tb, m, 0, i, lane), A1, B1, table_cell<real>(tb, m, 3, i, lane), ctx);
+    M::template pair2<D, false>(A0, B1, table_cell<real>(tb, m, 1, i, lane), A1, B0, table_cell<real>(tb, m, 2, i, lane), ctx);
     if (i < 31) { B0.shfl_from(src); B1.shfl_from(src); }
   }
   const int bf = (lane + rp.s0 + 31 * rp.g) & 31;
@@ -526,10 +570,8 @@ TL_D void intra_pass(typename M::real* sT, int t, uint32_t beg, uint32_t end, co
   for (int i = 0; i < 31; ++i) {
     const int x = xor_at(xp, i);
     O0.shfl_xor_of(S0, x); O1.shfl_xor_of(S1, x);
-    M::template pair<D>(S0, O0, table_cell<real>(tb, m, 0, x, lane), ctx);
-    M::template pair<D>(S1, O1, table_cell<real>(tb, m, 3, x, lane), ctx);
-    M::template pair_self<D>(S0, O1, table_cell<real>(tb, m, 1, x, lane), ctx);
-    M::template pair_self<D>(S1, O0, table_cell<real>(tb, m, 2, x, lane), ctx);
+    M::template pair2<D, false>(S0, O0, table_cell<real>(tb, m, 0, x, lane), S1, O1, table_cell<real>(tb, m, 3, x, lane), ctx);
+    M::template pair2<D, true>(S0, O1, table_cell<real>(tb, m, 1, x, lane), S1, O0, table_cell<real>(tb, m, 2, x, lane), ctx);
   }
   S0.store(sT, lane); S1.store(sT, lane + 32);
 }
