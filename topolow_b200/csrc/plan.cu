@@ -517,6 +517,9 @@ int topolow_fit_batch(int32_t n_jobs, const topolow_problem* problems, const top
       if (params[j].mode != TOPOLOW_MODE_COLOURED) throw BadArg("batch supports the coloured mode only");
       topolow_params pr = params[j];
       pr.device = device;
+      // Many independent fits: one CTA per fit (no grid barrier, plain launches that run side by
+      // side on different SMs) keeps every SM busy; a lone large fit still gets the whole chip.
+      if (n_jobs >= 16 && pr.max_ctas == 0) pr.max_ctas = 1;
       plans[j] = make_plan(problems[j], pr);
       left[j] = pr.n_iter;
     } catch (const CudaError& e) {
