@@ -8,7 +8,9 @@
 #include <algorithm>
 #include <cstring>
 #include <memory>
+#include <atomic>
 #include <random>
+#include <thread>
 #include <vector>
 
 #include "../../include/topolow_b200.h"
@@ -504,14 +506,16 @@ int topolow_fit_batch(int32_t n_jobs, const topolow_problem* problems, const top
   // round-robin so that the device always has several fits in flight.
   std::vector<std::unique_ptr<topolow_plan>> plans(n_jobs);
   std::vector<int> left(n_jobs, 0);
-  for (int j = 0; j < n_jobs; ++j) {
+  // Host-side set-up (relabelling, bucket sort, uploads) of the jobs is independent: spread it over
+  // the host cores, as the reference spreads whole fits with mclapply.
+  auto setup_one = [&](int j) {
     topolow_result& r = results[j];
     r.status = TOPOLOW_OK; r.message[0] = 0;
     try {
       if (problems[j].n < 2) {
         r.status = TOPOLOW_ERR_TOO_FEW_POINTS;
         set_msg(r.message, sizeof r.message, "Need at least 2 points for embedding");
-        continue;
+        return;
       }
       if (!r.positions) throw BadArg("result->positions must be caller-allocated");
       if (params[j].mode != TOPOLOW_MODE_COLOURED) throw BadArg("batch supports the coloured mode only");
@@ -527,6 +531,16 @@ int topolow_fit_batch(int32_t n_jobs, const topolow_problem* problems, const top
     } catch (const std::exception& e) {
       r.status = TOPOLOW_ERR_BAD_ARG; set_msg(r.message, sizeof r.message, e.what());
     }
+  };
+  {
+    const int n_threads = std::max(1, std::min<int>({(int)std::thread::hardware_concurrency(), 16, n_jobs}));
+    std::atomic<int> next{0};
+    std::vector<std::thread> pool;
+    for (int t = 0; t < n_threads; ++t)
+      pool.emplace_back([&] {
+        for (int j = next.fetch_add(1); j < n_jobs; j = next.fetch_add(1)) setup_one(j);
+      });
+    for (auto& th : pool) th.join();
   }
   try {
     bool any = true;
