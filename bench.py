@@ -38,6 +38,7 @@ WORKLOADS = {
     "cfg4": (100_000, 16, 0.99),
     "cfg3": (10_000, 10, 0.95),
     "small": (2_000, 5, 0.90),
+    "cfg5": (5_000, 5, 0.95),     # Euclidify grid: parameter samples x 4 folds, independent fits
 }
 HYPER = dict(k0=5.0, cooling_rate=0.01, c_repulsion=0.02, relative_epsilon=1e-4, convergence_check_freq=3)
 
@@ -173,6 +174,125 @@ def run_reference(args, n, d, missing):
     print(json.dumps(line), flush=True)
 
 
+
+def cfg5_jobs(n, missing, samples, fit_iters, seed):
+    """`samples` parameter draws x 4 CV folds on one synthetic matrix: the unit of work of
+    initial_parameter_optimization (R/adaptive_sampling.R:419-425,516-528)."""
+    from tools import synth
+    from topolow_b200 import cv
+    rng = np.random.default_rng(seed)
+    prob = synth.make_problem(n, 5, missing, seed=0, thresholds=False)
+    ei, ej, ed = prob["edge_i"], prob["edge_j"], prob["edge_dist"]
+    E = len(ei)
+    folds = []
+    perm = rng.permutation(E)
+    hold = E // 8            # floor(num_non_NA / (2 * folds)) cells = E/8 pairs in each of the 4 folds... per fold
+    for f in range(4):
+        mask = np.ones(E, dtype=bool)
+        mask[perm[f * hold:(f + 1) * hold]] = False
+        deg = (np.bincount(ei[mask], minlength=n) + np.bincount(ej[mask], minlength=n) + 1).astype(np.int32)
+        folds.append((mask, deg, perm[f * hold:(f + 1) * hold]))
+    jobs, meta = [], []
+    for s_ in range(samples):
+        ndim = int(rng.integers(2, 11))
+        k0, cr, c = float(rng.uniform(1, 15)), float(10 ** rng.uniform(-3, -1.3)), float(10 ** rng.uniform(-3, -1.3))
+        for f, (mask, deg, held) in enumerate(folds):
+            init = np.vstack([np.zeros((1, ndim)), np.cumsum(rng.uniform(0, 2 * ed.max() / n, size=(n - 1, ndim)), axis=0)])
+            jobs.append(dict(initial_positions=init, degrees=deg, edge_i=ei[mask], edge_j=ej[mask], edge_dist=ed[mask],
+                             edge_thresh=prob["edge_thresh"][mask], n_iter=fit_iters, k0=k0, cooling_rate=cr, c_repulsion=c,
+                             relative_epsilon=1e-4, convergence_window=5, seed=1000 * s_ + f))
+            meta.append((s_, f, held))
+    return prob, jobs, meta
+
+
+def main_cfg5(args, n, missing):
+    import torch
+    import torch.distributed as dist
+    from topolow_b200 import _lib
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    prob, jobs, meta = cfg5_jobs(n, missing, args.samples, args.fit_iters, seed=rank)
+    warm = [dict(j, n_iter=2) for j in jobs[:: max(1, len(jobs) // 18)]]   # loads every ndim variant of the kernel
+    _lib.fit_batch(warm, device=local)
+    for _ in range(max(args.warmup - 1, 0)):
+        _lib.fit_batch(warm, device=local)
+    barrier()
+    t0 = time.perf_counter()
+    done, pair_updates, dev_ms, held_mae = 0, 0, 0.0, []
+    with ClockSampler(local) as clk:
+        for _ in range(args.steps):
+            out = _lib.fit_batch(jobs, device=local)
+            for r, (s_, f, held) in zip(out, meta):
+                # hold-out residuals on the device (R/error_metrics.R:95-114, R/adaptive_sampling.R:2642-2647)
+                sa, cnt = _lib.holdout_errors(r["positions"], prob["edge_i"][held], prob["edge_j"][held],
+                                              prob["edge_dist"][held], local)
+                held_mae.append(sa / max(cnt, 1))
+            done += len(out)
+            pair_updates += sum(r["pair_updates"] for r in out)
+            dev_ms = max(dev_ms, max(r["device_ms"] for r in out))
+        barrier()
+    wall = time.perf_counter() - t0
+    t = torch.tensor([wall], dtype=torch.float64, device="cuda")
+    tot = torch.tensor([done, pair_updates], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    wall = float(t[0])
+    fits = float(tot[0])
+    cpu = None
+    if not args.no_cpu:
+        from oracle import cpu_oracle
+        from tools import synth
+        cpu_oracle.build(ref=False)
+        j = jobs[0]
+        t1 = time.perf_counter()
+        res = cpu_oracle.optimize_layout_exact(j["initial_positions"], j["degrees"], j["edge_i"], j["edge_j"], j["edge_dist"],
+                                               j["edge_thresh"], 2, j["k0"], j["cooling_rate"], j["c_repulsion"], 1e-4, 5, 3,
+                                               seed=0, dense=True)
+        dt = time.perf_counter() - t1
+        per_fit_s = dt / 2 * args.fit_iters
+        cores = os.cpu_count() or 1
+        cpu = {"value": 60.0 / per_fit_s * cores, "unit": "CV embeddings/min", "cores": cores, "kind": "port",
+               "sample": f"2 iterations of one fold fit on 1 core ({dt:.1f} s incl. set-up), scaled to {args.fit_iters} iterations "
+                         f"and to one fit per core on {cores} cores (mclapply, R/adaptive_sampling.R:645-672); no early stopping assumed"}
+    line = {
+        "metric": "CV embeddings/min", "value": fits / wall * 60.0, "unit": "CV embeddings/min", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"cfg5: Euclidify grid, {args.samples} parameter samples x 4 folds per GPU per step, {n}-point synthetic "
+                               f"matrix ({missing:.0%} missing), ndim sampled in 2..10, mapping_max_iter={args.fit_iters}, early stopping on",
+                   "fits_per_step_per_gpu": len(jobs), "parallelism": "independent fits, one CTA per fit, no collective",
+                   "l2": "each fit streams its own edge list (about 9 MB per iteration); 128 fits in flight exceed L2"},
+        "pair_updates_per_s": float(tot[1]) / wall, "mean_holdout_mae": float(np.mean(held_mae)),
+        "clocks": clk.summary(),
+        "e2e": {"value": fits / wall * 60.0, "unit": "CV embeddings/min",
+                "h2d_bytes_per_step": int(sum(j["initial_positions"].nbytes + len(j["edge_i"]) * 20 + n * 4 for j in jobs)),
+                "d2h_bytes_per_step": int(sum(j["initial_positions"].nbytes for j in jobs)),
+                "note": "the measured path IS end to end: topolow_fit_batch on host buffers (set-up, upload, fits, download) "
+                        "plus the hold-out residual kernel per fit"},
+        "gpu_launches": int(args.steps * len(jobs) * (-(-args.fit_iters // 50) + 1)),
+        "roofline": None, "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -183,8 +303,12 @@ def main():
     ap.add_argument("--precision", default="f32", choices=["f32", "f64"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--samples", type=int, default=32, help="cfg5: parameter samples per GPU per step (x 4 folds)")
+    ap.add_argument("--fit-iters", type=int, default=250, help="cfg5: mapping_max_iter of every fit (R/core.R:945)")
     args = ap.parse_args()
     n, d, missing = WORKLOADS[args.workload]
+    if args.workload == "cfg5":
+        return main_cfg5(args, n, missing)
 
     if args.impl == "reference":
         run_reference(args, n, d, missing)

@@ -9,6 +9,8 @@
 #include <cstring>
 #include <memory>
 #include <atomic>
+#include <chrono>
+#include <cstdlib>
 #include <random>
 #include <thread>
 #include <vector>
@@ -506,6 +508,9 @@ int topolow_fit_batch(int32_t n_jobs, const topolow_problem* problems, const top
   // round-robin so that the device always has several fits in flight.
   std::vector<std::unique_ptr<topolow_plan>> plans(n_jobs);
   std::vector<int> left(n_jobs, 0);
+  const bool dbg = std::getenv("TOPOLOW_DEBUG") != nullptr;
+  const auto t_begin = std::chrono::steady_clock::now();
+  auto since = [&]() { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count(); };
   // Host-side set-up (relabelling, bucket sort, uploads) of the jobs is independent: spread it over
   // the host cores, as the reference spreads whole fits with mclapply.
   auto setup_one = [&](int j) {
@@ -542,6 +547,7 @@ int topolow_fit_batch(int32_t n_jobs, const topolow_problem* problems, const top
       });
     for (auto& th : pool) th.join();
   }
+  if (dbg) std::fprintf(stderr, "[topolow] batch set-up of %d jobs: %.3f s\n", n_jobs, since());
   try {
     bool any = true;
     for (int j = 0; j < n_jobs; ++j) if (plans[j]) TL_CUDA(cudaEventRecord(plans[j]->ev0, plans[j]->stream));
@@ -555,6 +561,7 @@ int topolow_fit_batch(int32_t n_jobs, const topolow_problem* problems, const top
         any = true;
       }
     }
+    if (dbg) std::fprintf(stderr, "[topolow] batch launches issued: %.3f s\n", since());
     for (int j = 0; j < n_jobs; ++j) {
       if (!plans[j]) continue;
       TL_CUDA(cudaEventRecord(plans[j]->ev1, plans[j]->stream));
@@ -564,6 +571,9 @@ int topolow_fit_batch(int32_t n_jobs, const topolow_problem* problems, const top
       plans[j]->total_ms = ms;
       fill_result(*plans[j], results[j], false);
     }
+    if (dbg) std::fprintf(stderr, "[topolow] batch results read: %.3f s\n", since());
+    plans.clear();
+    if (dbg) std::fprintf(stderr, "[topolow] batch plans destroyed: %.3f s\n", since());
   } catch (const CudaError& e) {
     for (int j = 0; j < n_jobs; ++j)
       if (plans[j]) { results[j].status = TOPOLOW_ERR_CUDA; set_msg(results[j].message, sizeof results[j].message, e.what()); }
