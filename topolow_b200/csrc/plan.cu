@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "../../include/topolow_b200.h"
+#include "edges.h"
 #include "replay.h"
 #include "tilepass_launch.h"
 
@@ -70,12 +71,6 @@ void validate(const topolow_problem& pb, const topolow_params& pr) {
   if (pb.n_edges > 0 && (!pb.edge_i || !pb.edge_j || !pb.edge_dist || !pb.edge_thresh))
     throw BadArg("edge arrays are required when n_edges > 0");
   if (pb.n_edges < 0 || pb.n_edges >= (1ll << 32)) throw BadArg("n_edges out of range");
-  for (int64_t e = 0; e < pb.n_edges; ++e) {
-    const int64_t a = pb.edge_i[e], b = pb.edge_j[e];
-    if (a < 0 || b < 0 || a >= pb.n || b >= pb.n || a == b) throw BadArg("edge index out of range");
-    const int t = pb.edge_thresh[e];
-    if (t < -1 || t > 1) throw BadArg("edge_thresh must be -1, 0 or 1");
-  }
 }
 
 // Fisher-Yates with splitmix64: identical on every host.
@@ -210,40 +205,10 @@ void upload_points(topolow_plan& pl, const topolow_problem& pb, real phantom_coo
   TL_CUDA(cudaMemcpy(pl.dp1, hd.data(), hd.size() * sizeof(real), cudaMemcpyHostToDevice));
 }
 
-void upload_edges(topolow_plan& pl, const topolow_problem& pb) {
-  const int T = pl.geo.T;
-  const size_t nkeys = (size_t)T * T;
-  std::vector<uint32_t> off(nkeys + 1, 0);
-  std::vector<EdgeRec> recs(pl.E);
-  std::vector<uint64_t> keys(pl.E);
-  for (int64_t e = 0; e < pl.E; ++e) {
-    uint32_t sa = (uint32_t)pl.slot_of_point[pb.edge_i[e]], sb = (uint32_t)pl.slot_of_point[pb.edge_j[e]];
-    if (sa > sb) std::swap(sa, sb);  // lower slot first => lower (or equal) tile first
-    keys[e] = (uint64_t)(sa / kTile) * T + (sb / kTile);
-    off[keys[e] + 1]++;
-  }
-  for (size_t k = 0; k < nkeys; ++k) off[k + 1] += off[k];
-  std::vector<uint32_t> cur(off.begin(), off.end() - 1);
-  for (int64_t e = 0; e < pl.E; ++e) {  // stable: input order kept inside a bucket
-    uint32_t sa = (uint32_t)pl.slot_of_point[pb.edge_i[e]], sb = (uint32_t)pl.slot_of_point[pb.edge_j[e]];
-    if (sa > sb) std::swap(sa, sb);
-    const int t = pb.edge_thresh[e];
-    EdgeRec r;
-    r.target = pb.edge_dist[e];
-    r.slot_lo = sa;
-    r.slot_hi_type = sb | ((uint32_t)(t == 1 ? 1 : (t == -1 ? 2 : 0)) << 30);
-    recs[cur[keys[e]]++] = r;
-  }
-  TL_CUDA(cudaMalloc(&pl.edges, std::max<size_t>(recs.size(), 1) * sizeof(EdgeRec)));
-  TL_CUDA(cudaMalloc(&pl.bucket_off, off.size() * sizeof(uint32_t)));
-  if (!recs.empty()) TL_CUDA(cudaMemcpy(pl.edges, recs.data(), recs.size() * sizeof(EdgeRec), cudaMemcpyHostToDevice));
-  TL_CUDA(cudaMemcpy(pl.bucket_off, off.data(), off.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
-}
-
 std::unique_ptr<topolow_plan> make_plan(const topolow_problem& pb, const topolow_params& pr) {
   validate(pb, pr);
   if (pb.ndim > kMaxDim) throw BadArg("ndim > 16 is not built into libtopolow_b200 (coloured mode)");
-  if (pb.n > (1ll << 29)) throw BadArg("n too large");
+  if (pb.n > 1000000) throw BadArg("n > 1,000,000 is not supported (bucket table is T x T)");
   auto pl = std::make_unique<topolow_plan>();
   pl->device = pr.device;
   TL_CUDA(cudaSetDevice(pr.device));
@@ -268,7 +233,8 @@ std::unique_ptr<topolow_plan> make_plan(const topolow_problem& pb, const topolow
 
   if (pr.precision == TOPOLOW_PREC_F64_EXACT) upload_points<double>(*pl, pb, ExactF64::kPhantomCoord);
   else upload_points<float>(*pl, pb, FastF32::kPhantomCoord);
-  upload_edges(*pl, pb);
+  TL_CUDA(cudaStreamCreate(&pl->stream));
+  build_buckets(pb, pl->slot_of_point, g.T, pl->stream, &pl->edges, &pl->bucket_off);
 
   FitState st; state_init(st, pl->prm);
   TL_CUDA(cudaMalloc(&pl->state, sizeof(FitState)));
@@ -284,7 +250,6 @@ std::unique_ptr<topolow_plan> make_plan(const topolow_problem& pb, const topolow
   TL_CUDA(cudaHostAlloc((void**)&pl->h_flag, 2 * sizeof(int), cudaHostAllocMapped));
   pl->h_flag[0] = 0; pl->h_flag[1] = 0;
   TL_CUDA(cudaHostGetDevicePointer((void**)&pl->d_flag, (void*)pl->h_flag, 0));
-  TL_CUDA(cudaStreamCreate(&pl->stream));
   TL_CUDA(cudaEventCreate(&pl->ev0));
   TL_CUDA(cudaEventCreate(&pl->ev1));
 
