@@ -133,33 +133,24 @@ int64_t enumerate_schedule(const Geometry& g, const std::vector<int32_t>& pos, i
   auto ring = [&](int tA, int tB) {
     if (tA < 0 || tB < 0) return;
     const RingParams rp = ring_params(g, iter, tA, tB);
-    for (int i = 0; i < 32; ++i) {
-      for (int a = 0; a < 32; ++a) {
-        const int b = ring_b(rp, a, i);
-        emit(tA * kTile + a, tB * kTile + b);
-        emit(tA * kTile + a + 32, tB * kTile + b + 32);
-      }
-      for (int a = 0; a < 32; ++a) {
-        const int b = ring_b(rp, a, i);
-        emit(tA * kTile + a, tB * kTile + b + 32);
-        emit(tA * kTile + a + 32, tB * kTile + b);
-      }
-    }
+    for (int i = 0; i < 32; ++i)
+      for (int w = 0; w < kP; ++w)
+        for (int a = 0; a < 32; ++a)
+          for (int p0 = 0; p0 < kP; ++p0)
+            emit(tA * kTile + a + 32 * p0, tB * kTile + ring_b(rp, a, i) + 32 * ((p0 + w) % kP));
   };
   auto intra = [&](int t) {
     if (t < 0) return;
     const XorParams xp = xor_params(g, iter, t);
-    for (int a = 0; a < 32; ++a) emit(t * kTile + a, t * kTile + a + 32);
+    for (int a = 0; a < 32; ++a)
+      for (int p0 = 0; p0 < kP; ++p0)
+        for (int q0 = p0 + 1; q0 < kP; ++q0) emit(t * kTile + a + 32 * p0, t * kTile + a + 32 * q0);
     for (int i = 0; i < 31; ++i) {
       const int x = xor_at(xp, i);
-      for (int a = 0; a < 32; ++a) if (a < (a ^ x)) {
-        emit(t * kTile + a, t * kTile + (a ^ x));
-        emit(t * kTile + a + 32, t * kTile + (a ^ x) + 32);
-      }
-      for (int a = 0; a < 32; ++a) if (a < (a ^ x)) {
-        emit(t * kTile + a, t * kTile + (a ^ x) + 32);
-        emit(t * kTile + a + 32, t * kTile + (a ^ x));
-      }
+      for (int w = 0; w < kP; ++w)
+        for (int a = 0; a < 32; ++a) if (a < (a ^ x))
+          for (int p0 = 0; p0 < kP; ++p0)
+            emit(t * kTile + a + 32 * p0, t * kTile + (a ^ x) + 32 * ((w - p0 + kP) % kP));
     }
   };
   const int W = g.W;

@@ -29,7 +29,8 @@
 
 namespace tl {
 
-constexpr int kTile = 64;   // points per tile: every lane of a warp holds two
+constexpr int kP = 2;            // points of a tile held by one lane
+constexpr int kTile = 32 * kP;   // points per tile
 
 struct Geometry {
   int n;        // real points

@@ -14,10 +14,10 @@
 //                counting-sorted by (tile_lo, tile_hi); bucket_off[tile_lo * T + tile_hi]
 // On chip
 //   the 2W tiles of a CTA task sit in shared memory as [k][65] (dimension-major, padded);
-//   during a tile x tile pass lane a holds two A points (slots a, a+32) and two travelling B
-//   points in registers - four pair updates per ring step, two of them independent at a time -
+//   during a tile x tile pass lane a holds kP A points (slots a, a+32, ..) and kP travelling B
+//   points in registers - kP*kP pair updates per ring step, kP of them independent at a time -
 //   and the B points move with warp shuffles; measured pairs of the tile pair are scattered
-//   into a per-warp 4 x 32 x 32 target table + twelve 32-bit lane masks before the pass.
+//   into a per-warp kP*kP x 32 x 32 target table + 3*kP*kP 32-bit lane masks before the pass.
 #pragma once
 
 #include "schedule.h"
@@ -58,7 +58,7 @@ struct Cell {
   uint32_t meas, gt, lt;
 };
 
-constexpr int kRow = 65;   // shared-memory row of one dimension: 64 slots + 1 pad
+constexpr int kRow = kTile + 1;   // shared-memory row of one dimension: kTile slots + 1 pad (kTile % 32 == 0)
 
 // Two FP32 values in one 64-bit register: sm_100 has 2-wide FP32 FMA/ADD/MUL (SASS FFMA2 ...),
 // which halves the instruction count of the coordinate loops.
@@ -184,44 +184,63 @@ struct FastF32 {
       B.c[j] = fma2(delta[j], pB, B.c[j]);
     }
   }
-  // Two independent pair visits written in lock-step so that their dependency chains (distance ->
-  // rsqrt -> rcp -> factors) overlap: (P, Q) and (R, S) share no point.
-  template <int D, bool kSelfOnly>
-  static TL_D void pair2(Point<D>& P, Point<D>& Q, const Cell<float>& c0, Point<D>& R, Point<D>& S, const Cell<float>& c1,
-                         const Ctx& c) {
+  // One wave: kP independent pair visits (A[p], B[q(p)]) written in lock-step so that their dependency
+  // chains (distance -> rsqrt -> rcp -> factors) overlap.  q(p) = (p + w) % kP (kSum = false, ring pass)
+  // or (w - p) mod kP (kSum = true, intra pass: symmetric under swapping the two lanes).
+  template <int D, int W_, bool kSum>
+  static TL_D void wave(Point<D> (&A)[kP], Point<D> (&B)[kP], const Cell<float> (&cell)[kP], const Ctx& c) {
     constexpr int H = Point<D>::H;
     const f32x2 neg1 = pk2(-1.0f, -1.0f);
-    f32x2 d0[H], d1[H];
+    f32x2 d[kP][H];
+    float f[kP];
+    bool sp[kP];
 #pragma unroll
-    for (int j = 0; j < H; ++j) { d0[j] = fma2(P.c[j], neg1, Q.c[j]); d1[j] = fma2(R.c[j], neg1, S.c[j]); }
-    f32x2 a0 = mul2(d0[0], d0[0]), a1 = mul2(d1[0], d1[0]);
-    f32x2 b0 = pk2(0.f, 0.f), b1 = pk2(0.f, 0.f);
-    if (H > 1) { b0 = mul2(d0[1], d0[1]); b1 = mul2(d1[1], d1[1]); }
+    for (int j = 0; j < H; ++j)
 #pragma unroll
-    for (int j = 2; j < H; ++j) {
-      if (j & 1) { b0 = fma2(d0[j], d0[j], b0); b1 = fma2(d1[j], d1[j], b1); }
-      else { a0 = fma2(d0[j], d0[j], a0); a1 = fma2(d1[j], d1[j], a1); }
+      for (int p = 0; p < kP; ++p) {
+        const int q = kSum ? (W_ - p + kP) % kP : (p + W_) % kP;
+        d[p][j] = fma2(A[p].c[j], neg1, B[q].c[j]);
+      }
+    f32x2 acc0[kP], acc1[kP];
+#pragma unroll
+    for (int p = 0; p < kP; ++p) {
+      acc0[p] = mul2(d[p][0], d[p][0]);
+      acc1[p] = H > 1 ? mul2(d[p][1], d[p][1]) : pk2(0.f, 0.f);
     }
-    if (H > 1) { a0 = add2(a0, b0); a1 = add2(a1, b1); }
-    const float s0 = a0.x + a0.y, s1 = a1.x + a1.y;
-    const float r0 = rsqrt_fast(fmaxf(s0, 1e-35f)), r1 = rsqrt_fast(fmaxf(s1, 1e-35f));
-    const float dist0 = s0 * r0, dist1 = s1 * r1;
-    const float i0 = rcp_fast(dist0 + 0.01f), i1 = rcp_fast(dist1 + 0.01f);
-    const uint32_t bl0 = dist0 < c0.target ? ~0u : 0u, ab0 = dist0 > c0.target ? ~0u : 0u;
-    const uint32_t bl1 = dist1 < c1.target ? ~0u : 0u, ab1 = dist1 > c1.target ? ~0u : 0u;
-    const bool sp0 = (c0.meas & ((c0.gt & bl0) | (c0.lt & ab0) | ~(c0.gt | c0.lt))) != 0u;
-    const bool sp1 = (c1.meas & ((c1.gt & bl1) | (c1.lt & ab1) | ~(c1.gt | c1.lt))) != 0u;
-    const float f0 = (sp0 ? c.two_k * (c0.target - dist0) : c.c_half * i0 * i0) * i0;
-    const float f1 = (sp1 ? c.two_k * (c1.target - dist1) : c.c_half * i1 * i1) * i1;
-    const float fP = f0 * (sp0 ? P.rnorm : P.rdeg), fR = f1 * (sp1 ? R.rnorm : R.rdeg);
-    const f32x2 nP = pk2(-fP, -fP), nR = pk2(-fR, -fR);
 #pragma unroll
-    for (int j = 0; j < H; ++j) { P.c[j] = fma2(d0[j], nP, P.c[j]); R.c[j] = fma2(d1[j], nR, R.c[j]); }
-    if (!kSelfOnly) {
-      const float fQ = f0 * (sp0 ? Q.rnorm : Q.rdeg), fS = f1 * (sp1 ? S.rnorm : S.rdeg);
-      const f32x2 pQ = pk2(fQ, fQ), pS = pk2(fS, fS);
+    for (int j = 2; j < H; ++j)
 #pragma unroll
-      for (int j = 0; j < H; ++j) { Q.c[j] = fma2(d0[j], pQ, Q.c[j]); S.c[j] = fma2(d1[j], pS, S.c[j]); }
+      for (int p = 0; p < kP; ++p) {
+        if (j & 1) acc1[p] = fma2(d[p][j], d[p][j], acc1[p]);
+        else acc0[p] = fma2(d[p][j], d[p][j], acc0[p]);
+      }
+    float s2[kP], dist[kP], ids[kP];
+#pragma unroll
+    for (int p = 0; p < kP; ++p) {
+      const f32x2 t = H > 1 ? add2(acc0[p], acc1[p]) : acc0[p];
+      s2[p] = t.x + t.y;
+    }
+#pragma unroll
+    for (int p = 0; p < kP; ++p) dist[p] = s2[p] * rsqrt_fast(fmaxf(s2[p], 1e-35f));
+#pragma unroll
+    for (int p = 0; p < kP; ++p) ids[p] = rcp_fast(dist[p] + 0.01f);
+#pragma unroll
+    for (int p = 0; p < kP; ++p) {
+      const Cell<float>& cl = cell[p];
+      const uint32_t below = dist[p] < cl.target ? ~0u : 0u, above = dist[p] > cl.target ? ~0u : 0u;
+      sp[p] = (cl.meas & ((cl.gt & below) | (cl.lt & above) | ~(cl.gt | cl.lt))) != 0u;
+      f[p] = (sp[p] ? c.two_k * (cl.target - dist[p]) : c.c_half * ids[p] * ids[p]) * ids[p];
+    }
+#pragma unroll
+    for (int p = 0; p < kP; ++p) {
+      const int q = kSum ? (W_ - p + kP) % kP : (p + W_) % kP;
+      const float fA = f[p] * (sp[p] ? A[p].rnorm : A[p].rdeg), fB = f[p] * (sp[p] ? B[q].rnorm : B[q].rdeg);
+      const f32x2 nA = pk2(-fA, -fA), pB = pk2(fB, fB);
+#pragma unroll
+      for (int j = 0; j < H; ++j) {
+        A[p].c[j] = fma2(d[p][j], nA, A[p].c[j]);
+        B[q].c[j] = fma2(d[p][j], pB, B[q].c[j]);
+      }
     }
   }
   // Both lanes of an intra-tile pair run this, each moving only itself.
@@ -305,11 +324,13 @@ struct ExactF64 {
       B.c[k] = __dadd_rn(B.c[k], __ddiv_rn(force, nB));
     }
   }
-  template <int D, bool kSelfOnly>
-  static TL_D void pair2(Point<D>& P, Point<D>& Q, const Cell<double>& c0, Point<D>& R, Point<D>& S,
-                         const Cell<double>& c1, const Ctx& c) {
-    if (kSelfOnly) { pair_self<D>(P, Q, c0, c); pair_self<D>(R, S, c1, c); }
-    else { pair<D>(P, Q, c0, c); pair<D>(R, S, c1, c); }
+  template <int D, int W_, bool kSum>
+  static TL_D void wave(Point<D> (&A)[kP], Point<D> (&B)[kP], const Cell<double> (&cell)[kP], const Ctx& c) {
+#pragma unroll
+    for (int p = 0; p < kP; ++p) {
+      const int q = kSum ? (W_ - p + kP) % kP : (p + W_) % kP;
+      pair<D>(A[p], B[q], cell[p], c);
+    }
   }
   template <int D>
   static TL_D void pair_self(Point<D>& S, const Point<D>& O, const Cell<double>& cell, const Ctx& c) {
@@ -388,7 +409,7 @@ TL_D void gang_barrier(unsigned* bar, int G, unsigned& gen) {
 
 template <int D>
 struct TileShape {
-  static constexpr int kReals = (D + 1) * kRow;    // D coordinate rows + the dp1 row, 64 slots each
+  static constexpr int kReals = (D + 1) * kRow;    // D coordinate rows + the dp1 row, kTile slots each
 };
 
 // global AoS tile -> shared [k][65]
@@ -396,47 +417,50 @@ template <int D, class real>
 TL_D void load_tile(real* s, const real* gpos, const real* gdp1, int tile, int lane) {
   if (tile < 0) {
 #pragma unroll
-    for (int k = 0; k <= D; ++k) { s[k * kRow + lane] = (real)0; s[k * kRow + lane + 32] = (real)0; }
+    for (int k = 0; k <= D; ++k)
+#pragma unroll
+      for (int p = 0; p < kP; ++p) s[k * kRow + lane + 32 * p] = (real)0;
     return;
   }
   const real* base = gpos + (size_t)tile * (kTile * D);
 #pragma unroll
-  for (int j = 0; j < 2 * D; ++j) {
+  for (int j = 0; j < kP * D; ++j) {
     const int e = lane + 32 * j;
     s[(e % D) * kRow + (e / D)] = __ldcg(base + e);
   }
-  s[D * kRow + lane] = gdp1[(size_t)tile * kTile + lane];
-  s[D * kRow + lane + 32] = gdp1[(size_t)tile * kTile + lane + 32];
+#pragma unroll
+  for (int p = 0; p < kP; ++p) s[D * kRow + lane + 32 * p] = gdp1[(size_t)tile * kTile + lane + 32 * p];
 }
 template <int D, class real>
 TL_D void store_tile(const real* s, real* gpos, int tile, int lane) {
   if (tile < 0) return;
   real* base = gpos + (size_t)tile * (kTile * D);
 #pragma unroll
-  for (int j = 0; j < 2 * D; ++j) {
+  for (int j = 0; j < kP * D; ++j) {
     const int e = lane + 32 * j;
     __stcg(base + e, s[(e % D) * kRow + (e / D)]);
   }
 }
 
-// Per-warp table of the measured pairs of one tile pair.  Combination c = 2 * (A half) + (B half)
-// (half 0 = slots 0..31, half 1 = slots 32..63): tgt[c][step][lane], mask[c][kind][lane] with
+// Per-warp table of the measured pairs of one tile pair.  Combination c = kP * (A part) + (B part)
+// (part p = slots 32p .. 32p+31 of a tile): tgt[c][step][lane], mask[c][kind][lane] with
 // kind 0 = measured, 1 = '>', 2 = '<'.
-constexpr int kTableReals = 4 * 32 * 32;
-constexpr int kTableMasks = 4 * 3 * 32;
+constexpr int kCombos = kP * kP;
+constexpr int kTableReals = kCombos * 32 * 32;
+constexpr int kTableMasks = kCombos * 3 * 32;
 template <class real>
 struct WarpTable {
   real* tgt;
   uint32_t* mask;
 };
 struct LaneMasks {
-  uint32_t meas[4], gt[4], lt[4];
+  uint32_t meas[kCombos], gt[kCombos], lt[kCombos];
 };
 
 template <class real>
 TL_D void table_clear(const WarpTable<real>& tb, int lane) {
 #pragma unroll
-  for (int j = 0; j < 12; ++j) tb.mask[j * 32 + lane] = 0u;
+  for (int j = 0; j < 3 * kCombos; ++j) tb.mask[j * 32 + lane] = 0u;
   __syncwarp();
 }
 template <class real>
@@ -450,7 +474,7 @@ template <class real>
 TL_D LaneMasks table_masks(const WarpTable<real>& tb, int lane, bool filled) {
   LaneMasks m;
 #pragma unroll
-  for (int c = 0; c < 4; ++c) {
+  for (int c = 0; c < kCombos; ++c) {
     m.meas[c] = filled ? tb.mask[(c * 3 + 0) * 32 + lane] : 0u;
     m.gt[c] = filled ? tb.mask[(c * 3 + 1) * 32 + lane] : 0u;
     m.lt[c] = filled ? tb.mask[(c * 3 + 2) * 32 + lane] : 0u;
@@ -475,28 +499,28 @@ TL_D void fill_table_ring(const WarpTable<real>& tb, const EdgeRec* edges, uint3
                           const RingParams& rp, int lane) {
   for (uint32_t e = beg + lane; e < end; e += 32) {
     const EdgeRec r = edges[e];
-    const int lo = r.slot_lo & 63, hi = r.slot_hi_type & 63;
+    const int lo = (int)(r.slot_lo % kTile), hi = (int)((r.slot_hi_type & 0x3fffffffu) % kTile);
     const int ty = r.slot_hi_type >> 30;
     const int a = swap ? hi : lo, b = swap ? lo : hi;
     const int la = a & 31, lb = b & 31;
-    table_put<real>(tb, 2 * (a >> 5) + (b >> 5), ring_step(rp, la, lb), la, (real)r.target, ty);
+    table_put<real>(tb, kP * (a >> 5) + (b >> 5), ring_step(rp, la, lb), la, (real)r.target, ty);
   }
 }
-// Intra passes index by (combination seen from the lane, xor distance, lane); the pair of a lane's
-// own two slots sits at combination 1, index 0 (xor distance 0 never occurs otherwise).
+// Intra passes index by (combination seen from the lane, xor distance, lane); pairs among a lane's
+// own kP slots sit at index 0 (xor distance 0 never occurs otherwise).
 template <class real>
 TL_D void fill_table_xor(const WarpTable<real>& tb, const EdgeRec* edges, uint32_t beg, uint32_t end, int lane) {
   for (uint32_t e = beg + lane; e < end; e += 32) {
     const EdgeRec r = edges[e];
-    const int u = r.slot_lo & 63, v = r.slot_hi_type & 63;
+    const int u = (int)(r.slot_lo % kTile), v = (int)((r.slot_hi_type & 0x3fffffffu) % kTile);
     const int ty = r.slot_hi_type >> 30;
     const int lu = u & 31, lv = v & 31, pu = u >> 5, pv = v >> 5;
     const int x = lu ^ lv;
     if (x == 0) {
-      table_put<real>(tb, 1, 0, lu, (real)r.target, ty);
+      table_put<real>(tb, kP * pu + pv, 0, lu, (real)r.target, ty);   // pu < pv
     } else {
-      table_put<real>(tb, 2 * pu + pv, x, lu, (real)r.target, ty);
-      table_put<real>(tb, 2 * pv + pu, x, lv, (real)r.target, ty);
+      table_put<real>(tb, kP * pu + pv, x, lu, (real)r.target, ty);
+      table_put<real>(tb, kP * pv + pu, x, lv, (real)r.target, ty);
     }
   }
 }
@@ -517,9 +541,32 @@ TL_D uint2 bucket_range(const uint32_t* bucket_off, const EdgeRec* edges, int T,
   return r;
 }
 
-// tile A x tile B (64 x 64 pairs), 32 ring steps of 4 pair visits per lane.  Lane a keeps
-// A0 = A[a], A1 = A[a+32]; the travelling pair B0 = B[b], B1 = B[b+32] with b = ring_b(a, i).
-// Step i: (A0,B0) and (A1,B1) - independent, they interleave - then (A0,B1) and (A1,B0).
+// Compile-time loop over the kP waves of one step.
+template <int D, class M, bool kSum, int W_ = 0>
+struct Waves {
+  typedef typename M::real real;
+  static TL_D void run(typename M::template Point<D> (&A)[kP], typename M::template Point<D> (&B)[kP],
+                       const WarpTable<real>& tb, const LaneMasks& m, int idx, int lane, const typename M::Ctx& ctx) {
+    Cell<real> cell[kP];
+#pragma unroll
+    for (int p = 0; p < kP; ++p) {
+      const int q = kSum ? (W_ - p + kP) % kP : (p + W_) % kP;
+      cell[p] = table_cell<real>(tb, m, kP * p + q, idx, lane);
+    }
+    M::template wave<D, W_, kSum>(A, B, cell, ctx);
+    Waves<D, M, kSum, W_ + 1>::run(A, B, tb, m, idx, lane, ctx);
+  }
+};
+template <int D, class M, bool kSum>
+struct Waves<D, M, kSum, kP> {
+  typedef typename M::real real;
+  static TL_D void run(typename M::template Point<D> (&)[kP], typename M::template Point<D> (&)[kP],
+                       const WarpTable<real>&, const LaneMasks&, int, int, const typename M::Ctx&) {}
+};
+
+// tile A x tile B (kTile x kTile pairs), 32 ring steps of kP waves of kP pair visits per lane.  Lane a
+// keeps A[p] = slot a + 32p; the travelling B[q] = slot b + 32q with b = ring_b(a, i).  Wave w of a step
+// pairs A[p] with B[(p + w) % kP]: kP independent visits, a perfect matching over the warp.
 template <int D, class M>
 TL_D void ring_pass(typename M::real* sA, typename M::real* sB, int tA, int tB, uint32_t beg, uint32_t end,
                     const WarpTable<typename M::real>& tb, const TileDev<typename M::real>& dv, const Geometry& geo,
@@ -532,25 +579,28 @@ TL_D void ring_pass(typename M::real* sA, typename M::real* sB, int tA, int tB, 
     __syncwarp();
   }
   const LaneMasks m = table_masks<real>(tb, lane, beg != end);
-  typename M::template Point<D> A0, A1, B0, B1;
+  typename M::template Point<D> A[kP], B[kP];
   const int b0 = (lane + rp.s0) & 31;
-  A0.load(sA, lane, ctx); A1.load(sA, lane + 32, ctx);
-  B0.load(sB, b0, ctx); B1.load(sB, b0 + 32, ctx);
+#pragma unroll
+  for (int p = 0; p < kP; ++p) { A[p].load(sA, lane + 32 * p, ctx); B[p].load(sB, b0 + 32 * p, ctx); }
   const int src = (lane + rp.g) & 31;
 #pragma unroll 1
   for (int i = 0; i < 32; ++i) {
-    M::template pair2<D, false>(A0, B0, table_cell<real>(tb, m, 0, i, lane), A1, B1, table_cell<real>(tb, m, 3, i, lane), ctx);
-    M::template pair2<D, false>(A0, B1, table_cell<real>(tb, m, 1, i, lane), A1, B0, table_cell<real>(tb, m, 2, i, lane), ctx);
-    if (i < 31) { B0.shfl_from(src); B1.shfl_from(src); }
+    Waves<D, M, false>::run(A, B, tb, m, i, lane, ctx);
+    if (i < 31) {
+#pragma unroll
+      for (int p = 0; p < kP; ++p) B[p].shfl_from(src);
+    }
   }
   const int bf = (lane + rp.s0 + 31 * rp.g) & 31;
-  A0.store(sA, lane); A1.store(sA, lane + 32);
-  B0.store(sB, bf); B1.store(sB, bf + 32);
+#pragma unroll
+  for (int p = 0; p < kP; ++p) { A[p].store(sA, lane + 32 * p); B[p].store(sB, bf + 32 * p); }
 }
 
-// tile x itself (64 points).  Lane a owns S0 = slot a and S1 = slot a+32: first that pair, then 31
-// XOR steps against lane a^x: (S0,O0) and (S1,O1) computed two-sided on local copies of the partner's
-// points (the partner computes the same values), then (S0,O1) and (S1,O0) moving only the lane's own.
+// tile x itself.  Lane a owns S[p] = slot a + 32p: first the pairs among its own slots, then 31 XOR
+// steps against lane a^x.  Wave w of a step visits (S[p], O[(w - p) mod kP]) - the same set of pairs
+// seen from either lane - two-sided on the lane's local copies O of the partner's points, which the
+// partner updates identically for itself.
 template <int D, class M>
 TL_D void intra_pass(typename M::real* sT, int t, uint32_t beg, uint32_t end, const WarpTable<typename M::real>& tb,
                      const TileDev<typename M::real>& dv, const Geometry& geo, int iter,
@@ -562,18 +612,23 @@ TL_D void intra_pass(typename M::real* sT, int t, uint32_t beg, uint32_t end, co
     __syncwarp();
   }
   const LaneMasks m = table_masks<real>(tb, lane, beg != end);
-  typename M::template Point<D> S0, S1, O0, O1;
-  S0.load(sT, lane, ctx); S1.load(sT, lane + 32, ctx);
-  M::template pair<D>(S0, S1, table_cell<real>(tb, m, 1, 0, lane), ctx);
+  typename M::template Point<D> S[kP], O[kP];
+#pragma unroll
+  for (int p = 0; p < kP; ++p) S[p].load(sT, lane + 32 * p, ctx);
+#pragma unroll
+  for (int p = 0; p < kP; ++p)
+#pragma unroll
+    for (int q = p + 1; q < kP; ++q) M::template pair<D>(S[p], S[q], table_cell<real>(tb, m, kP * p + q, 0, lane), ctx);
   const XorParams xp = xor_params(geo, iter, t);
 #pragma unroll 1
   for (int i = 0; i < 31; ++i) {
     const int x = xor_at(xp, i);
-    O0.shfl_xor_of(S0, x); O1.shfl_xor_of(S1, x);
-    M::template pair2<D, false>(S0, O0, table_cell<real>(tb, m, 0, x, lane), S1, O1, table_cell<real>(tb, m, 3, x, lane), ctx);
-    M::template pair2<D, true>(S0, O1, table_cell<real>(tb, m, 1, x, lane), S1, O0, table_cell<real>(tb, m, 2, x, lane), ctx);
+#pragma unroll
+    for (int p = 0; p < kP; ++p) O[p].shfl_xor_of(S[p], x);
+    Waves<D, M, true>::run(S, O, tb, m, x, lane, ctx);
   }
-  S0.store(sT, lane); S1.store(sT, lane + 32);
+#pragma unroll
+  for (int p = 0; p < kP; ++p) S[p].store(sT, lane + 32 * p);
 }
 
 // Deterministic CTA reduction of (sum, count, flag); result valid in thread 0.
