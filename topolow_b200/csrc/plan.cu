@@ -92,7 +92,7 @@ Geometry choose_geometry(int64_t n, int D, int precision, int sms, int max_ctas,
   g.T = (int)((n + kTile - 1) / kTile);
   const size_t rs = precision == TOPOLOW_PREC_F64_EXACT ? sizeof(double) : sizeof(float);
   int wmax = precision == TOPOLOW_PREC_F64_EXACT ? ExactF64::kMaxWarps : FastF32::kMaxWarps;
-  while (wmax > 1 && tile_smem_bytes(D, wmax, rs) > 200 * 1024) --wmax;
+  while (wmax > 1 && tile_smem_bytes(D, wmax, rs) > 224 * 1024) --wmax;
   const int ctas = std::max(1, max_ctas > 0 ? std::min(max_ctas, sms) : sms);
   const int T = g.T;
   if (T <= 2 * wmax || ctas == 1) {

@@ -29,7 +29,7 @@
 
 namespace tl {
 
-constexpr int kP = 2;            // points of a tile held by one lane
+constexpr int kP = 3;            // points of a tile held by one lane
 constexpr int kTile = 32 * kP;   // points per tile
 
 struct Geometry {

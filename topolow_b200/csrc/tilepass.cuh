@@ -76,7 +76,7 @@ TL_D float rcp_fast(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(
 // another phantom the zero mass cancels the force, so no validity predicate is needed.
 struct FastF32 {
   typedef float real;
-  static constexpr int kMaxWarps = 8;   // 256 threads: up to 255 registers for the 4 resident points
+  static constexpr int kMaxWarps = 4;   // shared memory (kP*kP target tables per warp) and 255 registers per thread
   static constexpr float kPhantomCoord = 1.0e18f;
   struct Ctx { float two_k, c_half, k; };
   static TL_D Ctx make_ctx(double k, double c_rep) {
@@ -260,7 +260,7 @@ struct FastF32 {
 // the CPU loop executed on the order topolow_plan_enumerate() reports.
 struct ExactF64 {
   typedef double real;
-  static constexpr int kMaxWarps = 4;  // shared memory: 4 x 32 x 32 doubles of targets per warp
+  static constexpr int kMaxWarps = 2;  // shared memory: kP*kP x 32 x 32 doubles of targets per warp
   static constexpr double kPhantomCoord = 0.0;
   struct Ctx { double k, c_rep; };
   static TL_D Ctx make_ctx(double k, double c_rep) { Ctx c; c.k = k; c.c_rep = c_rep; return c; }
