@@ -98,6 +98,8 @@ typedef struct {
   int64_t pairs_per_iter;
   int32_t device;                   /* CUDA device ordinal */
   int32_t max_ctas;                 /* 0 = all SMs; cap on the persistent grid (tests / sharing) */
+  int32_t max_warps;                /* 0 = policy default; cap on warps (tiles) per CTA - lets an FP32 run use
+                                       the schedule an FP64 run of the same problem gets */
 } topolow_params;
 
 typedef struct {

@@ -112,7 +112,7 @@ def test_fp32_tracks_fp64_on_the_same_order(n, d, dens):
     args = small_problem(n, d, dens, 100 + n)
     hp = (5.0, 0.01, 0.02, 1e-4, 50, 3)
     a = _lib.fit(*args, 6, *hp, precision=_lib.PREC_F64_EXACT, seed=8)
-    b = _lib.fit(*args, 6, *hp, precision=_lib.PREC_F32, seed=8)
+    b = _lib.fit(*args, 6, *hp, precision=_lib.PREC_F32, seed=8, max_warps=2)   # the FP64 schedule
     scale = np.abs(a["positions"]).max()
     assert np.abs(a["positions"] - b["positions"]).max() <= 2e-4 * max(scale, 1.0)
     assert b["final_mae"] == pytest.approx(a["final_mae"], rel=1e-3)
@@ -270,7 +270,7 @@ def test_cfg3_size_fp32_against_fp64_and_pair_count():
     fa = synth.fit_args(prob)
     hp = (5.0, 0.01, 0.02, 1e-4, 100, 3)
     a = _lib.fit(*fa, 3, *hp, precision=_lib.PREC_F64_EXACT, seed=2)
-    b = _lib.fit(*fa, 3, *hp, precision=_lib.PREC_F32, seed=2)
+    b = _lib.fit(*fa, 3, *hp, precision=_lib.PREC_F32, seed=2, max_warps=2)      # the FP64 schedule
     assert a["pair_updates"] == b["pair_updates"] == 3 * 10_000 * 9_999 // 2
     assert np.abs(a["positions"] - b["positions"]).max() <= 1e-3 * np.abs(a["positions"]).max()
     assert b["final_mae"] == pytest.approx(a["final_mae"], rel=1e-3)

@@ -34,7 +34,7 @@ class Params(C.Structure):
                 ("convergence_window", C.c_int32), ("convergence_check_freq", C.c_int32),
                 ("verbose", C.c_int32), ("mode", C.c_int32), ("precision", C.c_int32), ("seed", C.c_uint64),
                 ("pair_order", _i32p), ("pairs_per_iter", C.c_int64), ("device", C.c_int32),
-                ("max_ctas", C.c_int32)]
+                ("max_ctas", C.c_int32), ("max_warps", C.c_int32)]
 
 
 class Result(C.Structure):
@@ -148,7 +148,7 @@ class ProblemArrays:
 
 def make_params(n_iter, k0, cooling_rate, c_repulsion, relative_epsilon=1e-4, convergence_window=5,
                 convergence_check_freq=3, verbose=False, mode=MODE_COLOURED, precision=PREC_F32, seed=0,
-                pair_order=None, device=0, max_ctas=0):
+                pair_order=None, device=0, max_ctas=0, max_warps=0):
     p = Params()
     p.n_iter = int(n_iter)
     p.k0, p.cooling_rate, p.c_repulsion = float(k0), float(cooling_rate), float(c_repulsion)
@@ -163,7 +163,7 @@ def make_params(n_iter, k0, cooling_rate, c_repulsion, relative_epsilon=1e-4, co
             raise ValueError("pair_order must be [n_iter][pairs][2]")
         p.pair_order = keep.ctypes.data_as(_i32p)
         p.pairs_per_iter = keep.shape[1]
-    p.device, p.max_ctas = int(device), int(max_ctas)
+    p.device, p.max_ctas, p.max_warps = int(device), int(max_ctas), int(max_warps)
     return p, keep
 
 
@@ -179,13 +179,13 @@ def result_dict(res: Result, positions: np.ndarray, trace=None):
 
 def fit(initial_positions, degrees, edge_i, edge_j, edge_dist, edge_thresh, n_iter, k0, cooling_rate,
         c_repulsion, relative_epsilon=1e-4, convergence_window=5, convergence_check_freq=3, *, verbose=False,
-        mode=MODE_COLOURED, precision=PREC_F32, seed=0, pair_order=None, device=0, max_ctas=0, trace=False,
-        interrupt=None):
+        mode=MODE_COLOURED, precision=PREC_F32, seed=0, pair_order=None, device=0, max_ctas=0, max_warps=0,
+        trace=False, interrupt=None):
     """One call of the native optimiser (the .Call boundary of R/core.R:439-456) on host buffers."""
     L = lib()
     pa = ProblemArrays(initial_positions, degrees, edge_i, edge_j, edge_dist, edge_thresh)
     pr, _keep = make_params(n_iter, k0, cooling_rate, c_repulsion, relative_epsilon, convergence_window,
-                            convergence_check_freq, verbose, mode, precision, seed, pair_order, device, max_ctas)
+                            convergence_check_freq, verbose, mode, precision, seed, pair_order, device, max_ctas, max_warps)
     out = np.empty((pa.n, pa.ndim), dtype=np.float64, order="F")
     res = Result()
     res.positions = out.ctypes.data_as(_dp)

@@ -86,12 +86,13 @@ std::vector<int32_t> random_permutation(int64_t n, uint64_t seed) {
   return p;
 }
 
-Geometry choose_geometry(int64_t n, int D, int precision, int sms, int max_ctas, uint64_t seed) {
+Geometry choose_geometry(int64_t n, int D, int precision, int sms, int max_ctas, uint64_t seed, int max_warps = 0) {
   Geometry g{};
   g.n = (int)n; g.D = D; g.seed = seed;
   g.T = (int)((n + kTile - 1) / kTile);
   const size_t rs = precision == TOPOLOW_PREC_F64_EXACT ? sizeof(double) : sizeof(float);
   int wmax = precision == TOPOLOW_PREC_F64_EXACT ? ExactF64::kMaxWarps : FastF32::kMaxWarps;
+  if (max_warps > 0) wmax = std::min(wmax, max_warps);
   while (wmax > 1 && tile_smem_bytes(D, wmax, rs) > 224 * 1024) --wmax;
   const int ctas = std::max(1, max_ctas > 0 ? std::min(max_ctas, sms) : sms);
   const int T = g.T;
@@ -209,7 +210,7 @@ std::unique_ptr<topolow_plan> make_plan(const topolow_problem& pb, const topolow
   pl->n = pb.n; pl->E = pb.n_edges; pl->D = pb.ndim;
   pl->prm = FitParams{pr.n_iter, pr.k0, pr.cooling_rate, pr.c_repulsion, pr.relative_epsilon,
                       pr.convergence_window, pr.convergence_check_freq};
-  pl->geo = choose_geometry(pb.n, pb.ndim, pr.precision, sms, pr.max_ctas, pr.seed);
+  pl->geo = choose_geometry(pb.n, pb.ndim, pr.precision, sms, pr.max_ctas, pr.seed, pr.max_warps);
   const Geometry& g = pl->geo;
   if (g.G > 1) {
     const int fit = pr.precision == TOPOLOW_PREC_F64_EXACT ? max_coresident_f64(g.D, g.W) : max_coresident_f32(g.D, g.W);
