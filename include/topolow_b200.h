@@ -100,6 +100,7 @@ typedef struct {
   int32_t max_ctas;                 /* 0 = all SMs; cap on the persistent grid (tests / sharing) */
   int32_t max_warps;                /* 0 = policy default; cap on warps (tiles) per CTA - lets an FP32 run use
                                        the schedule an FP64 run of the same problem gets */
+  int32_t tile_points;              /* 0 = auto; 32, 64 or 96: points per tile (1, 2 or 3 per lane) */
 } topolow_params;
 
 typedef struct {
@@ -156,7 +157,7 @@ TOPOLOW_API int topolow_plan_run(topolow_plan* plan, int32_t n_iters, void* stre
 TOPOLOW_API int topolow_plan_result(topolow_plan* plan, topolow_result* result);
 /* Geometry of the schedule: fills up to `cap` int64 values
  * {tiles, super_blocks, warps_per_cta, ctas, tasks_per_cta, rounds, pairs_per_iter, smem_bytes,
- * iterations_per_launch, kernel_launches_so_far}. */
+ * iterations_per_launch, kernel_launches_so_far, tile_points}. */
 TOPOLOW_API int topolow_plan_info(const topolow_plan* plan, int64_t* out, int32_t cap);
 TOPOLOW_API void topolow_plan_destroy(topolow_plan* plan);
 
@@ -169,7 +170,7 @@ TOPOLOW_API int64_t topolow_plan_enumerate(const topolow_plan* plan, int32_t ite
  * (n, ndim, precision, sm_count, max_ctas, seed).  out may be NULL (geometry only). */
 TOPOLOW_API int64_t topolow_schedule_enumerate(int64_t n, int32_t ndim, int32_t precision, int32_t sm_count,
                                    int32_t max_ctas, uint64_t seed, int32_t iter, int32_t* out,
-                                   int64_t cap_pairs, int64_t* geometry_out);
+                                   int64_t cap_pairs, int64_t* geometry_out, int32_t tile_points);
 
 /* ---- post-processing kernels --------------------------------------------- */
 /* est_distances[n x n] (column-major == row-major, symmetric) from positions[n x ndim col-major]. */

@@ -52,8 +52,9 @@ def test_replay_explicit_order_and_early_convergence():
 
 
 # ------------------------------------------------------------------ coloured mode, exact ------
-def _exact_case(args, iters, hp, seed, max_ctas=0):
-    plan = _lib.Plan(*args, iters, *hp, precision=_lib.PREC_F64_EXACT, seed=seed, max_ctas=max_ctas)
+def _exact_case(args, iters, hp, seed, max_ctas=0, tile_points=0):
+    plan = _lib.Plan(*args, iters, *hp, precision=_lib.PREC_F64_EXACT, seed=seed, max_ctas=max_ctas,
+                     tile_points=tile_points)
     order = np.stack([plan.enumerate(it) for it in range(iters)])
     info = plan.info()
     plan.run(iters)
@@ -63,25 +64,27 @@ def _exact_case(args, iters, hp, seed, max_ctas=0):
     return got, want, info
 
 
+@pytest.mark.parametrize("tile_points", [32, 64, 96])
 @pytest.mark.parametrize("n,d,dens", [(3, 2, 1.0), (33, 2, 0.5), (100, 7, 0.15), (150, 3, 0.2), (260, 16, 0.05)])
-def test_coloured_fp64_equals_cpu_loop_on_the_enumerated_order(n, d, dens):
+def test_coloured_fp64_equals_cpu_loop_on_the_enumerated_order(n, d, dens, tile_points):
     args = small_problem(n, d, dens, n)
-    got, want, info = _exact_case(args, 7, (5.0, 0.01, 0.02, 1e-4, 5, 3), seed=n)
-    assert info["ctas"] == 1
+    got, want, info = _exact_case(args, 7, (5.0, 0.01, 0.02, 1e-4, 5, 3), seed=n, tile_points=tile_points)
+    assert info["tile_points"] == tile_points
     assert np.array_equal(got["positions"], want["positions"])
     assert got["iterations"] == want["iterations"] and got["final_k"] == want["final_k"]
     assert got["final_mae"] == pytest.approx(want["final_mae"], rel=1e-12)
     assert got["pair_updates"] == 7 * n * (n - 1) // 2
 
 
-def test_coloured_fp64_multi_cta_barrier_path():
-    # n = 1100 -> 35 tiles -> several co-operating CTAs (grid barrier between rounds)
+@pytest.mark.parametrize("tile_points", [32, 64, 96])
+def test_coloured_fp64_multi_cta_barrier_path(tile_points):
+    # n = 1100 -> more tiles than one CTA holds -> several co-operating CTAs (grid barrier between rounds)
     args = small_problem(1100, 4, 0.03, 12)
-    got, want, info = _exact_case(args, 3, (5.0, 0.01, 0.02, 1e-4, 5, 3), seed=2)
+    got, want, info = _exact_case(args, 3, (5.0, 0.01, 0.02, 1e-4, 5, 3), seed=2, tile_points=tile_points)
     assert info["ctas"] > 1
     assert np.array_equal(got["positions"], want["positions"])
     # and a forced multi-task-per-CTA geometry
-    got, want, info = _exact_case(args, 2, (5.0, 0.01, 0.02, 1e-4, 5, 3), seed=3, max_ctas=2)
+    got, want, info = _exact_case(args, 2, (5.0, 0.01, 0.02, 1e-4, 5, 3), seed=3, max_ctas=2, tile_points=tile_points)
     assert info["tasks_per_cta"] >= 1 and info["ctas"] == 2
     assert np.array_equal(got["positions"], want["positions"])
 
@@ -107,12 +110,14 @@ def test_coloured_convergence_controller_matches():
 
 
 # ------------------------------------------------------------------ coloured mode, FP32 -------
+@pytest.mark.parametrize("tile_points,f64_warps", [(32, 8), (64, 4), (96, 2)])
 @pytest.mark.parametrize("n,d,dens", [(150, 3, 0.2), (300, 16, 0.05), (285, 5, 0.08), (1100, 5, 0.03)])
-def test_fp32_tracks_fp64_on_the_same_order(n, d, dens):
+def test_fp32_tracks_fp64_on_the_same_order(n, d, dens, tile_points, f64_warps):
     args = small_problem(n, d, dens, 100 + n)
     hp = (5.0, 0.01, 0.02, 1e-4, 50, 3)
-    a = _lib.fit(*args, 6, *hp, precision=_lib.PREC_F64_EXACT, seed=8)
-    b = _lib.fit(*args, 6, *hp, precision=_lib.PREC_F32, seed=8, max_warps=2)   # the FP64 schedule
+    a = _lib.fit(*args, 6, *hp, precision=_lib.PREC_F64_EXACT, seed=8, tile_points=tile_points)
+    b = _lib.fit(*args, 6, *hp, precision=_lib.PREC_F32, seed=8, tile_points=tile_points,
+                 max_warps=f64_warps)   # max_warps: the schedule the FP64 plan gets
     scale = np.abs(a["positions"]).max()
     assert np.abs(a["positions"] - b["positions"]).max() <= 2e-4 * max(scale, 1.0)
     assert b["final_mae"] == pytest.approx(a["final_mae"], rel=1e-3)
@@ -269,8 +274,8 @@ def test_cfg3_size_fp32_against_fp64_and_pair_count():
     prob = synth.make_problem(10_000, 10, 0.95, seed=1)
     fa = synth.fit_args(prob)
     hp = (5.0, 0.01, 0.02, 1e-4, 100, 3)
-    a = _lib.fit(*fa, 3, *hp, precision=_lib.PREC_F64_EXACT, seed=2)
-    b = _lib.fit(*fa, 3, *hp, precision=_lib.PREC_F32, seed=2, max_warps=2)      # the FP64 schedule
+    a = _lib.fit(*fa, 3, *hp, precision=_lib.PREC_F64_EXACT, seed=2, tile_points=64)
+    b = _lib.fit(*fa, 3, *hp, precision=_lib.PREC_F32, seed=2, tile_points=64, max_warps=4)   # the FP64 schedule
     assert a["pair_updates"] == b["pair_updates"] == 3 * 10_000 * 9_999 // 2
     assert np.abs(a["positions"] - b["positions"]).max() <= 1e-3 * np.abs(a["positions"]).max()
     assert b["final_mae"] == pytest.approx(a["final_mae"], rel=1e-3)

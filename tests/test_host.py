@@ -50,11 +50,13 @@ def test_too_few_points_status():
     assert res.message.decode() == "Need at least 2 points for embedding"   # src/optimization.cpp:131
 
 
-@pytest.mark.parametrize("n", [2, 3, 31, 32, 33, 64, 65, 97, 285, 335, 700, 1025, 1500])
+@pytest.mark.parametrize("n", [2, 3, 31, 33, 65, 97, 193, 335, 700, 1025, 1500])
 @pytest.mark.parametrize("prec", [_lib.PREC_F32, _lib.PREC_F64_EXACT])
-def test_schedule_visits_every_pair_exactly_once(n, prec):
+@pytest.mark.parametrize("tile_points", [32, 64, 96])
+def test_schedule_visits_every_pair_exactly_once(n, prec, tile_points):
     for it, max_ctas in ((0, 0), (7, 3)):
-        order, geo = _lib.schedule_enumerate(n, 5, it, precision=prec, seed=n + it, max_ctas=max_ctas)
+        order, geo = _lib.schedule_enumerate(n, 5, it, precision=prec, seed=n + it, max_ctas=max_ctas,
+                                             tile_points=tile_points)
         a = np.minimum(order[:, 0], order[:, 1]).astype(np.int64)
         b = np.maximum(order[:, 0], order[:, 1]).astype(np.int64)
         assert (a != b).all() and a.min() >= 0 and b.max() < n

@@ -34,7 +34,7 @@ class Params(C.Structure):
                 ("convergence_window", C.c_int32), ("convergence_check_freq", C.c_int32),
                 ("verbose", C.c_int32), ("mode", C.c_int32), ("precision", C.c_int32), ("seed", C.c_uint64),
                 ("pair_order", _i32p), ("pairs_per_iter", C.c_int64), ("device", C.c_int32),
-                ("max_ctas", C.c_int32), ("max_warps", C.c_int32)]
+                ("max_ctas", C.c_int32), ("max_warps", C.c_int32), ("tile_points", C.c_int32)]
 
 
 class Result(C.Structure):
@@ -98,7 +98,7 @@ def lib() -> C.CDLL:
     L.topolow_plan_enumerate.argtypes = [C.c_void_p, C.c_int32, _i32p, C.c_int64]
     L.topolow_schedule_enumerate.restype = C.c_int64
     L.topolow_schedule_enumerate.argtypes = [C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_uint64,
-                                             C.c_int32, _i32p, C.c_int64, _i64p]
+                                             C.c_int32, _i32p, C.c_int64, _i64p, C.c_int32]
     L.topolow_est_distances.restype = C.c_int
     L.topolow_est_distances.argtypes = [_dp, C.c_int64, C.c_int32, _dp, C.c_int32]
     L.topolow_holdout_errors.restype = C.c_int
@@ -148,7 +148,7 @@ class ProblemArrays:
 
 def make_params(n_iter, k0, cooling_rate, c_repulsion, relative_epsilon=1e-4, convergence_window=5,
                 convergence_check_freq=3, verbose=False, mode=MODE_COLOURED, precision=PREC_F32, seed=0,
-                pair_order=None, device=0, max_ctas=0, max_warps=0):
+                pair_order=None, device=0, max_ctas=0, max_warps=0, tile_points=0):
     p = Params()
     p.n_iter = int(n_iter)
     p.k0, p.cooling_rate, p.c_repulsion = float(k0), float(cooling_rate), float(c_repulsion)
@@ -164,6 +164,7 @@ def make_params(n_iter, k0, cooling_rate, c_repulsion, relative_epsilon=1e-4, co
         p.pair_order = keep.ctypes.data_as(_i32p)
         p.pairs_per_iter = keep.shape[1]
     p.device, p.max_ctas, p.max_warps = int(device), int(max_ctas), int(max_warps)
+    p.tile_points = int(tile_points)
     return p, keep
 
 
@@ -180,12 +181,13 @@ def result_dict(res: Result, positions: np.ndarray, trace=None):
 def fit(initial_positions, degrees, edge_i, edge_j, edge_dist, edge_thresh, n_iter, k0, cooling_rate,
         c_repulsion, relative_epsilon=1e-4, convergence_window=5, convergence_check_freq=3, *, verbose=False,
         mode=MODE_COLOURED, precision=PREC_F32, seed=0, pair_order=None, device=0, max_ctas=0, max_warps=0,
-        trace=False, interrupt=None):
+        tile_points=0, trace=False, interrupt=None):
     """One call of the native optimiser (the .Call boundary of R/core.R:439-456) on host buffers."""
     L = lib()
     pa = ProblemArrays(initial_positions, degrees, edge_i, edge_j, edge_dist, edge_thresh)
     pr, _keep = make_params(n_iter, k0, cooling_rate, c_repulsion, relative_epsilon, convergence_window,
-                            convergence_check_freq, verbose, mode, precision, seed, pair_order, device, max_ctas, max_warps)
+                            convergence_check_freq, verbose, mode, precision, seed, pair_order, device, max_ctas, max_warps,
+                            tile_points)
     out = np.empty((pa.n, pa.ndim), dtype=np.float64, order="F")
     res = Result()
     res.positions = out.ctypes.data_as(_dp)
@@ -239,11 +241,13 @@ class Plan:
 
     def __init__(self, initial_positions, degrees, edge_i, edge_j, edge_dist, edge_thresh, n_iter, k0,
                  cooling_rate, c_repulsion, relative_epsilon=1e-4, convergence_window=5,
-                 convergence_check_freq=3, *, precision=PREC_F32, seed=0, device=0, max_ctas=0):
+                 convergence_check_freq=3, *, precision=PREC_F32, seed=0, device=0, max_ctas=0, max_warps=0,
+                 tile_points=0):
         self._L = lib()
         self._pa = ProblemArrays(initial_positions, degrees, edge_i, edge_j, edge_dist, edge_thresh)
         pr, _ = make_params(n_iter, k0, cooling_rate, c_repulsion, relative_epsilon, convergence_window,
-                            convergence_check_freq, False, MODE_COLOURED, precision, seed, None, device, max_ctas)
+                            convergence_check_freq, False, MODE_COLOURED, precision, seed, None, device, max_ctas, max_warps,
+                            tile_points)
         self.n_iter = int(n_iter)
         self._h = C.c_void_p()
         msg = C.create_string_buffer(256)
@@ -272,10 +276,10 @@ class Plan:
         return result_dict(res, out, tr)
 
     def info(self):
-        v = (C.c_int64 * 10)()
-        self._L.topolow_plan_info(self._h, v, 10)
+        v = (C.c_int64 * 11)()
+        self._L.topolow_plan_info(self._h, v, 11)
         keys = ["tiles", "super_blocks", "warps_per_cta", "ctas", "tasks_per_cta", "rounds", "pairs_per_iter",
-                "smem_bytes", "iters_per_launch", "launches"]
+                "smem_bytes", "iters_per_launch", "launches", "tile_points"]
         return dict(zip(keys, [int(x) for x in v]))
 
     def enumerate(self, it):
@@ -298,14 +302,15 @@ class Plan:
             pass
 
 
-def schedule_enumerate(n, ndim, it, *, precision=PREC_F32, sm_count=148, max_ctas=0, seed=0, pairs=True):
+def schedule_enumerate(n, ndim, it, *, precision=PREC_F32, sm_count=148, max_ctas=0, seed=0, pairs=True,
+                       tile_points=0):
     """Host-only walk of the coloured schedule: (pair order [P][2], geometry dict)."""
     L = lib()
     P = n * (n - 1) // 2
     geo = (C.c_int64 * 8)()
     out = np.empty((P, 2), dtype=np.int32) if pairs else None
     got = L.topolow_schedule_enumerate(n, ndim, precision, sm_count, max_ctas, int(seed) & 0xFFFFFFFFFFFFFFFF,
-                                       int(it), out.ctypes.data_as(_i32p) if pairs else None, P, geo)
+                                       int(it), out.ctypes.data_as(_i32p) if pairs else None, P, geo, int(tile_points))
     keys = ["tiles", "super_blocks", "warps_per_cta", "ctas", "tasks_per_cta", "rounds", "pairs_per_iter",
             "smem_bytes"]
     g = dict(zip(keys, [int(x) for x in geo]))

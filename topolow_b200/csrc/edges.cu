@@ -13,7 +13,7 @@ namespace tl {
 namespace {
 
 __global__ void key_kernel(const int32_t* __restrict__ ei, const int32_t* __restrict__ ej, long long E, long long n,
-                           const int32_t* __restrict__ slot_of_point, int T, uint32_t* __restrict__ keys,
+                           const int32_t* __restrict__ slot_of_point, int T, uint32_t kTile, uint32_t* __restrict__ keys,
                            uint32_t* __restrict__ counts, int* __restrict__ bad) {
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < E; e += (long long)gridDim.x * blockDim.x) {
     const long long a = ei[e], b = ej[e];
@@ -93,7 +93,8 @@ T* dalloc(size_t count) {
 
 }  // namespace
 
-void build_buckets(const topolow_problem& pb, const std::vector<int32_t>& slot_of_point, int T, cudaStream_t stream,
+void build_buckets(const topolow_problem& pb, const std::vector<int32_t>& slot_of_point, int T, int tile_points,
+                   cudaStream_t stream,
                    EdgeRec** edges_out, uint32_t** bucket_off_out) {
   const long long E = pb.n_edges;
   const size_t nkeys = (size_t)T * T;
@@ -121,7 +122,7 @@ void build_buckets(const topolow_problem& pb, const std::vector<int32_t>& slot_o
     TL_CUDA(cudaMemsetAsync(d_bad, 0, 4, stream));
     const int blocks = 148 * 8, threads = 256;
     if (E > 0) {
-      key_kernel<<<blocks, threads, 0, stream>>>(d_ei, d_ej, E, pb.n, d_slot, T, d_keys, d_off, d_bad);
+      key_kernel<<<blocks, threads, 0, stream>>>(d_ei, d_ej, E, pb.n, d_slot, T, (uint32_t)tile_points, d_keys, d_off, d_bad);
       TL_CUDA(cudaGetLastError());
     }
     // exclusive offsets: counts were written at key + 1, so an inclusive scan yields them

@@ -86,14 +86,24 @@ std::vector<int32_t> random_permutation(int64_t n, uint64_t seed) {
   return p;
 }
 
-Geometry choose_geometry(int64_t n, int D, int precision, int sms, int max_ctas, uint64_t seed, int max_warps = 0) {
+// Points per lane: large single maps fill the chip with 96-point tiles (most work per shuffle, three
+// independent chains per lane); small and medium single fits want as many warps as possible (32-point
+// tiles); batches of fits run one CTA each and get 64-point tiles.
+int choose_tile_points(int64_t n, int requested) {
+  if (requested == 32 || requested == 64 || requested == 96) return requested / 32;
+  return n >= 40000 ? 3 : 1;
+}
+
+Geometry choose_geometry(int64_t n, int D, int precision, int sms, int max_ctas, uint64_t seed, int max_warps = 0,
+                         int P = 2) {
   Geometry g{};
-  g.n = (int)n; g.D = D; g.seed = seed;
+  g.n = (int)n; g.D = D; g.seed = seed; g.P = P;
+  const int kTile = 32 * P;
   g.T = (int)((n + kTile - 1) / kTile);
   const size_t rs = precision == TOPOLOW_PREC_F64_EXACT ? sizeof(double) : sizeof(float);
-  int wmax = precision == TOPOLOW_PREC_F64_EXACT ? ExactF64::kMaxWarps : FastF32::kMaxWarps;
+  int wmax = tile_max_warps(precision == TOPOLOW_PREC_F64_EXACT ? 1 : 0, P);
   if (max_warps > 0) wmax = std::min(wmax, max_warps);
-  while (wmax > 1 && tile_smem_bytes(D, wmax, rs) > 224 * 1024) --wmax;
+  while (wmax > 1 && tile_smem_bytes(D, wmax, rs, P) > 224 * 1024) --wmax;
   const int ctas = std::max(1, max_ctas > 0 ? std::min(max_ctas, sms) : sms);
   const int T = g.T;
   if (T <= 2 * wmax || ctas == 1) {
@@ -125,6 +135,7 @@ int64_t enumerate_schedule(const Geometry& g, const std::vector<int32_t>& pos, i
                            int64_t cap_pairs) {
   int64_t np = 0;
   bool overflow = false;
+  const int kP = g.P, kTile = 32 * g.P;
   auto emit = [&](int slot_a, int slot_b) {
     const int pa = pos[slot_a], pb = pos[slot_b];
     if (pa < 0 || pb < 0) return;
@@ -182,7 +193,7 @@ int64_t enumerate_schedule(const Geometry& g, const std::vector<int32_t>& pos, i
 
 template <class real>
 void upload_points(topolow_plan& pl, const topolow_problem& pb, real phantom_coord) {
-  const size_t slots = (size_t)pl.geo.T * kTile;
+  const size_t slots = (size_t)pl.geo.T * 32 * pl.geo.P;
   std::vector<real> hp(slots * pl.D, phantom_coord), hd(slots, (real)0);
   for (int64_t i = 0; i < pl.n; ++i) {
     const size_t s = pl.slot_of_point[i];
@@ -195,6 +206,47 @@ void upload_points(topolow_plan& pl, const topolow_problem& pb, real phantom_coo
   TL_CUDA(cudaMemcpy(pl.pos, hp.data(), hp.size() * sizeof(real), cudaMemcpyHostToDevice));
   TL_CUDA(cudaMemcpy(pl.best, hp.data(), hp.size() * sizeof(real), cudaMemcpyHostToDevice));
   TL_CUDA(cudaMemcpy(pl.dp1, hd.data(), hd.size() * sizeof(real), cudaMemcpyHostToDevice));
+}
+
+// Host-side bucket build for small edge lists (stable counting sort by tile pair; inside a bucket the
+// records are then ordered by (slot_lo, slot_hi) exactly as the device path orders them).
+void upload_edges(topolow_plan& pl, const topolow_problem& pb) {
+  const int T = pl.geo.T;
+  const uint32_t kTile = 32u * (uint32_t)pl.geo.P;
+  const size_t nkeys = (size_t)T * T;
+  std::vector<uint32_t> off(nkeys + 1, 0);
+  std::vector<EdgeRec> recs(pl.E);
+  std::vector<uint32_t> keys(pl.E);
+  for (int64_t e = 0; e < pl.E; ++e) {
+    const int64_t a = pb.edge_i[e], b = pb.edge_j[e];
+    if (a < 0 || b < 0 || a >= pl.n || b >= pl.n || a == b) throw BadArg("edge index out of range");
+    uint32_t sa = (uint32_t)pl.slot_of_point[a], sb = (uint32_t)pl.slot_of_point[b];
+    if (sa > sb) std::swap(sa, sb);  // lower slot first => lower (or equal) tile first
+    keys[e] = (sa / kTile) * (uint32_t)T + (sb / kTile);
+    off[keys[e] + 1]++;
+  }
+  for (size_t k = 0; k < nkeys; ++k) off[k + 1] += off[k];
+  std::vector<uint32_t> cur(off.begin(), off.end() - 1);
+  for (int64_t e = 0; e < pl.E; ++e) {
+    uint32_t sa = (uint32_t)pl.slot_of_point[pb.edge_i[e]], sb = (uint32_t)pl.slot_of_point[pb.edge_j[e]];
+    if (sa > sb) std::swap(sa, sb);
+    const int t = pb.edge_thresh[e];
+    EdgeRec r;
+    r.target = pb.edge_dist[e];
+    r.slot_lo = sa;
+    r.slot_hi_type = sb | ((uint32_t)(t == 0 ? 0 : (t == 1 ? 1 : 2)) << 30);   // src/optimization.cpp:237-243
+    recs[cur[keys[e]]++] = r;
+  }
+  for (size_t k = 0; k < nkeys; ++k)
+    if (off[k + 1] - off[k] > 1)
+      std::sort(recs.begin() + off[k], recs.begin() + off[k + 1], [](const EdgeRec& x, const EdgeRec& y) {
+        return x.slot_lo != y.slot_lo ? x.slot_lo < y.slot_lo
+                                      : (x.slot_hi_type & 0x3fffffffu) < (y.slot_hi_type & 0x3fffffffu);
+      });
+  TL_CUDA(cudaMalloc(&pl.edges, std::max<size_t>(recs.size(), 1) * sizeof(EdgeRec)));
+  TL_CUDA(cudaMalloc(&pl.bucket_off, off.size() * sizeof(uint32_t)));
+  if (!recs.empty()) TL_CUDA(cudaMemcpy(pl.edges, recs.data(), recs.size() * sizeof(EdgeRec), cudaMemcpyHostToDevice));
+  TL_CUDA(cudaMemcpy(pl.bucket_off, off.data(), off.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
 }
 
 std::unique_ptr<topolow_plan> make_plan(const topolow_problem& pb, const topolow_params& pr) {
@@ -210,23 +262,25 @@ std::unique_ptr<topolow_plan> make_plan(const topolow_problem& pb, const topolow
   pl->n = pb.n; pl->E = pb.n_edges; pl->D = pb.ndim;
   pl->prm = FitParams{pr.n_iter, pr.k0, pr.cooling_rate, pr.c_repulsion, pr.relative_epsilon,
                       pr.convergence_window, pr.convergence_check_freq};
-  pl->geo = choose_geometry(pb.n, pb.ndim, pr.precision, sms, pr.max_ctas, pr.seed, pr.max_warps);
+  pl->geo = choose_geometry(pb.n, pb.ndim, pr.precision, sms, pr.max_ctas, pr.seed, pr.max_warps,
+                            choose_tile_points(pb.n, pr.tile_points));
   const Geometry& g = pl->geo;
   if (g.G > 1) {
-    const int fit = pr.precision == TOPOLOW_PREC_F64_EXACT ? max_coresident_f64(g.D, g.W) : max_coresident_f32(g.D, g.W);
+    const int fit = pr.precision == TOPOLOW_PREC_F64_EXACT ? max_coresident_f64(g.D, g.W, g.P) : max_coresident_f32(g.D, g.W, g.P);
     if (fit < g.G) throw BadArg("schedule does not fit the device (co-resident CTAs)");
   }
-  pl->smem = tile_smem_bytes(g.D, g.W, pr.precision == TOPOLOW_PREC_F64_EXACT ? 8 : 4);
+  pl->smem = tile_smem_bytes(g.D, g.W, pr.precision == TOPOLOW_PREC_F64_EXACT ? 8 : 4, g.P);
 
   // random relabelling of points into slots; phantom slots pad the last tile
   pl->slot_of_point = random_permutation(pb.n, pr.seed);
-  pl->point_of_slot.assign((size_t)g.T * kTile, -1);
+  pl->point_of_slot.assign((size_t)g.T * 32 * g.P, -1);
   for (int64_t i = 0; i < pb.n; ++i) pl->point_of_slot[pl->slot_of_point[i]] = (int32_t)i;
 
-  if (pr.precision == TOPOLOW_PREC_F64_EXACT) upload_points<double>(*pl, pb, ExactF64::kPhantomCoord);
-  else upload_points<float>(*pl, pb, FastF32::kPhantomCoord);
+  if (pr.precision == TOPOLOW_PREC_F64_EXACT) upload_points<double>(*pl, pb, kPhantomCoordF64);
+  else upload_points<float>(*pl, pb, kPhantomCoordF32);
   TL_CUDA(cudaStreamCreate(&pl->stream));
-  build_buckets(pb, pl->slot_of_point, g.T, pl->stream, &pl->edges, &pl->bucket_off);
+  if (pb.n_edges >= (1 << 21)) build_buckets(pb, pl->slot_of_point, g.T, 32 * g.P, pl->stream, &pl->edges, &pl->bucket_off);
+  else upload_edges(*pl, pb);   // small lists: a host counting sort beats a dozen device allocations
 
   FitState st; state_init(st, pl->prm);
   TL_CUDA(cudaMalloc(&pl->state, sizeof(FitState)));
@@ -293,7 +347,7 @@ double run_plan(topolow_plan& pl, int n_iters, cudaStream_t stream_in, topolow_i
 
 template <class real>
 void download_best(const topolow_plan& pl, double* out) {
-  const size_t slots = (size_t)pl.geo.T * kTile;
+  const size_t slots = (size_t)pl.geo.T * 32 * pl.geo.P;
   std::vector<real> hp(slots * pl.D);
   TL_CUDA(cudaMemcpy(hp.data(), pl.best, hp.size() * sizeof(real), cudaMemcpyDeviceToHost));
   for (int64_t i = 0; i < pl.n; ++i) {
@@ -485,7 +539,10 @@ int topolow_fit_batch(int32_t n_jobs, const topolow_problem* problems, const top
       pr.device = device;
       // Many independent fits: one CTA per fit (no grid barrier, plain launches that run side by
       // side on different SMs) keeps every SM busy; a lone large fit still gets the whole chip.
-      if (n_jobs >= 16 && pr.max_ctas == 0) pr.max_ctas = 1;
+      if (n_jobs >= 16 && pr.max_ctas == 0) {
+        pr.max_ctas = 1;
+        if (pr.tile_points == 0) pr.tile_points = 64;
+      }
       plans[j] = make_plan(problems[j], pr);
       left[j] = pr.n_iter;
     } catch (const CudaError& e) {
@@ -585,9 +642,9 @@ int topolow_plan_result(topolow_plan* plan, topolow_result* result) {
 int topolow_plan_info(const topolow_plan* plan, int64_t* out, int32_t cap) {
   if (!plan || !out) return TOPOLOW_ERR_BAD_ARG;
   const Geometry& g = plan->geo;
-  const int64_t v[10] = {g.T, g.S, g.W, g.G, g.m, g.S, (int64_t)plan->n * (plan->n - 1) / 2, (int64_t)plan->smem,
-                         plan->chunk_iters, plan->launches};
-  for (int i = 0; i < cap && i < 10; ++i) out[i] = v[i];
+  const int64_t v[11] = {g.T, g.S, g.W, g.G, g.m, g.S, (int64_t)plan->n * (plan->n - 1) / 2, (int64_t)plan->smem,
+                         plan->chunk_iters, plan->launches, 32 * g.P};
+  for (int i = 0; i < cap && i < 11; ++i) out[i] = v[i];
   return TOPOLOW_OK;
 }
 
@@ -604,17 +661,17 @@ int64_t topolow_plan_enumerate(const topolow_plan* plan, int32_t iter, int32_t* 
 // topolow_plan_info.
 int64_t topolow_schedule_enumerate(int64_t n, int32_t ndim, int32_t precision, int32_t sm_count, int32_t max_ctas,
                                    uint64_t seed, int32_t iter, int32_t* out, int64_t cap_pairs,
-                                   int64_t* geometry_out) {
+                                   int64_t* geometry_out, int32_t tile_points) {
   if (n < 2 || ndim < 1 || ndim > kMaxDim || sm_count < 1) return -1;
-  const Geometry g = choose_geometry(n, ndim, precision, sm_count, max_ctas, seed);
+  const Geometry g = choose_geometry(n, ndim, precision, sm_count, max_ctas, seed, 0, choose_tile_points(n, tile_points));
   if (geometry_out) {
     const int64_t v[8] = {g.T, g.S, g.W, g.G, g.m, g.S, n * (n - 1) / 2,
-                          (int64_t)tile_smem_bytes(g.D, g.W, precision == TOPOLOW_PREC_F64_EXACT ? 8 : 4)};
+                          (int64_t)tile_smem_bytes(g.D, g.W, precision == TOPOLOW_PREC_F64_EXACT ? 8 : 4, g.P)};
     for (int i = 0; i < 8; ++i) geometry_out[i] = v[i];
   }
   if (!out) return 0;
   const std::vector<int32_t> sop = random_permutation(n, seed);
-  std::vector<int32_t> pos((size_t)g.T * kTile, -1);
+  std::vector<int32_t> pos((size_t)g.T * 32 * g.P, -1);
   for (int64_t i = 0; i < n; ++i) pos[sop[i]] = (int32_t)i;
   return enumerate_schedule(g, pos, iter, out, cap_pairs);
 }

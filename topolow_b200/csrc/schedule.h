@@ -8,19 +8,19 @@
 // the reference's Gauss-Seidel loop (src/optimization.cpp:199-282) - the order
 // topolow_plan_enumerate() writes out.
 //
-// Hierarchy (point -> tile of 64 -> super-block of W tiles -> S = 2*G*m super-blocks):
+// Hierarchy (point -> tile of 32*P -> super-block of W tiles -> S = 2*G*m super-blocks):
 //   level 2  round-robin tournament over super-blocks (circle method): S-1 cross rounds of
 //            S/2 disjoint super-block pairs (one CTA task each) + 1 diagonal round; a barrier
 //            across the G CTAs of the fit separates rounds.
 //   level 1  inside a cross task (X,Y): W sub-rounds, warp w takes tile X[w] x tile Y[(w+v)%W];
 //            inside a diagonal task: circle method over the W tiles of each super-block, then
 //            every tile against itself; __syncthreads() separates sub-rounds.
-//   level 0  tile x tile (64 x 64): 32 steps of a systolic ring - lane a keeps A[a], A[a+32] in
-//            registers, the B points travel through the lanes in pairs (B[b], B[b+32]) by an odd
-//            stride g, b = (a + s0 + g*i) mod 32; a step is two perfect matchings one after the
-//            other: {(A[a],B[b]), (A[a+32],B[b+32])} then {(A[a],B[b+32]), (A[a+32],B[b])}.
-//            tile x itself: the 32 pairs (a, a+32), then 31 XOR steps in which lane a meets lane
-//            a^x, again as two matchings per step.
+//   level 0  tile x tile (32P x 32P): 32 steps of a systolic ring - lane a keeps A[a + 32p], p < P, in
+//            registers, the B points travel through the lanes in groups (B[b + 32q]) by an odd stride
+//            g, b = (a + s0 + g*i) mod 32; a step is P perfect matchings ("waves") one after the
+//            other, wave w pairing A[a + 32p] with B[b + 32((p + w) mod P)].
+//            tile x itself: the pairs among a lane's own P slots, then 31 XOR steps in which lane a
+//            meets lane a^x, wave w pairing slot a + 32p with slot (a^x) + 32((w - p) mod P).
 // Randomisation per iteration (stateless hashes of (seed, iter)): the tile -> super-block
 // placement, the order of the rounds, the sub-round rotation and the ring's (s0, g).
 #pragma once
@@ -29,17 +29,16 @@
 
 namespace tl {
 
-constexpr int kP = 3;            // points of a tile held by one lane
-constexpr int kTile = 32 * kP;   // points per tile
 
 struct Geometry {
   int n;        // real points
-  int T;        // tiles = ceil(n / 32)
+  int T;        // tiles = ceil(n / (32 * P))
   int W;        // tiles per super-block == warps per CTA
   int G;        // CTAs cooperating on the fit
   int m;        // tasks per CTA per round
   int S;        // super-blocks = 2*G*m
   int D;        // dimensions
+  int P;        // points of a tile held by one lane: tile = 32 * P points (1, 2 or 3)
   uint64_t seed;
 };
 

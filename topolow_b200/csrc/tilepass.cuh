@@ -20,30 +20,20 @@
 //   into a per-warp kP*kP x 32 x 32 target table + 3*kP*kP 32-bit lane masks before the pass.
 #pragma once
 
-#include "schedule.h"
+#include "tiledev.h"
+
+#ifndef TL_KP
+#error "define TL_KP (points per lane: 1, 2 or 3) before including tilepass.cuh"
+#endif
+#define TL_PNS_CAT2(a, b) a##b
+#define TL_PNS_CAT(a, b) TL_PNS_CAT2(a, b)
+#define TL_PNS TL_PNS_CAT(p, TL_KP)
 
 namespace tl {
+namespace TL_PNS {   // one copy of everything below per tile size
 
-struct __align__(16) EdgeRec {
-  double target;
-  uint32_t slot_lo;        // slot in the lower-numbered tile (or lower slot when same tile)
-  uint32_t slot_hi_type;   // slot in the other tile | type << 30   (0 exact, 1 '>', 2 '<')
-};
-
-template <class real>
-struct TileDev {
-  real* pos;
-  real* best;
-  const real* dp1;
-  const EdgeRec* edges;
-  const uint32_t* bucket_off;
-  FitState* state;
-  double* partials;      // [G][4]: error sum, count, non-finite flag, unused
-  unsigned* barrier;     // [2]: arrivals, generation
-  double* trace;         // [n_iter] or null
-  long long n_edges;
-  unsigned long long pairs_per_iter;
-};
+constexpr int kP = TL_KP;        // points of a tile held by one lane
+constexpr int kTile = 32 * kP;   // points per tile
 
 // ---------------------------------------------------------------------------------------
 // Math policies.  A policy owns the register image of a point (`Point<D>`: coordinates + the
@@ -72,12 +62,11 @@ TL_D float rsqrt_fast(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "
 TL_D float rcp_fast(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 
 // FP32 production arithmetic.  A phantom slot (padding of the last tile) has zero mass and sits
-// at kPhantomCoord in every dimension: against a real point 1/ds^3 flushes to zero, against
+// at kPhantomCoordF32 in every dimension: against a real point 1/ds^3 flushes to zero, against
 // another phantom the zero mass cancels the force, so no validity predicate is needed.
 struct FastF32 {
   typedef float real;
-  static constexpr int kMaxWarps = 4;   // shared memory (kP*kP target tables per warp) and 255 registers per thread
-  static constexpr float kPhantomCoord = 1.0e18f;
+  static constexpr int kMaxWarps = kP == 1 ? 16 : (kP == 2 ? 8 : 4);   // shared memory (kP*kP target tables per warp), registers
   struct Ctx { float two_k, c_half, k; };
   static TL_D Ctx make_ctx(double k, double c_rep) {
     Ctx c; c.two_k = (float)(2.0 * k); c.c_half = (float)(0.5 * c_rep); c.k = (float)k; return c;
@@ -260,8 +249,7 @@ struct FastF32 {
 // the CPU loop executed on the order topolow_plan_enumerate() reports.
 struct ExactF64 {
   typedef double real;
-  static constexpr int kMaxWarps = 2;  // shared memory: kP*kP x 32 x 32 doubles of targets per warp
-  static constexpr double kPhantomCoord = 0.0;
+  static constexpr int kMaxWarps = kP == 1 ? 8 : (kP == 2 ? 4 : 2);  // shared memory: kP*kP x 32 x 32 doubles of targets per warp
   struct Ctx { double k, c_rep; };
   static TL_D Ctx make_ctx(double k, double c_rep) { Ctx c; c.k = k; c.c_rep = c_rep; return c; }
   template <int D>
@@ -835,4 +823,5 @@ tile_kernel(TileDev<typename M::real> dv, Geometry geo, FitParams prm, int n_ite
   }
 }
 
+}  // namespace TL_PNS
 }  // namespace tl

@@ -1,24 +1,30 @@
 // topolow_b200/csrc/tilepass_launch.h - host-visible launchers of the production kernel.
 #pragma once
-#include "tilepass.cuh"
+#include "tiledev.h"
 
 namespace tl {
 
 constexpr int kMaxDim = 16;
+constexpr int kMaxP = 3;
 
-// Dynamic shared memory of one CTA: 2W tiles + W (target table + masks) + 2W tile ids + W flags.
-inline size_t tile_smem_bytes(int D, int W, size_t real_size) {
-  const size_t tile = (size_t)(D + 1) * kRow * real_size;
-  return 2 * W * tile + (size_t)W * (kTableReals * real_size + kTableMasks * 4) + (size_t)3 * W * 4;
+// Warps per CTA the kernel is built for, by precision (0 = FP32, 1 = exact FP64) and points per lane.
+inline int tile_max_warps(int precision, int P) {
+  const int f32[4] = {0, 16, 8, 4}, f64[4] = {0, 8, 4, 2};
+  return precision ? f64[P] : f32[P];
+}
+// Dynamic shared memory of one CTA: 2W tiles + W (target tables + masks) + 2W tile ids + W flags.
+inline size_t tile_smem_bytes(int D, int W, size_t real_size, int P) {
+  const size_t tile = (size_t)(D + 1) * (32 * P + 1) * real_size;
+  return 2 * W * tile + (size_t)W * ((size_t)P * P * 1024 * real_size + (size_t)P * P * 96 * 4) + (size_t)3 * W * 4;
 }
 
-// Launch `n_iters` iterations (cooperative when geo.G > 1).  Throws CudaError.
+// Launch `n_iters` iterations (cooperative when geo.G > 1); geo.P selects the tile size.  Throws CudaError.
 void launch_tile_f32(const TileDev<float>& dv, const Geometry& geo, const FitParams& prm, int n_iters,
                      volatile int* host_flag, cudaStream_t stream);
 void launch_tile_f64(const TileDev<double>& dv, const Geometry& geo, const FitParams& prm, int n_iters,
                      volatile int* host_flag, cudaStream_t stream);
 // Largest CTA count of that instantiation that can be co-resident on the current device.
-int max_coresident_f32(int D, int W);
-int max_coresident_f64(int D, int W);
+int max_coresident_f32(int D, int W, int P);
+int max_coresident_f64(int D, int W, int P);
 
 }  // namespace tl
