@@ -184,7 +184,8 @@ TOPOLOW_API int topolow_holdout_errors(const double* positions, int64_t n, int32
 
 /* ---- measurement helpers --------------------------------------------------- */
 /* which: 0 FFMA (FP32 flop/s), 1 packed fma.f32x2, 2 DFMA, 3 SHFL (warp-instr/s), 4 MUFU.RSQ,
- * 5 device copy (bytes/s read+write).  value_out in the unit named. */
+ * 5 device copy (bytes/s read+write), 6/7/8 = milliseconds of a loop of 8 FFMA2 / 4 SHFL / both per trip
+ * (do the FMA pipe and the shuffle unit overlap?).  value_out in the unit named. */
 TOPOLOW_API int topolow_microbench(int32_t which, int32_t device, double* value_out);
 TOPOLOW_API int topolow_device_info(int32_t device, int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor,
                         int64_t* global_mem);

@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libtopolow_b200.so")
+LIB_PATH = os.environ.get("TOPOLOW_B200_LIB") or os.path.join(_HERE, "lib", "libtopolow_b200.so")
 
 OK, ERR_BAD_ARG, ERR_NONFINITE, ERR_CUDA, ERR_TOO_FEW_POINTS, ERR_INTERRUPTED = range(6)
 MODE_COLOURED, MODE_REPLAY = 0, 1

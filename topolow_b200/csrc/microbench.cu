@@ -94,6 +94,27 @@ __global__ void __launch_bounds__(256) rsq_kernel(float* out) {
   if (s == 123.456f) out[0] = s;
 }
 
+// FFMA2 and SHFL streams in the same warp (independent chains): does the shuffle unit run beside the
+// FMA pipe, or do the two share the sub-partition's dispatch slot?
+__global__ void __launch_bounds__(256) mix_kernel(float* out, float a, float b, int n_ffma2, int n_shfl) {
+  float2 x[kChains];
+  float y[kChains];
+  const float2 pa = make_float2(a, a), pb = make_float2(b, b);
+#pragma unroll
+  for (int c = 0; c < kChains; ++c) { x[c] = make_float2(threadIdx.x * 1e-3f + c, c); y[c] = threadIdx.x + c; }
+  for (int i = 0; i < kInner; ++i) {
+#pragma unroll
+    for (int c = 0; c < kChains; ++c) {
+      if (c < n_ffma2) x[c] = __ffma2_rn(x[c], pa, pb);
+      if (c < n_shfl) y[c] = __shfl_sync(0xffffffffu, y[c], (threadIdx.x + 1) & 31);
+    }
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int c = 0; c < kChains; ++c) s += x[c].x + x[c].y + y[c];
+  if (s == 123.456f) out[0] = s;
+}
+
 __global__ void copy_kernel(const float4* __restrict__ in, float4* __restrict__ out, size_t n4) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) out[i] = in[i];
@@ -125,6 +146,9 @@ extern "C" int topolow_microbench(int32_t which, int32_t device, double* value_o
         case 3: shfl_kernel<<<blocks, threads, 0, s>>>(d_out); break;
         case 4: rsq_kernel<<<blocks, threads, 0, s>>>(d_out); break;
         case 5: copy_kernel<<<prop.multiProcessorCount * 16, 512, 0, s>>>(d_a, d_b, copy_bytes / 16); break;
+        case 6: mix_kernel<<<blocks, threads, 0, s>>>(d_out, 1.0001f, 0.5f, 8, 0); break;   // 8 FFMA2 per trip
+        case 7: mix_kernel<<<blocks, threads, 0, s>>>(d_out, 1.0001f, 0.5f, 0, 4); break;   // 4 SHFL per trip
+        case 8: mix_kernel<<<blocks, threads, 0, s>>>(d_out, 1.0001f, 0.5f, 8, 4); break;   // both
         default: return TOPOLOW_ERR_BAD_ARG;
       }
       TL_CUDA(cudaGetLastError());
@@ -141,7 +165,8 @@ extern "C" int topolow_microbench(int32_t which, int32_t device, double* value_o
     else if (which == 2) v = thread_ops * 2.0 / sec;       // flop/s
     else if (which == 3) v = thread_ops / 32.0 / sec;      // warp instructions / s
     else if (which == 4) v = thread_ops / 32.0 / sec;      // warp MUFU instructions / s
-    else v = 2.0 * copy_bytes / sec;                       // bytes/s
+    else if (which == 5) v = 2.0 * copy_bytes / sec;       // bytes/s
+    else v = sec * 1e3;                                    // 6..8: milliseconds of the FFMA2 / SHFL / mixed loop
     *value_out = v;
     cudaFree(d_out); if (d_a) cudaFree(d_a); if (d_b) cudaFree(d_b);
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaStreamDestroy(s);

@@ -34,6 +34,10 @@ namespace TL_PNS {   // one copy of everything below per tile size
 
 constexpr int kP = TL_KP;        // points of a tile held by one lane
 constexpr int kTile = 32 * kP;   // points per tile
+#ifndef TL_STAGGER
+#define TL_STAGGER 0
+#endif
+constexpr int kStaggerCycles = TL_STAGGER;
 
 // ---------------------------------------------------------------------------------------
 // Math policies.  A policy owns the register image of a point (`Point<D>`: coordinates + the
@@ -572,6 +576,13 @@ TL_D void ring_pass(typename M::real* sA, typename M::real* sB, int tA, int tB, 
 #pragma unroll
   for (int p = 0; p < kP; ++p) { A[p].load(sA, lane + 32 * p, ctx); B[p].load(sB, b0 + 32 * p, ctx); }
   const int src = (lane + rp.g) & 31;
+  // Warps of one scheduler start their passes together and would stay in lock-step (all in the FMA
+  // sweep, then all in the shuffles): offset them by a fraction of a ring step so that the pipes of
+  // the sub-partition are used by different warps at the same time.
+  if (kStaggerCycles > 0) {
+    const long long until = clock64() + (long long)((threadIdx.x >> 7) % 4) * kStaggerCycles;
+    while (clock64() < until) { }
+  }
 #pragma unroll 1
   for (int i = 0; i < 32; ++i) {
     Waves<D, M, false>::run(A, B, tb, m, i, lane, ctx);
