@@ -34,10 +34,6 @@ namespace TL_PNS {   // one copy of everything below per tile size
 
 constexpr int kP = TL_KP;        // points of a tile held by one lane
 constexpr int kTile = 32 * kP;   // points per tile
-#ifndef TL_STAGGER
-#define TL_STAGGER 0
-#endif
-constexpr int kStaggerCycles = TL_STAGGER;
 
 // ---------------------------------------------------------------------------------------
 // Math policies.  A policy owns the register image of a point (`Point<D>`: coordinates + the
@@ -79,16 +75,16 @@ struct FastF32 {
   struct Point {
     static constexpr int H = (D + 1) / 2;
     f32x2 c[H];       // coordinates, two per register (odd D: the last high half is 0)
-    float rdeg;       // 1 / (deg + 1)          (0 for a phantom)
-    float rnorm;      // 1 / (4 (deg + 1) + k)  (0 for a phantom)
+    float rdeg;       // (c / 2) / (deg + 1)      repulsion weight, constant folded in (0 for a phantom)
+    float rnorm;      // 2k / (4 (deg + 1) + k)   spring weight, constant folded in    (0 for a phantom)
     TL_D void load(const float* s, int idx, const Ctx& ctx) {
 #pragma unroll
       for (int j = 0; j < H; ++j)
         c[j] = pk2(s[(2 * j) * kRow + idx], (2 * j + 1 < D) ? s[(2 * j + 1) * kRow + idx] : 0.f);
       const float dp1 = s[D * kRow + idx];
       const bool ok = dp1 > 0.f;
-      rdeg = ok ? rcp_fast(dp1) : 0.f;
-      rnorm = ok ? rcp_fast(fmaf(4.0f, dp1, ctx.k)) : 0.f;
+      rdeg = ok ? ctx.c_half * rcp_fast(dp1) : 0.f;
+      rnorm = ok ? ctx.two_k * rcp_fast(fmaf(4.0f, dp1, ctx.k)) : 0.f;
     }
     TL_D void store(float* s, int idx) const {
 #pragma unroll
@@ -157,8 +153,8 @@ struct FastF32 {
     // purpose: && / ?: would be compiled into divergent branches.
     const uint32_t below = dist < target ? ~0u : 0u, above = dist > target ? ~0u : 0u;
     const bool spring = (cell.meas & ((cell.gt & below) | (cell.lt & above) | ~(cell.gt | cell.lt))) != 0u;
-    const float rep = c.c_half * ids * ids;
-    const float spr = c.two_k * (target - dist);
+    const float rep = ids * ids;            // (c/2 and 2k live in the per-point weights)
+    const float spr = target - dist;
     const float f = (spring ? spr : rep) * ids;
     const float wA = spring ? A.rnorm : A.rdeg, wB = spring ? B.rnorm : B.rdeg;
     fA = f * wA;
@@ -222,7 +218,7 @@ struct FastF32 {
       const Cell<float>& cl = cell[p];
       const uint32_t below = dist[p] < cl.target ? ~0u : 0u, above = dist[p] > cl.target ? ~0u : 0u;
       sp[p] = (cl.meas & ((cl.gt & below) | (cl.lt & above) | ~(cl.gt | cl.lt))) != 0u;
-      f[p] = (sp[p] ? c.two_k * (cl.target - dist[p]) : c.c_half * ids[p] * ids[p]) * ids[p];
+      f[p] = (sp[p] ? cl.target - dist[p] : ids[p] * ids[p]) * ids[p];   // x weight: 2k(t-d)/ds or c/(2 ds^3)
     }
 #pragma unroll
     for (int p = 0; p < kP; ++p) {
@@ -576,13 +572,6 @@ TL_D void ring_pass(typename M::real* sA, typename M::real* sB, int tA, int tB, 
 #pragma unroll
   for (int p = 0; p < kP; ++p) { A[p].load(sA, lane + 32 * p, ctx); B[p].load(sB, b0 + 32 * p, ctx); }
   const int src = (lane + rp.g) & 31;
-  // Warps of one scheduler start their passes together and would stay in lock-step (all in the FMA
-  // sweep, then all in the shuffles): offset them by a fraction of a ring step so that the pipes of
-  // the sub-partition are used by different warps at the same time.
-  if (kStaggerCycles > 0) {
-    const long long until = clock64() + (long long)((threadIdx.x >> 7) % 4) * kStaggerCycles;
-    while (clock64() < until) { }
-  }
 #pragma unroll 1
   for (int i = 0; i < 32; ++i) {
     Waves<D, M, false>::run(A, B, tb, m, i, lane, ctx);
