@@ -398,7 +398,11 @@ def main():
     roofline = {"bound": "fp32", "kernel": "tile_kernel<D,%s>" % ("FastF32" if prec == 0 else "ExactF64"),
                 "achieved": ach / 1e12, "peak": ffma_peak / 1e12, "unit": "TFLOP/s", "frac": ach / ffma_peak,
                 "peak_source": "topolow_microbench FFMA, measured live on this GPU (not in MEASURED_PEAKS.json)",
-                "flop_per_iteration": flop, "traffic": None,
+                "flop_per_iteration": flop,
+                # dram__bytes_read + dram__bytes_write of one launch (= one iteration) of this kernel on this
+                # workload, from the ncu --set full capture summarised in profiles/r1_ncu_tile_kernel_cfg4.md
+                "traffic": 878.6e6 if (args.workload == "cfg4" and prec == 0) else None,
+                "traffic_unit": "bytes per launch (one iteration); algorithmic edge stream is bytes_per_iteration below",
                 "hbm": {"achieved": edge_bytes_per_iter(n, d, E) / kernel_s / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                         "frac": edge_bytes_per_iter(n, d, E) / kernel_s / 1e9 / peaks["hbm_gbs"], "peak_source": peak_src,
                         "bytes_per_iteration": edge_bytes_per_iter(n, d, E)}}
