@@ -27,8 +27,6 @@ namespace {
 struct ReplayDev {
   double* pos;        // [n][dim] row-major working positions
   double* best_pos;   // [n][dim]
-  const double* dist; // [n][n] dense targets, Inf = unmeasured (only i<j read, row-major [i][j])
-  const int8_t* thr;  // [n][n]
   const double* dp1;  // deg + 1
   const int* ei; const int* ej; const double* et; const int* ety; // COO edges for the MAE
   double* terms;      // [E] scratch
@@ -74,14 +72,25 @@ TL_D void pair_update_exact(double* __restrict__ pi, double* __restrict__ pj, in
   }
 }
 
-// One launch = `n_it` iterations of one fit.  pairs: packed (i<<16|j), sorted by level within
-// each iteration; lvl_off: per-iteration level offsets into pairs (absolute), terminated;
-// it_lvl: [n_it+1] index of each iteration's first entry in lvl_off.
+// A pair visit as the host ships it: the points and what the dense matrices of the reference call
+// hold for them (target = +Inf when the pair is unmeasured; src/optimization.cpp:217,230).
+struct __align__(16) PairRec {
+  double target;
+  uint32_t ij;     // i << 16 | j
+  int32_t type;
+};
+
+constexpr int kLvlCap = 4096;   // level offsets of one iteration staged in shared memory
+
+// One launch = `n_it` iterations of one fit.  pairs: records sorted by level within each iteration;
+// lvl_off: per-iteration level offsets into pairs (absolute), terminated; it_lvl: [n_it+1] index of
+// each iteration's first entry in lvl_off.
 __global__ void __launch_bounds__(1024)
-replay_kernel(ReplayDev dv, FitParams prm, const uint32_t* __restrict__ pairs,
+replay_kernel(ReplayDev dv, FitParams prm, const PairRec* __restrict__ pairs,
               const int* __restrict__ lvl_off, const int* __restrict__ it_lvl, int n_it,
               int use_smem, volatile int* host_flag) {
   extern __shared__ double smem_pos[];
+  __shared__ int s_lvl[kLvlCap];
   __shared__ FitState st;
   __shared__ double red_a, red_b;
   __shared__ long long red_cnt;
@@ -100,14 +109,29 @@ replay_kernel(ReplayDev dv, FitParams prm, const uint32_t* __restrict__ pairs,
     const int iter = st.iter;
     const double k = st.k;
     const int l0 = it_lvl[t], l1 = it_lvl[t + 1] - 1;  // levels are [lvl_off[l], lvl_off[l+1])
-    for (int l = l0; l < l1; ++l) {
-      const int b = lvl_off[l], e = lvl_off[l + 1];
+    const int nl = l1 - l0;
+    const bool staged = nl + 1 <= kLvlCap;
+    if (staged) {
+      for (int x = tid; x <= nl; x += nt) s_lvl[x] = lvl_off[l0 + x];
+      __syncthreads();
+    }
+    // the record of the next level is fetched while the current one is computed
+    PairRec nxt;
+    int nb = staged ? s_lvl[0] : lvl_off[l0], ne = nl > 0 ? (staged ? s_lvl[1] : lvl_off[l0 + 1]) : nb;
+    if (nb + tid < ne) nxt = pairs[nb + tid];
+    for (int l = 0; l < nl; ++l) {
+      const int b = nb, e = ne;
+      const PairRec cur = nxt;
+      if (l + 1 < nl) {
+        nb = e;
+        ne = staged ? s_lvl[l + 2] : lvl_off[l0 + l + 2];
+        if (nb + tid < ne) nxt = pairs[nb + tid];
+      }
       for (int p = b + tid; p < e; p += nt) {
-        const uint32_t pk = pairs[p];
-        const int i = pk >> 16, j = pk & 0xffff;
-        const size_t at = (size_t)i * n + j;
-        pair_update_exact(P + (size_t)i * dim, P + (size_t)j * dim, dim, dv.dist[at], dv.thr[at],
-                          dv.dp1[i], dv.dp1[j], k, prm.c_repulsion);
+        const PairRec r = (p == b + tid) ? cur : pairs[p];
+        const int i = r.ij >> 16, j = r.ij & 0xffff;
+        pair_update_exact(P + (size_t)i * dim, P + (size_t)j * dim, dim, r.target, r.type, dv.dp1[i], dv.dp1[j], k,
+                          prm.c_repulsion);
       }
       __syncthreads();
     }
@@ -209,8 +233,6 @@ void run_replay(const topolow_problem& pb, const topolow_params& pr, topolow_res
   dv.n = n; dv.dim = dim; dv.n_edges = (int)E;
   double* d_pos = dev_alloc<double>((size_t)n * dim);
   double* d_best = dev_alloc<double>((size_t)n * dim);
-  double* d_dist = dev_alloc<double>((size_t)n * n);
-  int8_t* d_thr = dev_alloc<int8_t>((size_t)n * n);
   double* d_dp1 = dev_alloc<double>(n);
   int* d_ei = dev_alloc<int>(E); int* d_ej = dev_alloc<int>(E);
   double* d_et = dev_alloc<double>(E); int* d_ety = dev_alloc<int>(E);
@@ -219,8 +241,6 @@ void run_replay(const topolow_problem& pb, const topolow_params& pr, topolow_res
   double* d_trace = res.trace_mae ? dev_alloc<double>(pr.n_iter) : nullptr;
   TL_CUDA(cudaMemcpy(d_pos, h_pos.data(), sizeof(double) * n * dim, cudaMemcpyHostToDevice));
   TL_CUDA(cudaMemcpy(d_best, h_pos.data(), sizeof(double) * n * dim, cudaMemcpyHostToDevice));
-  TL_CUDA(cudaMemcpy(d_dist, h_dist.data(), sizeof(double) * n * n, cudaMemcpyHostToDevice));
-  TL_CUDA(cudaMemcpy(d_thr, h_thr.data(), (size_t)n * n, cudaMemcpyHostToDevice));
   TL_CUDA(cudaMemcpy(d_dp1, h_dp1.data(), sizeof(double) * n, cudaMemcpyHostToDevice));
   if (E) {
     TL_CUDA(cudaMemcpy(d_ei, h_ei.data(), sizeof(int) * E, cudaMemcpyHostToDevice));
@@ -234,7 +254,7 @@ void run_replay(const topolow_problem& pb, const topolow_params& pr, topolow_res
   }
   FitState h_state; state_init(h_state, prm);
   TL_CUDA(cudaMemcpy(d_state, &h_state, sizeof h_state, cudaMemcpyHostToDevice));
-  dv.pos = d_pos; dv.best_pos = d_best; dv.dist = d_dist; dv.thr = d_thr; dv.dp1 = d_dp1;
+  dv.pos = d_pos; dv.best_pos = d_best; dv.dp1 = d_dp1;
   dv.ei = d_ei; dv.ej = d_ej; dv.et = d_et; dv.ety = d_ety; dv.terms = d_terms; dv.contrib = d_contrib;
   dv.state = d_state; dv.trace = d_trace;
 
@@ -247,19 +267,19 @@ void run_replay(const topolow_problem& pb, const topolow_params& pr, topolow_res
   threads = std::min(1024, std::max(64, threads));
 
   // ---- chunked, double-buffered order stream --------------------------------
-  const int64_t chunk_pairs_target = 1 << 22;
+  const int64_t chunk_pairs_target = 1 << 21;
   const int chunk_iters = (int)std::max<int64_t>(1, std::min<int64_t>(chunk_pairs_target / std::max<int64_t>(P, 1), 64));
   const int64_t ppi = pr.pair_order ? pr.pairs_per_iter : P;
   const size_t cap_pairs = (size_t)chunk_iters * ppi;
   const size_t cap_lvls = (size_t)chunk_iters * (ppi + 2);
-  uint32_t* h_pairs[2]; int* h_lvl[2]; int* h_itl[2];
-  uint32_t* d_pairs[2]; int* d_lvl[2]; int* d_itl[2];
+  PairRec* h_pairs[2]; int* h_lvl[2]; int* h_itl[2];
+  PairRec* d_pairs[2]; int* d_lvl[2]; int* d_itl[2];
   cudaEvent_t copied[2];
   for (int b = 0; b < 2; ++b) {
-    TL_CUDA(cudaMallocHost(&h_pairs[b], sizeof(uint32_t) * std::max<size_t>(cap_pairs, 1)));
+    TL_CUDA(cudaMallocHost(&h_pairs[b], sizeof(PairRec) * std::max<size_t>(cap_pairs, 1)));
     TL_CUDA(cudaMallocHost(&h_lvl[b], sizeof(int) * cap_lvls));
     TL_CUDA(cudaMallocHost(&h_itl[b], sizeof(int) * (chunk_iters + 1)));
-    d_pairs[b] = dev_alloc<uint32_t>(cap_pairs);
+    d_pairs[b] = dev_alloc<PairRec>(cap_pairs);
     d_lvl[b] = dev_alloc<int>(cap_lvls);
     d_itl[b] = dev_alloc<int>(chunk_iters + 1);
     TL_CUDA(cudaEventCreateWithFlags(&copied[b], cudaEventDisableTiming));
@@ -325,12 +345,17 @@ void run_replay(const topolow_problem& pb, const topolow_params& pr, topolow_res
       int run = (int)np;
       for (int l = 1; l <= max_l; ++l) { h_lvl[b][nl++] = run; const int cl = counts[l]; counts[l] = run; run += cl; }
       h_lvl[b][nl++] = run;
-      for (int64_t p = 0; p < cnt; ++p)
-        h_pairs[b][counts[lvl_of[p]]++] = ((uint32_t)ord[p].i << 16) | (uint32_t)ord[p].j;
+      for (int64_t p = 0; p < cnt; ++p) {
+        const size_t at = (size_t)ord[p].i * n + ord[p].j;
+        PairRec& r = h_pairs[b][counts[lvl_of[p]]++];
+        r.target = h_dist[at];
+        r.ij = ((uint32_t)ord[p].i << 16) | (uint32_t)ord[p].j;
+        r.type = h_thr[at];
+      }
       np = run;
     }
     h_itl[b][nit] = (int)nl;
-    TL_CUDA(cudaMemcpyAsync(d_pairs[b], h_pairs[b], sizeof(uint32_t) * np, cudaMemcpyHostToDevice, stream));
+    TL_CUDA(cudaMemcpyAsync(d_pairs[b], h_pairs[b], sizeof(PairRec) * np, cudaMemcpyHostToDevice, stream));
     TL_CUDA(cudaMemcpyAsync(d_lvl[b], h_lvl[b], sizeof(int) * nl, cudaMemcpyHostToDevice, stream));
     TL_CUDA(cudaMemcpyAsync(d_itl[b], h_itl[b], sizeof(int) * (nit + 1), cudaMemcpyHostToDevice, stream));
     TL_CUDA(cudaEventRecord(copied[b], stream));
@@ -365,7 +390,7 @@ void run_replay(const topolow_problem& pb, const topolow_params& pr, topolow_res
   }
   cudaFreeHost((void*)h_flag);
   cudaEventDestroy(ev0); cudaEventDestroy(ev1); cudaStreamDestroy(stream);
-  cudaFree(d_pos); cudaFree(d_best); cudaFree(d_dist); cudaFree(d_thr); cudaFree(d_dp1);
+  cudaFree(d_pos); cudaFree(d_best); cudaFree(d_dp1);
   cudaFree(d_ei); cudaFree(d_ej); cudaFree(d_et); cudaFree(d_ety); cudaFree(d_terms); cudaFree(d_contrib);
   cudaFree(d_state); if (d_trace) cudaFree(d_trace);
 }
