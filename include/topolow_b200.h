@@ -101,6 +101,8 @@ typedef struct {
   int32_t max_warps;                /* 0 = policy default; cap on warps (tiles) per CTA - lets an FP32 run use
                                        the schedule an FP64 run of the same problem gets */
   int32_t tile_points;              /* 0 = auto; 32, 64 or 96: points per tile (1, 2 or 3 per lane) */
+  int32_t n_shards;                 /* > 1: the map will be stepped job by job by that many ranks (see
+                                       topolow_plan_run_job); pads the tile count to a multiple of 2 * n_shards */
 } topolow_params;
 
 typedef struct {
@@ -160,6 +162,24 @@ TOPOLOW_API int topolow_plan_result(topolow_plan* plan, topolow_result* result);
  * iterations_per_launch, kernel_launches_so_far, tile_points}. */
 TOPOLOW_API int topolow_plan_info(const topolow_plan* plan, int64_t* out, int32_t cap);
 TOPOLOW_API void topolow_plan_destroy(topolow_plan* plan);
+
+/* ---- one large map across several GPUs (every rank holds a plan of the SAME problem and seed) ----
+ * An iteration is a tournament over 2R mega-blocks of tiles (R = n_shards): in each of the 2R-1
+ * rounds rank r runs ONE bipartite job (kind 1: every pair between tile ranges [t0,t0+tc) and
+ * [y0,y0+yc)), in the last round the kind-0 jobs (every pair inside a range) of its two mega-blocks;
+ * between rounds the caller all-gathers the position array (topolow_plan_positions: [slots][ndim],
+ * element size and slot count from topolow_plan_layout) so that every replica is current; then every
+ * rank calls topolow_plan_end_iteration (cooling, edge MAE, controller) on its identical replica.
+ * topolow_b200/sharded.py drives this with torch.distributed (NCCL). */
+TOPOLOW_API int topolow_plan_run_job(topolow_plan* plan, int32_t kind, int32_t t0, int32_t tc, int32_t y0, int32_t yc,
+                                     void* stream);
+TOPOLOW_API int topolow_plan_end_iteration(topolow_plan* plan, void* stream);
+/* out (up to 6 values): {total_tiles, tile_points, ndim, element_bytes, n_shards, total_slots}. */
+TOPOLOW_API int topolow_plan_layout(const topolow_plan* plan, int64_t* out, int32_t cap);
+TOPOLOW_API void* topolow_plan_positions(topolow_plan* plan);
+/* The sequential pair order one job is equivalent to (cf. topolow_plan_enumerate). */
+TOPOLOW_API int64_t topolow_plan_enumerate_job(const topolow_plan* plan, int32_t iter, int32_t kind, int32_t t0,
+                                               int32_t tc, int32_t y0, int32_t yc, int32_t* out, int64_t cap_pairs);
 
 /* The sequential pair order that is equivalent to iteration `iter` of a coloured-mode plan
  * (host-side walk of the same schedule functions the kernel executes).  out = [pairs][2]

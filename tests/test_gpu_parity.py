@@ -18,6 +18,7 @@ from conftest import load_fixture, load_golden, random_r_matrix, small_problem
 from oracle import cpu_oracle, r_glue
 from tools import synth
 from topolow_b200 import _lib, core, cv
+from topolow_b200.sharded import ShardedMap
 
 pytestmark = pytest.mark.gpu
 
@@ -107,6 +108,28 @@ def test_coloured_convergence_controller_matches():
     assert want["converged"] and want["iterations"] < 120
     assert (got["converged"], got["iterations"]) == (want["converged"], want["iterations"])
     assert np.array_equal(got["positions"], want["positions"])
+
+
+@pytest.mark.parametrize("world,tile_points,n", [(2, 32, 700), (4, 32, 1100), (2, 64, 900), (3, 96, 1300)])
+def test_sharded_map_is_one_sequential_order(world, tile_points, n):
+    """The multi-GPU schedule (mega-block tournament, bipartite + diagonal jobs) emulated on one GPU:
+    exact FP64 equals the CPU loop on the enumerated order, bit for bit."""
+    args = small_problem(n, 4, 0.04, 40 + n)
+    hp = (5.0, 0.01, 0.02, 1e-4, 5, 3)
+    sm = ShardedMap(*args, 4, *hp, world_size=world, precision=_lib.PREC_F64_EXACT, seed=5, tile_points=tile_points,
+                    emulate=True)
+    order = [sm.enumerate(it) for it in range(4)]
+    P = n * (n - 1) // 2
+    for o in order:                       # every pair exactly once per iteration
+        key = np.minimum(o[:, 0], o[:, 1]).astype(np.int64) * n + np.maximum(o[:, 0], o[:, 1])
+        assert len(o) == P and len(np.unique(key)) == P
+    sm.step(4)
+    got = sm.result()
+    sm.close()
+    want = cpu_oracle.optimize_layout_exact(*args, 4, *hp, pair_order=np.stack(order))
+    assert np.array_equal(got["positions"], want["positions"])
+    assert got["iterations"] == want["iterations"] and got["final_k"] == want["final_k"]
+    assert got["final_mae"] == pytest.approx(want["final_mae"], rel=1e-12)
 
 
 # ------------------------------------------------------------------ coloured mode, FP32 -------

@@ -34,7 +34,8 @@ class Params(C.Structure):
                 ("convergence_window", C.c_int32), ("convergence_check_freq", C.c_int32),
                 ("verbose", C.c_int32), ("mode", C.c_int32), ("precision", C.c_int32), ("seed", C.c_uint64),
                 ("pair_order", _i32p), ("pairs_per_iter", C.c_int64), ("device", C.c_int32),
-                ("max_ctas", C.c_int32), ("max_warps", C.c_int32), ("tile_points", C.c_int32)]
+                ("max_ctas", C.c_int32), ("max_warps", C.c_int32), ("tile_points", C.c_int32),
+                ("n_shards", C.c_int32)]
 
 
 class Result(C.Structure):
@@ -49,7 +50,8 @@ INTERRUPT_FN = C.CFUNCTYPE(C.c_int, C.c_void_p)
 EXPORTS = [
     "topolow_fit", "topolow_fit_interruptible", "topolow_optimize_layout_exact", "topolow_fit_batch",
     "topolow_plan_create", "topolow_plan_run", "topolow_plan_result", "topolow_plan_info",
-    "topolow_plan_destroy", "topolow_plan_enumerate", "topolow_schedule_enumerate",
+    "topolow_plan_destroy", "topolow_plan_enumerate", "topolow_schedule_enumerate", "topolow_plan_run_job",
+    "topolow_plan_end_iteration", "topolow_plan_layout", "topolow_plan_positions", "topolow_plan_enumerate_job",
     "topolow_est_distances", "topolow_holdout_errors", "topolow_microbench", "topolow_device_info",
     "topolow_version",
 ]
@@ -99,6 +101,17 @@ def lib() -> C.CDLL:
     L.topolow_schedule_enumerate.restype = C.c_int64
     L.topolow_schedule_enumerate.argtypes = [C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_uint64,
                                              C.c_int32, _i32p, C.c_int64, _i64p, C.c_int32]
+    L.topolow_plan_run_job.restype = C.c_int
+    L.topolow_plan_run_job.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
+    L.topolow_plan_end_iteration.restype = C.c_int
+    L.topolow_plan_end_iteration.argtypes = [C.c_void_p, C.c_void_p]
+    L.topolow_plan_layout.restype = C.c_int
+    L.topolow_plan_layout.argtypes = [C.c_void_p, _i64p, C.c_int32]
+    L.topolow_plan_positions.restype = C.c_void_p
+    L.topolow_plan_positions.argtypes = [C.c_void_p]
+    L.topolow_plan_enumerate_job.restype = C.c_int64
+    L.topolow_plan_enumerate_job.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                             _i32p, C.c_int64]
     L.topolow_est_distances.restype = C.c_int
     L.topolow_est_distances.argtypes = [_dp, C.c_int64, C.c_int32, _dp, C.c_int32]
     L.topolow_holdout_errors.restype = C.c_int
@@ -148,7 +161,7 @@ class ProblemArrays:
 
 def make_params(n_iter, k0, cooling_rate, c_repulsion, relative_epsilon=1e-4, convergence_window=5,
                 convergence_check_freq=3, verbose=False, mode=MODE_COLOURED, precision=PREC_F32, seed=0,
-                pair_order=None, device=0, max_ctas=0, max_warps=0, tile_points=0):
+                pair_order=None, device=0, max_ctas=0, max_warps=0, tile_points=0, n_shards=0):
     p = Params()
     p.n_iter = int(n_iter)
     p.k0, p.cooling_rate, p.c_repulsion = float(k0), float(cooling_rate), float(c_repulsion)
@@ -165,6 +178,7 @@ def make_params(n_iter, k0, cooling_rate, c_repulsion, relative_epsilon=1e-4, co
         p.pairs_per_iter = keep.shape[1]
     p.device, p.max_ctas, p.max_warps = int(device), int(max_ctas), int(max_warps)
     p.tile_points = int(tile_points)
+    p.n_shards = int(n_shards)
     return p, keep
 
 
@@ -242,12 +256,12 @@ class Plan:
     def __init__(self, initial_positions, degrees, edge_i, edge_j, edge_dist, edge_thresh, n_iter, k0,
                  cooling_rate, c_repulsion, relative_epsilon=1e-4, convergence_window=5,
                  convergence_check_freq=3, *, precision=PREC_F32, seed=0, device=0, max_ctas=0, max_warps=0,
-                 tile_points=0):
+                 tile_points=0, n_shards=0):
         self._L = lib()
         self._pa = ProblemArrays(initial_positions, degrees, edge_i, edge_j, edge_dist, edge_thresh)
         pr, _ = make_params(n_iter, k0, cooling_rate, c_repulsion, relative_epsilon, convergence_window,
                             convergence_check_freq, False, MODE_COLOURED, precision, seed, None, device, max_ctas, max_warps,
-                            tile_points)
+                            tile_points, n_shards)
         self.n_iter = int(n_iter)
         self._h = C.c_void_p()
         msg = C.create_string_buffer(256)
@@ -289,6 +303,36 @@ class Plan:
         if got != P:
             raise TopolowError(ERR_BAD_ARG, f"schedule enumerated {got} pairs, expected {P}")
         return out
+
+    # ---- job-by-job stepping of a map shared by several ranks (topolow_b200/sharded.py) ----
+    def run_job(self, kind, t0, tc, y0=0, yc=0, stream=None):
+        rc = self._L.topolow_plan_run_job(self._h, int(kind), int(t0), int(tc), int(y0), int(yc),
+                                          C.c_void_p(stream) if stream else None)
+        if rc != OK:
+            raise TopolowError(rc, f"topolow_plan_run_job failed with status {rc}")
+
+    def end_iteration(self, stream=None):
+        rc = self._L.topolow_plan_end_iteration(self._h, C.c_void_p(stream) if stream else None)
+        if rc != OK:
+            raise TopolowError(rc, f"topolow_plan_end_iteration failed with status {rc}")
+
+    def layout(self):
+        v = (C.c_int64 * 6)()
+        self._L.topolow_plan_layout(self._h, v, 6)
+        keys = ["total_tiles", "tile_points", "ndim", "element_bytes", "n_shards", "total_slots"]
+        return dict(zip(keys, [int(x) for x in v]))
+
+    def positions_ptr(self):
+        return int(self._L.topolow_plan_positions(self._h))
+
+    def enumerate_job(self, it, kind, t0, tc, y0=0, yc=0):
+        cap = self._pa.n * (self._pa.n - 1) // 2
+        out = np.empty((cap, 2), dtype=np.int32)
+        got = self._L.topolow_plan_enumerate_job(self._h, int(it), int(kind), int(t0), int(tc), int(y0), int(yc),
+                                                 out.ctypes.data_as(_i32p), cap)
+        if got < 0:
+            raise TopolowError(ERR_BAD_ARG, f"topolow_plan_enumerate_job failed ({got})")
+        return out[:got]
 
     def close(self):
         if self._h:

@@ -40,6 +40,7 @@ struct topolow_plan {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int chunk_iters = 1;
   int64_t launches = 0;
+  int wmax = 1, ctas = 1, n_shards = 0;
   double total_ms = 0.0;
   size_t smem = 0;
 
@@ -94,18 +95,16 @@ int choose_tile_points(int64_t n, int requested) {
   return n >= 40000 ? 3 : 1;
 }
 
-Geometry choose_geometry(int64_t n, int D, int precision, int sms, int max_ctas, uint64_t seed, int max_warps = 0,
-                         int P = 2) {
-  Geometry g{};
-  g.n = (int)n; g.D = D; g.seed = seed; g.P = P;
-  const int kTile = 32 * P;
-  g.T = (int)((n + kTile - 1) / kTile);
+int geometry_wmax(int D, int precision, int P, int max_warps) {
   const size_t rs = precision == TOPOLOW_PREC_F64_EXACT ? sizeof(double) : sizeof(float);
   int wmax = tile_max_warps(precision == TOPOLOW_PREC_F64_EXACT ? 1 : 0, P);
   if (max_warps > 0) wmax = std::min(wmax, max_warps);
   while (wmax > 1 && tile_smem_bytes(D, wmax, rs, P) > 224 * 1024) --wmax;
-  const int ctas = std::max(1, max_ctas > 0 ? std::min(max_ctas, sms) : sms);
-  const int T = g.T;
+  return wmax;
+}
+
+// (G, m, W, S) of a kind-0 job over T tiles.
+void shape_full(Geometry& g, int T, int wmax, int ctas) {
   if (T <= 2 * wmax || ctas == 1) {
     // one CTA: no inter-CTA barrier at all
     g.G = 1;
@@ -128,6 +127,30 @@ Geometry choose_geometry(int64_t n, int D, int precision, int sms, int max_ctas,
     }
   }
   g.S = 2 * g.G * g.m;
+}
+// (G, m, W, S) of a kind-1 job: S/2 = G*m super-blocks of W tiles on each side.
+void shape_bipartite(Geometry& g, int count, int wmax, int ctas) {
+  g.G = std::max(1, std::min(ctas, count));
+  g.m = 1;
+  g.W = (count + g.G - 1) / g.G;
+  if (g.W > wmax) {
+    g.m = (count + g.G * wmax - 1) / (g.G * wmax);
+    g.W = (count + g.G * g.m - 1) / (g.G * g.m);
+  }
+  g.S = 2 * g.G * g.m;
+}
+
+Geometry choose_geometry(int64_t n, int D, int precision, int sms, int max_ctas, uint64_t seed, int max_warps = 0,
+                         int P = 2, int n_shards = 0) {
+  Geometry g{};
+  g.n = (int)n; g.D = D; g.seed = seed; g.P = P;
+  const int kTile = 32 * P;
+  g.T = (int)((n + kTile - 1) / kTile);
+  if (n_shards > 1) g.T = ((g.T + 2 * n_shards - 1) / (2 * n_shards)) * (2 * n_shards);   // equal mega-blocks
+  const int wmax = geometry_wmax(D, precision, P, max_warps);
+  const int ctas = std::max(1, max_ctas > 0 ? std::min(max_ctas, sms) : sms);
+  shape_full(g, g.T, wmax, ctas);
+  g.kind = 0; g.t0 = 0; g.tc = g.T; g.y0 = 0; g.yc = 0; g.do_end = 1;
   return g;
 }
 
@@ -137,7 +160,7 @@ int64_t enumerate_schedule(const Geometry& g, const std::vector<int32_t>& pos, i
   bool overflow = false;
   const int kP = g.P, kTile = 32 * g.P;
   auto emit = [&](int slot_a, int slot_b) {
-    const int pa = pos[slot_a], pb = pos[slot_b];
+    const int pa = pos[slot_a], pb = pos[slot_b];   // -1: phantom slot (padding of the last / extra tiles)
     if (pa < 0 || pb < 0) return;
     if (np >= cap_pairs) { overflow = true; return; }
     out[2 * np] = pa; out[2 * np + 1] = pb; ++np;
@@ -166,18 +189,18 @@ int64_t enumerate_schedule(const Geometry& g, const std::vector<int32_t>& pos, i
     }
   };
   const int W = g.W;
-  for (int r = 0; r < g.S - 1; ++r) {
+  for (int r = 0; r < cross_rounds(g); ++r) {
     const int rr = round_at(g, iter, r);
     for (int q = 0; q < g.S / 2; ++q) {
       int X, Y;
-      circle_pair(g.S, rr, q, X, Y);
+      cross_task(g, rr, q, X, Y);
       const int rot = cross_rot(g, iter, X, Y);
       for (int v = 0; v < W; ++v)
         for (int w = 0; w < W; ++w)
-          ring(tile_at(g, iter, X * W + w), tile_at(g, iter, Y * W + (w + v + rot) % W));
+          ring(tile_at(g, iter, X * W + w, 0), tile_at(g, iter, Y * W + (w + v + rot) % W, g.kind));
     }
   }
-  for (int q = 0; q < g.S / 2; ++q) {
+  for (int q = 0; q < (g.kind == 0 ? g.S / 2 : 0); ++q) {
     const int Mt = diag_subrounds(W), rot = diag_rot(g, iter, q);
     for (int u = 0; u < Mt; ++u)
       for (int w = 0; w < W; ++w) {
@@ -262,8 +285,11 @@ std::unique_ptr<topolow_plan> make_plan(const topolow_problem& pb, const topolow
   pl->n = pb.n; pl->E = pb.n_edges; pl->D = pb.ndim;
   pl->prm = FitParams{pr.n_iter, pr.k0, pr.cooling_rate, pr.c_repulsion, pr.relative_epsilon,
                       pr.convergence_window, pr.convergence_check_freq};
-  pl->geo = choose_geometry(pb.n, pb.ndim, pr.precision, sms, pr.max_ctas, pr.seed, pr.max_warps,
-                            choose_tile_points(pb.n, pr.tile_points));
+  pl->n_shards = pr.n_shards > 1 ? pr.n_shards : 0;
+  const int P = (pl->n_shards && pr.tile_points == 0) ? 1 : choose_tile_points(pb.n, pr.tile_points);
+  pl->geo = choose_geometry(pb.n, pb.ndim, pr.precision, sms, pr.max_ctas, pr.seed, pr.max_warps, P, pl->n_shards);
+  pl->wmax = geometry_wmax(pb.ndim, pr.precision, P, pr.max_warps);
+  pl->ctas = std::max(1, pr.max_ctas > 0 ? std::min(pr.max_ctas, sms) : sms);
   const Geometry& g = pl->geo;
   if (g.G > 1) {
     const int fit = pr.precision == TOPOLOW_PREC_F64_EXACT ? max_coresident_f64(g.D, g.W, g.P) : max_coresident_f32(g.D, g.W, g.P);
@@ -285,8 +311,8 @@ std::unique_ptr<topolow_plan> make_plan(const topolow_problem& pb, const topolow
   FitState st; state_init(st, pl->prm);
   TL_CUDA(cudaMalloc(&pl->state, sizeof(FitState)));
   TL_CUDA(cudaMemcpy(pl->state, &st, sizeof st, cudaMemcpyHostToDevice));
-  TL_CUDA(cudaMalloc(&pl->partials, sizeof(double) * 4 * g.G));
-  TL_CUDA(cudaMemset(pl->partials, 0, sizeof(double) * 4 * g.G));
+  TL_CUDA(cudaMalloc(&pl->partials, sizeof(double) * 4 * 1024));   // any job geometry: G <= SM count
+  TL_CUDA(cudaMemset(pl->partials, 0, sizeof(double) * 4 * 1024));
   TL_CUDA(cudaMalloc(&pl->barrier, 2 * sizeof(unsigned)));
   TL_CUDA(cudaMemset(pl->barrier, 0, 2 * sizeof(unsigned)));
   const int ntr = std::max(pr.n_iter, 1);
@@ -307,19 +333,35 @@ std::unique_ptr<topolow_plan> make_plan(const topolow_problem& pb, const topolow
   return pl;
 }
 
-void launch_chunk(topolow_plan& pl, int n_iters, cudaStream_t stream) {
+void launch_geo(topolow_plan& pl, const Geometry& geo, int n_iters, cudaStream_t stream) {
   const unsigned long long ppi = (unsigned long long)pl.n * (unsigned long long)(pl.n - 1) / 2ull;
   if (pl.precision == TOPOLOW_PREC_F64_EXACT) {
     TileDev<double> dv{(double*)pl.pos, (double*)pl.best, (const double*)pl.dp1, pl.edges, pl.bucket_off, pl.state,
                        pl.partials, pl.barrier, pl.trace, (long long)pl.E, ppi};
-    launch_tile_f64(dv, pl.geo, pl.prm, n_iters, pl.d_flag, stream);
-    pl.launches++;
+    launch_tile_f64(dv, geo, pl.prm, n_iters, pl.d_flag, stream);
   } else {
     TileDev<float> dv{(float*)pl.pos, (float*)pl.best, (const float*)pl.dp1, pl.edges, pl.bucket_off, pl.state,
                       pl.partials, pl.barrier, pl.trace, (long long)pl.E, ppi};
-    launch_tile_f32(dv, pl.geo, pl.prm, n_iters, pl.d_flag, stream);
-    pl.launches++;
+    launch_tile_f32(dv, geo, pl.prm, n_iters, pl.d_flag, stream);
   }
+  pl.launches++;
+}
+void launch_chunk(topolow_plan& pl, int n_iters, cudaStream_t stream) { launch_geo(pl, pl.geo, n_iters, stream); }
+
+// Geometry of one job of a sharded iteration (see topolow_plan_run_job).
+Geometry job_geometry(const topolow_plan& pl, int kind, int t0, int tc, int y0, int yc) {
+  Geometry g = pl.geo;
+  g.kind = kind; g.t0 = t0; g.tc = tc; g.y0 = y0; g.yc = yc; g.do_end = 0;
+  if (kind == 0) shape_full(g, tc, pl.wmax, pl.ctas);
+  else if (kind == 1) shape_bipartite(g, std::max(tc, yc), pl.wmax, pl.ctas);
+  else g.do_end = 1;   // kind 2: the default geometry's CTAs run the end phase
+  return g;
+}
+void check_job(const topolow_plan& pl, int kind, int t0, int tc, int y0, int yc) {
+  const int T = pl.geo.T;
+  if (kind < 0 || kind > 1 || t0 < 0 || tc < 1 || t0 + tc > T) throw BadArg("job tile range out of bounds");
+  if (kind == 1 && (y0 < 0 || yc < 1 || y0 + yc > T || !(y0 >= t0 + tc || t0 >= y0 + yc)))
+    throw BadArg("bipartite job needs two disjoint tile ranges");
 }
 
 // Runs up to n_iters iterations; returns device milliseconds.
@@ -646,6 +688,56 @@ int topolow_plan_info(const topolow_plan* plan, int64_t* out, int32_t cap) {
                          plan->chunk_iters, plan->launches, 32 * g.P};
   for (int i = 0; i < cap && i < 11; ++i) out[i] = v[i];
   return TOPOLOW_OK;
+}
+
+// ---- sharded iteration: one job at a time ------------------------------------------------
+int topolow_plan_run_job(topolow_plan* plan, int32_t kind, int32_t t0, int32_t tc, int32_t y0, int32_t yc, void* stream) {
+  if (!plan) return TOPOLOW_ERR_BAD_ARG;
+  try {
+    TL_CUDA(cudaSetDevice(plan->device));
+    check_job(*plan, kind, t0, tc, y0, yc);
+    launch_geo(*plan, job_geometry(*plan, kind, t0, tc, y0, yc), 1, stream ? (cudaStream_t)stream : plan->stream);
+    return TOPOLOW_OK;
+  } catch (const CudaError&) {
+    cudaGetLastError();
+    return TOPOLOW_ERR_CUDA;
+  } catch (const std::exception&) {
+    return TOPOLOW_ERR_BAD_ARG;
+  }
+}
+
+int topolow_plan_end_iteration(topolow_plan* plan, void* stream) {
+  if (!plan) return TOPOLOW_ERR_BAD_ARG;
+  try {
+    TL_CUDA(cudaSetDevice(plan->device));
+    launch_geo(*plan, job_geometry(*plan, 2, 0, 0, 0, 0), 1, stream ? (cudaStream_t)stream : plan->stream);
+    return TOPOLOW_OK;
+  } catch (const CudaError&) {
+    cudaGetLastError();
+    return TOPOLOW_ERR_CUDA;
+  }
+}
+
+int topolow_plan_layout(const topolow_plan* plan, int64_t* out, int32_t cap) {
+  if (!plan || !out) return TOPOLOW_ERR_BAD_ARG;
+  const Geometry& g = plan->geo;
+  const int64_t v[6] = {g.T, 32 * g.P, g.D, plan->precision == TOPOLOW_PREC_F64_EXACT ? 8 : 4, plan->n_shards,
+                        (int64_t)g.T * 32 * g.P};
+  for (int i = 0; i < cap && i < 6; ++i) out[i] = v[i];
+  return TOPOLOW_OK;
+}
+
+void* topolow_plan_positions(topolow_plan* plan) { return plan ? plan->pos : nullptr; }
+
+int64_t topolow_plan_enumerate_job(const topolow_plan* plan, int32_t iter, int32_t kind, int32_t t0, int32_t tc,
+                                   int32_t y0, int32_t yc, int32_t* out, int64_t cap_pairs) {
+  if (!plan || !out) return -1;
+  try {
+    check_job(*plan, kind, t0, tc, y0, yc);
+    return enumerate_schedule(job_geometry(*plan, kind, t0, tc, y0, yc), plan->point_of_slot, iter, out, cap_pairs);
+  } catch (const std::exception&) {
+    return -1;
+  }
 }
 
 void topolow_plan_destroy(topolow_plan* plan) { delete plan; }

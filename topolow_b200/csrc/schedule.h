@@ -39,6 +39,12 @@ struct Geometry {
   int S;        // super-blocks = 2*G*m
   int D;        // dimensions
   int P;        // points of a tile held by one lane: tile = 32 * P points (1, 2 or 3)
+  // The job this launch executes (a whole fit is kind 0 over all tiles with do_end = 1):
+  int kind;     // 0: every pair among the tiles [t0, t0 + tc);  1: every pair between [t0, t0 + tc) and [y0, y0 + yc);
+                // 2: no pair updates (end-of-iteration phase only)
+  int t0, tc;   // first tile / number of tiles of the (X) range
+  int y0, yc;   // the Y range of a kind-1 job
+  int do_end;   // run the end-of-iteration phase (cooling, MAE, controller) after the pair updates
   uint64_t seed;
 };
 
@@ -66,22 +72,33 @@ TL_HD uint64_t iter_key(const Geometry& g, int iter, uint32_t salt) {
   return mix64(g.seed ^ mix64(((uint64_t)(uint32_t)iter << 32) | salt));
 }
 
-// Tile held by tile-slot `slot` (super-block slot/W, position slot%W) in this iteration, or -1.
-TL_HD int tile_at(const Geometry& g, int iter, int slot) {
-  const uint32_t t = feistel_perm((uint32_t)slot, (uint32_t)(g.S * g.W), iter_key(g, iter, 1));
-  return (int)t < g.T ? (int)t : -1;
-}
-
-// The r-th cross round executed in this iteration (a permutation of [0, S-1)).
-TL_HD int round_at(const Geometry& g, int iter, int r) {
-  return (int)feistel_perm((uint32_t)r, (uint32_t)(g.S - 1), iter_key(g, iter, 2));
-}
-
 // Circle method: the q-th pair (q in [0, S/2)) of round rr in a tournament of S (even) teams.
 TL_HD void circle_pair(int S, int rr, int q, int& x, int& y) {
   const int M = S - 1;
   if (q == 0) { x = M; y = rr; }
   else { x = (rr + q) % M; y = (rr - q + M) % M; }
+}
+
+// Tile held by tile-slot `slot` (super-block slot/W, position slot%W) in this iteration, or -1.
+// kind 0: S*W slots over the tc tiles of the job.  kind 1: S/2 super-blocks per side, (S/2)*W slots
+// over the tc (side 0) or yc (side 1) tiles of that side.
+TL_HD int tile_at(const Geometry& g, int iter, int slot, int side = 0) {
+  const uint32_t slots = (uint32_t)((g.kind == 0 ? g.S : g.S / 2) * g.W);
+  const uint32_t t = feistel_perm((uint32_t)slot, slots, iter_key(g, iter, side == 0 ? 1u : 7u) ^ (uint64_t)(uint32_t)(side ? g.y0 : g.t0));
+  const int count = side ? g.yc : g.tc, base = side ? g.y0 : g.t0;
+  return (int)t < count ? base + (int)t : -1;
+}
+
+// Number of cross rounds of the job and the r-th one executed in this iteration (a permutation).
+TL_HD int cross_rounds(const Geometry& g) { return g.kind == 0 ? g.S - 1 : (g.kind == 1 ? g.S / 2 : 0); }
+TL_HD int round_at(const Geometry& g, int iter, int r) {
+  return (int)feistel_perm((uint32_t)r, (uint32_t)cross_rounds(g), iter_key(g, iter, 2) ^ (uint64_t)(uint32_t)(g.t0 * 131 + g.y0));
+}
+// The q-th CTA task of cross round rr: super-block X (side 0) against super-block Y (side 0 for a
+// kind-0 job: circle method; side 1 for a kind-1 job: Latin square).
+TL_HD void cross_task(const Geometry& g, int rr, int q, int& x, int& y) {
+  if (g.kind == 0) circle_pair(g.S, rr, q, x, y);
+  else { x = q; y = (q + rr) % (g.S / 2); }
 }
 
 struct RingParams { int s0, g, ginv; };

@@ -670,12 +670,12 @@ tile_kernel(TileDev<typename M::real> dv, Geometry geo, FitParams prm, int n_ite
     const typename M::Ctx ctx = M::make_ctx(st.k, prm.c_repulsion);
 
     // ---------------- cross rounds ----------------
-    for (int r = 0; r < geo.S - 1; ++r) {
+    for (int r = 0; r < cross_rounds(geo); ++r) {
       const int rr = round_at(geo, iter, r);
       for (int tt = 0; tt < geo.m; ++tt) {
         int X, Y;
-        circle_pair(geo.S, rr, cta * geo.m + tt, X, Y);
-        const int tX = tile_at(geo, iter, X * W + warp), tY = tile_at(geo, iter, Y * W + warp);
+        cross_task(geo, rr, cta * geo.m + tt, X, Y);
+        const int tX = tile_at(geo, iter, X * W + warp, 0), tY = tile_at(geo, iter, Y * W + warp, geo.kind);
         if (lane == 0) { s_tid[warp] = tX; s_tid[W + warp] = tY; s_flag[warp] = 0; }
         load_tile<D, real>(s_tiles + (size_t)warp * TS, dv.pos, dv.dp1, tX, lane);
         load_tile<D, real>(s_tiles + (size_t)(W + warp) * TS, dv.pos, dv.dp1, tY, lane);
@@ -708,8 +708,8 @@ tile_kernel(TileDev<typename M::real> dv, Geometry geo, FitParams prm, int n_ite
       gang_barrier(dv.barrier, geo.G, gen);
     }
 
-    // ---------------- diagonal round ----------------
-    for (int tt = 0; tt < geo.m; ++tt) {
+    // ---------------- diagonal round (kind 0 only) ----------------
+    for (int tt = 0; tt < (geo.kind == 0 ? geo.m : 0); ++tt) {
       const int q = cta * geo.m + tt;
       const int tX = tile_at(geo, iter, (2 * q) * W + warp), tY = tile_at(geo, iter, (2 * q + 1) * W + warp);
       if (lane == 0) { s_tid[warp] = tX; s_tid[W + warp] = tY; }
@@ -750,6 +750,8 @@ tile_kernel(TileDev<typename M::real> dv, Geometry geo, FitParams prm, int n_ite
       __syncwarp();
     }
     gang_barrier(dv.barrier, geo.G, gen);
+
+    if (!geo.do_end) continue;   // a job of a sharded iteration: the end phase is a launch of its own
 
     // ---------------- end of iteration: cooling, MAE, controller, finite check ----------------
     const bool check = is_check_iter(iter, prm);
