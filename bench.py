@@ -303,6 +303,9 @@ def main():
     ap.add_argument("--precision", default="f32", choices=["f32", "f64"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--multi", default="sharded", choices=["sharded", "replicas"],
+                    help="cfg4 with --gpus > 1: one map sharded over the GPUs (exact, position all-gather between rounds) "
+                         "or one independent replica per GPU")
     ap.add_argument("--samples", type=int, default=32, help="cfg5: parameter samples per GPU per step (x 4 folds)")
     ap.add_argument("--fit-iters", type=int, default=250, help="cfg5: mapping_max_iter of every fit (R/core.R:945)")
     args = ap.parse_args()
@@ -341,36 +344,66 @@ def main():
     total_iters = args.steps + args.warmup
     nw = total_iters + 1  # convergence window > n_iter: no early stop
 
+    sharded = world > 1 and args.multi == "sharded"
+    hp = (HYPER["k0"], HYPER["cooling_rate"], HYPER["c_repulsion"], HYPER["relative_epsilon"])
     # ---- device-resident leg -------------------------------------------------------------------
-    plan = _lib.Plan(*fa, total_iters, HYPER["k0"], HYPER["cooling_rate"], HYPER["c_repulsion"],
-                     HYPER["relative_epsilon"], nw, HYPER["convergence_check_freq"], precision=prec, seed=0, device=local)
-    info0 = plan.info()
-    plan.run(max(args.warmup, 3) if args.warmup else 0)
-    launches_before = plan.info()["launches"]
-    barrier()
-    with ClockSampler(local) as clk:
-        t0 = time.perf_counter()
-        ms = plan.run(args.steps)
+    if sharded:
+        from topolow_b200.sharded import ShardedMap
+        sm = ShardedMap(*fa, total_iters, *hp, nw, HYPER["convergence_check_freq"], world_size=world, rank=rank,
+                        device=local, precision=prec, seed=0)
+        info0 = dict(sm.plan.info(), mega_blocks=sm.M, tiles_per_mega_block=sm.Tm)
+        sm.step(max(args.warmup, 3) if args.warmup else 0)
+        launches_before = sm.plan.info()["launches"]
         barrier()
-        wall_ms = (time.perf_counter() - t0) * 1e3
-    info1 = plan.info()
-    res = plan.result()
-    plan.close()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with ClockSampler(local) as clk:
+            t0 = time.perf_counter()
+            ev0.record()                      # jobs and NCCL exchanges all run on torch's current stream
+            sm.step(args.steps)
+            ev1.record()
+            barrier()
+            wall_ms = (time.perf_counter() - t0) * 1e3
+        ms = ev0.elapsed_time(ev1)
+        info1 = sm.plan.info()
+        res = sm.result()
+        sm.close()
+    else:
+        plan = _lib.Plan(*fa, total_iters, *hp, nw, HYPER["convergence_check_freq"], precision=prec, seed=0, device=local)
+        info0 = plan.info()
+        plan.run(max(args.warmup, 3) if args.warmup else 0)
+        launches_before = plan.info()["launches"]
+        barrier()
+        with ClockSampler(local) as clk:
+            t0 = time.perf_counter()
+            ms = plan.run(args.steps)
+            barrier()
+            wall_ms = (time.perf_counter() - t0) * 1e3
+        info1 = plan.info()
+        res = plan.result()
+        plan.close()
     launches = info1["launches"] - launches_before
     t = torch.tensor([ms, wall_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max, wall_max = float(t[0]), float(t[1])
-    # N > 1 (this round): every rank runs an independent replica of the workload
-    value = world * pairs * args.steps / (ms_max * 1e-3)
+    # sharded: ONE map, every unordered pair once per iteration whatever the rank count (strong scaling);
+    # replicas: `world` independent maps (weak scaling)
+    value = (1 if sharded else world) * pairs * args.steps / (ms_max * 1e-3)
 
-    # ---- end-to-end leg: host buffers through the C ABI ----------------------------------------
+    # ---- end-to-end leg: host buffers through the public call -----------------------------------
     e2e = None
     if not args.no_e2e:
         barrier()
         t0 = time.perf_counter()
-        r2 = _lib.fit(*fa, args.steps, HYPER["k0"], HYPER["cooling_rate"], HYPER["c_repulsion"], HYPER["relative_epsilon"],
-                      args.steps + 1, HYPER["convergence_check_freq"], precision=prec, seed=0, device=local)
+        if sharded:
+            sm = ShardedMap(*fa, args.steps, *hp, args.steps + 1, HYPER["convergence_check_freq"], world_size=world,
+                            rank=rank, device=local, precision=prec, seed=0)
+            sm.step(args.steps)
+            r2 = sm.result()
+            sm.close()
+        else:
+            r2 = _lib.fit(*fa, args.steps, *hp, args.steps + 1, HYPER["convergence_check_freq"], precision=prec, seed=0,
+                          device=local)
         barrier()
         wall = time.perf_counter() - t0
         tt = torch.tensor([wall], dtype=torch.float64, device="cuda")
@@ -378,9 +411,9 @@ def main():
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         h2d = n * d * 8 + n * 4 + E * (4 + 4 + 8 + 4)
         d2h = n * d * 8
-        e2e = {"value": world * pairs * r2["iterations_run"] / float(tt[0]), "unit": "pair-updates/s",
+        e2e = {"value": (1 if sharded else world) * pairs * r2["iterations_run"] / float(tt[0]), "unit": "pair-updates/s",
                "h2d_bytes_per_step": h2d // max(args.steps, 1), "d2h_bytes_per_step": d2h // max(args.steps, 1),
-               "note": "one topolow_fit() call of K iterations on pageable host buffers: upload, bucket build, "
+               "note": "one fit of K iterations from pageable host buffers (per rank when sharded): upload, bucket build, "
                        "K iterations, download; bytes are the call's totals divided by K",
                "wall_s": float(tt[0]), "kernel_ms": r2["device_ms"]}
 
@@ -393,8 +426,8 @@ def main():
     peaks, peak_src = measured_peaks()
     ffma_peak = _lib.microbench(0, local)      # flop/s, measured now on this GPU
     flop = flop_per_iter(n, d, E)
-    kernel_s = ms_max * 1e-3 / args.steps        # one launch covers iters_per_launch iterations
-    ach = flop / kernel_s
+    kernel_s = ms_max * 1e-3 / args.steps        # device time of one iteration (all of it is tile_kernel launches)
+    ach = flop / kernel_s / (world if sharded else 1)   # per GPU
     roofline = {"bound": "fp32", "kernel": "tile_kernel<D,%s>" % ("FastF32" if prec == 0 else "ExactF64"),
                 "achieved": ach / 1e12, "peak": ffma_peak / 1e12, "unit": "TFLOP/s", "frac": ach / ffma_peak,
                 "peak_source": "topolow_microbench FFMA, measured live on this GPU (not in MEASURED_PEAKS.json)",
@@ -419,11 +452,14 @@ def main():
     line = {
         "metric": "pair-updates/s", "value": value, "unit": "pair-updates/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
-        "scaling": "weak" if world > 1 else "strong", "vs_baseline": None,
+        "scaling": "weak" if (world > 1 and not sharded) else "strong", "vs_baseline": None,
         "dtype": "f32" if prec == 0 else "f64", "data": "synthetic",
         "config": {"workload": f"{args.workload}: synthetic low-rank, {n} points, {missing:.0%} missing, ndim={d}",
                    "n_points": n, "ndim": d, "n_edges": E, "pairs_per_iteration": pairs, "schedule": info0,
-                   "parallelism": "1 GPU" if world == 1 else f"{world} independent replicas (no collective)",
+                   "parallelism": "1 GPU" if world == 1 else (
+                       f"one map row-sharded over {world} GPUs: tournament over {2 * world} mega-blocks, NCCL all-gather of the "
+                       "changed position blocks after each of its rounds, exact sequential semantics" if sharded
+                       else f"{world} independent replicas (no collective)"),
                    "l2": "edge stream (%.0f MB/iteration) exceeds L2; the %.1f MB position array is the resident working set"
                          % (E * 16 / 1e6, n * d * 4 / 1e6),
                    "early_stop": "disabled (convergence_counter = n_iter + 1)"},
