@@ -52,6 +52,15 @@ def test_replay_explicit_order_and_early_convergence():
     assert np.array_equal(g2["positions"], w2["positions"])
 
 
+def test_replay_positions_in_global_memory_path():
+    # n * ndim * 8 bytes exceeds the shared-memory budget of the replay kernel: positions stay in L2
+    args = small_problem(900, 24, 0.02, 77)
+    want = cpu_oracle.optimize_layout_exact(*args, 3, 5.0, 0.01, 0.02, seed=11)
+    got = _lib.fit(*args, 3, 5.0, 0.01, 0.02, mode=_lib.MODE_REPLAY, seed=11)
+    assert np.array_equal(got["positions"], want["positions"])
+    assert got["pair_updates"] == 3 * 900 * 899 // 2
+
+
 # ------------------------------------------------------------------ coloured mode, exact ------
 def _exact_case(args, iters, hp, seed, max_ctas=0, tile_points=0):
     plan = _lib.Plan(*args, iters, *hp, precision=_lib.PREC_F64_EXACT, seed=seed, max_ctas=max_ctas,

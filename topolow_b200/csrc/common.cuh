@@ -28,6 +28,47 @@ inline void cuda_check(cudaError_t e, const char* what, const char* file, int li
 }
 #define TL_CUDA(x) ::tl::cuda_check((x), #x, __FILE__, __LINE__)
 
+// Owning handles: everything a host routine allocates is released on every exit path.
+template <class T>
+struct DeviceBuf {
+  T* p = nullptr;
+  DeviceBuf() {}
+  explicit DeviceBuf(size_t count) { TL_CUDA(cudaMalloc(&p, (count ? count : 1) * sizeof(T))); }
+  DeviceBuf(const DeviceBuf&) = delete;
+  DeviceBuf& operator=(const DeviceBuf&) = delete;
+  DeviceBuf(DeviceBuf&& o) noexcept : p(o.p) { o.p = nullptr; }
+  ~DeviceBuf() { if (p) cudaFree(p); }
+  T* release() { T* r = p; p = nullptr; return r; }
+  operator T*() const { return p; }
+};
+template <class T>
+struct PinnedBuf {
+  T* p = nullptr;
+  PinnedBuf() {}
+  explicit PinnedBuf(size_t count, unsigned flags = cudaHostAllocDefault) {
+    TL_CUDA(cudaHostAlloc((void**)&p, (count ? count : 1) * sizeof(T), flags));
+  }
+  PinnedBuf(const PinnedBuf&) = delete;
+  PinnedBuf& operator=(const PinnedBuf&) = delete;
+  PinnedBuf(PinnedBuf&& o) noexcept : p(o.p) { o.p = nullptr; }
+  ~PinnedBuf() { if (p) cudaFreeHost(p); }
+  operator T*() const { return p; }
+};
+struct StreamGuard {
+  cudaStream_t s = nullptr;
+  StreamGuard() { TL_CUDA(cudaStreamCreate(&s)); }
+  StreamGuard(const StreamGuard&) = delete;
+  ~StreamGuard() { if (s) cudaStreamDestroy(s); }
+  operator cudaStream_t() const { return s; }
+};
+struct EventGuard {
+  cudaEvent_t e = nullptr;
+  explicit EventGuard(unsigned flags = cudaEventDefault) { TL_CUDA(cudaEventCreateWithFlags(&e, flags)); }
+  EventGuard(const EventGuard&) = delete;
+  ~EventGuard() { if (e) cudaEventDestroy(e); }
+  operator cudaEvent_t() const { return e; }
+};
+
 // ---------------------------------------------------------------------------
 // Convergence controller.  One instance per fit lives in device memory and is
 // advanced by one thread; the host reads it back between launches.

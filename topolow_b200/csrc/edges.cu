@@ -84,13 +84,6 @@ __global__ void bucket_sort_kernel(const EdgeRec* __restrict__ in, EdgeRec* __re
   }
 }
 
-template <class T>
-T* dalloc(size_t count) {
-  T* p = nullptr;
-  TL_CUDA(cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T)));
-  return p;
-}
-
 }  // namespace
 
 void build_buckets(const topolow_problem& pb, const std::vector<int32_t>& slot_of_point, int T, int tile_points,
@@ -98,19 +91,14 @@ void build_buckets(const topolow_problem& pb, const std::vector<int32_t>& slot_o
                    EdgeRec** edges_out, uint32_t** bucket_off_out) {
   const long long E = pb.n_edges;
   const size_t nkeys = (size_t)T * T;
-  int32_t *d_ei = dalloc<int32_t>(E), *d_ej = dalloc<int32_t>(E), *d_thr = dalloc<int32_t>(E);
-  int32_t* d_slot = dalloc<int32_t>(slot_of_point.size());
-  double* d_dist = dalloc<double>(E);
-  uint32_t *d_keys = dalloc<uint32_t>(E), *d_off = dalloc<uint32_t>(nkeys + 1), *d_cur = dalloc<uint32_t>(nkeys + 1);
+  DeviceBuf<int32_t> d_ei(E), d_ej(E), d_thr(E), d_slot(slot_of_point.size());
+  DeviceBuf<double> d_dist(E);
+  DeviceBuf<uint32_t> d_keys(E), d_off(nkeys + 1), d_cur(nkeys + 1);
   const size_t nblk = (nkeys + 1 + 1023) / 1024;
-  uint32_t* d_sums = dalloc<uint32_t>(nblk);
-  int* d_bad = dalloc<int>(1);
-  EdgeRec *d_tmp = dalloc<EdgeRec>(E), *d_out = dalloc<EdgeRec>(E);
-  auto free_all = [&]() {
-    cudaFree(d_ei); cudaFree(d_ej); cudaFree(d_thr); cudaFree(d_slot); cudaFree(d_dist); cudaFree(d_keys);
-    cudaFree(d_cur); cudaFree(d_sums); cudaFree(d_bad); cudaFree(d_tmp);
-  };
-  try {
+  DeviceBuf<uint32_t> d_sums(nblk);
+  DeviceBuf<int> d_bad(1);
+  DeviceBuf<EdgeRec> d_tmp(E), d_out(E);
+  {
     TL_CUDA(cudaMemcpyAsync(d_slot, slot_of_point.data(), slot_of_point.size() * 4, cudaMemcpyHostToDevice, stream));
     if (E > 0) {
       TL_CUDA(cudaMemcpyAsync(d_ei, pb.edge_i, E * 4, cudaMemcpyHostToDevice, stream));
@@ -146,13 +134,9 @@ void build_buckets(const topolow_problem& pb, const std::vector<int32_t>& slot_o
       TL_CUDA(cudaGetLastError());
     }
     TL_CUDA(cudaStreamSynchronize(stream));
-  } catch (...) {
-    free_all(); cudaFree(d_off); cudaFree(d_out);
-    throw;
   }
-  free_all();
-  *edges_out = d_out;
-  *bucket_off_out = d_off;
+  *edges_out = d_out.release();
+  *bucket_off_out = d_off.release();
 }
 
 }  // namespace tl

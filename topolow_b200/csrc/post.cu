@@ -83,21 +83,18 @@ std::vector<double> to_row_major(const double* cm, int64_t n, int dim) {
 extern "C" int topolow_est_distances(const double* positions, int64_t n, int32_t ndim, double* est, int32_t device) {
   using namespace tl;
   if (!positions || !est || n < 1 || ndim < 1 || ndim > 1024) return TOPOLOW_ERR_BAD_ARG;
-  double *d_pos = nullptr, *d_out = nullptr;
   try {
     TL_CUDA(cudaSetDevice(device));
     const std::vector<double> rm = to_row_major(positions, n, ndim);
-    TL_CUDA(cudaMalloc(&d_pos, rm.size() * sizeof(double)));
-    TL_CUDA(cudaMalloc(&d_out, (size_t)n * n * sizeof(double)));
+    DeviceBuf<double> d_pos(rm.size()), d_out((size_t)n * n);
     TL_CUDA(cudaMemcpy(d_pos, rm.data(), rm.size() * sizeof(double), cudaMemcpyHostToDevice));
     const unsigned nb = (unsigned)((n + 31) / 32);
     dist_kernel<<<dim3(nb, nb), 256, 2 * 32 * ndim * sizeof(double)>>>(d_pos, n, ndim, d_out);
     TL_CUDA(cudaGetLastError());
     TL_CUDA(cudaMemcpy(est, d_out, (size_t)n * n * sizeof(double), cudaMemcpyDeviceToHost));
-    cudaFree(d_pos); cudaFree(d_out);
     return TOPOLOW_OK;
   } catch (const CudaError&) {
-    cudaFree(d_pos); cudaFree(d_out); cudaGetLastError();
+    cudaGetLastError();
     return TOPOLOW_ERR_CUDA;
   }
 }
@@ -109,20 +106,13 @@ extern "C" int topolow_holdout_errors(const double* positions, int64_t n, int32_
   if (!positions || n < 1 || ndim < 1 || n_cells < 0 || !sum_abs_out || !count_out) return TOPOLOW_ERR_BAD_ARG;
   for (int64_t e = 0; e < n_cells; ++e)
     if (cell_i[e] < 0 || cell_j[e] < 0 || cell_i[e] >= n || cell_j[e] >= n) return TOPOLOW_ERR_BAD_ARG;
-  double *d_pos = nullptr, *d_truth = nullptr, *d_ps = nullptr;
-  int32_t *d_ci = nullptr, *d_cj = nullptr;
-  unsigned long long* d_pc = nullptr;
   try {
     TL_CUDA(cudaSetDevice(device));
     const std::vector<double> rm = to_row_major(positions, n, ndim);
     const int blocks = 296;
-    const size_t nc = (size_t)std::max<int64_t>(n_cells, 1);
-    TL_CUDA(cudaMalloc(&d_pos, rm.size() * sizeof(double)));
-    TL_CUDA(cudaMalloc(&d_truth, nc * sizeof(double)));
-    TL_CUDA(cudaMalloc(&d_ci, nc * sizeof(int32_t)));
-    TL_CUDA(cudaMalloc(&d_cj, nc * sizeof(int32_t)));
-    TL_CUDA(cudaMalloc(&d_ps, blocks * sizeof(double)));
-    TL_CUDA(cudaMalloc(&d_pc, blocks * sizeof(unsigned long long)));
+    DeviceBuf<double> d_pos(rm.size()), d_truth(n_cells), d_ps(blocks);
+    DeviceBuf<int32_t> d_ci(n_cells), d_cj(n_cells);
+    DeviceBuf<unsigned long long> d_pc(blocks);
     TL_CUDA(cudaMemcpy(d_pos, rm.data(), rm.size() * sizeof(double), cudaMemcpyHostToDevice));
     if (n_cells > 0) {
       TL_CUDA(cudaMemcpy(d_truth, truth, n_cells * sizeof(double), cudaMemcpyHostToDevice));
@@ -138,10 +128,8 @@ extern "C" int topolow_holdout_errors(const double* positions, int64_t n, int32_
     double s = 0.0; unsigned long long c = 0;
     for (int b = 0; b < blocks; ++b) { s += ps[b]; c += pc[b]; }
     *sum_abs_out = s; *count_out = (int64_t)c;
-    cudaFree(d_pos); cudaFree(d_truth); cudaFree(d_ci); cudaFree(d_cj); cudaFree(d_ps); cudaFree(d_pc);
     return TOPOLOW_OK;
   } catch (const CudaError&) {
-    cudaFree(d_pos); cudaFree(d_truth); cudaFree(d_ci); cudaFree(d_cj); cudaFree(d_ps); cudaFree(d_pc);
     cudaGetLastError();
     return TOPOLOW_ERR_CUDA;
   }

@@ -193,13 +193,6 @@ replay_kernel(ReplayDev dv, FitParams prm, const PairRec* __restrict__ pairs,
   }
 }
 
-template <class T>
-T* dev_alloc(size_t count) {
-  T* p = nullptr;
-  TL_CUDA(cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T)));
-  return p;
-}
-
 }  // namespace
 
 int replay_max_n() { return 8192; }
@@ -231,14 +224,10 @@ void run_replay(const topolow_problem& pb, const topolow_params& pr, topolow_res
 
   ReplayDev dv{};
   dv.n = n; dv.dim = dim; dv.n_edges = (int)E;
-  double* d_pos = dev_alloc<double>((size_t)n * dim);
-  double* d_best = dev_alloc<double>((size_t)n * dim);
-  double* d_dp1 = dev_alloc<double>(n);
-  int* d_ei = dev_alloc<int>(E); int* d_ej = dev_alloc<int>(E);
-  double* d_et = dev_alloc<double>(E); int* d_ety = dev_alloc<int>(E);
-  double* d_terms = dev_alloc<double>(E); int* d_contrib = dev_alloc<int>(E);
-  FitState* d_state = dev_alloc<FitState>(1);
-  double* d_trace = res.trace_mae ? dev_alloc<double>(pr.n_iter) : nullptr;
+  DeviceBuf<double> d_pos((size_t)n * dim), d_best((size_t)n * dim), d_dp1(n), d_et(E), d_terms(E);
+  DeviceBuf<int> d_ei(E), d_ej(E), d_ety(E), d_contrib(E);
+  DeviceBuf<FitState> d_state(1);
+  DeviceBuf<double> d_trace(res.trace_mae ? pr.n_iter : 0);
   TL_CUDA(cudaMemcpy(d_pos, h_pos.data(), sizeof(double) * n * dim, cudaMemcpyHostToDevice));
   TL_CUDA(cudaMemcpy(d_best, h_pos.data(), sizeof(double) * n * dim, cudaMemcpyHostToDevice));
   TL_CUDA(cudaMemcpy(d_dp1, h_dp1.data(), sizeof(double) * n, cudaMemcpyHostToDevice));
@@ -248,7 +237,7 @@ void run_replay(const topolow_problem& pb, const topolow_params& pr, topolow_res
     TL_CUDA(cudaMemcpy(d_et, pb.edge_dist, sizeof(double) * E, cudaMemcpyHostToDevice));
     TL_CUDA(cudaMemcpy(d_ety, pb.edge_thresh, sizeof(int) * E, cudaMemcpyHostToDevice));
   }
-  if (d_trace) {
+  if (res.trace_mae) {
     std::vector<double> nanv(pr.n_iter, NAN);
     TL_CUDA(cudaMemcpy(d_trace, nanv.data(), sizeof(double) * pr.n_iter, cudaMemcpyHostToDevice));
   }
@@ -256,7 +245,7 @@ void run_replay(const topolow_problem& pb, const topolow_params& pr, topolow_res
   TL_CUDA(cudaMemcpy(d_state, &h_state, sizeof h_state, cudaMemcpyHostToDevice));
   dv.pos = d_pos; dv.best_pos = d_best; dv.dp1 = d_dp1;
   dv.ei = d_ei; dv.ej = d_ej; dv.et = d_et; dv.ety = d_ety; dv.terms = d_terms; dv.contrib = d_contrib;
-  dv.state = d_state; dv.trace = d_trace;
+  dv.state = d_state; dv.trace = res.trace_mae ? (double*)d_trace : nullptr;
 
   // ---- launch geometry ----------------------------------------------------
   const size_t smem_need = sizeof(double) * (size_t)n * dim;
@@ -272,24 +261,20 @@ void run_replay(const topolow_problem& pb, const topolow_params& pr, topolow_res
   const int64_t ppi = pr.pair_order ? pr.pairs_per_iter : P;
   const size_t cap_pairs = (size_t)chunk_iters * ppi;
   const size_t cap_lvls = (size_t)chunk_iters * (ppi + 2);
-  PairRec* h_pairs[2]; int* h_lvl[2]; int* h_itl[2];
-  PairRec* d_pairs[2]; int* d_lvl[2]; int* d_itl[2];
-  cudaEvent_t copied[2];
-  for (int b = 0; b < 2; ++b) {
-    TL_CUDA(cudaMallocHost(&h_pairs[b], sizeof(PairRec) * std::max<size_t>(cap_pairs, 1)));
-    TL_CUDA(cudaMallocHost(&h_lvl[b], sizeof(int) * cap_lvls));
-    TL_CUDA(cudaMallocHost(&h_itl[b], sizeof(int) * (chunk_iters + 1)));
-    d_pairs[b] = dev_alloc<PairRec>(cap_pairs);
-    d_lvl[b] = dev_alloc<int>(cap_lvls);
-    d_itl[b] = dev_alloc<int>(chunk_iters + 1);
-    TL_CUDA(cudaEventCreateWithFlags(&copied[b], cudaEventDisableTiming));
-  }
-  volatile int* h_flag = nullptr; int* d_flag = nullptr;
-  TL_CUDA(cudaHostAlloc((void**)&h_flag, 2 * sizeof(int), cudaHostAllocMapped));
+  PinnedBuf<PairRec> h_pairs[2] = {PinnedBuf<PairRec>(cap_pairs), PinnedBuf<PairRec>(cap_pairs)};
+  PinnedBuf<int> h_lvl[2] = {PinnedBuf<int>(cap_lvls), PinnedBuf<int>(cap_lvls)};
+  PinnedBuf<int> h_itl[2] = {PinnedBuf<int>(chunk_iters + 1), PinnedBuf<int>(chunk_iters + 1)};
+  DeviceBuf<PairRec> d_pairs[2] = {DeviceBuf<PairRec>(cap_pairs), DeviceBuf<PairRec>(cap_pairs)};
+  DeviceBuf<int> d_lvl[2] = {DeviceBuf<int>(cap_lvls), DeviceBuf<int>(cap_lvls)};
+  DeviceBuf<int> d_itl[2] = {DeviceBuf<int>(chunk_iters + 1), DeviceBuf<int>(chunk_iters + 1)};
+  EventGuard copied[2] = {EventGuard(cudaEventDisableTiming), EventGuard(cudaEventDisableTiming)};
+  PinnedBuf<int> h_flag_buf(2, cudaHostAllocMapped);
+  volatile int* h_flag = h_flag_buf.p;
+  int* d_flag = nullptr;
   h_flag[0] = 0; h_flag[1] = 0;
   TL_CUDA(cudaHostGetDevicePointer((void**)&d_flag, (void*)h_flag, 0));
-  cudaStream_t stream; TL_CUDA(cudaStreamCreate(&stream));
-  cudaEvent_t ev0, ev1; TL_CUDA(cudaEventCreate(&ev0)); TL_CUDA(cudaEventCreate(&ev1));
+  StreamGuard stream;
+  EventGuard ev0, ev1;
   TL_CUDA(cudaEventRecord(ev0, stream));
 
   struct PairIdx { int i, j; };
@@ -384,15 +369,6 @@ void run_replay(const topolow_problem& pb, const topolow_params& pr, topolow_res
   res.fail_iter = h_state.fail_iter;
   if (res.trace_mae) TL_CUDA(cudaMemcpy(res.trace_mae, d_trace, sizeof(double) * pr.n_iter, cudaMemcpyDeviceToHost));
 
-  for (int b = 0; b < 2; ++b) {
-    cudaFreeHost(h_pairs[b]); cudaFreeHost(h_lvl[b]); cudaFreeHost(h_itl[b]);
-    cudaFree(d_pairs[b]); cudaFree(d_lvl[b]); cudaFree(d_itl[b]); cudaEventDestroy(copied[b]);
-  }
-  cudaFreeHost((void*)h_flag);
-  cudaEventDestroy(ev0); cudaEventDestroy(ev1); cudaStreamDestroy(stream);
-  cudaFree(d_pos); cudaFree(d_best); cudaFree(d_dp1);
-  cudaFree(d_ei); cudaFree(d_ej); cudaFree(d_et); cudaFree(d_ety); cudaFree(d_terms); cudaFree(d_contrib);
-  cudaFree(d_state); if (d_trace) cudaFree(d_trace);
 }
 
 }  // namespace tl

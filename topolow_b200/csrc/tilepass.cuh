@@ -232,17 +232,6 @@ struct FastF32 {
       }
     }
   }
-  // Both lanes of an intra-tile pair run this, each moving only itself.
-  template <int D>
-  static TL_D void pair_self(Point<D>& S, const Point<D>& O, const Cell<float>& cell, const Ctx& c) {
-    constexpr int H = Point<D>::H;
-    f32x2 delta[H];
-    float fS, fO;
-    force<D>(S, O, delta, cell, c, fS, fO);
-    const f32x2 nS = pk2(-fS, -fS);
-#pragma unroll
-    for (int j = 0; j < H; ++j) S.c[j] = fma2(delta[j], nS, S.c[j]);
-  }
 };
 
 // IEEE double, one rounding per reference operation, no FMA contraction: bit-comparable with
@@ -319,18 +308,6 @@ struct ExactF64 {
       const int q = kSum ? (W_ - p + kP) % kP : (p + W_) % kP;
       pair<D>(A[p], B[q], cell[p], c);
     }
-  }
-  template <int D>
-  static TL_D void pair_self(Point<D>& S, const Point<D>& O, const Cell<double>& cell, const Ctx& c) {
-    if (!(S.dp1 > 0.0 && O.dp1 > 0.0)) return;
-    double delta[D];
-#pragma unroll
-    for (int k = 0; k < D; ++k) delta[k] = __dsub_rn(O.c[k], S.c[k]);
-    bool spring; double factor;
-    scalars<D>(delta, cell, c, spring, factor);
-    const double nS = norm(spring, S.dp1, c);
-#pragma unroll
-    for (int k = 0; k < D; ++k) S.c[k] = __dsub_rn(S.c[k], __ddiv_rn(__dmul_rn(delta[k], factor), nS));
   }
 };
 
