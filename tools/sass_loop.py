@@ -18,7 +18,7 @@ for name, ins in kernels.items():
     addr = {a: i for i, (a, _) in enumerate(ins)}
     loops = []
     for i, (a, t) in enumerate(ins):
-        m = re.search(r"BRA\s+(0x[0-9a-f]+)", t)
+        m = re.search(r"BRA(?:\.U)?\s+(?:!?U?P\d+,\s*)?(0x[0-9a-f]+)", t)
         if m and "BRA.DIV" not in t:
             tgt = int(m.group(1), 16)
             if tgt < a and tgt in addr:

@@ -17,13 +17,16 @@
 //   during a tile x tile pass lane a holds kP A points (slots a, a+32, ..) and kP travelling B
 //   points in registers - kP*kP pair updates per ring step, kP of them independent at a time -
 //   and the B points move with warp shuffles; measured pairs of the tile pair are scattered
-//   into a per-warp kP*kP x 32 x 32 target table + 3*kP*kP 32-bit lane masks before the pass.
+//   into a per-warp kP*kP x 32 x 32 target table + 2*kP*kP 32-bit lane masks before the pass.
 #pragma once
 
 #include "tiledev.h"
 
 #ifndef TL_KP
 #error "define TL_KP (points per lane: 1, 2 or 3) before including tilepass.cuh"
+#endif
+#ifndef TL_RING_UNROLL
+#define TL_RING_UNROLL 2   // ring steps per loop trip: the shuffles of one step overlap the first wave of the next
 #endif
 #define TL_PNS_CAT2(a, b) a##b
 #define TL_PNS_CAT(a, b) TL_PNS_CAT2(a, b)
@@ -34,18 +37,21 @@ namespace TL_PNS {   // one copy of everything below per tile size
 
 constexpr int kP = TL_KP;        // points of a tile held by one lane
 constexpr int kTile = 32 * kP;   // points per tile
+constexpr int kRingUnroll = TL_RING_UNROLL;
 
 // ---------------------------------------------------------------------------------------
 // Math policies.  A policy owns the register image of a point (`Point<D>`: coordinates + the
 // mass terms that travel with it) and the arithmetic of one pair visit.
 // ---------------------------------------------------------------------------------------
 
-// One pair visit's measurement: `meas` / `gt` / `lt` are zero or non-zero words (the lane's mask
-// ANDed with the step bit), `target` is only meaningful when meas != 0.
+// One pair visit's measurement.  `pos` / `neg` are zero or non-zero words (the lane's masks ANDed with
+// the step bit): pos = the pair pulls when the embedded distance is BELOW the target (an exact value
+// or a '>' threshold, src/optimization.cpp:237-239), neg = it pulls when ABOVE (exact or '<', :240-242).
+// Both zero = unmeasured pair; `target` is only meaningful otherwise.
 template <class real>
 struct Cell {
   real target;
-  uint32_t meas, gt, lt;
+  uint32_t pos, neg;
 };
 
 constexpr int kRow = kTile + 1;   // shared-memory row of one dimension: kTile slots + 1 pad (kTile % 32 == 0)
@@ -58,7 +64,7 @@ TL_D void upk2(f32x2 v, float& lo, float& hi) { lo = v.x; hi = v.y; }
 TL_D f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { return __ffma2_rn(a, b, c); }
 TL_D f32x2 mul2(f32x2 a, f32x2 b) { return __fmul2_rn(a, b); }
 TL_D f32x2 add2(f32x2 a, f32x2 b) { return __fadd2_rn(a, b); }
-TL_D float rsqrt_fast(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+TL_D float sqrt_fast(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 TL_D float rcp_fast(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 
 // FP32 production arithmetic.  A phantom slot (padding of the last tile) has zero mass and sits
@@ -125,6 +131,9 @@ struct FastF32 {
 
   // delta = B - A, and the scalar with which it is applied to each endpoint
   // (src/optimization.cpp:207-281 with reciprocals hoisted out of the coordinate loop).
+  static TL_D bool is_spring(float target_minus_dist, const Cell<float>& cell) {
+    return (target_minus_dist > 0.f ? cell.pos : cell.neg) != 0u;
+  }
   template <int D>
   static TL_D void force(const Point<D>& A, const Point<D>& B, f32x2 (&delta)[Point<D>::H], const Cell<float>& cell,
                          const Ctx& c, float& fA, float& fB) {
@@ -144,17 +153,15 @@ struct FastF32 {
     if (H > 1) acc0 = add2(acc0, acc1);
     float lo, hi;
     upk2(acc0, lo, hi);
-    const float d2 = lo + hi;
-    const float dist = d2 * rsqrt_fast(fmaxf(d2, 1e-35f));
+    const float dist = sqrt_fast(lo + hi);
     const float ids = rcp_fast(dist + 0.01f);
     // Branch-free choice between repulsion c / (2 ds^3) and spring 2k (t - d) / ds: the target cell is
-    // read unconditionally (stale / garbage when the pair is not measured, discarded by the selects).
-    // ('>' threshold: spring iff dist < target; '<': iff dist > target; exact: always) - bitwise on
-    // purpose: && / ?: would be compiled into divergent branches.
-    const uint32_t below = dist < target ? ~0u : 0u, above = dist > target ? ~0u : 0u;
-    const bool spring = (cell.meas & ((cell.gt & below) | (cell.lt & above) | ~(cell.gt | cell.lt))) != 0u;
-    const float rep = ids * ids;            // (c/2 and 2k live in the per-point weights)
+    // read unconditionally (stale / garbage when the pair is not measured; then both masks are zero
+    // and the selects discard it).  One compare picks the mask that applies on this side of the target.
+    // (At dist == target exactly a '<' pair gets the zero spring force instead of the repulsion.)
     const float spr = target - dist;
+    const bool spring = is_spring(spr, cell);
+    const float rep = ids * ids;            // (c/2 and 2k live in the per-point weights)
     const float f = (spring ? spr : rep) * ids;
     const float wA = spring ? A.rnorm : A.rdeg, wB = spring ? B.rnorm : B.rdeg;
     fA = f * wA;
@@ -176,8 +183,10 @@ struct FastF32 {
   // One wave: kP independent pair visits (A[p], B[q(p)]) written in lock-step so that their dependency
   // chains (distance -> rsqrt -> rcp -> factors) overlap.  q(p) = (p + w) % kP (kSum = false, ring pass)
   // or (w - p) mod kP (kSum = true, intra pass: symmetric under swapping the two lanes).
-  template <int D, int W_, bool kSum>
-  static TL_D void wave(Point<D> (&A)[kP], Point<D> (&B)[kP], const Cell<float> (&cell)[kP], const Ctx& c) {
+  // kRotate (last wave of a ring step): every B point moves on to lane `src` as soon as its update is
+  // written, so that the shuffles issue between the FMAs of the A updates instead of after them.
+  template <int D, int W_, bool kSum, bool kRotate>
+  static TL_D void wave(Point<D> (&A)[kP], Point<D> (&B)[kP], const Cell<float> (&cell)[kP], const Ctx& c, int src) {
     constexpr int H = Point<D>::H;
     const f32x2 neg1 = pk2(-1.0f, -1.0f);
     f32x2 d[kP][H];
@@ -190,45 +199,59 @@ struct FastF32 {
         const int q = kSum ? (W_ - p + kP) % kP : (p + W_) % kP;
         d[p][j] = fma2(A[p].c[j], neg1, B[q].c[j]);
       }
-    f32x2 acc0[kP], acc1[kP];
+    // squared distance: one accumulator chain per visit when kP visits interleave (their chains hide
+    // each other's latency and every instruction counts), two when the lane has a single visit
+    constexpr int kAcc = (kP == 1 && H > 1) ? 2 : 1;
+    f32x2 acc[kP][kAcc];
+#pragma unroll
+    for (int j = 0; j < H; ++j)
+#pragma unroll
+      for (int p = 0; p < kP; ++p)
+        acc[p][j % kAcc] = j < kAcc ? mul2(d[p][j], d[p][j]) : fma2(d[p][j], d[p][j], acc[p][j % kAcc]);
+    float dist[kP], ids[kP];
 #pragma unroll
     for (int p = 0; p < kP; ++p) {
-      acc0[p] = mul2(d[p][0], d[p][0]);
-      acc1[p] = H > 1 ? mul2(d[p][1], d[p][1]) : pk2(0.f, 0.f);
+      const f32x2 t = kAcc > 1 ? add2(acc[p][0], acc[p][kAcc - 1]) : acc[p][0];
+      dist[p] = sqrt_fast(t.x + t.y);
     }
-#pragma unroll
-    for (int j = 2; j < H; ++j)
-#pragma unroll
-      for (int p = 0; p < kP; ++p) {
-        if (j & 1) acc1[p] = fma2(d[p][j], d[p][j], acc1[p]);
-        else acc0[p] = fma2(d[p][j], d[p][j], acc0[p]);
-      }
-    float s2[kP], dist[kP], ids[kP];
-#pragma unroll
-    for (int p = 0; p < kP; ++p) {
-      const f32x2 t = H > 1 ? add2(acc0[p], acc1[p]) : acc0[p];
-      s2[p] = t.x + t.y;
-    }
-#pragma unroll
-    for (int p = 0; p < kP; ++p) dist[p] = s2[p] * rsqrt_fast(fmaxf(s2[p], 1e-35f));
 #pragma unroll
     for (int p = 0; p < kP; ++p) ids[p] = rcp_fast(dist[p] + 0.01f);
 #pragma unroll
     for (int p = 0; p < kP; ++p) {
-      const Cell<float>& cl = cell[p];
-      const uint32_t below = dist[p] < cl.target ? ~0u : 0u, above = dist[p] > cl.target ? ~0u : 0u;
-      sp[p] = (cl.meas & ((cl.gt & below) | (cl.lt & above) | ~(cl.gt | cl.lt))) != 0u;
-      f[p] = (sp[p] ? cl.target - dist[p] : ids[p] * ids[p]) * ids[p];   // x weight: 2k(t-d)/ds or c/(2 ds^3)
+      const float spr = cell[p].target - dist[p];
+      sp[p] = is_spring(spr, cell[p]);
+      f[p] = (sp[p] ? spr : ids[p] * ids[p]) * ids[p];   // x weight: 2k(t-d)/ds or c/(2 ds^3)
     }
+    if (!kRotate) {
 #pragma unroll
-    for (int p = 0; p < kP; ++p) {
-      const int q = kSum ? (W_ - p + kP) % kP : (p + W_) % kP;
-      const float fA = f[p] * (sp[p] ? A[p].rnorm : A[p].rdeg), fB = f[p] * (sp[p] ? B[q].rnorm : B[q].rdeg);
-      const f32x2 nA = pk2(-fA, -fA), pB = pk2(fB, fB);
+      for (int p = 0; p < kP; ++p) {
+        const int q = kSum ? (W_ - p + kP) % kP : (p + W_) % kP;
+        const float fA = f[p] * (sp[p] ? A[p].rnorm : A[p].rdeg), fB = f[p] * (sp[p] ? B[q].rnorm : B[q].rdeg);
+        const f32x2 nA = pk2(-fA, -fA), pB = pk2(fB, fB);
 #pragma unroll
-      for (int j = 0; j < H; ++j) {
-        A[p].c[j] = fma2(d[p][j], nA, A[p].c[j]);
-        B[q].c[j] = fma2(d[p][j], pB, B[q].c[j]);
+        for (int j = 0; j < H; ++j) {
+          A[p].c[j] = fma2(d[p][j], nA, A[p].c[j]);
+          B[q].c[j] = fma2(d[p][j], pB, B[q].c[j]);
+        }
+      }
+    } else {
+      float fA[kP];
+#pragma unroll
+      for (int p = 0; p < kP; ++p) {
+        const int q = kSum ? (W_ - p + kP) % kP : (p + W_) % kP;
+        fA[p] = f[p] * (sp[p] ? A[p].rnorm : A[p].rdeg);
+        const float fB = f[p] * (sp[p] ? B[q].rnorm : B[q].rdeg);
+        const f32x2 pB = pk2(fB, fB);
+#pragma unroll
+        for (int j = 0; j < H; ++j) B[q].c[j] = fma2(d[p][j], pB, B[q].c[j]);
+      }
+#pragma unroll
+      for (int q = 0; q < kP; ++q) B[q].shfl_from(src);
+#pragma unroll
+      for (int p = 0; p < kP; ++p) {
+        const f32x2 nA = pk2(-fA[p], -fA[p]);
+#pragma unroll
+        for (int j = 0; j < H; ++j) A[p].c[j] = fma2(d[p][j], nA, A[p].c[j]);
       }
     }
   }
@@ -275,9 +298,9 @@ struct ExactF64 {
     const double ds = __dadd_rn(dist, 0.01);
     spring = false;
     double target = 0.0;
-    if (cell.meas) {
+    if (cell.pos | cell.neg) {
       target = cell.target;
-      spring = (cell.gt | cell.lt) == 0u ? true : (cell.gt ? dist < target : dist > target);
+      spring = (cell.pos && cell.neg) ? true : (cell.pos ? dist < target : dist > target);
     }
     if (spring) factor = __ddiv_rn(__dmul_rn(__dmul_rn(2.0, c.k), __dsub_rn(target, dist)), ds);
     else factor = __ddiv_rn(c.c_rep, __dmul_rn(__dmul_rn(__dmul_rn(2.0, ds), ds), ds));
@@ -301,12 +324,16 @@ struct ExactF64 {
       B.c[k] = __dadd_rn(B.c[k], __ddiv_rn(force, nB));
     }
   }
-  template <int D, int W_, bool kSum>
-  static TL_D void wave(Point<D> (&A)[kP], Point<D> (&B)[kP], const Cell<double> (&cell)[kP], const Ctx& c) {
+  template <int D, int W_, bool kSum, bool kRotate>
+  static TL_D void wave(Point<D> (&A)[kP], Point<D> (&B)[kP], const Cell<double> (&cell)[kP], const Ctx& c, int src) {
 #pragma unroll
     for (int p = 0; p < kP; ++p) {
       const int q = kSum ? (W_ - p + kP) % kP : (p + W_) % kP;
       pair<D>(A[p], B[q], cell[p], c);
+    }
+    if (kRotate) {
+#pragma unroll
+      for (int q = 0; q < kP; ++q) B[q].shfl_from(src);
     }
   }
 };
@@ -333,11 +360,16 @@ TL_D void store_state(FitState* dst, const FitState& src) {
   for (int i = 0; i < (int)(sizeof(FitState) / 8); ++i) __stcg(d + i, s[i]);
 }
 
+// A condition every lane of the warp agrees on, in a form the compiler can see is warp-uniform (a
+// vote result): the pass functions below are compiled as convergent code only if every branch around
+// their call sites is provably uniform.
+TL_D bool warp_uniform(bool c) { return __all_sync(0xffffffffu, c); }
+
 // Hand-off flags in shared memory (one per travelling tile).  Every lane polls the same word (one
 // broadcast load), so the warp leaves the loop together: a single-lane spin would leave the warp
 // diverged and every later shuffle would take the slow divergent path.
 TL_D void wait_flag(volatile int* flag, int want) {
-  while (*flag < want) { }
+  while (!__all_sync(0xffffffffu, *flag >= want)) { }   // vote: a loop exit the compiler can see is uniform
   __threadfence_block();
   __syncwarp();
 }
@@ -409,40 +441,38 @@ TL_D void store_tile(const real* s, real* gpos, int tile, int lane) {
 
 // Per-warp table of the measured pairs of one tile pair.  Combination c = kP * (A part) + (B part)
 // (part p = slots 32p .. 32p+31 of a tile): tgt[c][step][lane], mask[c][kind][lane] with
-// kind 0 = measured, 1 = '>', 2 = '<'.
+// kind 0 = "pulls when closer than the target" (exact or '>'), 1 = "pulls when farther" (exact or '<').
 constexpr int kCombos = kP * kP;
 constexpr int kTableReals = kCombos * 32 * 32;
-constexpr int kTableMasks = kCombos * 3 * 32;
+constexpr int kTableMasks = kCombos * 2 * 32;
 template <class real>
 struct WarpTable {
   real* tgt;
   uint32_t* mask;
 };
 struct LaneMasks {
-  uint32_t meas[kCombos], gt[kCombos], lt[kCombos];
+  uint32_t pos[kCombos], neg[kCombos];
 };
 
 template <class real>
 TL_D void table_clear(const WarpTable<real>& tb, int lane) {
 #pragma unroll
-  for (int j = 0; j < 3 * kCombos; ++j) tb.mask[j * 32 + lane] = 0u;
+  for (int j = 0; j < 2 * kCombos; ++j) tb.mask[j * 32 + lane] = 0u;
   __syncwarp();
 }
 template <class real>
 TL_D void table_put(const WarpTable<real>& tb, int c, int idx, int lane_of, real target, int ty) {
   tb.tgt[(c * 32 + idx) * 32 + lane_of] = target;
-  atomicOr(&tb.mask[(c * 3 + 0) * 32 + lane_of], 1u << idx);
-  if (ty == 1) atomicOr(&tb.mask[(c * 3 + 1) * 32 + lane_of], 1u << idx);
-  if (ty == 2) atomicOr(&tb.mask[(c * 3 + 2) * 32 + lane_of], 1u << idx);
+  if (ty != 2) atomicOr(&tb.mask[(c * 2 + 0) * 32 + lane_of], 1u << idx);
+  if (ty != 1) atomicOr(&tb.mask[(c * 2 + 1) * 32 + lane_of], 1u << idx);
 }
 template <class real>
 TL_D LaneMasks table_masks(const WarpTable<real>& tb, int lane, bool filled) {
   LaneMasks m;
 #pragma unroll
   for (int c = 0; c < kCombos; ++c) {
-    m.meas[c] = filled ? tb.mask[(c * 3 + 0) * 32 + lane] : 0u;
-    m.gt[c] = filled ? tb.mask[(c * 3 + 1) * 32 + lane] : 0u;
-    m.lt[c] = filled ? tb.mask[(c * 3 + 2) * 32 + lane] : 0u;
+    m.pos[c] = filled ? tb.mask[(c * 2 + 0) * 32 + lane] : 0u;
+    m.neg[c] = filled ? tb.mask[(c * 2 + 1) * 32 + lane] : 0u;
   }
   return m;
 }
@@ -451,32 +481,55 @@ TL_D Cell<real> table_cell(const WarpTable<real>& tb, const LaneMasks& m, int c,
   Cell<real> cell;
   const uint32_t bit = 1u << idx;
   cell.target = tb.tgt[(c * 32 + idx) * 32 + lane];   // garbage when not measured: discarded by the policy
-  cell.meas = m.meas[c] & bit;
-  cell.gt = m.gt[c] & bit;
-  cell.lt = m.lt[c] & bit;
+  cell.pos = m.pos[c] & bit;
+  cell.neg = m.neg[c] & bit;
   return cell;
 }
 
 // Scatter the measured pairs of bucket (lo, hi) into the warp's table.  `swap` = the A side is the
 // higher-numbered tile.  Ring passes index by (combination, ring step, A lane).
+// Warp-wide walk over edge records [beg, end): four independent 16-byte loads per lane are in flight
+// before the first is used (the records come from L2 at best: one latency per 128 records, not four).
+template <class F>
+TL_D void for_each_edge(const EdgeRec* edges, uint32_t beg, uint32_t end, int lane, F&& fn) {
+  for (uint32_t base = beg + lane; base < end; base += 128) {
+    uint4 raw[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (base + 32 * k < end) raw[k] = __ldg(reinterpret_cast<const uint4*>(edges + base + 32 * k));
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (base + 32 * k < end) {
+        EdgeRec r;
+        r.target = __hiloint2double((int)raw[k].y, (int)raw[k].x);
+        r.slot_lo = raw[k].z;
+        r.slot_hi_type = raw[k].w;
+        fn(r);
+      }
+  }
+}
+// (Called by the kernel right before the pass function: the pass loops keep their register allocation
+// to themselves.)
 template <class real>
 TL_D void fill_table_ring(const WarpTable<real>& tb, const EdgeRec* edges, uint32_t beg, uint32_t end, bool swap,
                           const RingParams& rp, int lane) {
-  for (uint32_t e = beg + lane; e < end; e += 32) {
-    const EdgeRec r = edges[e];
+  if (beg == end) return;   // warp-uniform
+  table_clear<real>(tb, lane);
+  for_each_edge(edges, beg, end, lane, [&](const EdgeRec& r) {
     const int lo = (int)(r.slot_lo % kTile), hi = (int)((r.slot_hi_type & 0x3fffffffu) % kTile);
     const int ty = r.slot_hi_type >> 30;
     const int a = swap ? hi : lo, b = swap ? lo : hi;
     const int la = a & 31, lb = b & 31;
     table_put<real>(tb, kP * (a >> 5) + (b >> 5), ring_step(rp, la, lb), la, (real)r.target, ty);
-  }
+  });
 }
 // Intra passes index by (combination seen from the lane, xor distance, lane); pairs among a lane's
 // own kP slots sit at index 0 (xor distance 0 never occurs otherwise).
 template <class real>
 TL_D void fill_table_xor(const WarpTable<real>& tb, const EdgeRec* edges, uint32_t beg, uint32_t end, int lane) {
-  for (uint32_t e = beg + lane; e < end; e += 32) {
-    const EdgeRec r = edges[e];
+  if (beg == end) return;
+  table_clear<real>(tb, lane);
+  for_each_edge(edges, beg, end, lane, [&](const EdgeRec& r) {
     const int u = (int)(r.slot_lo % kTile), v = (int)((r.slot_hi_type & 0x3fffffffu) % kTile);
     const int ty = r.slot_hi_type >> 30;
     const int lu = u & 31, lv = v & 31, pu = u >> 5, pv = v >> 5;
@@ -487,7 +540,7 @@ TL_D void fill_table_xor(const WarpTable<real>& tb, const EdgeRec* edges, uint32
       table_put<real>(tb, kP * pu + pv, x, lu, (real)r.target, ty);
       table_put<real>(tb, kP * pv + pu, x, lv, (real)r.target, ty);
     }
-  }
+  });
 }
 
 TL_D void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
@@ -511,53 +564,51 @@ template <int D, class M, bool kSum, int W_ = 0>
 struct Waves {
   typedef typename M::real real;
   static TL_D void run(typename M::template Point<D> (&A)[kP], typename M::template Point<D> (&B)[kP],
-                       const WarpTable<real>& tb, const LaneMasks& m, int idx, int lane, const typename M::Ctx& ctx) {
+                       const WarpTable<real>& tb, const LaneMasks& m, int idx, int lane, const typename M::Ctx& ctx,
+                       int src) {
     Cell<real> cell[kP];
 #pragma unroll
     for (int p = 0; p < kP; ++p) {
       const int q = kSum ? (W_ - p + kP) % kP : (p + W_) % kP;
       cell[p] = table_cell<real>(tb, m, kP * p + q, idx, lane);
     }
-    M::template wave<D, W_, kSum>(A, B, cell, ctx);
-    Waves<D, M, kSum, W_ + 1>::run(A, B, tb, m, idx, lane, ctx);
+    M::template wave<D, W_, kSum, !kSum && W_ == kP - 1>(A, B, cell, ctx, src);   // ring pass: rotate B in the last wave
+    Waves<D, M, kSum, W_ + 1>::run(A, B, tb, m, idx, lane, ctx, src);
   }
 };
 template <int D, class M, bool kSum>
 struct Waves<D, M, kSum, kP> {
   typedef typename M::real real;
   static TL_D void run(typename M::template Point<D> (&)[kP], typename M::template Point<D> (&)[kP],
-                       const WarpTable<real>&, const LaneMasks&, int, int, const typename M::Ctx&) {}
+                       const WarpTable<real>&, const LaneMasks&, int, int, const typename M::Ctx&, int) {}
 };
 
 // tile A x tile B (kTile x kTile pairs), 32 ring steps of kP waves of kP pair visits per lane.  Lane a
 // keeps A[p] = slot a + 32p; the travelling B[q] = slot b + 32q with b = ring_b(a, i).  Wave w of a step
 // pairs A[p] with B[(p + w) % kP]: kP independent visits, a perfect matching over the warp.
+//
+// A function of its own on purpose (not inlined, arguments by value): inside the kernel the compiler
+// cannot prove that a warp is converged where the pass is called (the conditions around it are loaded
+// from shared memory) and guards every group of shuffles with a divergence check (BRA.DIV) which
+// nothing can be scheduled across; a function body is compiled as convergent code, so the shuffles
+// issue between the FMAs.  The callers guarantee convergence (warp-uniform branches, __syncwarp).
 template <int D, class M>
-TL_D void ring_pass(typename M::real* sA, typename M::real* sB, int tA, int tB, uint32_t beg, uint32_t end,
-                    const WarpTable<typename M::real>& tb, const TileDev<typename M::real>& dv, const Geometry& geo,
-                    int iter, const typename M::Ctx& ctx, int lane) {
+__device__ __noinline__ void ring_pass(typename M::real* sA, typename M::real* sB, RingParams rp, bool filled,
+                                       const WarpTable<typename M::real>& tb, const typename M::Ctx& ctx, int lane) {
   typedef typename M::real real;
-  const RingParams rp = ring_params(geo, iter, tA, tB);
-  if (beg != end) {  // warp-uniform
-    table_clear<real>(tb, lane);
-    fill_table_ring<real>(tb, dv.edges, beg, end, tA > tB, rp, lane);
-    __syncwarp();
-  }
-  const LaneMasks m = table_masks<real>(tb, lane, beg != end);
+  const LaneMasks m = table_masks<real>(tb, lane, filled);
   typename M::template Point<D> A[kP], B[kP];
   const int b0 = (lane + rp.s0) & 31;
 #pragma unroll
   for (int p = 0; p < kP; ++p) { A[p].load(sA, lane + 32 * p, ctx); B[p].load(sB, b0 + 32 * p, ctx); }
   const int src = (lane + rp.g) & 31;
-#pragma unroll 1
+#pragma unroll kRingUnroll
   for (int i = 0; i < 32; ++i) {
-    Waves<D, M, false>::run(A, B, tb, m, i, lane, ctx);
-    if (i < 31) {
-#pragma unroll
-      for (int p = 0; p < kP; ++p) B[p].shfl_from(src);
-    }
+    // the last wave of every step hands the B points on (also after step 31: that rotation brings every
+    // B point back to the lane that loaded it)
+    Waves<D, M, false>::run(A, B, tb, m, i, lane, ctx, src);
   }
-  const int bf = (lane + rp.s0 + 31 * rp.g) & 31;
+  const int bf = b0;
 #pragma unroll
   for (int p = 0; p < kP; ++p) { A[p].store(sA, lane + 32 * p); B[p].store(sB, bf + 32 * p); }
 }
@@ -567,16 +618,10 @@ TL_D void ring_pass(typename M::real* sA, typename M::real* sB, int tA, int tB, 
 // seen from either lane - two-sided on the lane's local copies O of the partner's points, which the
 // partner updates identically for itself.
 template <int D, class M>
-TL_D void intra_pass(typename M::real* sT, int t, uint32_t beg, uint32_t end, const WarpTable<typename M::real>& tb,
-                     const TileDev<typename M::real>& dv, const Geometry& geo, int iter,
-                     const typename M::Ctx& ctx, int lane) {
+__device__ __noinline__ void intra_pass(typename M::real* sT, XorParams xp, bool filled,
+                                        const WarpTable<typename M::real>& tb, const typename M::Ctx& ctx, int lane) {
   typedef typename M::real real;
-  if (beg != end) {
-    table_clear<real>(tb, lane);
-    fill_table_xor<real>(tb, dv.edges, beg, end, lane);
-    __syncwarp();
-  }
-  const LaneMasks m = table_masks<real>(tb, lane, beg != end);
+  const LaneMasks m = table_masks<real>(tb, lane, filled);
   typename M::template Point<D> S[kP], O[kP];
 #pragma unroll
   for (int p = 0; p < kP; ++p) S[p].load(sT, lane + 32 * p, ctx);
@@ -584,13 +629,12 @@ TL_D void intra_pass(typename M::real* sT, int t, uint32_t beg, uint32_t end, co
   for (int p = 0; p < kP; ++p)
 #pragma unroll
     for (int q = p + 1; q < kP; ++q) M::template pair<D>(S[p], S[q], table_cell<real>(tb, m, kP * p + q, 0, lane), ctx);
-  const XorParams xp = xor_params(geo, iter, t);
 #pragma unroll 1
   for (int i = 0; i < 31; ++i) {
     const int x = xor_at(xp, i);
 #pragma unroll
     for (int p = 0; p < kP; ++p) O[p].shfl_xor_of(S[p], x);
-    Waves<D, M, true>::run(S, O, tb, m, x, lane, ctx);
+    Waves<D, M, true>::run(S, O, tb, m, x, lane, ctx, 0);
   }
 #pragma unroll
   for (int p = 0; p < kP; ++p) S[p].store(sT, lane + 32 * p);
@@ -672,9 +716,12 @@ tile_kernel(TileDev<typename M::real> dv, Geometry geo, FitParams prm, int n_ite
           const int tA = s_tid[warp], tB = s_tid[W + bw];
           const uint32_t beg = __shfl_sync(0xffffffffu, my_rng.x, v), end = __shfl_sync(0xffffffffu, my_rng.y, v);
           wait_flag(s_flag + bw, v);
-          if (tA >= 0 && tB >= 0)
-            ring_pass<D, M>(s_tiles + (size_t)warp * TS, s_tiles + (size_t)(W + bw) * TS, tA, tB, beg, end, tb, dv,
-                            geo, iter, ctx, lane);
+          if (warp_uniform(tA >= 0 && tB >= 0)) {
+            const RingParams rp = ring_params(geo, iter, tA, tB);
+            fill_table_ring<real>(tb, dv.edges, beg, end, tA > tB, rp, lane);
+            __syncwarp();
+            ring_pass<D, M>(s_tiles + (size_t)warp * TS, s_tiles + (size_t)(W + bw) * TS, rp, beg != end, tb, ctx, lane);
+          }
           post_flag(s_flag + bw, v + 1, lane);
         }
         wait_flag(s_flag + warp, W);   // every pass on Y[warp] is done: this warp writes it back
@@ -708,19 +755,31 @@ tile_kernel(TileDev<typename M::real> dv, Geometry geo, FitParams prm, int n_ite
       for (int u = 0; u < Mt; ++u) {
         int sb, ia, ib;
         const uint32_t beg = __shfl_sync(0xffffffffu, my_rng.x, u), end = __shfl_sync(0xffffffffu, my_rng.y, u);
-        if (diag_pair(W, u, rot, warp, sb, ia, ib)) {
+        if (warp_uniform(diag_pair(W, u, rot, warp, sb, ia, ib))) {
           const int tA = s_tid[sb * W + ia], tB = s_tid[sb * W + ib];
-          if (tA >= 0 && tB >= 0)
-            ring_pass<D, M>(s_tiles + (size_t)(sb * W + ia) * TS, s_tiles + (size_t)(sb * W + ib) * TS, tA, tB, beg, end,
-                            tb, dv, geo, iter, ctx, lane);
+          if (warp_uniform(tA >= 0 && tB >= 0)) {
+            const RingParams rp = ring_params(geo, iter, tA, tB);
+            fill_table_ring<real>(tb, dv.edges, beg, end, tA > tB, rp, lane);
+            __syncwarp();
+            ring_pass<D, M>(s_tiles + (size_t)(sb * W + ia) * TS, s_tiles + (size_t)(sb * W + ib) * TS, rp, beg != end,
+                            tb, ctx, lane);
+          }
         }
         __syncthreads();
       }
       {
         const uint32_t bx = __shfl_sync(0xffffffffu, my_rng.x, 16), ex = __shfl_sync(0xffffffffu, my_rng.y, 16);
         const uint32_t by = __shfl_sync(0xffffffffu, my_rng.x, 17), ey = __shfl_sync(0xffffffffu, my_rng.y, 17);
-        if (tX >= 0) intra_pass<D, M>(s_tiles + (size_t)warp * TS, tX, bx, ex, tb, dv, geo, iter, ctx, lane);
-        if (tY >= 0) intra_pass<D, M>(s_tiles + (size_t)(W + warp) * TS, tY, by, ey, tb, dv, geo, iter, ctx, lane);
+        if (warp_uniform(tX >= 0)) {
+          fill_table_xor<real>(tb, dv.edges, bx, ex, lane);
+          __syncwarp();
+          intra_pass<D, M>(s_tiles + (size_t)warp * TS, xor_params(geo, iter, tX), bx != ex, tb, ctx, lane);
+        }
+        if (warp_uniform(tY >= 0)) {
+          fill_table_xor<real>(tb, dv.edges, by, ey, lane);
+          __syncwarp();
+          intra_pass<D, M>(s_tiles + (size_t)(W + warp) * TS, xor_params(geo, iter, tY), by != ey, tb, ctx, lane);
+        }
       }
       store_tile<D, real>(s_tiles + (size_t)warp * TS, dv.pos, tX, lane);
       store_tile<D, real>(s_tiles + (size_t)(W + warp) * TS, dv.pos, tY, lane);
