@@ -313,8 +313,10 @@ std::unique_ptr<topolow_plan> make_plan(const topolow_problem& pb, const topolow
   TL_CUDA(cudaMemcpy(pl->state, &st, sizeof st, cudaMemcpyHostToDevice));
   TL_CUDA(cudaMalloc(&pl->partials, sizeof(double) * 4 * 1024));   // any job geometry: G <= SM count
   TL_CUDA(cudaMemset(pl->partials, 0, sizeof(double) * 4 * 1024));
-  TL_CUDA(cudaMalloc(&pl->barrier, 2 * sizeof(unsigned)));
-  TL_CUDA(cudaMemset(pl->barrier, 0, 2 * sizeof(unsigned)));
+  // [0], [1]: grid barrier; from word 32 on: one round counter per super-block of any job geometry (S <= 2T + 2)
+  const size_t barrier_words = 32 + 2 * (size_t)g.T + 64;
+  TL_CUDA(cudaMalloc(&pl->barrier, barrier_words * sizeof(unsigned)));
+  TL_CUDA(cudaMemset(pl->barrier, 0, barrier_words * sizeof(unsigned)));
   const int ntr = std::max(pr.n_iter, 1);
   std::vector<double> nanv(ntr, NAN);
   TL_CUDA(cudaMalloc(&pl->trace, sizeof(double) * ntr));

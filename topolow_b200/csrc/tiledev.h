@@ -24,7 +24,7 @@ struct TileDev {
   const uint32_t* bucket_off;
   FitState* state;
   double* partials;      // [G][4]: error sum, count, non-finite flag, unused
-  unsigned* barrier;     // [2]: arrivals, generation
+  unsigned* barrier;     // [0] arrivals, [1] generation of the grid barrier; [32 + b]: round counter of super-block b
   double* trace;         // [n_iter] or null
   long long n_edges;
   unsigned long long pairs_per_iter;

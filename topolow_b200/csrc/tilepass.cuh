@@ -404,6 +404,29 @@ TL_D void gang_barrier(unsigned* bar, int G, unsigned& gen) {
   }
 }
 
+// Round-to-round dependencies between the CTAs of a fit.  Every super-block takes part in exactly one
+// task per cross round, so the task that uses super-block b in round r only has to wait for the task
+// that used b in round r - 1 - not for the whole grid: done[b] counts the warps that have written
+// their tile of b back (W per round), and a warp waits for r * W on both of its super-blocks.  Slack
+// of a CTA then carries over to later rounds instead of being lost at a grid barrier per round.
+TL_D void wait_blocks(const unsigned* done, int a, int b, unsigned want, int G) {
+  if (G > 1) {
+    while (ld_acquire_u32(done + a) < want || ld_acquire_u32(done + b) < want) { __nanosleep(20); }
+    __syncwarp();
+  }
+}
+TL_D void post_blocks(unsigned* done, int a, int b, int G, int lane) {
+  if (G > 1) {
+    __syncwarp();
+    if (lane == 0) {
+      __threadfence();
+      atomicAdd(done + a, 1u);
+      atomicAdd(done + b, 1u);
+    }
+  }
+}
+constexpr int kDoneOffset = 32;   // words of dv.barrier before the done[] counters (own cache lines)
+
 template <int D>
 struct TileShape {
   static constexpr int kReals = (D + 1) * kRow;    // D coordinate rows + the dp1 row, kTile slots each
@@ -684,6 +707,12 @@ tile_kernel(TileDev<typename M::real> dv, Geometry geo, FitParams prm, int n_ite
   if (tid == 0) load_state(st, dv.state);
   if (geo.G > 1) gen = ld_acquire_u32(&dv.barrier[1]);
   __syncthreads();
+  unsigned* done = dv.barrier + kDoneOffset;
+  unsigned epoch = 0;   // cross rounds completed since the start of this launch
+  if (geo.G > 1) {
+    for (int b = cta * blockDim.x + tid; b < geo.S; b += geo.G * blockDim.x) __stcg(done + b, 0u);
+    gang_barrier(dv.barrier, geo.G, gen);
+  }
 
   for (int it = 0; it < n_iters; ++it) {
     if (st.stop) break;
@@ -697,6 +726,8 @@ tile_kernel(TileDev<typename M::real> dv, Geometry geo, FitParams prm, int n_ite
         int X, Y;
         cross_task(geo, rr, cta * geo.m + tt, X, Y);
         const int tX = tile_at(geo, iter, X * W + warp, 0), tY = tile_at(geo, iter, Y * W + warp, geo.kind);
+        const int bX = X, bY = geo.kind == 1 ? geo.S / 2 + Y : Y;   // counters: the two sides of a bipartite job apart
+        wait_blocks(done, bX, bY, epoch * (unsigned)W, geo.G);
         if (lane == 0) { s_tid[warp] = tX; s_tid[W + warp] = tY; s_flag[warp] = 0; }
         load_tile<D, real>(s_tiles + (size_t)warp * TS, dv.pos, dv.dp1, tX, lane);
         load_tile<D, real>(s_tiles + (size_t)(W + warp) * TS, dv.pos, dv.dp1, tY, lane);
@@ -727,15 +758,16 @@ tile_kernel(TileDev<typename M::real> dv, Geometry geo, FitParams prm, int n_ite
         wait_flag(s_flag + warp, W);   // every pass on Y[warp] is done: this warp writes it back
         store_tile<D, real>(s_tiles + (size_t)warp * TS, dv.pos, tX, lane);
         store_tile<D, real>(s_tiles + (size_t)(W + warp) * TS, dv.pos, tY, lane);
-        __syncwarp();
+        post_blocks(done, bX, bY, geo.G, lane);
       }
-      gang_barrier(dv.barrier, geo.G, gen);
+      ++epoch;
     }
 
     // ---------------- diagonal round (kind 0 only) ----------------
     for (int tt = 0; tt < (geo.kind == 0 ? geo.m : 0); ++tt) {
       const int q = cta * geo.m + tt;
       const int tX = tile_at(geo, iter, (2 * q) * W + warp), tY = tile_at(geo, iter, (2 * q + 1) * W + warp);
+      wait_blocks(done, 2 * q, 2 * q + 1, epoch * (unsigned)W, geo.G);
       if (lane == 0) { s_tid[warp] = tX; s_tid[W + warp] = tY; }
       load_tile<D, real>(s_tiles + (size_t)warp * TS, dv.pos, dv.dp1, tX, lane);
       load_tile<D, real>(s_tiles + (size_t)(W + warp) * TS, dv.pos, dv.dp1, tY, lane);
