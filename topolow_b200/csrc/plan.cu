@@ -332,6 +332,7 @@ std::unique_ptr<topolow_plan> make_plan(const topolow_problem& pb, const topolow
   const double pairs = 0.5 * (double)pb.n * (double)(pb.n - 1);
   const double est_ms = pairs / 1.0e8 + 0.03;
   pl->chunk_iters = (int)std::max(1.0, std::min(50.0, 50.0 / est_ms));
+  if (const char* e = std::getenv("TOPOLOW_CHUNK_ITERS")) pl->chunk_iters = std::max(1, std::atoi(e));   // measurement aid
   return pl;
 }
 

@@ -663,6 +663,46 @@ __device__ __noinline__ void intra_pass(typename M::real* sT, XorParams xp, bool
   for (int p = 0; p < kP; ++p) S[p].store(sT, lane + 32 * p);
 }
 
+// One point's coordinates from global memory (through L2: other CTAs wrote them), 128-bit loads when
+// the row size allows.
+template <int D, class real>
+TL_D void load_row(const real* p, real (&out)[D]) {
+  constexpr int kVec = 16 / (int)sizeof(real);
+  if ((D % kVec) == 0) {
+#pragma unroll
+    for (int j = 0; j < D / kVec; ++j) {
+      const uint4 v = __ldcg(reinterpret_cast<const uint4*>(p) + j);
+      if (sizeof(real) == 4) {
+        out[4 * j + 0] = (real)__uint_as_float(v.x); out[4 * j + 1] = (real)__uint_as_float(v.y);
+        out[4 * j + 2] = (real)__uint_as_float(v.z); out[4 * j + 3] = (real)__uint_as_float(v.w);
+      } else {
+        out[2 * j + 0] = (real)__hiloint2double((int)v.y, (int)v.x);
+        out[2 * j + 1] = (real)__hiloint2double((int)v.w, (int)v.z);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < D; ++j) out[j] = __ldcg(p + j);
+  }
+}
+
+// One edge's term of the MAE (src/optimization.cpp:62-76): |target - dist| of a measured pair, and of a
+// threshold pair only while the threshold is violated.  `raw` is the 16-byte EdgeRec.
+template <int D, class real>
+TL_D void edge_error(const uint4& raw, const real (&ra)[D], const real (&rb)[D], double& e_sum, double& e_cnt) {
+  const double target = __hiloint2double((int)raw.y, (int)raw.x);
+  const int ty = raw.w >> 30;
+  double ss = 0.0;
+#pragma unroll
+  for (int j = 0; j < D; ++j) {
+    const double df = (double)rb[j] - (double)ra[j];
+    ss = __dadd_rn(ss, __dmul_rn(df, df));
+  }
+  const double dist = __dsqrt_rn(ss);
+  const bool contributes = (ty == 0) || (ty == 1 && dist < target) || (ty == 2 && dist > target);
+  if (contributes) { e_sum += fabs(target - dist); e_cnt += 1.0; }
+}
+
 // Deterministic CTA reduction of (sum, count, flag); result valid in thread 0.
 TL_D void block_reduce3(double& a, double& b, double& c, double* scratch /* [3*32] */) {
   const unsigned full = 0xffffffffu;
@@ -703,6 +743,10 @@ tile_kernel(TileDev<typename M::real> dv, Geometry geo, FitParams prm, int n_ite
   int* s_flag = s_tid + 2 * W;
   const WarpTable<real> tb{s_tgt + (size_t)warp * kTableReals, s_mask + warp * kTableMasks};
 
+#ifdef TL_DEBUG_CLOCK
+  long long dbg_c0 = clock64(); unsigned long long dbg_t0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t0));
+#endif
   unsigned gen = 0;
   if (tid == 0) load_state(st, dv.state);
   if (geo.G > 1) gen = ld_acquire_u32(&dv.barrier[1]);
@@ -831,20 +875,31 @@ tile_kernel(TileDev<typename M::real> dv, Geometry geo, FitParams prm, int n_ite
     if (check || fin) {
       double e_sum = 0.0, e_cnt = 0.0, bad = 0.0;
       if (check) {
-        for (long long e = (long long)cta * blockDim.x + tid; e < dv.n_edges; e += (long long)geo.G * blockDim.x) {
-          const EdgeRec rec = dv.edges[e];
-          const real* pa = dv.pos + (size_t)rec.slot_lo * D;
-          const real* pb = dv.pos + (size_t)(rec.slot_hi_type & 0x3fffffffu) * D;
-          const int ty = rec.slot_hi_type >> 30;
-          double ss = 0.0;
+        // Edge MAE (src/optimization.cpp:54-81): kEB edges per thread and trip, every load of the batch
+        // issued before the first use - the CTAs of the pair loop are all the threads there are, so the
+        // memory parallelism has to come from inside a thread.
+        constexpr int kEB = sizeof(real) == 4 ? 4 : 2;
+        const long long stride = (long long)geo.G * blockDim.x;
+        long long e0 = (long long)cta * blockDim.x + tid;
+        for (; e0 + (kEB - 1) * stride < dv.n_edges; e0 += stride * kEB) {
+          uint4 raw[kEB];
 #pragma unroll
-          for (int k = 0; k < D; ++k) {
-            const double df = (double)__ldcg(pb + k) - (double)__ldcg(pa + k);
-            ss = __dadd_rn(ss, __dmul_rn(df, df));
+          for (int k = 0; k < kEB; ++k) raw[k] = __ldcs(reinterpret_cast<const uint4*>(dv.edges + e0 + k * stride));
+          real ra[kEB][D], rb[kEB][D];
+#pragma unroll
+          for (int k = 0; k < kEB; ++k) {
+            load_row<D, real>(dv.pos + (size_t)raw[k].z * D, ra[k]);
+            load_row<D, real>(dv.pos + (size_t)(raw[k].w & 0x3fffffffu) * D, rb[k]);
           }
-          const double dist = __dsqrt_rn(ss);
-          const bool contributes = (ty == 0) || (ty == 1 && dist < rec.target) || (ty == 2 && dist > rec.target);
-          if (contributes) { e_sum += fabs(rec.target - dist); e_cnt += 1.0; }
+#pragma unroll
+          for (int k = 0; k < kEB; ++k) edge_error<D, real>(raw[k], ra[k], rb[k], e_sum, e_cnt);
+        }
+        for (; e0 < dv.n_edges; e0 += stride) {   // fewer than kEB edges left for this thread
+          const uint4 raw = __ldcs(reinterpret_cast<const uint4*>(dv.edges + e0));
+          real ra[D], rb[D];
+          load_row<D, real>(dv.pos + (size_t)raw.z * D, ra);
+          load_row<D, real>(dv.pos + (size_t)(raw.w & 0x3fffffffu) * D, rb);
+          edge_error<D, real>(raw, ra, rb, e_sum, e_cnt);
         }
       }
       if (fin) {
@@ -887,6 +942,13 @@ tile_kernel(TileDev<typename M::real> dv, Geometry geo, FitParams prm, int n_ite
       __syncthreads();
     }
   }
+#ifdef TL_DEBUG_CLOCK
+  if ((cta == 0 || cta == 77) && tid == 0) {
+    unsigned long long dbg_t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t1));
+    const long long c = clock64() - dbg_c0;
+    printf("cta %d: %lld cycles in %llu ns = %.1f MHz\n", cta, c, dbg_t1 - dbg_t0, 1e3 * (double)c / (double)(dbg_t1 - dbg_t0));
+  }
+#endif
   if (cta == 0 && tid == 0) {
     store_state(dv.state, st);
     if (host_flag) { host_flag[1] = st.iter; __threadfence_system(); host_flag[0] = st.stop; }
