@@ -393,6 +393,9 @@ def main():
     # ---- end-to-end leg: host buffers through the public call -----------------------------------
     e2e = None
     if not args.no_e2e:
+        # the step's inputs wait in pinned host memory (page-locked views handed to the C ABI as plain pointers)
+        keep_pinned = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in fa[1:]]
+        fa = (fa[0],) + tuple(t.numpy() for t in keep_pinned)
         barrier()
         t0 = time.perf_counter()
         if sharded:
@@ -413,7 +416,7 @@ def main():
         d2h = n * d * 8
         e2e = {"value": (1 if sharded else world) * pairs * r2["iterations_run"] / float(tt[0]), "unit": "pair-updates/s",
                "h2d_bytes_per_step": h2d // max(args.steps, 1), "d2h_bytes_per_step": d2h // max(args.steps, 1),
-               "note": "one fit of K iterations from pageable host buffers (per rank when sharded): upload, bucket build, "
+               "note": "one fit of K iterations from pinned host buffers (per rank when sharded): upload, bucket build, "
                        "K iterations, download; bytes are the call's totals divided by K",
                "wall_s": float(tt[0]), "kernel_ms": r2["device_ms"]}
 

@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 
 #include <cfloat>
+#include <chrono>
+#include <cstdlib>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -41,6 +43,27 @@ struct DeviceBuf {
   T* release() { T* r = p; p = nullptr; return r; }
   operator T*() const { return p; }
 };
+// Stream-ordered scratch from the device's default memory pool (kept by the pool between calls: the
+// first fit pays for the allocation, the following ones reuse it).
+template <class T>
+struct AsyncBuf {
+  T* p = nullptr;
+  cudaStream_t s = nullptr;
+  AsyncBuf(size_t count, cudaStream_t stream) : s(stream) {
+    TL_CUDA(cudaMallocAsync((void**)&p, (count ? count : 1) * sizeof(T), stream));
+  }
+  AsyncBuf(const AsyncBuf&) = delete;
+  AsyncBuf& operator=(const AsyncBuf&) = delete;
+  ~AsyncBuf() { if (p) cudaFreeAsync(p, s); }
+  operator T*() const { return p; }
+};
+inline void keep_pool_memory(int device) {
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+    unsigned long long keep = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  }
+}
 template <class T>
 struct PinnedBuf {
   T* p = nullptr;
@@ -67,6 +90,22 @@ struct EventGuard {
   EventGuard(const EventGuard&) = delete;
   ~EventGuard() { if (e) cudaEventDestroy(e); }
   operator cudaEvent_t() const { return e; }
+};
+
+// Phase timer for TOPOLOW_DEBUG=1 runs: prints host wall-clock milliseconds per labelled phase (and
+// synchronises the stream at every mark, so it is off unless asked for).
+struct PhaseTimer {
+  bool on;
+  cudaStream_t s;
+  std::chrono::steady_clock::time_point t;
+  explicit PhaseTimer(cudaStream_t stream) : on(std::getenv("TOPOLOW_DEBUG") != nullptr), s(stream), t(std::chrono::steady_clock::now()) {}
+  void mark(const char* what) {
+    if (!on) return;
+    cudaStreamSynchronize(s);
+    const auto now = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[topolow] %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(now - t).count());
+    t = now;
+  }
 };
 
 // ---------------------------------------------------------------------------

@@ -91,13 +91,18 @@ void build_buckets(const topolow_problem& pb, const std::vector<int32_t>& slot_o
                    EdgeRec** edges_out, uint32_t** bucket_off_out) {
   const long long E = pb.n_edges;
   const size_t nkeys = (size_t)T * T;
-  DeviceBuf<int32_t> d_ei(E), d_ej(E), d_thr(E), d_slot(slot_of_point.size());
-  DeviceBuf<double> d_dist(E);
-  DeviceBuf<uint32_t> d_keys(E), d_off(nkeys + 1), d_cur(nkeys + 1);
+  // the two results live as long as the plan; everything else is stream-ordered scratch
+  DeviceBuf<uint32_t> d_off(nkeys + 1);
+  DeviceBuf<EdgeRec> d_out(E);
+  AsyncBuf<int32_t> d_ei(E, stream), d_ej(E, stream), d_thr(E, stream), d_slot(slot_of_point.size(), stream);
+  AsyncBuf<double> d_dist(E, stream);
+  AsyncBuf<uint32_t> d_keys(E, stream), d_cur(nkeys + 1, stream);
   const size_t nblk = (nkeys + 1 + 1023) / 1024;
-  DeviceBuf<uint32_t> d_sums(nblk);
-  DeviceBuf<int> d_bad(1);
-  DeviceBuf<EdgeRec> d_tmp(E), d_out(E);
+  AsyncBuf<uint32_t> d_sums(nblk, stream);
+  AsyncBuf<int> d_bad(1, stream);
+  AsyncBuf<EdgeRec> d_tmp(E, stream);
+  PhaseTimer pt(stream);
+  pt.mark("edges: allocations");
   {
     TL_CUDA(cudaMemcpyAsync(d_slot, slot_of_point.data(), slot_of_point.size() * 4, cudaMemcpyHostToDevice, stream));
     if (E > 0) {
@@ -106,6 +111,7 @@ void build_buckets(const topolow_problem& pb, const std::vector<int32_t>& slot_o
       TL_CUDA(cudaMemcpyAsync(d_dist, pb.edge_dist, E * 8, cudaMemcpyHostToDevice, stream));
       TL_CUDA(cudaMemcpyAsync(d_thr, pb.edge_thresh, E * 4, cudaMemcpyHostToDevice, stream));
     }
+    pt.mark("edges: host to device");
     TL_CUDA(cudaMemsetAsync(d_off, 0, (nkeys + 1) * 4, stream));
     TL_CUDA(cudaMemsetAsync(d_bad, 0, 4, stream));
     const int blocks = 148 * 8, threads = 256;
@@ -121,6 +127,7 @@ void build_buckets(const topolow_problem& pb, const std::vector<int32_t>& slot_o
     TL_CUDA(cudaMemcpyAsync(sums.data(), d_sums, nblk * 4, cudaMemcpyDeviceToHost, stream));
     TL_CUDA(cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, stream));
     TL_CUDA(cudaStreamSynchronize(stream));
+    pt.mark("edges: keys + scan");
     if (bad) throw std::invalid_argument("edge index out of range");
     for (size_t i = 1; i < nblk; ++i) sums[i] += sums[i - 1];
     TL_CUDA(cudaMemcpyAsync(d_sums, sums.data(), nblk * 4, cudaMemcpyHostToDevice, stream));
@@ -130,10 +137,12 @@ void build_buckets(const topolow_problem& pb, const std::vector<int32_t>& slot_o
       TL_CUDA(cudaMemcpyAsync(d_cur, d_off, (nkeys + 1) * 4, cudaMemcpyDeviceToDevice, stream));
       scatter_kernel<<<blocks, threads, 0, stream>>>(d_ei, d_ej, d_dist, d_thr, E, d_slot, d_keys, d_cur, d_tmp);
       TL_CUDA(cudaGetLastError());
+      pt.mark("edges: scatter");
       bucket_sort_kernel<<<blocks, threads, 0, stream>>>(d_tmp, d_out, d_off, nkeys);
       TL_CUDA(cudaGetLastError());
     }
     TL_CUDA(cudaStreamSynchronize(stream));
+    pt.mark("edges: sort inside buckets");
   }
   *edges_out = d_out.release();
   *bucket_off_out = d_off.release();

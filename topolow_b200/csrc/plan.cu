@@ -279,6 +279,7 @@ std::unique_ptr<topolow_plan> make_plan(const topolow_problem& pb, const topolow
   auto pl = std::make_unique<topolow_plan>();
   pl->device = pr.device;
   TL_CUDA(cudaSetDevice(pr.device));
+  keep_pool_memory(pr.device);
   int sms = 0;
   TL_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, pr.device));
   pl->precision = pr.precision;
@@ -297,6 +298,8 @@ std::unique_ptr<topolow_plan> make_plan(const topolow_problem& pb, const topolow
   }
   pl->smem = tile_smem_bytes(g.D, g.W, pr.precision == TOPOLOW_PREC_F64_EXACT ? 8 : 4, g.P);
 
+  PhaseTimer pt(nullptr);
+  pt.mark("plan: geometry");
   // random relabelling of points into slots; phantom slots pad the last tile
   pl->slot_of_point = random_permutation(pb.n, pr.seed);
   pl->point_of_slot.assign((size_t)g.T * 32 * g.P, -1);
@@ -305,9 +308,11 @@ std::unique_ptr<topolow_plan> make_plan(const topolow_problem& pb, const topolow
   if (pr.precision == TOPOLOW_PREC_F64_EXACT) upload_points<double>(*pl, pb, kPhantomCoordF64);
   else upload_points<float>(*pl, pb, kPhantomCoordF32);
   TL_CUDA(cudaStreamCreate(&pl->stream));
+  pt.mark("plan: points");
   if (pb.n_edges >= (1 << 21)) build_buckets(pb, pl->slot_of_point, g.T, 32 * g.P, pl->stream, &pl->edges, &pl->bucket_off);
   else upload_edges(*pl, pb);   // small lists: a host counting sort beats a dozen device allocations
 
+  pt.mark("plan: edges");
   FitState st; state_init(st, pl->prm);
   TL_CUDA(cudaMalloc(&pl->state, sizeof(FitState)));
   TL_CUDA(cudaMemcpy(pl->state, &st, sizeof st, cudaMemcpyHostToDevice));
@@ -332,6 +337,7 @@ std::unique_ptr<topolow_plan> make_plan(const topolow_problem& pb, const topolow
   const double pairs = 0.5 * (double)pb.n * (double)(pb.n - 1);
   const double est_ms = pairs / 1.0e8 + 0.03;
   pl->chunk_iters = (int)std::max(1.0, std::min(50.0, 50.0 / est_ms));
+  pt.mark("plan: state");
   if (const char* e = std::getenv("TOPOLOW_CHUNK_ITERS")) pl->chunk_iters = std::max(1, std::atoi(e));   // measurement aid
   return pl;
 }
