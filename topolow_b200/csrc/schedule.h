@@ -82,18 +82,25 @@ TL_HD void circle_pair(int S, int rr, int q, int& x, int& y) {
 // Tile held by tile-slot `slot` (super-block slot/W, position slot%W) in this iteration, or -1.
 // kind 0: S*W slots over the tc tiles of the job.  kind 1: S/2 super-blocks per side, (S/2)*W slots
 // over the tc (side 0) or yc (side 1) tiles of that side.
-TL_HD int tile_at(const Geometry& g, int iter, int slot, int side = 0) {
+// (Every function below exists twice: `f_k(..., key)` takes the iteration key it needs - iter_key(g, iter,
+// salt), which the kernel computes once per iteration - and `f(..., iter, ...)` derives it.)
+constexpr int kIterKeys = 8;   // salts 0..7
+TL_HD int tile_at_k(const Geometry& g, uint64_t key /* salt 1 (side 0) or 7 (side 1) */, int slot, int side = 0) {
   const uint32_t slots = (uint32_t)((g.kind == 0 ? g.S : g.S / 2) * g.W);
-  const uint32_t t = feistel_perm((uint32_t)slot, slots, iter_key(g, iter, side == 0 ? 1u : 7u) ^ (uint64_t)(uint32_t)(side ? g.y0 : g.t0));
+  const uint32_t t = feistel_perm((uint32_t)slot, slots, key ^ (uint64_t)(uint32_t)(side ? g.y0 : g.t0));
   const int count = side ? g.yc : g.tc, base = side ? g.y0 : g.t0;
   return (int)t < count ? base + (int)t : -1;
+}
+TL_HD int tile_at(const Geometry& g, int iter, int slot, int side = 0) {
+  return tile_at_k(g, iter_key(g, iter, side == 0 ? 1u : 7u), slot, side);
 }
 
 // Number of cross rounds of the job and the r-th one executed in this iteration (a permutation).
 TL_HD int cross_rounds(const Geometry& g) { return g.kind == 0 ? g.S - 1 : (g.kind == 1 ? g.S / 2 : 0); }
-TL_HD int round_at(const Geometry& g, int iter, int r) {
-  return (int)feistel_perm((uint32_t)r, (uint32_t)cross_rounds(g), iter_key(g, iter, 2) ^ (uint64_t)(uint32_t)(g.t0 * 131 + g.y0));
+TL_HD int round_at_k(const Geometry& g, uint64_t key /* salt 2 */, int r) {
+  return (int)feistel_perm((uint32_t)r, (uint32_t)cross_rounds(g), key ^ (uint64_t)(uint32_t)(g.t0 * 131 + g.y0));
 }
+TL_HD int round_at(const Geometry& g, int iter, int r) { return round_at_k(g, iter_key(g, iter, 2), r); }
 // The q-th CTA task of cross round rr: super-block X (side 0) against super-block Y (side 0 for a
 // kind-0 job: circle method; side 1 for a kind-1 job: Latin square).
 TL_HD void cross_task(const Geometry& g, int rr, int q, int& x, int& y) {
@@ -103,14 +110,17 @@ TL_HD void cross_task(const Geometry& g, int rr, int q, int& x, int& y) {
 
 struct RingParams { int s0, g, ginv; };
 // Ring offset / stride for tile pair (ta, tb) (actual tile ids, order-insensitive).
-TL_HD RingParams ring_params(const Geometry& geo, int iter, int ta, int tb) {
+TL_HD RingParams ring_params_k(uint64_t key /* salt 3 */, int ta, int tb) {
   const int lo = ta < tb ? ta : tb, hi = ta < tb ? tb : ta;
-  const uint64_t h = mix64(iter_key(geo, iter, 3) ^ (((uint64_t)(uint32_t)lo << 32) | (uint32_t)hi));
+  const uint64_t h = mix64(key ^ (((uint64_t)(uint32_t)lo << 32) | (uint32_t)hi));
   RingParams p;
   p.s0 = (int)(h & 31);
   p.g = (int)((h >> 5) & 15) * 2 + 1;
   p.ginv = (p.g * (2 - p.g * p.g)) & 31;  // Newton step: g*g == 1 (mod 8) so this is g^-1 (mod 32)
   return p;
+}
+TL_HD RingParams ring_params(const Geometry& geo, int iter, int ta, int tb) {
+  return ring_params_k(iter_key(geo, iter, 3), ta, tb);
 }
 // B index that lane `a` holds at ring step i.
 TL_HD int ring_b(const RingParams& p, int a, int i) { return (a + p.s0 + p.g * i) & 31; }
@@ -118,21 +128,23 @@ TL_HD int ring_b(const RingParams& p, int a, int i) { return (a + p.s0 + p.g * i
 TL_HD int ring_step(const RingParams& p, int a, int b) { return (p.ginv * (b - a - p.s0)) & 31; }
 
 struct XorParams { int s0, g; };
-TL_HD XorParams xor_params(const Geometry& geo, int iter, int t) {
-  const uint64_t h = mix64(iter_key(geo, iter, 4) ^ (uint64_t)(uint32_t)t);
+TL_HD XorParams xor_params_k(uint64_t key /* salt 4 */, int t) {
+  const uint64_t h = mix64(key ^ (uint64_t)(uint32_t)t);
   XorParams p;
   p.s0 = (int)(h % 31);
   p.g = (int)((h >> 8) % 30) + 1;  // 1..30, coprime with 31
   return p;
 }
+TL_HD XorParams xor_params(const Geometry& geo, int iter, int t) { return xor_params_k(iter_key(geo, iter, 4), t); }
 // XOR distance used at intra-tile step i (i in [0,31)): a permutation of 1..31.
 TL_HD int xor_at(const XorParams& p, int i) { return (p.s0 + p.g * i) % 31 + 1; }
 
 // Sub-round rotation of a cross task.
-TL_HD int cross_rot(const Geometry& geo, int iter, int x, int y) {
+TL_HD int cross_rot_k(const Geometry& geo, uint64_t key /* salt 5 */, int x, int y) {
   const int lo = x < y ? x : y, hi = x < y ? y : x;
-  return (int)(mix64(iter_key(geo, iter, 5) ^ (((uint64_t)(uint32_t)lo << 32) | (uint32_t)hi)) % (uint32_t)geo.W);
+  return (int)(mix64(key ^ (((uint64_t)(uint32_t)lo << 32) | (uint32_t)hi)) % (uint32_t)geo.W);
 }
+TL_HD int cross_rot(const Geometry& geo, int iter, int x, int y) { return cross_rot_k(geo, iter_key(geo, iter, 5), x, y); }
 // Diagonal task: number of tile-level sub-rounds inside one super-block, and the pair a warp
 // takes.  Returns false when warp `w` idles in sub-round u.  sb_sel: 0 -> first super-block of
 // the task, 1 -> second.  (ia, ib) are tile positions inside that super-block.
@@ -153,9 +165,10 @@ TL_HD bool diag_pair(int W, int u, int rot, int w, int& sb_sel, int& ia, int& ib
   circle_pair(Wp, uu, z, ia, ib);
   return ia < W && ib < W;
 }
-TL_HD int diag_rot(const Geometry& geo, int iter, int q) {
+TL_HD int diag_rot_k(const Geometry& geo, uint64_t key /* salt 6 */, int q) {
   const int Mt = diag_subrounds(geo.W);
-  return Mt > 0 ? (int)(mix64(iter_key(geo, iter, 6) ^ (uint64_t)(uint32_t)q) % (uint32_t)Mt) : 0;
+  return Mt > 0 ? (int)(mix64(key ^ (uint64_t)(uint32_t)q) % (uint32_t)Mt) : 0;
 }
+TL_HD int diag_rot(const Geometry& geo, int iter, int q) { return diag_rot_k(geo, iter_key(geo, iter, 6), q); }
 
 }  // namespace tl

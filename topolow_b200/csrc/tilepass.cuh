@@ -531,20 +531,44 @@ TL_D void for_each_edge(const EdgeRec* edges, uint32_t beg, uint32_t end, int la
       }
   }
 }
+// Per-warp staging area for the edge records of the NEXT tile pass: filled by cp.async while the current
+// pass runs, so that the scatter into the table reads shared memory instead of waiting for L2.
+constexpr int kStage = 64 * kP;   // records per warp (a 1 %-dense 96 x 96 tile pair holds ~92); longer buckets
+                                  // read their tail from global memory
+TL_D void stage_issue(EdgeRec* stage, const EdgeRec* edges, uint32_t beg, uint32_t end, int lane) {
+  const uint32_t n = min(end - beg, (uint32_t)kStage);
+  for (uint32_t i = lane; i < n; i += 32) {
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(stage + i);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(edges + beg + i) : "memory");
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+TL_D void stage_wait() {
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncwarp();
+}
+template <class F>
+TL_D void for_each_staged(const EdgeRec* stage, uint32_t count, int lane, F&& fn) {
+  for (uint32_t i = lane; i < count; i += 32) fn(stage[i]);
+}
+
 // (Called by the kernel right before the pass function: the pass loops keep their register allocation
-// to themselves.)
+// to themselves.)  The first min(end - beg, kStage) records are read from `stage` when it is not null.
 template <class real>
-TL_D void fill_table_ring(const WarpTable<real>& tb, const EdgeRec* edges, uint32_t beg, uint32_t end, bool swap,
-                          const RingParams& rp, int lane) {
+TL_D void fill_table_ring(const WarpTable<real>& tb, const EdgeRec* edges, const EdgeRec* stage, uint32_t beg,
+                          uint32_t end, bool swap, const RingParams& rp, int lane) {
   if (beg == end) return;   // warp-uniform
   table_clear<real>(tb, lane);
-  for_each_edge(edges, beg, end, lane, [&](const EdgeRec& r) {
+  auto put = [&](const EdgeRec& r) {
     const int lo = (int)(r.slot_lo % kTile), hi = (int)((r.slot_hi_type & 0x3fffffffu) % kTile);
     const int ty = r.slot_hi_type >> 30;
     const int a = swap ? hi : lo, b = swap ? lo : hi;
     const int la = a & 31, lb = b & 31;
     table_put<real>(tb, kP * (a >> 5) + (b >> 5), ring_step(rp, la, lb), la, (real)r.target, ty);
-  });
+  };
+  const uint32_t ns = stage ? min(end - beg, (uint32_t)kStage) : 0u;
+  for_each_staged(stage, ns, lane, put);
+  for_each_edge(edges, beg + ns, end, lane, put);
 }
 // Intra passes index by (combination seen from the lane, xor distance, lane); pairs among a lane's
 // own kP slots sit at index 0 (xor distance 0 never occurs otherwise).
@@ -733,6 +757,7 @@ tile_kernel(TileDev<typename M::real> dv, Geometry geo, FitParams prm, int n_ite
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ FitState st;
   __shared__ double red_scratch[96];
+  __shared__ unsigned long long s_key[kIterKeys];   // iter_key(geo, iter, salt) of the running iteration
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int W = geo.W, cta = blockIdx.x;
@@ -741,6 +766,7 @@ tile_kernel(TileDev<typename M::real> dv, Geometry geo, FitParams prm, int n_ite
   uint32_t* s_mask = reinterpret_cast<uint32_t*>(s_tgt + (size_t)W * kTableReals);
   int* s_tid = reinterpret_cast<int*>(s_mask + W * kTableMasks);
   int* s_flag = s_tid + 2 * W;
+  EdgeRec* s_stage = reinterpret_cast<EdgeRec*>((reinterpret_cast<uintptr_t>(s_flag + W) + 15) & ~(uintptr_t)15) + warp * kStage;
   const WarpTable<real> tb{s_tgt + (size_t)warp * kTableReals, s_mask + warp * kTableMasks};
 
 #ifdef TL_DEBUG_CLOCK
@@ -762,27 +788,30 @@ tile_kernel(TileDev<typename M::real> dv, Geometry geo, FitParams prm, int n_ite
     if (st.stop) break;
     const int iter = st.iter;
     const typename M::Ctx ctx = M::make_ctx(st.k, prm.c_repulsion);
+    if (tid < kIterKeys) s_key[tid] = iter_key(geo, iter, (uint32_t)tid);
+    __syncthreads();
 
     // ---------------- cross rounds ----------------
     for (int r = 0; r < cross_rounds(geo); ++r) {
-      const int rr = round_at(geo, iter, r);
+      const int rr = round_at_k(geo, s_key[2], r);
       for (int tt = 0; tt < geo.m; ++tt) {
         int X, Y;
         cross_task(geo, rr, cta * geo.m + tt, X, Y);
-        const int tX = tile_at(geo, iter, X * W + warp, 0), tY = tile_at(geo, iter, Y * W + warp, geo.kind);
+        const int tX = tile_at_k(geo, s_key[1], X * W + warp, 0), tY = tile_at_k(geo, s_key[geo.kind ? 7 : 1], Y * W + warp, geo.kind);
         const int bX = X, bY = geo.kind == 1 ? geo.S / 2 + Y : Y;   // counters: the two sides of a bipartite job apart
         wait_blocks(done, bX, bY, epoch * (unsigned)W, geo.G);
         if (lane == 0) { s_tid[warp] = tX; s_tid[W + warp] = tY; s_flag[warp] = 0; }
         load_tile<D, real>(s_tiles + (size_t)warp * TS, dv.pos, dv.dp1, tX, lane);
         load_tile<D, real>(s_tiles + (size_t)(W + warp) * TS, dv.pos, dv.dp1, tY, lane);
         __syncthreads();
-        const int rot = cross_rot(geo, iter, X, Y);
+        const int rot = cross_rot_k(geo, s_key[5], X, Y);
         // lane v fetches the bucket range of this warp's sub-round v and prefetches its records
         uint2 my_rng = make_uint2(0u, 0u);
         if (lane < W) {
           const int tA = s_tid[warp], tB = s_tid[W + (warp + lane + rot) % W];
           if (tA >= 0 && tB >= 0) my_rng = bucket_range(dv.bucket_off, dv.edges, geo.T, tA, tB);
         }
+        stage_issue(s_stage, dv.edges, __shfl_sync(0xffffffffu, my_rng.x, 0), __shfl_sync(0xffffffffu, my_rng.y, 0), lane);
         // Sub-rounds without a CTA barrier: tile Y[b] is handed from warp to warp.  s_flag[b] counts
         // the passes completed on Y[b]; the pass of sub-round v needs exactly v of them (the one
         // before it ran on warp + 1), so the waits form chains that end at sub-round 0.
@@ -790,13 +819,17 @@ tile_kernel(TileDev<typename M::real> dv, Geometry geo, FitParams prm, int n_ite
           const int bw = (warp + v + rot) % W;
           const int tA = s_tid[warp], tB = s_tid[W + bw];
           const uint32_t beg = __shfl_sync(0xffffffffu, my_rng.x, v), end = __shfl_sync(0xffffffffu, my_rng.y, v);
+          const int vn = v + 1 < W ? v + 1 : v;
+          const uint32_t nbeg = __shfl_sync(0xffffffffu, my_rng.x, vn), nend = __shfl_sync(0xffffffffu, my_rng.y, vn);
           wait_flag(s_flag + bw, v);
-          if (warp_uniform(tA >= 0 && tB >= 0)) {
-            const RingParams rp = ring_params(geo, iter, tA, tB);
-            fill_table_ring<real>(tb, dv.edges, beg, end, tA > tB, rp, lane);
-            __syncwarp();
+          const bool live = warp_uniform(tA >= 0 && tB >= 0);
+          const RingParams rp = ring_params_k(s_key[3], tA, tB);
+          stage_wait();
+          if (live) fill_table_ring<real>(tb, dv.edges, s_stage, beg, end, tA > tB, rp, lane);
+          __syncwarp();
+          if (v + 1 < W) stage_issue(s_stage, dv.edges, nbeg, nend, lane);   // records of the next sub-round, in flight during this pass
+          if (live)
             ring_pass<D, M>(s_tiles + (size_t)warp * TS, s_tiles + (size_t)(W + bw) * TS, rp, beg != end, tb, ctx, lane);
-          }
           post_flag(s_flag + bw, v + 1, lane);
         }
         wait_flag(s_flag + warp, W);   // every pass on Y[warp] is done: this warp writes it back
@@ -810,13 +843,13 @@ tile_kernel(TileDev<typename M::real> dv, Geometry geo, FitParams prm, int n_ite
     // ---------------- diagonal round (kind 0 only) ----------------
     for (int tt = 0; tt < (geo.kind == 0 ? geo.m : 0); ++tt) {
       const int q = cta * geo.m + tt;
-      const int tX = tile_at(geo, iter, (2 * q) * W + warp), tY = tile_at(geo, iter, (2 * q + 1) * W + warp);
+      const int tX = tile_at_k(geo, s_key[1], (2 * q) * W + warp), tY = tile_at_k(geo, s_key[1], (2 * q + 1) * W + warp);
       wait_blocks(done, 2 * q, 2 * q + 1, epoch * (unsigned)W, geo.G);
       if (lane == 0) { s_tid[warp] = tX; s_tid[W + warp] = tY; }
       load_tile<D, real>(s_tiles + (size_t)warp * TS, dv.pos, dv.dp1, tX, lane);
       load_tile<D, real>(s_tiles + (size_t)(W + warp) * TS, dv.pos, dv.dp1, tY, lane);
       __syncthreads();
-      const int Mt = diag_subrounds(W), rot = diag_rot(geo, iter, q);
+      const int Mt = diag_subrounds(W), rot = diag_rot_k(geo, s_key[6], q);
       // lanes 0..Mt-1: bucket of this warp's tile pair in sub-round `lane`; lanes 16, 17: own tiles
       uint2 my_rng = make_uint2(0u, 0u);
       {
@@ -834,8 +867,8 @@ tile_kernel(TileDev<typename M::real> dv, Geometry geo, FitParams prm, int n_ite
         if (warp_uniform(diag_pair(W, u, rot, warp, sb, ia, ib))) {
           const int tA = s_tid[sb * W + ia], tB = s_tid[sb * W + ib];
           if (warp_uniform(tA >= 0 && tB >= 0)) {
-            const RingParams rp = ring_params(geo, iter, tA, tB);
-            fill_table_ring<real>(tb, dv.edges, beg, end, tA > tB, rp, lane);
+            const RingParams rp = ring_params_k(s_key[3], tA, tB);
+            fill_table_ring<real>(tb, dv.edges, nullptr, beg, end, tA > tB, rp, lane);
             __syncwarp();
             ring_pass<D, M>(s_tiles + (size_t)(sb * W + ia) * TS, s_tiles + (size_t)(sb * W + ib) * TS, rp, beg != end,
                             tb, ctx, lane);
@@ -849,12 +882,12 @@ tile_kernel(TileDev<typename M::real> dv, Geometry geo, FitParams prm, int n_ite
         if (warp_uniform(tX >= 0)) {
           fill_table_xor<real>(tb, dv.edges, bx, ex, lane);
           __syncwarp();
-          intra_pass<D, M>(s_tiles + (size_t)warp * TS, xor_params(geo, iter, tX), bx != ex, tb, ctx, lane);
+          intra_pass<D, M>(s_tiles + (size_t)warp * TS, xor_params_k(s_key[4], tX), bx != ex, tb, ctx, lane);
         }
         if (warp_uniform(tY >= 0)) {
           fill_table_xor<real>(tb, dv.edges, by, ey, lane);
           __syncwarp();
-          intra_pass<D, M>(s_tiles + (size_t)(W + warp) * TS, xor_params(geo, iter, tY), by != ey, tb, ctx, lane);
+          intra_pass<D, M>(s_tiles + (size_t)(W + warp) * TS, xor_params_k(s_key[4], tY), by != ey, tb, ctx, lane);
         }
       }
       store_tile<D, real>(s_tiles + (size_t)warp * TS, dv.pos, tX, lane);

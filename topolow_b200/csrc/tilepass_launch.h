@@ -12,10 +12,12 @@ inline int tile_max_warps(int precision, int P) {
   const int f32[4] = {0, 16, 8, 4}, f64[4] = {0, 8, 4, 2};
   return precision ? f64[P] : f32[P];
 }
-// Dynamic shared memory of one CTA: 2W tiles + W (target tables + masks) + 2W tile ids + W flags.
+// Dynamic shared memory of one CTA: 2W tiles + W (target tables + masks) + 2W tile ids + W flags +
+// W staging areas of 64 P edge records (16-byte aligned).
 inline size_t tile_smem_bytes(int D, int W, size_t real_size, int P) {
   const size_t tile = (size_t)(D + 1) * (32 * P + 1) * real_size;
-  return 2 * W * tile + (size_t)W * ((size_t)P * P * 1024 * real_size + (size_t)P * P * 64 * 4) + (size_t)3 * W * 4;
+  return 2 * W * tile + (size_t)W * ((size_t)P * P * 1024 * real_size + (size_t)P * P * 64 * 4) + (size_t)3 * W * 4 +
+         16 + (size_t)W * 64 * P * 16;
 }
 
 // Launch `n_iters` iterations (cooperative when geo.G > 1); geo.P selects the tile size.  Throws CudaError.
