@@ -13,6 +13,10 @@
 #include <cstdlib>
 #include <random>
 #include <thread>
+#include <map>
+#include <functional>
+#include <tuple>
+#include <string>
 #include <vector>
 
 #include "../../include/topolow_b200.h"
@@ -22,6 +26,17 @@
 
 using namespace tl;
 
+// The part of a plan that depends only on the edge list and the tile geometry: the relabelling of the
+// points into slots and the bucketed edge records on the device.  The fits of a CV grid that run on the
+// same fold (same edge arrays) share one store (topolow_fit_batch).
+struct EdgeStore {
+  std::vector<int32_t> point_of_slot;  // -1 = phantom
+  std::vector<int32_t> slot_of_point;
+  EdgeRec* edges = nullptr;
+  uint32_t* bucket_off = nullptr;
+  ~EdgeStore() { cudaFree(edges); cudaFree(bucket_off); }
+};
+
 struct topolow_plan {
   int device = 0;
   int precision = 0;
@@ -29,11 +44,9 @@ struct topolow_plan {
   int D = 0;
   Geometry geo{};
   FitParams prm{};
-  std::vector<int32_t> point_of_slot;  // -1 = phantom
-  std::vector<int32_t> slot_of_point;
+  std::shared_ptr<EdgeStore> store;
   // device
   void* pos = nullptr; void* best = nullptr; void* dp1 = nullptr;
-  EdgeRec* edges = nullptr; uint32_t* bucket_off = nullptr;
   FitState* state = nullptr; double* partials = nullptr; unsigned* barrier = nullptr; double* trace = nullptr;
   volatile int* h_flag = nullptr; int* d_flag = nullptr;
   cudaStream_t stream = nullptr;
@@ -45,7 +58,7 @@ struct topolow_plan {
   size_t smem = 0;
 
   ~topolow_plan() {
-    cudaFree(pos); cudaFree(best); cudaFree(dp1); cudaFree(edges); cudaFree(bucket_off);
+    cudaFree(pos); cudaFree(best); cudaFree(dp1);
     cudaFree(state); cudaFree(partials); cudaFree(barrier); cudaFree(trace);
     if (h_flag) cudaFreeHost((void*)h_flag);
     if (ev0) cudaEventDestroy(ev0);
@@ -219,7 +232,7 @@ void upload_points(topolow_plan& pl, const topolow_problem& pb, real phantom_coo
   const size_t slots = (size_t)pl.geo.T * 32 * pl.geo.P;
   std::vector<real> hp(slots * pl.D, phantom_coord), hd(slots, (real)0);
   for (int64_t i = 0; i < pl.n; ++i) {
-    const size_t s = pl.slot_of_point[i];
+    const size_t s = pl.store->slot_of_point[i];
     for (int d = 0; d < pl.D; ++d) hp[s * pl.D + d] = (real)pb.initial_positions[(size_t)d * pl.n + i];
     hd[s] = (real)((double)pb.degrees[i] + 1.0);
   }
@@ -233,25 +246,25 @@ void upload_points(topolow_plan& pl, const topolow_problem& pb, real phantom_coo
 
 // Host-side bucket build for small edge lists (stable counting sort by tile pair; inside a bucket the
 // records are then ordered by (slot_lo, slot_hi) exactly as the device path orders them).
-void upload_edges(topolow_plan& pl, const topolow_problem& pb) {
-  const int T = pl.geo.T;
-  const uint32_t kTile = 32u * (uint32_t)pl.geo.P;
+void upload_edges(EdgeStore& st, const topolow_problem& pb, int T, int P) {
+  const uint32_t kTile = 32u * (uint32_t)P;
   const size_t nkeys = (size_t)T * T;
+  const int64_t E = pb.n_edges;
   std::vector<uint32_t> off(nkeys + 1, 0);
-  std::vector<EdgeRec> recs(pl.E);
-  std::vector<uint32_t> keys(pl.E);
-  for (int64_t e = 0; e < pl.E; ++e) {
+  std::vector<EdgeRec> recs(E);
+  std::vector<uint32_t> keys(E);
+  for (int64_t e = 0; e < E; ++e) {
     const int64_t a = pb.edge_i[e], b = pb.edge_j[e];
-    if (a < 0 || b < 0 || a >= pl.n || b >= pl.n || a == b) throw BadArg("edge index out of range");
-    uint32_t sa = (uint32_t)pl.slot_of_point[a], sb = (uint32_t)pl.slot_of_point[b];
+    if (a < 0 || b < 0 || a >= pb.n || b >= pb.n || a == b) throw BadArg("edge index out of range");
+    uint32_t sa = (uint32_t)st.slot_of_point[a], sb = (uint32_t)st.slot_of_point[b];
     if (sa > sb) std::swap(sa, sb);  // lower slot first => lower (or equal) tile first
     keys[e] = (sa / kTile) * (uint32_t)T + (sb / kTile);
     off[keys[e] + 1]++;
   }
   for (size_t k = 0; k < nkeys; ++k) off[k + 1] += off[k];
   std::vector<uint32_t> cur(off.begin(), off.end() - 1);
-  for (int64_t e = 0; e < pl.E; ++e) {
-    uint32_t sa = (uint32_t)pl.slot_of_point[pb.edge_i[e]], sb = (uint32_t)pl.slot_of_point[pb.edge_j[e]];
+  for (int64_t e = 0; e < E; ++e) {
+    uint32_t sa = (uint32_t)st.slot_of_point[pb.edge_i[e]], sb = (uint32_t)st.slot_of_point[pb.edge_j[e]];
     if (sa > sb) std::swap(sa, sb);
     const int t = pb.edge_thresh[e];
     EdgeRec r;
@@ -266,13 +279,34 @@ void upload_edges(topolow_plan& pl, const topolow_problem& pb) {
         return x.slot_lo != y.slot_lo ? x.slot_lo < y.slot_lo
                                       : (x.slot_hi_type & 0x3fffffffu) < (y.slot_hi_type & 0x3fffffffu);
       });
-  TL_CUDA(cudaMalloc(&pl.edges, std::max<size_t>(recs.size(), 1) * sizeof(EdgeRec)));
-  TL_CUDA(cudaMalloc(&pl.bucket_off, off.size() * sizeof(uint32_t)));
-  if (!recs.empty()) TL_CUDA(cudaMemcpy(pl.edges, recs.data(), recs.size() * sizeof(EdgeRec), cudaMemcpyHostToDevice));
-  TL_CUDA(cudaMemcpy(pl.bucket_off, off.data(), off.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  TL_CUDA(cudaMalloc(&st.edges, std::max<size_t>(recs.size(), 1) * sizeof(EdgeRec)));
+  TL_CUDA(cudaMalloc(&st.bucket_off, off.size() * sizeof(uint32_t)));
+  if (!recs.empty()) TL_CUDA(cudaMemcpy(st.edges, recs.data(), recs.size() * sizeof(EdgeRec), cudaMemcpyHostToDevice));
+  TL_CUDA(cudaMemcpy(st.bucket_off, off.data(), off.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
 }
 
-std::unique_ptr<topolow_plan> make_plan(const topolow_problem& pb, const topolow_params& pr) {
+// Relabelling + bucketed records of one edge list for tiles of 32 P points.  The relabelling is a
+// fixed pseudo-random permutation of the points (it only has to decorrelate the caller's row order
+// from the tiles; the per-fit randomness of the schedule comes from the seed-keyed hashes of
+// schedule.h), so every fit of the same edge list can use the same store.
+constexpr uint64_t kLayoutSeed = 0x746f706f6c6f77ULL;
+std::shared_ptr<EdgeStore> make_store(const topolow_problem& pb, int T, int P, int device) {
+  TL_CUDA(cudaSetDevice(device));
+  auto st = std::make_shared<EdgeStore>();
+  st->slot_of_point = random_permutation(pb.n, kLayoutSeed);
+  st->point_of_slot.assign((size_t)T * 32 * P, -1);
+  for (int64_t i = 0; i < pb.n; ++i) st->point_of_slot[st->slot_of_point[i]] = (int32_t)i;
+  if (pb.n_edges >= (1 << 21)) {
+    StreamGuard stream;
+    build_buckets(pb, st->slot_of_point, T, 32 * P, stream, &st->edges, &st->bucket_off);
+  } else {
+    upload_edges(*st, pb, T, P);   // small lists: a host counting sort beats a dozen device allocations
+  }
+  return st;
+}
+
+std::unique_ptr<topolow_plan> make_plan(const topolow_problem& pb, const topolow_params& pr,
+                                        std::shared_ptr<EdgeStore> shared = nullptr) {
   validate(pb, pr);
   if (pb.ndim > kMaxDim) throw BadArg("ndim > 16 is not built into libtopolow_b200 (coloured mode)");
   if (pb.n > 1000000) throw BadArg("n > 1,000,000 is not supported (bucket table is T x T)");
@@ -300,19 +334,16 @@ std::unique_ptr<topolow_plan> make_plan(const topolow_problem& pb, const topolow
 
   PhaseTimer pt(nullptr);
   pt.mark("plan: geometry");
-  // random relabelling of points into slots; phantom slots pad the last tile
-  pl->slot_of_point = random_permutation(pb.n, pr.seed);
-  pl->point_of_slot.assign((size_t)g.T * 32 * g.P, -1);
-  for (int64_t i = 0; i < pb.n; ++i) pl->point_of_slot[pl->slot_of_point[i]] = (int32_t)i;
-
+  // relabelling of points into slots (phantom slots pad the last tile) + bucketed edge records
+  pl->store = shared ? shared : make_store(pb, g.T, g.P, pr.device);
+  if ((int64_t)pl->store->slot_of_point.size() != pb.n || pl->store->point_of_slot.size() != (size_t)g.T * 32 * g.P)
+    throw BadArg("shared edge store does not match the problem");
+  pt.mark("plan: edges");
   if (pr.precision == TOPOLOW_PREC_F64_EXACT) upload_points<double>(*pl, pb, kPhantomCoordF64);
   else upload_points<float>(*pl, pb, kPhantomCoordF32);
   TL_CUDA(cudaStreamCreate(&pl->stream));
   pt.mark("plan: points");
-  if (pb.n_edges >= (1 << 21)) build_buckets(pb, pl->slot_of_point, g.T, 32 * g.P, pl->stream, &pl->edges, &pl->bucket_off);
-  else upload_edges(*pl, pb);   // small lists: a host counting sort beats a dozen device allocations
 
-  pt.mark("plan: edges");
   FitState st; state_init(st, pl->prm);
   TL_CUDA(cudaMalloc(&pl->state, sizeof(FitState)));
   TL_CUDA(cudaMemcpy(pl->state, &st, sizeof st, cudaMemcpyHostToDevice));
@@ -345,11 +376,11 @@ std::unique_ptr<topolow_plan> make_plan(const topolow_problem& pb, const topolow
 void launch_geo(topolow_plan& pl, const Geometry& geo, int n_iters, cudaStream_t stream) {
   const unsigned long long ppi = (unsigned long long)pl.n * (unsigned long long)(pl.n - 1) / 2ull;
   if (pl.precision == TOPOLOW_PREC_F64_EXACT) {
-    TileDev<double> dv{(double*)pl.pos, (double*)pl.best, (const double*)pl.dp1, pl.edges, pl.bucket_off, pl.state,
+    TileDev<double> dv{(double*)pl.pos, (double*)pl.best, (const double*)pl.dp1, pl.store->edges, pl.store->bucket_off, pl.state,
                        pl.partials, pl.barrier, pl.trace, (long long)pl.E, ppi};
     launch_tile_f64(dv, geo, pl.prm, n_iters, pl.d_flag, stream);
   } else {
-    TileDev<float> dv{(float*)pl.pos, (float*)pl.best, (const float*)pl.dp1, pl.edges, pl.bucket_off, pl.state,
+    TileDev<float> dv{(float*)pl.pos, (float*)pl.best, (const float*)pl.dp1, pl.store->edges, pl.store->bucket_off, pl.state,
                       pl.partials, pl.barrier, pl.trace, (long long)pl.E, ppi};
     launch_tile_f32(dv, geo, pl.prm, n_iters, pl.d_flag, stream);
   }
@@ -402,7 +433,7 @@ void download_best(const topolow_plan& pl, double* out) {
   std::vector<real> hp(slots * pl.D);
   TL_CUDA(cudaMemcpy(hp.data(), pl.best, hp.size() * sizeof(real), cudaMemcpyDeviceToHost));
   for (int64_t i = 0; i < pl.n; ++i) {
-    const size_t s = pl.slot_of_point[i];
+    const size_t s = pl.store->slot_of_point[i];
     for (int d = 0; d < pl.D; ++d) out[(size_t)d * pl.n + i] = (double)hp[s * pl.D + d];
   }
 }
@@ -573,8 +604,67 @@ int topolow_fit_batch(int32_t n_jobs, const topolow_problem* problems, const top
   const bool dbg = std::getenv("TOPOLOW_DEBUG") != nullptr;
   const auto t_begin = std::chrono::steady_clock::now();
   auto since = [&]() { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count(); };
-  // Host-side set-up (relabelling, bucket sort, uploads) of the jobs is independent: spread it over
-  // the host cores, as the reference spreads whole fits with mclapply.
+  // Many independent fits: one CTA per fit (no grid barrier, plain launches that run side by side on
+  // different SMs) keeps every SM busy; a lone large fit still gets the whole chip.
+  auto job_params = [&](int j) {
+    topolow_params pr = params[j];
+    pr.device = device;
+    if (n_jobs >= 16 && pr.max_ctas == 0) {
+      pr.max_ctas = 1;
+      if (pr.tile_points == 0) pr.tile_points = 64;
+    }
+    return pr;
+  };
+  // Jobs that point at the same edge arrays (the parameter samples of a CV grid evaluated on the same
+  // fold, R/adaptive_sampling.R:2605-2667) share one relabelling and one set of bucketed records.
+  struct StoreKey {
+    const void *ei, *ej, *ed, *et; int64_t E, n; int P;
+    bool operator<(const StoreKey& o) const {
+      return std::tie(ei, ej, ed, et, E, n, P) < std::tie(o.ei, o.ej, o.ed, o.et, o.E, o.n, o.P);
+    }
+  };
+  struct StoreSlot { std::shared_ptr<EdgeStore> store; int first_job = -1; int status = TOPOLOW_OK; std::string error; };
+  std::map<StoreKey, int> key_index;
+  std::vector<StoreSlot> slots;
+  std::vector<int> slot_of_job(n_jobs, -1);
+  for (int j = 0; j < n_jobs; ++j) {
+    const topolow_problem& pb = problems[j];
+    if (pb.n < 2 || pb.n > 1000000 || params[j].mode != TOPOLOW_MODE_COLOURED || params[j].n_shards > 1) continue;
+    const topolow_params pr = job_params(j);
+    const StoreKey key{pb.edge_i, pb.edge_j, pb.edge_dist, pb.edge_thresh, pb.n_edges, pb.n, choose_tile_points(pb.n, pr.tile_points)};
+    auto it = key_index.find(key);
+    if (it == key_index.end()) {
+      it = key_index.emplace(key, (int)slots.size()).first;
+      slots.emplace_back();
+      slots.back().first_job = j;
+    }
+    slot_of_job[j] = it->second;
+  }
+  auto run_pool = [&](int count, const std::function<void(int)>& fn) {
+    const int n_threads = std::max(1, std::min<int>({(int)std::thread::hardware_concurrency(), 16, count}));
+    std::atomic<int> next{0};
+    std::vector<std::thread> pool;
+    for (int t = 0; t < n_threads; ++t)
+      pool.emplace_back([&] { for (int i = next.fetch_add(1); i < count; i = next.fetch_add(1)) fn(i); });
+    for (auto& th : pool) th.join();
+  };
+  run_pool((int)slots.size(), [&](int k) {
+    StoreSlot& sl = slots[k];
+    const topolow_problem& pb = problems[sl.first_job];
+    try {
+      const topolow_params pr = job_params(sl.first_job);
+      validate(pb, pr);
+      const int P = choose_tile_points(pb.n, pr.tile_points);
+      sl.store = make_store(pb, (int)((pb.n + 32 * P - 1) / (32 * P)), P, device);
+    } catch (const CudaError& e) {
+      sl.status = TOPOLOW_ERR_CUDA; sl.error = e.what(); cudaGetLastError();
+    } catch (const std::exception& e) {
+      sl.status = TOPOLOW_ERR_BAD_ARG; sl.error = e.what();
+    }
+  });
+  if (dbg) std::fprintf(stderr, "[topolow] batch: %zu edge stores for %d jobs: %.3f s\n", slots.size(), n_jobs, since());
+  // Per-job set-up (point upload, state) is independent: spread it over the host cores, as the reference
+  // spreads whole fits with mclapply.
   auto setup_one = [&](int j) {
     topolow_result& r = results[j];
     r.status = TOPOLOW_OK; r.message[0] = 0;
@@ -586,15 +676,14 @@ int topolow_fit_batch(int32_t n_jobs, const topolow_problem* problems, const top
       }
       if (!r.positions) throw BadArg("result->positions must be caller-allocated");
       if (params[j].mode != TOPOLOW_MODE_COLOURED) throw BadArg("batch supports the coloured mode only");
-      topolow_params pr = params[j];
-      pr.device = device;
-      // Many independent fits: one CTA per fit (no grid barrier, plain launches that run side by
-      // side on different SMs) keeps every SM busy; a lone large fit still gets the whole chip.
-      if (n_jobs >= 16 && pr.max_ctas == 0) {
-        pr.max_ctas = 1;
-        if (pr.tile_points == 0) pr.tile_points = 64;
+      const topolow_params pr = job_params(j);
+      std::shared_ptr<EdgeStore> store;
+      if (slot_of_job[j] >= 0) {
+        const StoreSlot& sl = slots[slot_of_job[j]];
+        if (sl.status != TOPOLOW_OK) { r.status = sl.status; set_msg(r.message, sizeof r.message, sl.error.c_str()); return; }
+        store = sl.store;
       }
-      plans[j] = make_plan(problems[j], pr);
+      plans[j] = make_plan(problems[j], pr, store);
       left[j] = pr.n_iter;
     } catch (const CudaError& e) {
       r.status = TOPOLOW_ERR_CUDA; set_msg(r.message, sizeof r.message, e.what()); cudaGetLastError();
@@ -602,16 +691,7 @@ int topolow_fit_batch(int32_t n_jobs, const topolow_problem* problems, const top
       r.status = TOPOLOW_ERR_BAD_ARG; set_msg(r.message, sizeof r.message, e.what());
     }
   };
-  {
-    const int n_threads = std::max(1, std::min<int>({(int)std::thread::hardware_concurrency(), 16, n_jobs}));
-    std::atomic<int> next{0};
-    std::vector<std::thread> pool;
-    for (int t = 0; t < n_threads; ++t)
-      pool.emplace_back([&] {
-        for (int j = next.fetch_add(1); j < n_jobs; j = next.fetch_add(1)) setup_one(j);
-      });
-    for (auto& th : pool) th.join();
-  }
+  run_pool(n_jobs, setup_one);
   if (dbg) std::fprintf(stderr, "[topolow] batch set-up of %d jobs: %.3f s\n", n_jobs, since());
   try {
     bool any = true;
@@ -743,7 +823,7 @@ int64_t topolow_plan_enumerate_job(const topolow_plan* plan, int32_t iter, int32
   if (!plan || !out) return -1;
   try {
     check_job(*plan, kind, t0, tc, y0, yc);
-    return enumerate_schedule(job_geometry(*plan, kind, t0, tc, y0, yc), plan->point_of_slot, iter, out, cap_pairs);
+    return enumerate_schedule(job_geometry(*plan, kind, t0, tc, y0, yc), plan->store->point_of_slot, iter, out, cap_pairs);
   } catch (const std::exception&) {
     return -1;
   }
@@ -754,7 +834,7 @@ void topolow_plan_destroy(topolow_plan* plan) { delete plan; }
 // Host walk of the schedule the kernel executes (same functions, same loop nest).
 int64_t topolow_plan_enumerate(const topolow_plan* plan, int32_t iter, int32_t* out, int64_t cap_pairs) {
   if (!plan || !out) return -1;
-  return enumerate_schedule(plan->geo, plan->point_of_slot, iter, out, cap_pairs);
+  return enumerate_schedule(plan->geo, plan->store->point_of_slot, iter, out, cap_pairs);
 }
 
 // The same walk without a device: geometry + relabelling are pure functions of
@@ -771,7 +851,7 @@ int64_t topolow_schedule_enumerate(int64_t n, int32_t ndim, int32_t precision, i
     for (int i = 0; i < 8; ++i) geometry_out[i] = v[i];
   }
   if (!out) return 0;
-  const std::vector<int32_t> sop = random_permutation(n, seed);
+  const std::vector<int32_t> sop = random_permutation(n, kLayoutSeed);   // as make_store()
   std::vector<int32_t> pos((size_t)g.T * 32 * g.P, -1);
   for (int64_t i = 0; i < n; ++i) pos[sop[i]] = (int32_t)i;
   return enumerate_schedule(g, pos, iter, out, cap_pairs);
