@@ -373,18 +373,32 @@ std::unique_ptr<topolow_plan> make_plan(const topolow_problem& pb, const topolow
   return pl;
 }
 
-void launch_geo(topolow_plan& pl, const Geometry& geo, int n_iters, cudaStream_t stream) {
+template <class real>
+TileDev<real> device_view(const topolow_plan& pl) {
   const unsigned long long ppi = (unsigned long long)pl.n * (unsigned long long)(pl.n - 1) / 2ull;
-  if (pl.precision == TOPOLOW_PREC_F64_EXACT) {
-    TileDev<double> dv{(double*)pl.pos, (double*)pl.best, (const double*)pl.dp1, pl.store->edges, pl.store->bucket_off, pl.state,
+  return TileDev<real>{(real*)pl.pos, (real*)pl.best, (const real*)pl.dp1, pl.store->edges, pl.store->bucket_off, pl.state,
                        pl.partials, pl.barrier, pl.trace, (long long)pl.E, ppi};
-    launch_tile_f64(dv, geo, pl.prm, n_iters, pl.d_flag, stream);
-  } else {
-    TileDev<float> dv{(float*)pl.pos, (float*)pl.best, (const float*)pl.dp1, pl.store->edges, pl.store->bucket_off, pl.state,
-                      pl.partials, pl.barrier, pl.trace, (long long)pl.E, ppi};
-    launch_tile_f32(dv, geo, pl.prm, n_iters, pl.d_flag, stream);
-  }
+}
+void launch_geo(topolow_plan& pl, const Geometry& geo, int n_iters, cudaStream_t stream) {
+  if (pl.precision == TOPOLOW_PREC_F64_EXACT) launch_tile_f64(device_view<double>(pl), geo, pl.prm, n_iters, pl.d_flag, stream);
+  else launch_tile_f32(device_view<float>(pl), geo, pl.prm, n_iters, pl.d_flag, stream);
   pl.launches++;
+}
+// One launch for the next chunk of many single-CTA fits with 64-point tiles and equal (D, precision, W).
+template <class real>
+void launch_group(const std::vector<topolow_plan*>& members, const std::vector<int>& n_iters, cudaStream_t stream) {
+  std::vector<BatchJob<real>> jobs(members.size());
+  for (size_t i = 0; i < members.size(); ++i) {
+    topolow_plan& pl = *members[i];
+    jobs[i] = BatchJob<real>{device_view<real>(pl), pl.geo, pl.prm, n_iters[i], 0, pl.d_flag};
+    pl.launches++;
+  }
+  AsyncBuf<BatchJob<real>> d_jobs(jobs.size(), stream);
+  // (pageable source: the call returns once the source has been staged, so `jobs` may go out of scope)
+  TL_CUDA(cudaMemcpyAsync(d_jobs, jobs.data(), jobs.size() * sizeof(BatchJob<real>), cudaMemcpyHostToDevice, stream));
+  const topolow_plan& p0 = *members[0];
+  if (sizeof(real) == 8) launch_tile_batch_f64_(p0.D, (const BatchJob<double>*)(const void*)d_jobs, (int)jobs.size(), p0.geo.W, stream);
+  else launch_tile_batch_f32_(p0.D, (const BatchJob<float>*)(const void*)d_jobs, (int)jobs.size(), p0.geo.W, stream);
 }
 void launch_chunk(topolow_plan& pl, int n_iters, cudaStream_t stream) { launch_geo(pl, pl.geo, n_iters, stream); }
 
@@ -694,12 +708,51 @@ int topolow_fit_batch(int32_t n_jobs, const topolow_problem* problems, const top
   run_pool(n_jobs, setup_one);
   if (dbg) std::fprintf(stderr, "[topolow] batch set-up of %d jobs: %.3f s\n", n_jobs, since());
   try {
+    // Single-CTA fits with 64-point tiles are launched many per kernel (one CTA each), grouped by
+    // (ndim, precision, warps): the device runs at most 128 kernels side by side, fewer than it has SMs.
+    struct Group { std::vector<int> jobs; std::unique_ptr<StreamGuard> stream; std::unique_ptr<EventGuard> ev0, ev1; };
+    std::map<std::tuple<int, int, int>, Group> groups;
+    std::vector<char> grouped(n_jobs, 0);
+    for (int j = 0; j < n_jobs; ++j) {
+      if (!plans[j] || plans[j]->geo.G != 1 || plans[j]->geo.P != 2) continue;
+      groups[std::make_tuple(plans[j]->D, plans[j]->precision, plans[j]->geo.W)].jobs.push_back(j);
+      grouped[j] = 1;
+    }
+    for (auto& kv : groups) {   // load every kernel the batch needs before the first one starts
+      const int gd = std::get<0>(kv.first), gw = std::get<2>(kv.first);
+      if (std::get<1>(kv.first) == TOPOLOW_PREC_F64_EXACT) launch_tile_batch_f64_(gd, nullptr, 0, gw, nullptr);
+      else launch_tile_batch_f32_(gd, nullptr, 0, gw, nullptr);
+    }
+    for (auto& kv : groups) {
+      Group& g = kv.second;
+      g.stream.reset(new StreamGuard()); g.ev0.reset(new EventGuard()); g.ev1.reset(new EventGuard());
+      TL_CUDA(cudaEventRecord(*g.ev0, *g.stream));
+    }
+    for (int j = 0; j < n_jobs; ++j)
+      if (plans[j] && !grouped[j]) TL_CUDA(cudaEventRecord(plans[j]->ev0, plans[j]->stream));
     bool any = true;
-    for (int j = 0; j < n_jobs; ++j) if (plans[j]) TL_CUDA(cudaEventRecord(plans[j]->ev0, plans[j]->stream));
     while (any) {
       any = false;
+      // (reverse key order = highest ndim first: the longest fits are handed to the SMs first.  A batch
+      // cannot be interrupted, so every fit runs to its own stop in one launch - no chunk boundaries at
+      // which a group would have to wait for its slowest member.)
+      for (auto it = groups.rbegin(); it != groups.rend(); ++it) {
+        auto& kv = *it;
+        Group& g = kv.second;
+        std::vector<topolow_plan*> members; std::vector<int> iters;
+        for (int j : g.jobs) {
+          if (left[j] <= 0 || plans[j]->h_flag[0]) continue;
+          const int c = left[j];
+          members.push_back(plans[j].get()); iters.push_back(c);
+          left[j] -= c;
+        }
+        if (members.empty()) continue;
+        if (std::get<1>(kv.first) == TOPOLOW_PREC_F64_EXACT) launch_group<double>(members, iters, *g.stream);
+        else launch_group<float>(members, iters, *g.stream);
+        any = true;
+      }
       for (int j = 0; j < n_jobs; ++j) {
-        if (!plans[j] || left[j] <= 0 || plans[j]->h_flag[0]) continue;
+        if (!plans[j] || grouped[j] || left[j] <= 0 || plans[j]->h_flag[0]) continue;
         const int c = std::min(left[j], plans[j]->chunk_iters);
         launch_chunk(*plans[j], c, plans[j]->stream);
         left[j] -= c;
@@ -707,13 +760,23 @@ int topolow_fit_batch(int32_t n_jobs, const topolow_problem* problems, const top
       }
     }
     if (dbg) std::fprintf(stderr, "[topolow] batch launches issued: %.3f s\n", since());
+    for (auto& kv : groups) {
+      Group& g = kv.second;
+      TL_CUDA(cudaEventRecord(*g.ev1, *g.stream));
+      TL_CUDA(cudaEventSynchronize(*g.ev1));
+      float ms = 0.f;
+      TL_CUDA(cudaEventElapsedTime(&ms, *g.ev0, *g.ev1));
+      for (int j : g.jobs) plans[j]->total_ms = ms;   // the fits of a group share its launches
+    }
     for (int j = 0; j < n_jobs; ++j) {
       if (!plans[j]) continue;
-      TL_CUDA(cudaEventRecord(plans[j]->ev1, plans[j]->stream));
-      TL_CUDA(cudaEventSynchronize(plans[j]->ev1));
-      float ms = 0.f;
-      TL_CUDA(cudaEventElapsedTime(&ms, plans[j]->ev0, plans[j]->ev1));
-      plans[j]->total_ms = ms;
+      if (!grouped[j]) {
+        TL_CUDA(cudaEventRecord(plans[j]->ev1, plans[j]->stream));
+        TL_CUDA(cudaEventSynchronize(plans[j]->ev1));
+        float ms = 0.f;
+        TL_CUDA(cudaEventElapsedTime(&ms, plans[j]->ev0, plans[j]->ev1));
+        plans[j]->total_ms = ms;
+      }
       fill_result(*plans[j], results[j], false);
     }
     if (dbg) std::fprintf(stderr, "[topolow] batch results read: %.3f s\n", since());

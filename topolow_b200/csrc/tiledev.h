@@ -30,4 +30,15 @@ struct TileDev {
   unsigned long long pairs_per_iter;
 };
 
+// One entry of a many-fits launch (tile_batch_kernel).
+template <class real>
+struct BatchJob {
+  TileDev<real> dv;
+  Geometry geo;
+  FitParams prm;
+  int n_iters;
+  int pad;
+  volatile int* host_flag;
+};
+
 }  // namespace tl

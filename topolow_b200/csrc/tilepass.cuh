@@ -747,11 +747,12 @@ TL_D void block_reduce3(double& a, double& b, double& c, double* scratch /* [3*3
 }
 
 // ---------------------------------------------------------------------------------------
-// The persistent kernel: up to n_iters iterations of one fit, G CTAs of W warps.
+// The persistent loop: up to n_iters iterations of one fit, run by G CTAs of W warps (`cta` = this
+// CTA's index among them).
 // ---------------------------------------------------------------------------------------
 template <int D, class M>
-__global__ void __launch_bounds__(M::kMaxWarps * 32, 1)
-tile_kernel(TileDev<typename M::real> dv, Geometry geo, FitParams prm, int n_iters, volatile int* host_flag) {
+TL_D void tile_body(const TileDev<typename M::real>& dv, const Geometry& geo, const FitParams& prm, int n_iters,
+                    volatile int* host_flag, const int cta) {
   typedef typename M::real real;
   constexpr int TS = TileShape<D>::kReals;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -760,7 +761,7 @@ tile_kernel(TileDev<typename M::real> dv, Geometry geo, FitParams prm, int n_ite
   __shared__ unsigned long long s_key[kIterKeys];   // iter_key(geo, iter, salt) of the running iteration
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int W = geo.W, cta = blockIdx.x;
+  const int W = geo.W;
   real* s_tiles = reinterpret_cast<real*>(smem_raw);
   real* s_tgt = s_tiles + (size_t)2 * W * TS;
   uint32_t* s_mask = reinterpret_cast<uint32_t*>(s_tgt + (size_t)W * kTableReals);
@@ -769,10 +770,6 @@ tile_kernel(TileDev<typename M::real> dv, Geometry geo, FitParams prm, int n_ite
   EdgeRec* s_stage = reinterpret_cast<EdgeRec*>((reinterpret_cast<uintptr_t>(s_flag + W) + 15) & ~(uintptr_t)15) + warp * kStage;
   const WarpTable<real> tb{s_tgt + (size_t)warp * kTableReals, s_mask + warp * kTableMasks};
 
-#ifdef TL_DEBUG_CLOCK
-  long long dbg_c0 = clock64(); unsigned long long dbg_t0;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t0));
-#endif
   unsigned gen = 0;
   if (tid == 0) load_state(st, dv.state);
   if (geo.G > 1) gen = ld_acquire_u32(&dv.barrier[1]);
@@ -975,17 +972,32 @@ tile_kernel(TileDev<typename M::real> dv, Geometry geo, FitParams prm, int n_ite
       __syncthreads();
     }
   }
-#ifdef TL_DEBUG_CLOCK
-  if ((cta == 0 || cta == 77) && tid == 0) {
-    unsigned long long dbg_t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t1));
-    const long long c = clock64() - dbg_c0;
-    printf("cta %d: %lld cycles in %llu ns = %.1f MHz\n", cta, c, dbg_t1 - dbg_t0, 1e3 * (double)c / (double)(dbg_t1 - dbg_t0));
-  }
-#endif
   if (cta == 0 && tid == 0) {
     store_state(dv.state, st);
     if (host_flag) { host_flag[1] = st.iter; __threadfence_system(); host_flag[0] = st.stop; }
   }
+}
+
+// One fit per launch: G CTAs (co-operative launch when G > 1).
+template <int D, class M>
+__global__ void __launch_bounds__(M::kMaxWarps * 32, 1)
+tile_kernel(TileDev<typename M::real> dv, Geometry geo, FitParams prm, int n_iters, volatile int* host_flag) {
+  tile_body<D, M>(dv, geo, prm, n_iters, host_flag, (int)blockIdx.x);
+}
+
+// Many fits per launch, one CTA each (the CV grid): CTA b runs jobs[b].  All jobs of a launch have the
+// same D, precision and W; fits that have already stopped return at once.
+template <int D, class M>
+__global__ void __launch_bounds__(M::kMaxWarps * 32, 1)
+tile_batch_kernel(const BatchJob<typename M::real>* __restrict__ jobs) {
+  typedef BatchJob<typename M::real> Job;
+  __shared__ Job job;
+  static_assert(sizeof(Job) % 4 == 0, "BatchJob is copied as 32-bit words");
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(jobs + blockIdx.x);
+  uint32_t* dst = reinterpret_cast<uint32_t*>(&job);
+  for (int i = threadIdx.x; i < (int)(sizeof(Job) / 4); i += blockDim.x) dst[i] = src[i];
+  __syncthreads();
+  tile_body<D, M>(job.dv, job.geo, job.prm, job.n_iters, job.host_flag, 0);
 }
 
 }  // namespace TL_PNS

@@ -25,6 +25,10 @@ void launch_tile_f32(const TileDev<float>& dv, const Geometry& geo, const FitPar
                      volatile int* host_flag, cudaStream_t stream);
 void launch_tile_f64(const TileDev<double>& dv, const Geometry& geo, const FitParams& prm, int n_iters,
                      volatile int* host_flag, cudaStream_t stream);
+// Many fits in one launch, one CTA each, 64-point tiles (geo.P == 2): d_jobs is a device array of n_jobs
+// entries with equal D and W.
+void launch_tile_batch_f32_(int D, const BatchJob<float>* d_jobs, int n_jobs, int W, cudaStream_t stream);
+void launch_tile_batch_f64_(int D, const BatchJob<double>* d_jobs, int n_jobs, int W, cudaStream_t stream);
 // Largest CTA count of that instantiation that can be co-resident on the current device.
 int max_coresident_f32(int D, int W, int P);
 int max_coresident_f64(int D, int W, int P);
