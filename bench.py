@@ -191,15 +191,19 @@ def cfg5_jobs(n, missing, samples, fit_iters, seed):
         mask = np.ones(E, dtype=bool)
         mask[perm[f * hold:(f + 1) * hold]] = False
         deg = (np.bincount(ei[mask], minlength=n) + np.bincount(ej[mask], minlength=n) + 1).astype(np.int32)
-        folds.append((mask, deg, perm[f * hold:(f + 1) * hold]))
+        # one training edge list per fold, shared by every parameter sample (topolow_fit_batch then builds
+        # its device records once per fold; cv.likelihood_batch hands over its folds the same way)
+        train = dict(edge_i=np.ascontiguousarray(ei[mask], dtype=np.int32), edge_j=np.ascontiguousarray(ej[mask], dtype=np.int32),
+                     edge_dist=np.ascontiguousarray(ed[mask], dtype=np.float64),
+                     edge_thresh=np.ascontiguousarray(prob["edge_thresh"][mask], dtype=np.int32))
+        folds.append((train, deg, perm[f * hold:(f + 1) * hold]))
     jobs, meta = [], []
     for s_ in range(samples):
         ndim = int(rng.integers(2, 11))
         k0, cr, c = float(rng.uniform(1, 15)), float(10 ** rng.uniform(-3, -1.3)), float(10 ** rng.uniform(-3, -1.3))
-        for f, (mask, deg, held) in enumerate(folds):
+        for f, (train, deg, held) in enumerate(folds):
             init = np.vstack([np.zeros((1, ndim)), np.cumsum(rng.uniform(0, 2 * ed.max() / n, size=(n - 1, ndim)), axis=0)])
-            jobs.append(dict(initial_positions=init, degrees=deg, edge_i=ei[mask], edge_j=ej[mask], edge_dist=ed[mask],
-                             edge_thresh=prob["edge_thresh"][mask], n_iter=fit_iters, k0=k0, cooling_rate=cr, c_repulsion=c,
+            jobs.append(dict(initial_positions=init, degrees=deg, **train, n_iter=fit_iters, k0=k0, cooling_rate=cr, c_repulsion=c,
                              relative_epsilon=1e-4, convergence_window=5, seed=1000 * s_ + f))
             meta.append((s_, f, held))
     return prob, jobs, meta
@@ -230,13 +234,17 @@ def main_cfg5(args, n, missing):
     barrier()
     t0 = time.perf_counter()
     done, pair_updates, dev_ms, held_mae = 0, 0, 0.0, []
+    held_cells = {}   # the hold-out cells of a fold (fixed for the whole grid)
+    for (_s, f, held) in meta:
+        if f not in held_cells:
+            held_cells[f] = (np.ascontiguousarray(prob["edge_i"][held]), np.ascontiguousarray(prob["edge_j"][held]),
+                             np.ascontiguousarray(prob["edge_dist"][held]))
     with ClockSampler(local) as clk:
         for _ in range(args.steps):
             out = _lib.fit_batch(jobs, device=local)
             for r, (s_, f, held) in zip(out, meta):
                 # hold-out residuals on the device (R/error_metrics.R:95-114, R/adaptive_sampling.R:2642-2647)
-                sa, cnt = _lib.holdout_errors(r["positions"], prob["edge_i"][held], prob["edge_j"][held],
-                                              prob["edge_dist"][held], local)
+                sa, cnt = _lib.holdout_errors(r["positions"], *held_cells[f], local)
                 held_mae.append(sa / max(cnt, 1))
             done += len(out)
             pair_updates += sum(r["pair_updates"] for r in out)
@@ -306,7 +314,7 @@ def main():
     ap.add_argument("--multi", default="sharded", choices=["sharded", "replicas"],
                     help="cfg4 with --gpus > 1: one map sharded over the GPUs (exact, position all-gather between rounds) "
                          "or one independent replica per GPU")
-    ap.add_argument("--samples", type=int, default=32, help="cfg5: parameter samples per GPU per step (x 4 folds)")
+    ap.add_argument("--samples", type=int, default=74, help="cfg5: parameter samples per GPU per step (x 4 folds)")
     ap.add_argument("--fit-iters", type=int, default=250, help="cfg5: mapping_max_iter of every fit (R/core.R:945)")
     args = ap.parse_args()
     n, d, missing = WORKLOADS[args.workload]

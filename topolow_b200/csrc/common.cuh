@@ -55,8 +55,17 @@ struct AsyncBuf {
   AsyncBuf(const AsyncBuf&) = delete;
   AsyncBuf& operator=(const AsyncBuf&) = delete;
   ~AsyncBuf() { if (p) cudaFreeAsync(p, s); }
+  T* release() { T* r = p; p = nullptr; return r; }
   operator T*() const { return p; }
 };
+// Long-lived device buffers of plans and edge stores come from the same pool (a CV grid creates and
+// destroys hundreds of plans per call; cudaMalloc / cudaFree would serialise them on the driver).
+template <class T>
+inline void pool_alloc(T*& p, size_t bytes) {
+  TL_CUDA(cudaMallocAsync((void**)&p, bytes ? bytes : 1, cudaStreamPerThread));
+}
+inline void pool_ready() { TL_CUDA(cudaStreamSynchronize(cudaStreamPerThread)); }   // allocations usable on any stream
+inline void pool_free(void* p) { if (p) cudaFreeAsync(p, cudaStreamPerThread); }
 inline void keep_pool_memory(int device) {
   cudaMemPool_t pool;
   if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {

@@ -92,8 +92,8 @@ void build_buckets(const topolow_problem& pb, const std::vector<int32_t>& slot_o
   const long long E = pb.n_edges;
   const size_t nkeys = (size_t)T * T;
   // the two results live as long as the plan; everything else is stream-ordered scratch
-  DeviceBuf<uint32_t> d_off(nkeys + 1);
-  DeviceBuf<EdgeRec> d_out(E);
+  AsyncBuf<uint32_t> d_off(nkeys + 1, stream);   // released to the caller: free with pool_free()
+  AsyncBuf<EdgeRec> d_out(E, stream);
   AsyncBuf<int32_t> d_ei(E, stream), d_ej(E, stream), d_thr(E, stream), d_slot(slot_of_point.size(), stream);
   AsyncBuf<double> d_dist(E, stream);
   AsyncBuf<uint32_t> d_keys(E, stream), d_cur(nkeys + 1, stream);

@@ -34,7 +34,7 @@ struct EdgeStore {
   std::vector<int32_t> slot_of_point;
   EdgeRec* edges = nullptr;
   uint32_t* bucket_off = nullptr;
-  ~EdgeStore() { cudaFree(edges); cudaFree(bucket_off); }
+  ~EdgeStore() { pool_free(edges); pool_free(bucket_off); }
 };
 
 struct topolow_plan {
@@ -58,8 +58,8 @@ struct topolow_plan {
   size_t smem = 0;
 
   ~topolow_plan() {
-    cudaFree(pos); cudaFree(best); cudaFree(dp1);
-    cudaFree(state); cudaFree(partials); cudaFree(barrier); cudaFree(trace);
+    pool_free(pos); pool_free(best); pool_free(dp1);
+    pool_free(state); pool_free(partials); pool_free(barrier); pool_free(trace);
     if (h_flag) cudaFreeHost((void*)h_flag);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
@@ -236,9 +236,10 @@ void upload_points(topolow_plan& pl, const topolow_problem& pb, real phantom_coo
     for (int d = 0; d < pl.D; ++d) hp[s * pl.D + d] = (real)pb.initial_positions[(size_t)d * pl.n + i];
     hd[s] = (real)((double)pb.degrees[i] + 1.0);
   }
-  TL_CUDA(cudaMalloc(&pl.pos, hp.size() * sizeof(real)));
-  TL_CUDA(cudaMalloc(&pl.best, hp.size() * sizeof(real)));
-  TL_CUDA(cudaMalloc(&pl.dp1, hd.size() * sizeof(real)));
+  pool_alloc(pl.pos, hp.size() * sizeof(real));
+  pool_alloc(pl.best, hp.size() * sizeof(real));
+  pool_alloc(pl.dp1, hd.size() * sizeof(real));
+  pool_ready();
   TL_CUDA(cudaMemcpy(pl.pos, hp.data(), hp.size() * sizeof(real), cudaMemcpyHostToDevice));
   TL_CUDA(cudaMemcpy(pl.best, hp.data(), hp.size() * sizeof(real), cudaMemcpyHostToDevice));
   TL_CUDA(cudaMemcpy(pl.dp1, hd.data(), hd.size() * sizeof(real), cudaMemcpyHostToDevice));
@@ -279,8 +280,9 @@ void upload_edges(EdgeStore& st, const topolow_problem& pb, int T, int P) {
         return x.slot_lo != y.slot_lo ? x.slot_lo < y.slot_lo
                                       : (x.slot_hi_type & 0x3fffffffu) < (y.slot_hi_type & 0x3fffffffu);
       });
-  TL_CUDA(cudaMalloc(&st.edges, std::max<size_t>(recs.size(), 1) * sizeof(EdgeRec)));
-  TL_CUDA(cudaMalloc(&st.bucket_off, off.size() * sizeof(uint32_t)));
+  pool_alloc(st.edges, recs.size() * sizeof(EdgeRec));
+  pool_alloc(st.bucket_off, off.size() * sizeof(uint32_t));
+  pool_ready();
   if (!recs.empty()) TL_CUDA(cudaMemcpy(st.edges, recs.data(), recs.size() * sizeof(EdgeRec), cudaMemcpyHostToDevice));
   TL_CUDA(cudaMemcpy(st.bucket_off, off.data(), off.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
 }
@@ -292,6 +294,7 @@ void upload_edges(EdgeStore& st, const topolow_problem& pb, int T, int P) {
 constexpr uint64_t kLayoutSeed = 0x746f706f6c6f77ULL;
 std::shared_ptr<EdgeStore> make_store(const topolow_problem& pb, int T, int P, int device) {
   TL_CUDA(cudaSetDevice(device));
+  keep_pool_memory(device);
   auto st = std::make_shared<EdgeStore>();
   st->slot_of_point = random_permutation(pb.n, kLayoutSeed);
   st->point_of_slot.assign((size_t)T * 32 * P, -1);
@@ -345,17 +348,18 @@ std::unique_ptr<topolow_plan> make_plan(const topolow_problem& pb, const topolow
   pt.mark("plan: points");
 
   FitState st; state_init(st, pl->prm);
-  TL_CUDA(cudaMalloc(&pl->state, sizeof(FitState)));
-  TL_CUDA(cudaMemcpy(pl->state, &st, sizeof st, cudaMemcpyHostToDevice));
-  TL_CUDA(cudaMalloc(&pl->partials, sizeof(double) * 4 * 1024));   // any job geometry: G <= SM count
-  TL_CUDA(cudaMemset(pl->partials, 0, sizeof(double) * 4 * 1024));
-  // [0], [1]: grid barrier; from word 32 on: one round counter per super-block of any job geometry (S <= 2T + 2)
+  // barrier: [0], [1] grid barrier; from word 32 on one round counter per super-block of any job geometry (S <= 2T + 2)
   const size_t barrier_words = 32 + 2 * (size_t)g.T + 64;
-  TL_CUDA(cudaMalloc(&pl->barrier, barrier_words * sizeof(unsigned)));
-  TL_CUDA(cudaMemset(pl->barrier, 0, barrier_words * sizeof(unsigned)));
   const int ntr = std::max(pr.n_iter, 1);
+  pool_alloc(pl->state, sizeof(FitState));
+  pool_alloc(pl->partials, sizeof(double) * 4 * 1024);   // any job geometry: G <= SM count
+  pool_alloc(pl->barrier, barrier_words * sizeof(unsigned));
+  pool_alloc(pl->trace, sizeof(double) * ntr);
+  pool_ready();
+  TL_CUDA(cudaMemcpy(pl->state, &st, sizeof st, cudaMemcpyHostToDevice));
+  TL_CUDA(cudaMemset(pl->partials, 0, sizeof(double) * 4 * 1024));
+  TL_CUDA(cudaMemset(pl->barrier, 0, barrier_words * sizeof(unsigned)));
   std::vector<double> nanv(ntr, NAN);
-  TL_CUDA(cudaMalloc(&pl->trace, sizeof(double) * ntr));
   TL_CUDA(cudaMemcpy(pl->trace, nanv.data(), sizeof(double) * ntr, cudaMemcpyHostToDevice));
   TL_CUDA(cudaHostAlloc((void**)&pl->h_flag, 2 * sizeof(int), cudaHostAllocMapped));
   pl->h_flag[0] = 0; pl->h_flag[1] = 0;

@@ -110,9 +110,12 @@ extern "C" int topolow_holdout_errors(const double* positions, int64_t n, int32_
     TL_CUDA(cudaSetDevice(device));
     const std::vector<double> rm = to_row_major(positions, n, ndim);
     const int blocks = 296;
-    DeviceBuf<double> d_pos(rm.size()), d_truth(n_cells), d_ps(blocks);
-    DeviceBuf<int32_t> d_ci(n_cells), d_cj(n_cells);
-    DeviceBuf<unsigned long long> d_pc(blocks);
+    // (pool scratch: a CV grid calls this once per fit)
+    cudaStream_t ps_ = cudaStreamPerThread;
+    AsyncBuf<double> d_pos(rm.size(), ps_), d_truth(n_cells, ps_), d_ps(blocks, ps_);
+    AsyncBuf<int32_t> d_ci(n_cells, ps_), d_cj(n_cells, ps_);
+    AsyncBuf<unsigned long long> d_pc(blocks, ps_);
+    TL_CUDA(cudaStreamSynchronize(ps_));
     TL_CUDA(cudaMemcpy(d_pos, rm.data(), rm.size() * sizeof(double), cudaMemcpyHostToDevice));
     if (n_cells > 0) {
       TL_CUDA(cudaMemcpy(d_truth, truth, n_cells * sizeof(double), cudaMemcpyHostToDevice));
