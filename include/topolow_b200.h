@@ -79,6 +79,14 @@ typedef struct {
   const int32_t* edge_thresh;       /* 0 exact, +1 '>' , -1 '<'  (R/core.R:346,358-359) */
   const int32_t* degrees;           /* rowSums(!is.na), diagonal included (R/core.R:340-341) */
   const double* initial_positions;  /* n x ndim, column-major like an R matrix */
+  /* ---- optional: cells held out of this fit, scored on the final (best) positions before they leave
+   * the device (the OutSampleError reduction of R/error_metrics.R:95-114 as pooled by
+   * R/adaptive_sampling.R:2642-2647; same numbers as topolow_holdout_errors on the returned positions).
+   * n_holdout = 0 (all-zero tail) = none. ---- */
+  int64_t n_holdout;
+  const int32_t* holdout_i;         /* 0-based rows */
+  const int32_t* holdout_j;
+  const double* holdout_truth;      /* true dissimilarity of the cell; NaN = dropped */
 } topolow_problem;
 
 typedef struct {
@@ -117,6 +125,8 @@ typedef struct {
   int64_t pair_updates;             /* pair visits executed */
   double device_ms;                 /* CUDA-event time of the optimisation kernels */
   double* trace_mae;                /* optional, length n_iter; NaN where no check ran */
+  double holdout_sum_abs;           /* sum |truth - ||x_i - x_j||| over the problem's hold-out cells (0 if none) */
+  int64_t holdout_count;            /* cells that entered the sum */
   char message[256];
 } topolow_result;
 

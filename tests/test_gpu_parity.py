@@ -303,6 +303,59 @@ def test_batch_equals_individual_fits():
     assert out[4]["status"] == _lib.ERR_TOO_FEW_POINTS      # per-job status, the batch itself succeeds
 
 
+def test_cv_grid_batch_shares_fold_records_and_launches():
+    # >= 16 jobs: one CTA per fit, many fits per launch (grouped by ndim / precision), and the jobs that
+    # point at the same edge arrays share one set of device records.  None of that may change a result:
+    # every job equals the same fit run alone with the same geometry (one CTA, 64-point tiles).
+    a = small_problem(300, 4, 0.3, 91)
+    b = small_problem(300, 4, 0.3, 92)
+    rng = np.random.default_rng(5)
+    jobs, want = [], []
+    for j in range(18):
+        src = a if j % 2 == 0 else b            # two "folds", shared by reference across the samples
+        d = 2 + j % 3
+        prec = _lib.PREC_F64_EXACT if j % 6 == 5 else _lib.PREC_F32
+        init = rng.normal(size=(300, d))
+        kw = dict(n_iter=12, k0=2.0 + j, cooling_rate=0.02, c_repulsion=0.01, seed=100 + j, precision=prec)
+        jobs.append(dict(initial_positions=init, degrees=src[1], edge_i=src[2], edge_j=src[3], edge_dist=src[4],
+                         edge_thresh=src[5], **kw))
+        want.append(_lib.fit(init, src[1], src[2], src[3], src[4], src[5], 12, 2.0 + j, 0.02, 0.01, seed=100 + j,
+                             precision=prec, max_ctas=1, tile_points=64))
+    out = _lib.fit_batch(jobs)
+    for got, ref in zip(out, want):
+        assert got["status"] == _lib.OK
+        assert np.array_equal(got["positions"], ref["positions"])
+        assert got["final_mae"] == ref["final_mae"] and got["iterations"] == ref["iterations"]
+    # the same batch with private copies of the edge arrays (nothing shared) gives the same bits
+    copies = [dict(j, edge_i=np.array(j["edge_i"]), edge_j=np.array(j["edge_j"]), edge_dist=np.array(j["edge_dist"]),
+                   edge_thresh=np.array(j["edge_thresh"])) for j in jobs]
+    for got, ref in zip(_lib.fit_batch(copies), out):
+        assert np.array_equal(got["positions"], ref["positions"])
+
+
+def test_holdout_scored_inside_the_fit_equals_the_separate_kernel():
+    # topolow_problem.holdout_*: same numbers as topolow_holdout_errors on the returned positions
+    a = small_problem(220, 3, 0.25, 17)
+    rng = np.random.default_rng(3)
+    ci, cj = rng.integers(0, 220, 500).astype(np.int32), rng.integers(0, 220, 500).astype(np.int32)
+    truth = rng.uniform(0.5, 9.0, 500)
+    truth[::37] = np.nan                                   # NA truth cells are dropped
+    for kw in (dict(), dict(precision=_lib.PREC_F64_EXACT), dict(mode=_lib.MODE_REPLAY)):
+        r = _lib.fit(*a, 15, 3.0, 0.02, 0.01, seed=4, holdout=(ci, cj, truth), **kw)
+        s_abs, cnt = _lib.holdout_errors(r["positions"], ci, cj, truth)
+        assert r["holdout_count"] == cnt == int(np.sum(~np.isnan(truth)))
+        assert r["holdout_sum_abs"] == s_abs
+        d = np.linalg.norm(r["positions"][ci] - r["positions"][cj], axis=1)
+        assert s_abs == pytest.approx(np.nansum(np.abs(truth - d)), rel=1e-12)
+    jobs = [dict(initial_positions=a[0], degrees=a[1], edge_i=a[2], edge_j=a[3], edge_dist=a[4], edge_thresh=a[5],
+                 n_iter=15, k0=3.0, cooling_rate=0.02, c_repulsion=0.01, seed=s, holdout=(ci, cj, truth)) for s in range(17)]
+    for r in _lib.fit_batch(jobs):
+        s_abs, cnt = _lib.holdout_errors(r["positions"], ci, cj, truth)
+        assert (r["holdout_sum_abs"], r["holdout_count"]) == (s_abs, cnt)
+    with pytest.raises(_lib.TopolowError):
+        _lib.fit(*a, 2, 3.0, 0.02, 0.01, holdout=(np.array([220], dtype=np.int32), np.array([0], dtype=np.int32), np.array([1.0])))
+
+
 # ------------------------------------------------------------------ full-size properties ------
 def test_cfg3_size_fp32_against_fp64_and_pair_count():
     prob = synth.make_problem(10_000, 10, 0.95, seed=1)

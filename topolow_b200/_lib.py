@@ -25,7 +25,8 @@ _i64p = C.POINTER(C.c_int64)
 class Problem(C.Structure):
     _fields_ = [("n", C.c_int64), ("ndim", C.c_int32), ("n_edges", C.c_int64), ("edge_i", _i32p),
                 ("edge_j", _i32p), ("edge_dist", _dp), ("edge_thresh", _i32p), ("degrees", _i32p),
-                ("initial_positions", _dp)]
+                ("initial_positions", _dp), ("n_holdout", C.c_int64), ("holdout_i", _i32p), ("holdout_j", _i32p),
+                ("holdout_truth", _dp)]
 
 
 class Params(C.Structure):
@@ -42,7 +43,8 @@ class Result(C.Structure):
     _fields_ = [("positions", _dp), ("converged", C.c_int32), ("iterations", C.c_int32),
                 ("final_mae", C.c_double), ("final_k", C.c_double), ("status", C.c_int32),
                 ("fail_iter", C.c_int32), ("iterations_run", C.c_int32), ("pair_updates", C.c_int64),
-                ("device_ms", C.c_double), ("trace_mae", _dp), ("message", C.c_char * 256)]
+                ("device_ms", C.c_double), ("trace_mae", _dp), ("holdout_sum_abs", C.c_double),
+                ("holdout_count", C.c_int64), ("message", C.c_char * 256)]
 
 
 INTERRUPT_FN = C.CFUNCTYPE(C.c_int, C.c_void_p)
@@ -138,7 +140,7 @@ class TopolowError(RuntimeError):
 class ProblemArrays:
     """Owns the numpy buffers a `Problem` struct points into."""
 
-    def __init__(self, initial_positions, degrees, edge_i, edge_j, edge_dist, edge_thresh):
+    def __init__(self, initial_positions, degrees, edge_i, edge_j, edge_dist, edge_thresh, holdout=None):
         init = np.asarray(initial_positions, dtype=np.float64)
         if init.ndim != 2:
             raise ValueError("initial_positions must be a matrix")
@@ -156,7 +158,17 @@ class ProblemArrays:
         self.struct = Problem(self.n, self.ndim, len(self.edge_i), self.edge_i.ctypes.data_as(_i32p),
                               self.edge_j.ctypes.data_as(_i32p), self.edge_dist.ctypes.data_as(_dp),
                               self.edge_thresh.ctypes.data_as(_i32p), self.degrees.ctypes.data_as(_i32p),
-                              self.init.ctypes.data_as(_dp))
+                              self.init.ctypes.data_as(_dp), 0, None, None, None)
+        if holdout is not None:   # (cell_i, cell_j, truth): scored on the final positions inside the call
+            self.hold_i = np.ascontiguousarray(holdout[0], dtype=np.int32)
+            self.hold_j = np.ascontiguousarray(holdout[1], dtype=np.int32)
+            self.hold_t = np.ascontiguousarray(holdout[2], dtype=np.float64)
+            if not (len(self.hold_i) == len(self.hold_j) == len(self.hold_t)):
+                raise ValueError("hold-out arrays must have equal length")
+            self.struct.n_holdout = len(self.hold_i)
+            self.struct.holdout_i = self.hold_i.ctypes.data_as(_i32p)
+            self.struct.holdout_j = self.hold_j.ctypes.data_as(_i32p)
+            self.struct.holdout_truth = self.hold_t.ctypes.data_as(_dp)
 
 
 def make_params(n_iter, k0, cooling_rate, c_repulsion, relative_epsilon=1e-4, convergence_window=5,
@@ -186,7 +198,8 @@ def result_dict(res: Result, positions: np.ndarray, trace=None):
     out = dict(positions=np.ascontiguousarray(positions), converged=bool(res.converged),
                iterations=int(res.iterations), final_mae=float(res.final_mae), final_k=float(res.final_k),
                iterations_run=int(res.iterations_run), pair_updates=int(res.pair_updates),
-               device_ms=float(res.device_ms), status=int(res.status))
+               device_ms=float(res.device_ms), status=int(res.status),
+               holdout_sum_abs=float(res.holdout_sum_abs), holdout_count=int(res.holdout_count))
     if trace is not None:
         out["trace_mae"] = trace
     return out
@@ -195,10 +208,11 @@ def result_dict(res: Result, positions: np.ndarray, trace=None):
 def fit(initial_positions, degrees, edge_i, edge_j, edge_dist, edge_thresh, n_iter, k0, cooling_rate,
         c_repulsion, relative_epsilon=1e-4, convergence_window=5, convergence_check_freq=3, *, verbose=False,
         mode=MODE_COLOURED, precision=PREC_F32, seed=0, pair_order=None, device=0, max_ctas=0, max_warps=0,
-        tile_points=0, trace=False, interrupt=None):
-    """One call of the native optimiser (the .Call boundary of R/core.R:439-456) on host buffers."""
+        tile_points=0, trace=False, interrupt=None, holdout=None):
+    """One call of the native optimiser (the .Call boundary of R/core.R:439-456) on host buffers.
+    holdout = (cell_i, cell_j, truth): also return sum |truth - distance| and the count over those cells."""
     L = lib()
-    pa = ProblemArrays(initial_positions, degrees, edge_i, edge_j, edge_dist, edge_thresh)
+    pa = ProblemArrays(initial_positions, degrees, edge_i, edge_j, edge_dist, edge_thresh, holdout)
     pr, _keep = make_params(n_iter, k0, cooling_rate, c_repulsion, relative_epsilon, convergence_window,
                             convergence_check_freq, verbose, mode, precision, seed, pair_order, device, max_ctas, max_warps,
                             tile_points)
@@ -230,7 +244,7 @@ def fit_batch(jobs, device=0):
     for j, job in enumerate(jobs):
         job = dict(job)
         pa = ProblemArrays(job.pop("initial_positions"), job.pop("degrees"), job.pop("edge_i"), job.pop("edge_j"),
-                           job.pop("edge_dist"), job.pop("edge_thresh"))
+                           job.pop("edge_dist"), job.pop("edge_thresh"), job.pop("holdout", None))
         pr, k2 = make_params(job.pop("n_iter"), job.pop("k0"), job.pop("cooling_rate"), job.pop("c_repulsion"),
                              device=device, **job)
         out = np.empty((pa.n, pa.ndim), dtype=np.float64, order="F")

@@ -48,6 +48,7 @@ struct topolow_plan {
   // device
   void* pos = nullptr; void* best = nullptr; void* dp1 = nullptr;
   FitState* state = nullptr; double* partials = nullptr; unsigned* barrier = nullptr; double* trace = nullptr;
+  int64_t n_holdout = 0; int32_t* hold_si = nullptr; int32_t* hold_sj = nullptr; double* hold_truth = nullptr;   // slots of the hold-out cells
   volatile int* h_flag = nullptr; int* d_flag = nullptr;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -60,12 +61,19 @@ struct topolow_plan {
   ~topolow_plan() {
     pool_free(pos); pool_free(best); pool_free(dp1);
     pool_free(state); pool_free(partials); pool_free(barrier); pool_free(trace);
+    pool_free(hold_si); pool_free(hold_sj); pool_free(hold_truth);
     if (h_flag) cudaFreeHost((void*)h_flag);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
     if (stream) cudaStreamDestroy(stream);
   }
 };
+
+namespace tl {
+void holdout_resident(const void* best, bool is_f64, int dim, int64_t n_cells, const int32_t* d_slot_i,
+                      const int32_t* d_slot_j, const double* d_truth, cudaStream_t stream, double* sum_abs,
+                      int64_t* count);   // post.cu
+}
 
 namespace {
 
@@ -361,6 +369,23 @@ std::unique_ptr<topolow_plan> make_plan(const topolow_problem& pb, const topolow
   TL_CUDA(cudaMemset(pl->barrier, 0, barrier_words * sizeof(unsigned)));
   std::vector<double> nanv(ntr, NAN);
   TL_CUDA(cudaMemcpy(pl->trace, nanv.data(), sizeof(double) * ntr, cudaMemcpyHostToDevice));
+  if (pb.n_holdout > 0) {   // hold-out cells, relabelled to slots, wait on the device for the end of the fit
+    if (!pb.holdout_i || !pb.holdout_j || !pb.holdout_truth) throw BadArg("hold-out arrays missing");
+    std::vector<int32_t> si(pb.n_holdout), sj(pb.n_holdout);
+    for (int64_t e = 0; e < pb.n_holdout; ++e) {
+      const int64_t a = pb.holdout_i[e], b = pb.holdout_j[e];
+      if (a < 0 || b < 0 || a >= pb.n || b >= pb.n) throw BadArg("hold-out index out of range");
+      si[e] = pl->store->slot_of_point[a]; sj[e] = pl->store->slot_of_point[b];
+    }
+    pl->n_holdout = pb.n_holdout;
+    pool_alloc(pl->hold_si, pb.n_holdout * sizeof(int32_t));
+    pool_alloc(pl->hold_sj, pb.n_holdout * sizeof(int32_t));
+    pool_alloc(pl->hold_truth, pb.n_holdout * sizeof(double));
+    pool_ready();
+    TL_CUDA(cudaMemcpy(pl->hold_si, si.data(), si.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    TL_CUDA(cudaMemcpy(pl->hold_sj, sj.data(), sj.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    TL_CUDA(cudaMemcpy(pl->hold_truth, pb.holdout_truth, pb.n_holdout * sizeof(double), cudaMemcpyHostToDevice));
+  }
   TL_CUDA(cudaHostAlloc((void**)&pl->h_flag, 2 * sizeof(int), cudaHostAllocMapped));
   pl->h_flag[0] = 0; pl->h_flag[1] = 0;
   TL_CUDA(cudaHostGetDevicePointer((void**)&pl->d_flag, (void*)pl->h_flag, 0));
@@ -392,17 +417,21 @@ void launch_geo(topolow_plan& pl, const Geometry& geo, int n_iters, cudaStream_t
 template <class real>
 void launch_group(const std::vector<topolow_plan*>& members, const std::vector<int>& n_iters, cudaStream_t stream) {
   std::vector<BatchJob<real>> jobs(members.size());
+  const topolow_plan& first = *members[0];
+  const size_t base = tile_smem_bytes(first.D, first.geo.W, sizeof(real), first.geo.P);
+  size_t smem = base;
   for (size_t i = 0; i < members.size(); ++i) {
     topolow_plan& pl = *members[i];
     jobs[i] = BatchJob<real>{device_view<real>(pl), pl.geo, pl.prm, n_iters[i], 0, pl.d_flag};
+    smem = std::max(smem, with_perm_table(jobs[i].geo, base));
     pl.launches++;
   }
   AsyncBuf<BatchJob<real>> d_jobs(jobs.size(), stream);
   // (pageable source: the call returns once the source has been staged, so `jobs` may go out of scope)
   TL_CUDA(cudaMemcpyAsync(d_jobs, jobs.data(), jobs.size() * sizeof(BatchJob<real>), cudaMemcpyHostToDevice, stream));
   const topolow_plan& p0 = *members[0];
-  if (sizeof(real) == 8) launch_tile_batch_f64_(p0.D, (const BatchJob<double>*)(const void*)d_jobs, (int)jobs.size(), p0.geo.W, stream);
-  else launch_tile_batch_f32_(p0.D, (const BatchJob<float>*)(const void*)d_jobs, (int)jobs.size(), p0.geo.W, stream);
+  if (sizeof(real) == 8) launch_tile_batch_f64(p0.D, p0.geo.P, (const BatchJob<double>*)(const void*)d_jobs, (int)jobs.size(), p0.geo.W, smem, stream);
+  else launch_tile_batch_f32(p0.D, p0.geo.P, (const BatchJob<float>*)(const void*)d_jobs, (int)jobs.size(), p0.geo.W, smem, stream);
 }
 void launch_chunk(topolow_plan& pl, int n_iters, cudaStream_t stream) { launch_geo(pl, pl.geo, n_iters, stream); }
 
@@ -471,6 +500,10 @@ void fill_result(topolow_plan& pl, topolow_result& res, bool interrupted) {
   res.iterations_run = st.iter;
   res.pair_updates = (int64_t)st.pair_updates;
   res.device_ms = pl.total_ms;
+  res.holdout_sum_abs = 0.0; res.holdout_count = 0;
+  if (pl.n_holdout > 0)
+    holdout_resident(pl.best, pl.precision == TOPOLOW_PREC_F64_EXACT, pl.D, pl.n_holdout, pl.hold_si, pl.hold_sj,
+                     pl.hold_truth, pl.stream, &res.holdout_sum_abs, &res.holdout_count);
   res.fail_iter = st.fail_iter;
   res.status = TOPOLOW_OK;
   res.message[0] = 0;
@@ -501,6 +534,7 @@ int fit_impl(const topolow_problem* pb, const topolow_params* pr, topolow_result
   if (!pb || !pr || !res) return TOPOLOW_ERR_BAD_ARG;
   res->message[0] = 0;
   res->status = TOPOLOW_OK;
+  res->holdout_sum_abs = 0.0; res->holdout_count = 0;
   try {
     if (pb->n < 2) {
       res->status = TOPOLOW_ERR_TOO_FEW_POINTS;
@@ -517,6 +551,10 @@ int fit_impl(const topolow_problem* pb, const topolow_params* pr, topolow_result
       if (pr->pair_order && pr->pairs_per_iter <= 0) throw BadArg("pairs_per_iter must be > 0 with pair_order");
       TL_CUDA(cudaSetDevice(pr->device));
       run_replay(*pb, *pr, *res, poll, user);
+      if (res->status == TOPOLOW_OK && pb->n_holdout > 0 &&
+          topolow_holdout_errors(res->positions, pb->n, pb->ndim, pb->n_holdout, pb->holdout_i, pb->holdout_j,
+                                 pb->holdout_truth, &res->holdout_sum_abs, &res->holdout_count, pr->device) != TOPOLOW_OK)
+        throw BadArg("hold-out cells out of range");
       if (res->status == TOPOLOW_ERR_NONFINITE)
         std::snprintf(res->message, sizeof res->message,
                       "Numerical instability at iteration %d. Reduce k0 or c_repulsion.", res->fail_iter);
@@ -612,6 +650,12 @@ int topolow_optimize_layout_exact(const double* initial_positions, int32_t n, in
   return rc;
 }
 
+// Tile size of the one-CTA-per-fit path (TOPOLOW_BATCH_TILE overrides: measurement aid).
+static int batch_tile_points() {
+  if (const char* e = std::getenv("TOPOLOW_BATCH_TILE")) { const int v = std::atoi(e); if (v == 32 || v == 64 || v == 96) return v; }
+  return 64;
+}
+
 int topolow_fit_batch(int32_t n_jobs, const topolow_problem* problems, const topolow_params* params,
                       topolow_result* results, int32_t device) {
   if (n_jobs < 0 || (n_jobs > 0 && (!problems || !params || !results))) return TOPOLOW_ERR_BAD_ARG;
@@ -629,7 +673,7 @@ int topolow_fit_batch(int32_t n_jobs, const topolow_problem* problems, const top
     pr.device = device;
     if (n_jobs >= 16 && pr.max_ctas == 0) {
       pr.max_ctas = 1;
-      if (pr.tile_points == 0) pr.tile_points = 64;
+      if (pr.tile_points == 0) pr.tile_points = batch_tile_points();
     }
     return pr;
   };
@@ -715,17 +759,17 @@ int topolow_fit_batch(int32_t n_jobs, const topolow_problem* problems, const top
     // Single-CTA fits with 64-point tiles are launched many per kernel (one CTA each), grouped by
     // (ndim, precision, warps): the device runs at most 128 kernels side by side, fewer than it has SMs.
     struct Group { std::vector<int> jobs; std::unique_ptr<StreamGuard> stream; std::unique_ptr<EventGuard> ev0, ev1; };
-    std::map<std::tuple<int, int, int>, Group> groups;
+    std::map<std::tuple<int, int, int, int>, Group> groups;   // (ndim, precision, warps, points per lane)
     std::vector<char> grouped(n_jobs, 0);
     for (int j = 0; j < n_jobs; ++j) {
-      if (!plans[j] || plans[j]->geo.G != 1 || plans[j]->geo.P != 2) continue;
-      groups[std::make_tuple(plans[j]->D, plans[j]->precision, plans[j]->geo.W)].jobs.push_back(j);
+      if (!plans[j] || plans[j]->geo.G != 1 || plans[j]->geo.P > 2) continue;
+      groups[std::make_tuple(plans[j]->D, plans[j]->precision, plans[j]->geo.W, plans[j]->geo.P)].jobs.push_back(j);
       grouped[j] = 1;
     }
     for (auto& kv : groups) {   // load every kernel the batch needs before the first one starts
-      const int gd = std::get<0>(kv.first), gw = std::get<2>(kv.first);
-      if (std::get<1>(kv.first) == TOPOLOW_PREC_F64_EXACT) launch_tile_batch_f64_(gd, nullptr, 0, gw, nullptr);
-      else launch_tile_batch_f32_(gd, nullptr, 0, gw, nullptr);
+      const int gd = std::get<0>(kv.first), gw = std::get<2>(kv.first), gp = std::get<3>(kv.first);
+      if (std::get<1>(kv.first) == TOPOLOW_PREC_F64_EXACT) launch_tile_batch_f64(gd, gp, nullptr, 0, gw, 0, nullptr);
+      else launch_tile_batch_f32(gd, gp, nullptr, 0, gw, 0, nullptr);
     }
     for (auto& kv : groups) {
       Group& g = kv.second;

@@ -70,6 +70,40 @@ __global__ void __launch_bounds__(256) holdout_kernel(const double* __restrict__
   if (threadIdx.x == 0) { part_sum[blockIdx.x] = ss_[0]; part_cnt[blockIdx.x] = cc_[0]; }
 }
 
+// The same reduction on positions that are still on the device in slot order (`real` = float or double;
+// a float converts to double exactly, so the terms equal those of holdout_kernel on the downloaded
+// positions, and the grid and the summation order are the same).
+template <class real>
+__global__ void __launch_bounds__(256) holdout_slots_kernel(const real* __restrict__ pos, int dim, int64_t n_cells,
+                                                            const int32_t* __restrict__ si, const int32_t* __restrict__ sj,
+                                                            const double* __restrict__ truth, double* __restrict__ part_sum,
+                                                            unsigned long long* __restrict__ part_cnt) {
+  double s = 0.0;
+  unsigned long long c = 0;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n_cells; e += (int64_t)gridDim.x * blockDim.x) {
+    const double t = truth[e];
+    if (isnan(t)) continue;
+    const real* a = pos + (int64_t)si[e] * dim;
+    const real* b = pos + (int64_t)sj[e] * dim;
+    double ss = 0.0;
+    for (int d = 0; d < dim; ++d) {
+      const double df = __dsub_rn((double)a[d], (double)b[d]);
+      ss = __dadd_rn(ss, __dmul_rn(df, df));
+    }
+    s += fabs(t - __dsqrt_rn(ss));
+    c += 1;
+  }
+  __shared__ double ss_[256];
+  __shared__ unsigned long long cc_[256];
+  ss_[threadIdx.x] = s; cc_[threadIdx.x] = c;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) { ss_[threadIdx.x] += ss_[threadIdx.x + o]; cc_[threadIdx.x] += cc_[threadIdx.x + o]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { part_sum[blockIdx.x] = ss_[0]; part_cnt[blockIdx.x] = cc_[0]; }
+}
+
 std::vector<double> to_row_major(const double* cm, int64_t n, int dim) {
   std::vector<double> rm((size_t)n * dim);
   for (int64_t i = 0; i < n; ++i)
@@ -98,6 +132,28 @@ extern "C" int topolow_est_distances(const double* positions, int64_t n, int32_t
     return TOPOLOW_ERR_CUDA;
   }
 }
+
+namespace tl {
+// Hold-out residuals of a finished fit from its device-resident best positions ([slot][dim], FP32 or FP64).
+void holdout_resident(const void* best, bool is_f64, int dim, int64_t n_cells, const int32_t* d_slot_i,
+                      const int32_t* d_slot_j, const double* d_truth, cudaStream_t stream, double* sum_abs,
+                      int64_t* count) {
+  const int blocks = 296;
+  AsyncBuf<double> d_ps(blocks, stream);
+  AsyncBuf<unsigned long long> d_pc(blocks, stream);
+  if (is_f64) holdout_slots_kernel<double><<<blocks, 256, 0, stream>>>((const double*)best, dim, n_cells, d_slot_i, d_slot_j, d_truth, d_ps, d_pc);
+  else holdout_slots_kernel<float><<<blocks, 256, 0, stream>>>((const float*)best, dim, n_cells, d_slot_i, d_slot_j, d_truth, d_ps, d_pc);
+  TL_CUDA(cudaGetLastError());
+  std::vector<double> ps(blocks);
+  std::vector<unsigned long long> pc(blocks);
+  TL_CUDA(cudaMemcpyAsync(ps.data(), d_ps, blocks * sizeof(double), cudaMemcpyDeviceToHost, stream));
+  TL_CUDA(cudaMemcpyAsync(pc.data(), d_pc, blocks * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+  TL_CUDA(cudaStreamSynchronize(stream));
+  double s = 0.0; unsigned long long c = 0;
+  for (int b = 0; b < blocks; ++b) { s += ps[b]; c += pc[b]; }
+  *sum_abs = s; *count = (int64_t)c;
+}
+}  // namespace tl
 
 extern "C" int topolow_holdout_errors(const double* positions, int64_t n, int32_t ndim, int64_t n_cells,
                                       const int32_t* cell_i, const int32_t* cell_j, const double* truth,

@@ -45,6 +45,8 @@ struct Geometry {
   int t0, tc;   // first tile / number of tiles of the (X) range
   int y0, yc;   // the Y range of a kind-1 job
   int do_end;   // run the end-of-iteration phase (cooling, MAE, controller) after the pair updates
+  int table;    // device only, set by the launcher: the CTA keeps this iteration's tile placement and round
+                // order in a shared-memory table (perm_table_entries) instead of hashing them per task
   uint64_t seed;
 };
 
@@ -101,6 +103,10 @@ TL_HD int round_at_k(const Geometry& g, uint64_t key /* salt 2 */, int r) {
   return (int)feistel_perm((uint32_t)r, (uint32_t)cross_rounds(g), key ^ (uint64_t)(uint32_t)(g.t0 * 131 + g.y0));
 }
 TL_HD int round_at(const Geometry& g, int iter, int r) { return round_at_k(g, iter_key(g, iter, 2), r); }
+// Entries of the per-iteration lookup table: tile_at of every side-0 slot, then of every side-1 slot
+// (kind 1), then round_at of every round.
+TL_HD int perm_table_side0(const Geometry& g) { return (g.kind == 0 ? g.S : g.S / 2) * g.W; }
+TL_HD int perm_table_entries(const Geometry& g) { return g.S * g.W + cross_rounds(g); }
 // The q-th CTA task of cross round rr: super-block X (side 0) against super-block Y (side 0 for a
 // kind-0 job: circle method; side 1 for a kind-1 job: Latin square).
 TL_HD void cross_task(const Geometry& g, int rr, int q, int& x, int& y) {

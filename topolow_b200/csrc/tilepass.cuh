@@ -767,7 +767,14 @@ TL_D void tile_body(const TileDev<typename M::real>& dv, const Geometry& geo, co
   uint32_t* s_mask = reinterpret_cast<uint32_t*>(s_tgt + (size_t)W * kTableReals);
   int* s_tid = reinterpret_cast<int*>(s_mask + W * kTableMasks);
   int* s_flag = s_tid + 2 * W;
-  EdgeRec* s_stage = reinterpret_cast<EdgeRec*>((reinterpret_cast<uintptr_t>(s_flag + W) + 15) & ~(uintptr_t)15) + warp * kStage;
+  EdgeRec* s_stage_all = reinterpret_cast<EdgeRec*>((reinterpret_cast<uintptr_t>(s_flag + W) + 15) & ~(uintptr_t)15);
+  EdgeRec* s_stage = s_stage_all + warp * kStage;
+  // this iteration's tile placement and round order (geo.table): [side-0 slots][side-1 slots][rounds]
+  int* s_perm = reinterpret_cast<int*>(s_stage_all + W * kStage);
+  const int n_side0 = perm_table_side0(geo), n_slots = geo.S * W;
+  auto tile_of = [&](int slot, int side) {
+    return geo.table ? s_perm[(side ? n_side0 : 0) + slot] : tile_at_k(geo, s_key[side ? 7 : 1], slot, side);
+  };
   const WarpTable<real> tb{s_tgt + (size_t)warp * kTableReals, s_mask + warp * kTableMasks};
 
   unsigned gen = 0;
@@ -786,15 +793,21 @@ TL_D void tile_body(const TileDev<typename M::real>& dv, const Geometry& geo, co
     const int iter = st.iter;
     const typename M::Ctx ctx = M::make_ctx(st.k, prm.c_repulsion);
     if (tid < kIterKeys) s_key[tid] = iter_key(geo, iter, (uint32_t)tid);
+    if (geo.table) {
+      const uint64_t k1 = iter_key(geo, iter, 1u), k7 = iter_key(geo, iter, 7u), k2 = iter_key(geo, iter, 2u);
+      for (int i = tid; i < n_slots; i += blockDim.x)
+        s_perm[i] = i < n_side0 ? tile_at_k(geo, k1, i, 0) : tile_at_k(geo, k7, i - n_side0, 1);
+      for (int r = tid; r < cross_rounds(geo); r += blockDim.x) s_perm[n_slots + r] = round_at_k(geo, k2, r);
+    }
     __syncthreads();
 
     // ---------------- cross rounds ----------------
     for (int r = 0; r < cross_rounds(geo); ++r) {
-      const int rr = round_at_k(geo, s_key[2], r);
+      const int rr = geo.table ? s_perm[n_slots + r] : round_at_k(geo, s_key[2], r);
       for (int tt = 0; tt < geo.m; ++tt) {
         int X, Y;
         cross_task(geo, rr, cta * geo.m + tt, X, Y);
-        const int tX = tile_at_k(geo, s_key[1], X * W + warp, 0), tY = tile_at_k(geo, s_key[geo.kind ? 7 : 1], Y * W + warp, geo.kind);
+        const int tX = tile_of(X * W + warp, 0), tY = tile_of(Y * W + warp, geo.kind);
         const int bX = X, bY = geo.kind == 1 ? geo.S / 2 + Y : Y;   // counters: the two sides of a bipartite job apart
         wait_blocks(done, bX, bY, epoch * (unsigned)W, geo.G);
         if (lane == 0) { s_tid[warp] = tX; s_tid[W + warp] = tY; s_flag[warp] = 0; }
@@ -840,7 +853,7 @@ TL_D void tile_body(const TileDev<typename M::real>& dv, const Geometry& geo, co
     // ---------------- diagonal round (kind 0 only) ----------------
     for (int tt = 0; tt < (geo.kind == 0 ? geo.m : 0); ++tt) {
       const int q = cta * geo.m + tt;
-      const int tX = tile_at_k(geo, s_key[1], (2 * q) * W + warp), tY = tile_at_k(geo, s_key[1], (2 * q + 1) * W + warp);
+      const int tX = tile_of((2 * q) * W + warp, 0), tY = tile_of((2 * q + 1) * W + warp, 0);
       wait_blocks(done, 2 * q, 2 * q + 1, epoch * (unsigned)W, geo.G);
       if (lane == 0) { s_tid[warp] = tX; s_tid[W + warp] = tY; }
       load_tile<D, real>(s_tiles + (size_t)warp * TS, dv.pos, dv.dp1, tX, lane);

@@ -114,6 +114,16 @@ def likelihood_batch(dissimilarity_matrix, samples, mapping_max_iter, relative_e
         fold_indices = make_folds(dissimilarity_matrix, folds, rng)
     prec_c = {"f32": _lib.PREC_F32, "f64": _lib.PREC_F64_EXACT}[precision]
     fold_jobs = [_fold_job(value, code, is_na, np.asarray(h), preserve_order) for h in fold_indices]
+    # hold-out cells in the row numbering of the fold's training problem: they are scored on the device
+    # at the end of each fit (topolow_problem.holdout_*), the positions need not come back for that
+    fold_holdout = []
+    for prob, ci, cj, tr in fold_jobs:
+        if prob["order"] is not None:
+            inv = np.empty(len(prob["order"]), dtype=np.int64)
+            inv[prob["order"]] = np.arange(len(prob["order"]))
+            ci, cj = inv[ci], inv[cj]
+        fold_holdout.append((np.ascontiguousarray(ci, dtype=np.int32), np.ascontiguousarray(cj, dtype=np.int32),
+                             np.ascontiguousarray(tr, dtype=np.float64)))
     jobs, meta = [], []
     for s_idx, s in enumerate(samples):
         for f_idx, (prob, ci, cj, tr) in enumerate(fold_jobs):
@@ -129,7 +139,7 @@ def likelihood_batch(dissimilarity_matrix, samples, mapping_max_iter, relative_e
                              edge_j=prob["edge_j"], edge_dist=prob["edge_dist"], edge_thresh=prob["edge_thresh"],
                              n_iter=int(mapping_max_iter), k0=s["k0"], cooling_rate=s["cooling_rate"],
                              c_repulsion=s["c_repulsion"], relative_epsilon=relative_epsilon, convergence_window=5,
-                             precision=prec_c, seed=seed + 1000003 * s_idx + f_idx))
+                             precision=prec_c, seed=seed + 1000003 * s_idx + f_idx, holdout=fold_holdout[f_idx]))
             meta.append((s_idx, f_idx, len(jobs) - 1))
     results = _lib.fit_batch(jobs, device=device) if jobs else []
 
@@ -137,14 +147,8 @@ def likelihood_batch(dissimilarity_matrix, samples, mapping_max_iter, relative_e
     for s_idx, f_idx, j in meta:
         row = dict(Holdout_MAE=math.nan, n_samples=0, sum_abs_errors=0.0, iter=math.nan, converged=0)
         if j is not None and results[j].get("status", 1) == _lib.OK:
-            prob, ci, cj, tr = fold_jobs[f_idx]
             res = results[j]
-            pos = res["positions"]
-            if prob["order"] is not None:  # undo the reorder so cells index the caller's rows
-                back = np.empty_like(pos)
-                back[prob["order"]] = pos
-                pos = back
-            s_abs, cnt = _lib.holdout_errors(pos, ci, cj, tr, device)
+            s_abs, cnt = res["holdout_sum_abs"], res["holdout_count"]
             row = dict(Holdout_MAE=s_abs / cnt if cnt > 0 else math.nan, n_samples=cnt, sum_abs_errors=s_abs,
                        iter=res["iterations"], converged=int(res["converged"]))
         per_sample[s_idx].append(row)
