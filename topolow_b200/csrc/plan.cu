@@ -49,7 +49,7 @@ struct topolow_plan {
   void* pos = nullptr; void* best = nullptr; void* dp1 = nullptr;
   FitState* state = nullptr; double* partials = nullptr; unsigned* barrier = nullptr; double* trace = nullptr;
   int64_t n_holdout = 0; int32_t* hold_si = nullptr; int32_t* hold_sj = nullptr; double* hold_truth = nullptr;   // slots of the hold-out cells
-  volatile int* h_flag = nullptr; int* d_flag = nullptr;
+  volatile int* h_flag = nullptr; int* d_flag = nullptr; bool owns_flag = true;   // mapped host words: stop flag, iterations done
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int chunk_iters = 1;
@@ -62,7 +62,7 @@ struct topolow_plan {
     pool_free(pos); pool_free(best); pool_free(dp1);
     pool_free(state); pool_free(partials); pool_free(barrier); pool_free(trace);
     pool_free(hold_si); pool_free(hold_sj); pool_free(hold_truth);
-    if (h_flag) cudaFreeHost((void*)h_flag);
+    if (h_flag && owns_flag) cudaFreeHost((void*)h_flag);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
     if (stream) cudaStreamDestroy(stream);
@@ -316,8 +316,10 @@ std::shared_ptr<EdgeStore> make_store(const topolow_problem& pb, int T, int P, i
   return st;
 }
 
+// shared: records + relabelling built for this edge list by the caller; shared_flag: two mapped host
+// words of a block the caller owns (a batch allocates one block for all its plans).
 std::unique_ptr<topolow_plan> make_plan(const topolow_problem& pb, const topolow_params& pr,
-                                        std::shared_ptr<EdgeStore> shared = nullptr) {
+                                        std::shared_ptr<EdgeStore> shared = nullptr, int* shared_flag = nullptr) {
   validate(pb, pr);
   if (pb.ndim > kMaxDim) throw BadArg("ndim > 16 is not built into libtopolow_b200 (coloured mode)");
   if (pb.n > 1000000) throw BadArg("n > 1,000,000 is not supported (bucket table is T x T)");
@@ -386,7 +388,8 @@ std::unique_ptr<topolow_plan> make_plan(const topolow_problem& pb, const topolow
     TL_CUDA(cudaMemcpy(pl->hold_sj, sj.data(), sj.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
     TL_CUDA(cudaMemcpy(pl->hold_truth, pb.holdout_truth, pb.n_holdout * sizeof(double), cudaMemcpyHostToDevice));
   }
-  TL_CUDA(cudaHostAlloc((void**)&pl->h_flag, 2 * sizeof(int), cudaHostAllocMapped));
+  if (shared_flag) { pl->h_flag = shared_flag; pl->owns_flag = false; }
+  else TL_CUDA(cudaHostAlloc((void**)&pl->h_flag, 2 * sizeof(int), cudaHostAllocMapped));
   pl->h_flag[0] = 0; pl->h_flag[1] = 0;
   TL_CUDA(cudaHostGetDevicePointer((void**)&pl->d_flag, (void*)pl->h_flag, 0));
   TL_CUDA(cudaEventCreate(&pl->ev0));
@@ -661,6 +664,7 @@ int topolow_fit_batch(int32_t n_jobs, const topolow_problem* problems, const top
   if (n_jobs < 0 || (n_jobs > 0 && (!problems || !params || !results))) return TOPOLOW_ERR_BAD_ARG;
   // Independent fits: every job gets its own plan and stream; chunks of all jobs are issued
   // round-robin so that the device always has several fits in flight.
+  std::unique_ptr<PinnedBuf<int>> flags;   // declared before the plans: outlives them
   std::vector<std::unique_ptr<topolow_plan>> plans(n_jobs);
   std::vector<int> left(n_jobs, 0);
   const bool dbg = std::getenv("TOPOLOW_DEBUG") != nullptr;
@@ -745,7 +749,7 @@ int topolow_fit_batch(int32_t n_jobs, const topolow_problem* problems, const top
         if (sl.status != TOPOLOW_OK) { r.status = sl.status; set_msg(r.message, sizeof r.message, sl.error.c_str()); return; }
         store = sl.store;
       }
-      plans[j] = make_plan(problems[j], pr, store);
+      plans[j] = make_plan(problems[j], pr, store, flags ? (int*)*flags + 2 * j : nullptr);
       left[j] = pr.n_iter;
     } catch (const CudaError& e) {
       r.status = TOPOLOW_ERR_CUDA; set_msg(r.message, sizeof r.message, e.what()); cudaGetLastError();
@@ -753,6 +757,9 @@ int topolow_fit_batch(int32_t n_jobs, const topolow_problem* problems, const top
       r.status = TOPOLOW_ERR_BAD_ARG; set_msg(r.message, sizeof r.message, e.what());
     }
   };
+  try {
+    if (n_jobs > 0) { TL_CUDA(cudaSetDevice(device)); flags.reset(new PinnedBuf<int>(2 * (size_t)n_jobs, cudaHostAllocMapped)); }
+  } catch (const CudaError&) { cudaGetLastError(); flags.reset(); }   // plans then allocate their own
   run_pool(n_jobs, setup_one);
   if (dbg) std::fprintf(stderr, "[topolow] batch set-up of %d jobs: %.3f s\n", n_jobs, since());
   try {
