@@ -717,10 +717,18 @@ TL_D void edge_error(const uint4& raw, const real (&ra)[D], const real (&rb)[D],
   const double target = __hiloint2double((int)raw.y, (int)raw.x);
   const int ty = raw.w >> 30;
   double ss = 0.0;
+  if (sizeof(real) == 8) {   // exact policy: the reference's operations, one rounding each
 #pragma unroll
-  for (int j = 0; j < D; ++j) {
-    const double df = (double)rb[j] - (double)ra[j];
-    ss = __dadd_rn(ss, __dmul_rn(df, df));
+    for (int j = 0; j < D; ++j) {
+      const double df = __dsub_rn((double)rb[j], (double)ra[j]);
+      ss = __dadd_rn(ss, __dmul_rn(df, df));
+    }
+  } else {                   // FP32 positions: difference in FP32 (exact for nearby coordinates), squares summed in FP64
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+      const double df = (double)(rb[j] - ra[j]);
+      ss = fma(df, df, ss);
+    }
   }
   const double dist = __dsqrt_rn(ss);
   const bool contributes = (ty == 0) || (ty == 1 && dist < target) || (ty == 2 && dist > target);
