@@ -220,6 +220,9 @@ TOPOLOW_API int topolow_microbench(int32_t which, int32_t device, double* value_
 TOPOLOW_API int topolow_device_info(int32_t device, int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor,
                         int64_t* global_mem);
 TOPOLOW_API const char* topolow_version(void);
+/* sizeof(topolow_problem), sizeof(topolow_params), sizeof(topolow_result): lets a binding check its own
+ * struct declarations against the library it loaded. */
+TOPOLOW_API void topolow_abi_sizes(int64_t out[3]);
 
 #ifdef __cplusplus
 }

@@ -1,5 +1,6 @@
 """CPU tests of the host side: C-ABI surface, schedule coverage, the Python mirror of the R glue
 (against oracle/r_glue.py), fold construction, sharding over ranks (gloo, world size 2)."""
+import ctypes as C
 import os
 import re
 import subprocess
@@ -25,6 +26,9 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(L, name)
     assert b"sm_100a" in L.topolow_version()
+    sizes = (C.c_int64 * 3)()
+    L.topolow_abi_sizes(C.byref(sizes))       # the ctypes mirror of the three structs matches the header
+    assert list(sizes) == [C.sizeof(_lib.Problem), C.sizeof(_lib.Params), C.sizeof(_lib.Result)]
 
 
 @pytest.mark.skipif(has_cuda(), reason="checks the no-GPU failure mode")

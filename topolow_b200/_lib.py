@@ -55,7 +55,7 @@ EXPORTS = [
     "topolow_plan_destroy", "topolow_plan_enumerate", "topolow_schedule_enumerate", "topolow_plan_run_job",
     "topolow_plan_end_iteration", "topolow_plan_layout", "topolow_plan_positions", "topolow_plan_enumerate_job",
     "topolow_est_distances", "topolow_holdout_errors", "topolow_microbench", "topolow_device_info",
-    "topolow_version",
+    "topolow_version", "topolow_abi_sizes",
 ]
 
 _lib = None
@@ -125,6 +125,13 @@ def lib() -> C.CDLL:
     L.topolow_device_info.argtypes = [C.c_int32, _i32p, _i32p, _i32p, _i64p]
     L.topolow_version.restype = C.c_char_p
     L.topolow_version.argtypes = []
+    L.topolow_abi_sizes.restype = None
+    L.topolow_abi_sizes.argtypes = [C.POINTER(C.c_int64 * 3)]
+    sizes = (C.c_int64 * 3)()
+    L.topolow_abi_sizes(C.byref(sizes))
+    if list(sizes) != [C.sizeof(Problem), C.sizeof(Params), C.sizeof(Result)]:
+        raise ImportError(f"libtopolow_b200 struct sizes {list(sizes)} differ from the ctypes declarations "
+                          f"{[C.sizeof(Problem), C.sizeof(Params), C.sizeof(Result)]}: rebuild the library")
     _lib = L
     return L
 

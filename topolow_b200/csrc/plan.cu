@@ -596,6 +596,10 @@ extern "C" {
 
 const char* topolow_version(void) { return "topolow_b200 0.1 (sm_100a)"; }
 
+void topolow_abi_sizes(int64_t out[3]) {
+  out[0] = (int64_t)sizeof(topolow_problem); out[1] = (int64_t)sizeof(topolow_params); out[2] = (int64_t)sizeof(topolow_result);
+}
+
 int topolow_device_info(int32_t device, int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor, int64_t* global_mem) {
   cudaDeviceProp p;
   if (cudaGetDeviceProperties(&p, device) != cudaSuccess) { cudaGetLastError(); return TOPOLOW_ERR_CUDA; }
