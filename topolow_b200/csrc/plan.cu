@@ -108,12 +108,14 @@ std::vector<int32_t> random_permutation(int64_t n, uint64_t seed) {
   return p;
 }
 
-// Points per lane: large single maps fill the chip with 96-point tiles (most work per shuffle, three
-// independent chains per lane); small and medium single fits want as many warps as possible (32-point
-// tiles); batches of fits run one CTA each and get 64-point tiles.
+// Points per lane.  More points per lane = more work per shuffle and more independent chains in a
+// lane, but n / (64 P) warps must still fill the 592 sub-partitions of the chip: measured on B200 (ms per
+// iteration, 32 / 64 / 96-point tiles) n = 20k: 3.7 / 3.9 / 5.3, n = 40k: 8.5 / 7.8 / 10.6,
+// n = 60k: - / 12.0 / 15.1, n = 100k: 25.8 / 27.9 / 23.8.  Batches of fits run one CTA each with
+// 64-point tiles (topolow_fit_batch).
 int choose_tile_points(int64_t n, int requested) {
   if (requested == 32 || requested == 64 || requested == 96) return requested / 32;
-  return n >= 40000 ? 3 : 1;
+  return n >= 80000 ? 3 : (n >= 30000 ? 2 : 1);
 }
 
 int geometry_wmax(int D, int precision, int P, int max_warps) {
