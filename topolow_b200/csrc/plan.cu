@@ -325,6 +325,7 @@ std::unique_ptr<topolow_plan> make_plan(const topolow_problem& pb, const topolow
   validate(pb, pr);
   if (pb.ndim > kMaxDim) throw BadArg("ndim > 16 is not built into libtopolow_b200 (coloured mode)");
   if (pb.n > 1000000) throw BadArg("n > 1,000,000 is not supported (bucket table is T x T)");
+  if (pr.n_shards < 0 || pr.n_shards > 64) throw BadArg("n_shards must be in 0..64");
   auto pl = std::make_unique<topolow_plan>();
   pl->device = pr.device;
   TL_CUDA(cudaSetDevice(pr.device));
