@@ -292,7 +292,8 @@ def main_cfg5(args, n, missing):
                 "d2h_bytes_per_step": int(sum(j["initial_positions"].nbytes for j in jobs)),
                 "note": "the measured path IS end to end: topolow_fit_batch on host buffers (set-up, upload, fits, download) "
                         "including the hold-out residual kernel of every fit"},
-        "gpu_launches": int(args.steps * len(jobs) * (-(-args.fit_iters // 50) + 1)),
+        # per step: one tile_batch_kernel launch per ndim group (one CTA per fit) + one hold-out kernel per fit
+        "gpu_launches": int(args.steps * (len({j["initial_positions"].shape[1] for j in jobs}) + len(jobs))),
         "roofline": None, "cpu_baseline": cpu,
     }
     print(json.dumps(line), flush=True)
