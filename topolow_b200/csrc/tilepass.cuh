@@ -465,6 +465,7 @@ TL_D void store_tile(const real* s, real* gpos, int tile, int lane) {
 // Per-warp table of the measured pairs of one tile pair.  Combination c = kP * (A part) + (B part)
 // (part p = slots 32p .. 32p+31 of a tile): tgt[c][step][lane], mask[c][kind][lane] with
 // kind 0 = "pulls when closer than the target" (exact or '>'), 1 = "pulls when farther" (exact or '<').
+// (Two 32-bit shared atomics per record: a 64-bit OR on shared memory is a compare-and-swap loop.)
 constexpr int kCombos = kP * kP;
 constexpr int kTableReals = kCombos * 32 * 32;
 constexpr int kTableMasks = kCombos * 2 * 32;
@@ -486,8 +487,9 @@ TL_D void table_clear(const WarpTable<real>& tb, int lane) {
 template <class real>
 TL_D void table_put(const WarpTable<real>& tb, int c, int idx, int lane_of, real target, int ty) {
   tb.tgt[(c * 32 + idx) * 32 + lane_of] = target;
-  if (ty != 2) atomicOr(&tb.mask[(c * 2 + 0) * 32 + lane_of], 1u << idx);
-  if (ty != 1) atomicOr(&tb.mask[(c * 2 + 1) * 32 + lane_of], 1u << idx);
+  const uint32_t bit = 1u << idx;   // (selects instead of branches: nearly every record sets both masks)
+  atomicOr(&tb.mask[(c * 2 + 0) * 32 + lane_of], ty != 2 ? bit : 0u);
+  atomicOr(&tb.mask[(c * 2 + 1) * 32 + lane_of], ty != 1 ? bit : 0u);
 }
 template <class real>
 TL_D LaneMasks table_masks(const WarpTable<real>& tb, int lane, bool filled) {
@@ -929,7 +931,7 @@ TL_D void tile_body(const TileDev<typename M::real>& dv, const Geometry& geo, co
         // Edge MAE (src/optimization.cpp:54-81): kEB edges per thread and trip, every load of the batch
         // issued before the first use - the CTAs of the pair loop are all the threads there are, so the
         // memory parallelism has to come from inside a thread.
-        constexpr int kEB = sizeof(real) == 4 ? 4 : 2;
+        constexpr int kEB = sizeof(real) == 4 ? (D <= 8 ? 8 : 4) : 2;   // ~128 registers of row data
         const long long stride = (long long)geo.G * blockDim.x;
         long long e0 = (long long)cta * blockDim.x + tid;
         for (; e0 + (kEB - 1) * stride < dv.n_edges; e0 += stride * kEB) {
