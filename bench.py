@@ -146,7 +146,7 @@ def run_reference(args, n, d, missing):
         return
     prob = synth.make_problem(n, d, missing, seed=0)
     pairs = n * (n - 1) // 2
-    sample = int(min(pairs, 4e7))
+    sample = int(min(pairs, 4e7, 3e8 / max(args.steps, 1)))   # bounded: the whole run stays within a few minutes
     from oracle import cpu_oracle
     cpu_oracle.build(ref=False)
     for w in range(args.warmup):
