@@ -737,6 +737,25 @@ TL_D void edge_error(const uint4& raw, const real (&ra)[D], const real (&rb)[D],
   if (contributes) { e_sum += fabs(target - dist); e_cnt += 1.0; }
 }
 
+// This thread's edges e0, e0 + stride, ... in batches of K with every load of a batch issued before its
+// first use; stops (and leaves e0) where fewer than K edges remain.
+template <int D, class real, int K>
+TL_D void edge_batches(const TileDev<real>& dv, long long& e0, long long stride, double& e_sum, double& e_cnt) {
+  for (; e0 + (K - 1) * stride < dv.n_edges; e0 += stride * K) {
+    uint4 raw[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) raw[k] = __ldcs(reinterpret_cast<const uint4*>(dv.edges + e0 + k * stride));
+    real ra[K][D], rb[K][D];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      load_row<D, real>(dv.pos + (size_t)raw[k].z * D, ra[k]);
+      load_row<D, real>(dv.pos + (size_t)(raw[k].w & 0x3fffffffu) * D, rb[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) edge_error<D, real>(raw[k], ra[k], rb[k], e_sum, e_cnt);
+  }
+}
+
 // Deterministic CTA reduction of (sum, count, flag); result valid in thread 0.
 TL_D void block_reduce3(double& a, double& b, double& c, double* scratch /* [3*32] */) {
   const unsigned full = 0xffffffffu;
@@ -934,26 +953,9 @@ TL_D void tile_body(const TileDev<typename M::real>& dv, const Geometry& geo, co
         constexpr int kEB = sizeof(real) == 4 ? (D <= 8 ? 8 : 4) : 2;   // ~128 registers of row data
         const long long stride = (long long)geo.G * blockDim.x;
         long long e0 = (long long)cta * blockDim.x + tid;
-        for (; e0 + (kEB - 1) * stride < dv.n_edges; e0 += stride * kEB) {
-          uint4 raw[kEB];
-#pragma unroll
-          for (int k = 0; k < kEB; ++k) raw[k] = __ldcs(reinterpret_cast<const uint4*>(dv.edges + e0 + k * stride));
-          real ra[kEB][D], rb[kEB][D];
-#pragma unroll
-          for (int k = 0; k < kEB; ++k) {
-            load_row<D, real>(dv.pos + (size_t)raw[k].z * D, ra[k]);
-            load_row<D, real>(dv.pos + (size_t)(raw[k].w & 0x3fffffffu) * D, rb[k]);
-          }
-#pragma unroll
-          for (int k = 0; k < kEB; ++k) edge_error<D, real>(raw[k], ra[k], rb[k], e_sum, e_cnt);
-        }
-        for (; e0 < dv.n_edges; e0 += stride) {   // fewer than kEB edges left for this thread
-          const uint4 raw = __ldcs(reinterpret_cast<const uint4*>(dv.edges + e0));
-          real ra[D], rb[D];
-          load_row<D, real>(dv.pos + (size_t)raw.z * D, ra);
-          load_row<D, real>(dv.pos + (size_t)(raw.w & 0x3fffffffu) * D, rb);
-          edge_error<D, real>(raw, ra, rb, e_sum, e_cnt);
-        }
+        edge_batches<D, real, kEB>(dv, e0, stride, e_sum, e_cnt);
+        if (kEB > 2) edge_batches<D, real, 2>(dv, e0, stride, e_sum, e_cnt);   // short lists: keep the tail parallel too
+        edge_batches<D, real, 1>(dv, e0, stride, e_sum, e_cnt);
       }
       if (fin) {
         const size_t total = (size_t)geo.T * kTile * D;
