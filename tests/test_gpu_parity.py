@@ -174,6 +174,38 @@ def test_statistical_parity_with_the_random_shuffle_loop():
     assert abs(diff) <= max(2 * se, 0.02 * cpu.mean()), (gpu, cpu)
 
 
+def test_heldout_mae_parity_with_the_random_shuffle_loop():
+    """The north-star acceptance check: on the same training edges and initial positions the production
+    mode reproduces the reference loop's HELD-OUT MAE (cells the fit never saw) and its distance-
+    reconstruction error (all measured cells, train + held-out) - mean over 10 seeds within
+    max(2 x SE of the difference, 3 %)."""
+    n, d = 180, 3
+    res = {"gpu": ([], []), "cpu": ([], [])}
+    for seed in range(10):
+        init, deg, ei, ej, ed, et = small_problem(n, d, 0.2, 2000 + seed, thresholds=False)
+        rng = np.random.default_rng(seed)
+        held = rng.random(len(ei)) < 0.1
+        tr = ~held
+        deg_tr = (np.bincount(ei[tr], minlength=n) + np.bincount(ej[tr], minlength=n) + 1).astype(np.int32)
+        train = (init, deg_tr, ei[tr], ej[tr], ed[tr], et[tr])
+        hp = (5.0, 0.01, 0.02, 1e-4, 5, 3)
+        g = _lib.fit(*train, 200, *hp, precision=_lib.PREC_F32, seed=seed, holdout=(ei[held], ej[held], ed[held]))
+        c = cpu_oracle.optimize_layout_exact(*train, 200, *hp, seed=seed)
+        for key, pos, hold_mae in (("gpu", g["positions"], g["holdout_sum_abs"] / g["holdout_count"]),
+                                   ("cpu", c["positions"], None)):
+            dist = np.linalg.norm(pos[ei] - pos[ej], axis=1)
+            if hold_mae is None:
+                hold_mae = np.abs(ed[held] - dist[held]).mean()
+            else:
+                assert hold_mae == pytest.approx(np.abs(ed[held] - dist[held]).mean(), rel=1e-9)
+            res[key][0].append(hold_mae)
+            res[key][1].append(np.abs(ed - dist).mean())
+    for k in (0, 1):
+        gpu, cpu = np.array(res["gpu"][k]), np.array(res["cpu"][k])
+        se = np.sqrt(gpu.var(ddof=1) / 10 + cpu.var(ddof=1) / 10)
+        assert abs(gpu.mean() - cpu.mean()) <= max(2 * se, 0.03 * cpu.mean()), (k, gpu, cpu)
+
+
 # ------------------------------------------------------------------ edge cases ---------------
 def test_degenerate_inputs_stay_finite():
     # tests/testthat/test-edge-cases.R:5-82,243-263
