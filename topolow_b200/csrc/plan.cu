@@ -1,7 +1,7 @@
 // topolow_b200/csrc/plan.cu
 //
-// Host driver of the production (coloured) mode and the C ABI declared in
-// include/topolow_b200.h.  Builds the device image of one fit (relabelled positions, masses,
+// Host driver of the production (coloured) mode and the single-fit / plan part of the C ABI declared in
+// include/topolow_b200.h (the many-fits entry is batch.cu).  Builds the device image of one fit (relabelled positions, masses,
 // bucketed edge records), picks the schedule geometry, launches the persistent kernel in
 // chunks of iterations and assembles the five results of
 // optimize_layout_exact_cpp (src/optimization.cpp:375-381).
@@ -22,68 +22,11 @@
 #include "../../include/topolow_b200.h"
 #include "edges.h"
 #include "replay.h"
-#include "tilepass_launch.h"
+#include "plan.h"
 
 using namespace tl;
 
-// The part of a plan that depends only on the edge list and the tile geometry: the relabelling of the
-// points into slots and the bucketed edge records on the device.  The fits of a CV grid that run on the
-// same fold (same edge arrays) share one store (topolow_fit_batch).
-struct EdgeStore {
-  std::vector<int32_t> point_of_slot;  // -1 = phantom
-  std::vector<int32_t> slot_of_point;
-  EdgeRec* edges = nullptr;
-  uint32_t* bucket_off = nullptr;
-  ~EdgeStore() { pool_free(edges); pool_free(bucket_off); }
-};
-
-struct topolow_plan {
-  int device = 0;
-  int precision = 0;
-  int64_t n = 0, E = 0;
-  int D = 0;
-  Geometry geo{};
-  FitParams prm{};
-  std::shared_ptr<EdgeStore> store;
-  // device
-  void* pos = nullptr; void* best = nullptr; void* dp1 = nullptr;
-  FitState* state = nullptr; double* partials = nullptr; unsigned* barrier = nullptr; double* trace = nullptr;
-  int64_t n_holdout = 0; int32_t* hold_si = nullptr; int32_t* hold_sj = nullptr; double* hold_truth = nullptr;   // slots of the hold-out cells
-  volatile int* h_flag = nullptr; int* d_flag = nullptr; bool owns_flag = true;   // mapped host words: stop flag, iterations done
-  cudaStream_t stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  int chunk_iters = 1;
-  int64_t launches = 0;
-  int wmax = 1, ctas = 1, n_shards = 0;
-  double total_ms = 0.0;
-  size_t smem = 0;
-
-  ~topolow_plan() {
-    pool_free(pos); pool_free(best); pool_free(dp1);
-    pool_free(state); pool_free(partials); pool_free(barrier); pool_free(trace);
-    pool_free(hold_si); pool_free(hold_sj); pool_free(hold_truth);
-    if (h_flag && owns_flag) cudaFreeHost((void*)h_flag);
-    if (ev0) cudaEventDestroy(ev0);
-    if (ev1) cudaEventDestroy(ev1);
-    if (stream) cudaStreamDestroy(stream);
-  }
-};
-
 namespace tl {
-void holdout_resident(const void* best, bool is_f64, int dim, int64_t n_cells, const int32_t* d_slot_i,
-                      const int32_t* d_slot_j, const double* d_truth, cudaStream_t stream, double* sum_abs,
-                      int64_t* count);   // post.cu
-}
-
-namespace {
-
-struct BadArg : std::runtime_error {
-  using std::runtime_error::runtime_error;
-};
-
-void set_msg(char* dst, int len, const char* src) {
-  if (dst && len > 0) std::snprintf(dst, len, "%s", src);
-}
 
 void validate(const topolow_problem& pb, const topolow_params& pr) {
   if (pb.n < 2) throw BadArg("Need at least 2 points for embedding");
@@ -321,7 +264,7 @@ std::shared_ptr<EdgeStore> make_store(const topolow_problem& pb, int T, int P, i
 // shared: records + relabelling built for this edge list by the caller; shared_flag: two mapped host
 // words of a block the caller owns (a batch allocates one block for all its plans).
 std::unique_ptr<topolow_plan> make_plan(const topolow_problem& pb, const topolow_params& pr,
-                                        std::shared_ptr<EdgeStore> shared = nullptr, int* shared_flag = nullptr) {
+                                        std::shared_ptr<EdgeStore> shared, int* shared_flag) {
   validate(pb, pr);
   if (pb.ndim > kMaxDim) throw BadArg("ndim > 16 is not built into libtopolow_b200 (coloured mode)");
   if (pb.n > 1000000) throw BadArg("n > 1,000,000 is not supported (bucket table is T x T)");
@@ -408,36 +351,10 @@ std::unique_ptr<topolow_plan> make_plan(const topolow_problem& pb, const topolow
   return pl;
 }
 
-template <class real>
-TileDev<real> device_view(const topolow_plan& pl) {
-  const unsigned long long ppi = (unsigned long long)pl.n * (unsigned long long)(pl.n - 1) / 2ull;
-  return TileDev<real>{(real*)pl.pos, (real*)pl.best, (const real*)pl.dp1, pl.store->edges, pl.store->bucket_off, pl.state,
-                       pl.partials, pl.barrier, pl.trace, (long long)pl.E, ppi};
-}
 void launch_geo(topolow_plan& pl, const Geometry& geo, int n_iters, cudaStream_t stream) {
   if (pl.precision == TOPOLOW_PREC_F64_EXACT) launch_tile_f64(device_view<double>(pl), geo, pl.prm, n_iters, pl.d_flag, stream);
   else launch_tile_f32(device_view<float>(pl), geo, pl.prm, n_iters, pl.d_flag, stream);
   pl.launches++;
-}
-// One launch for the next chunk of many single-CTA fits with 64-point tiles and equal (D, precision, W).
-template <class real>
-void launch_group(const std::vector<topolow_plan*>& members, const std::vector<int>& n_iters, cudaStream_t stream) {
-  std::vector<BatchJob<real>> jobs(members.size());
-  const topolow_plan& first = *members[0];
-  const size_t base = tile_smem_bytes(first.D, first.geo.W, sizeof(real), first.geo.P);
-  size_t smem = base;
-  for (size_t i = 0; i < members.size(); ++i) {
-    topolow_plan& pl = *members[i];
-    jobs[i] = BatchJob<real>{device_view<real>(pl), pl.geo, pl.prm, n_iters[i], 0, pl.d_flag};
-    smem = std::max(smem, with_perm_table(jobs[i].geo, base));
-    pl.launches++;
-  }
-  AsyncBuf<BatchJob<real>> d_jobs(jobs.size(), stream);
-  // (pageable source: the call returns once the source has been staged, so `jobs` may go out of scope)
-  TL_CUDA(cudaMemcpyAsync(d_jobs, jobs.data(), jobs.size() * sizeof(BatchJob<real>), cudaMemcpyHostToDevice, stream));
-  const topolow_plan& p0 = *members[0];
-  if (sizeof(real) == 8) launch_tile_batch_f64(p0.D, p0.geo.P, (const BatchJob<double>*)(const void*)d_jobs, (int)jobs.size(), p0.geo.W, smem, stream);
-  else launch_tile_batch_f32(p0.D, p0.geo.P, (const BatchJob<float>*)(const void*)d_jobs, (int)jobs.size(), p0.geo.W, smem, stream);
 }
 void launch_chunk(topolow_plan& pl, int n_iters, cudaStream_t stream) { launch_geo(pl, pl.geo, n_iters, stream); }
 
@@ -590,7 +507,7 @@ int fit_impl(const topolow_problem* pb, const topolow_params* pr, topolow_result
   return res->status;
 }
 
-}  // namespace
+}  // namespace tl
 
 // ------------------------------------------------------------------------------------------
 // C ABI
@@ -658,199 +575,6 @@ int topolow_optimize_layout_exact(const double* initial_positions, int32_t n, in
   if (final_k_out) *final_k_out = rs.final_k;
   set_msg(message, message_len, rs.message);
   return rc;
-}
-
-// Tile size of the one-CTA-per-fit path (TOPOLOW_BATCH_TILE overrides: measurement aid).
-static int batch_tile_points() {
-  if (const char* e = std::getenv("TOPOLOW_BATCH_TILE")) { const int v = std::atoi(e); if (v == 32 || v == 64 || v == 96) return v; }
-  return 64;
-}
-
-int topolow_fit_batch(int32_t n_jobs, const topolow_problem* problems, const topolow_params* params,
-                      topolow_result* results, int32_t device) {
-  if (n_jobs < 0 || (n_jobs > 0 && (!problems || !params || !results))) return TOPOLOW_ERR_BAD_ARG;
-  // Independent fits: every job gets its own plan and stream; chunks of all jobs are issued
-  // round-robin so that the device always has several fits in flight.
-  std::unique_ptr<PinnedBuf<int>> flags;   // declared before the plans: outlives them
-  std::vector<std::unique_ptr<topolow_plan>> plans(n_jobs);
-  std::vector<int> left(n_jobs, 0);
-  const bool dbg = std::getenv("TOPOLOW_DEBUG") != nullptr;
-  const auto t_begin = std::chrono::steady_clock::now();
-  auto since = [&]() { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count(); };
-  // Many independent fits: one CTA per fit (no grid barrier, plain launches that run side by side on
-  // different SMs) keeps every SM busy; a lone large fit still gets the whole chip.
-  auto job_params = [&](int j) {
-    topolow_params pr = params[j];
-    pr.device = device;
-    if (n_jobs >= 16 && pr.max_ctas == 0) {
-      pr.max_ctas = 1;
-      if (pr.tile_points == 0) pr.tile_points = batch_tile_points();
-    }
-    return pr;
-  };
-  // Jobs that point at the same edge arrays (the parameter samples of a CV grid evaluated on the same
-  // fold, R/adaptive_sampling.R:2605-2667) share one relabelling and one set of bucketed records.
-  struct StoreKey {
-    const void *ei, *ej, *ed, *et; int64_t E, n; int P;
-    bool operator<(const StoreKey& o) const {
-      return std::tie(ei, ej, ed, et, E, n, P) < std::tie(o.ei, o.ej, o.ed, o.et, o.E, o.n, o.P);
-    }
-  };
-  struct StoreSlot { std::shared_ptr<EdgeStore> store; int first_job = -1; int status = TOPOLOW_OK; std::string error; };
-  std::map<StoreKey, int> key_index;
-  std::vector<StoreSlot> slots;
-  std::vector<int> slot_of_job(n_jobs, -1);
-  for (int j = 0; j < n_jobs; ++j) {
-    const topolow_problem& pb = problems[j];
-    if (pb.n < 2 || pb.n > 1000000 || params[j].mode != TOPOLOW_MODE_COLOURED || params[j].n_shards > 1) continue;
-    const topolow_params pr = job_params(j);
-    const StoreKey key{pb.edge_i, pb.edge_j, pb.edge_dist, pb.edge_thresh, pb.n_edges, pb.n, choose_tile_points(pb.n, pr.tile_points)};
-    auto it = key_index.find(key);
-    if (it == key_index.end()) {
-      it = key_index.emplace(key, (int)slots.size()).first;
-      slots.emplace_back();
-      slots.back().first_job = j;
-    }
-    slot_of_job[j] = it->second;
-  }
-  auto run_pool = [&](int count, const std::function<void(int)>& fn) {
-    const int n_threads = std::max(1, std::min<int>({(int)std::thread::hardware_concurrency(), 16, count}));
-    std::atomic<int> next{0};
-    std::vector<std::thread> pool;
-    for (int t = 0; t < n_threads; ++t)
-      pool.emplace_back([&] { for (int i = next.fetch_add(1); i < count; i = next.fetch_add(1)) fn(i); });
-    for (auto& th : pool) th.join();
-  };
-  run_pool((int)slots.size(), [&](int k) {
-    StoreSlot& sl = slots[k];
-    const topolow_problem& pb = problems[sl.first_job];
-    try {
-      const topolow_params pr = job_params(sl.first_job);
-      validate(pb, pr);
-      const int P = choose_tile_points(pb.n, pr.tile_points);
-      sl.store = make_store(pb, (int)((pb.n + 32 * P - 1) / (32 * P)), P, device);
-    } catch (const CudaError& e) {
-      sl.status = TOPOLOW_ERR_CUDA; sl.error = e.what(); cudaGetLastError();
-    } catch (const std::exception& e) {
-      sl.status = TOPOLOW_ERR_BAD_ARG; sl.error = e.what();
-    }
-  });
-  if (dbg) std::fprintf(stderr, "[topolow] batch: %zu edge stores for %d jobs: %.3f s\n", slots.size(), n_jobs, since());
-  // Per-job set-up (point upload, state) is independent: spread it over the host cores, as the reference
-  // spreads whole fits with mclapply.
-  auto setup_one = [&](int j) {
-    topolow_result& r = results[j];
-    r.status = TOPOLOW_OK; r.message[0] = 0;
-    try {
-      if (problems[j].n < 2) {
-        r.status = TOPOLOW_ERR_TOO_FEW_POINTS;
-        set_msg(r.message, sizeof r.message, "Need at least 2 points for embedding");
-        return;
-      }
-      if (!r.positions) throw BadArg("result->positions must be caller-allocated");
-      if (params[j].mode != TOPOLOW_MODE_COLOURED) throw BadArg("batch supports the coloured mode only");
-      const topolow_params pr = job_params(j);
-      std::shared_ptr<EdgeStore> store;
-      if (slot_of_job[j] >= 0) {
-        const StoreSlot& sl = slots[slot_of_job[j]];
-        if (sl.status != TOPOLOW_OK) { r.status = sl.status; set_msg(r.message, sizeof r.message, sl.error.c_str()); return; }
-        store = sl.store;
-      }
-      plans[j] = make_plan(problems[j], pr, store, flags ? (int*)*flags + 2 * j : nullptr);
-      left[j] = pr.n_iter;
-    } catch (const CudaError& e) {
-      r.status = TOPOLOW_ERR_CUDA; set_msg(r.message, sizeof r.message, e.what()); cudaGetLastError();
-    } catch (const std::exception& e) {
-      r.status = TOPOLOW_ERR_BAD_ARG; set_msg(r.message, sizeof r.message, e.what());
-    }
-  };
-  try {
-    if (n_jobs > 0) { TL_CUDA(cudaSetDevice(device)); flags.reset(new PinnedBuf<int>(2 * (size_t)n_jobs, cudaHostAllocMapped)); }
-  } catch (const CudaError&) { cudaGetLastError(); flags.reset(); }   // plans then allocate their own
-  run_pool(n_jobs, setup_one);
-  if (dbg) std::fprintf(stderr, "[topolow] batch set-up of %d jobs: %.3f s\n", n_jobs, since());
-  try {
-    // Single-CTA fits with 64-point tiles are launched many per kernel (one CTA each), grouped by
-    // (ndim, precision, warps): the device runs at most 128 kernels side by side, fewer than it has SMs.
-    struct Group { std::vector<int> jobs; std::unique_ptr<StreamGuard> stream; std::unique_ptr<EventGuard> ev0, ev1; };
-    std::map<std::tuple<int, int, int, int>, Group> groups;   // (ndim, precision, warps, points per lane)
-    std::vector<char> grouped(n_jobs, 0);
-    for (int j = 0; j < n_jobs; ++j) {
-      if (!plans[j] || plans[j]->geo.G != 1 || plans[j]->geo.P > 2) continue;
-      groups[std::make_tuple(plans[j]->D, plans[j]->precision, plans[j]->geo.W, plans[j]->geo.P)].jobs.push_back(j);
-      grouped[j] = 1;
-    }
-    for (auto& kv : groups) {   // load every kernel the batch needs before the first one starts
-      const int gd = std::get<0>(kv.first), gw = std::get<2>(kv.first), gp = std::get<3>(kv.first);
-      if (std::get<1>(kv.first) == TOPOLOW_PREC_F64_EXACT) launch_tile_batch_f64(gd, gp, nullptr, 0, gw, 0, nullptr);
-      else launch_tile_batch_f32(gd, gp, nullptr, 0, gw, 0, nullptr);
-    }
-    for (auto& kv : groups) {
-      Group& g = kv.second;
-      g.stream.reset(new StreamGuard()); g.ev0.reset(new EventGuard()); g.ev1.reset(new EventGuard());
-      TL_CUDA(cudaEventRecord(*g.ev0, *g.stream));
-    }
-    for (int j = 0; j < n_jobs; ++j)
-      if (plans[j] && !grouped[j]) TL_CUDA(cudaEventRecord(plans[j]->ev0, plans[j]->stream));
-    bool any = true;
-    while (any) {
-      any = false;
-      // (reverse key order = highest ndim first: the longest fits are handed to the SMs first.  A batch
-      // cannot be interrupted, so every fit runs to its own stop in one launch - no chunk boundaries at
-      // which a group would have to wait for its slowest member.)
-      for (auto it = groups.rbegin(); it != groups.rend(); ++it) {
-        auto& kv = *it;
-        Group& g = kv.second;
-        std::vector<topolow_plan*> members; std::vector<int> iters;
-        for (int j : g.jobs) {
-          if (left[j] <= 0 || plans[j]->h_flag[0]) continue;
-          const int c = left[j];
-          members.push_back(plans[j].get()); iters.push_back(c);
-          left[j] -= c;
-        }
-        if (members.empty()) continue;
-        if (std::get<1>(kv.first) == TOPOLOW_PREC_F64_EXACT) launch_group<double>(members, iters, *g.stream);
-        else launch_group<float>(members, iters, *g.stream);
-        any = true;
-      }
-      for (int j = 0; j < n_jobs; ++j) {
-        if (!plans[j] || grouped[j] || left[j] <= 0 || plans[j]->h_flag[0]) continue;
-        const int c = std::min(left[j], plans[j]->chunk_iters);
-        launch_chunk(*plans[j], c, plans[j]->stream);
-        left[j] -= c;
-        any = true;
-      }
-    }
-    if (dbg) std::fprintf(stderr, "[topolow] batch launches issued: %.3f s\n", since());
-    for (auto& kv : groups) {
-      Group& g = kv.second;
-      TL_CUDA(cudaEventRecord(*g.ev1, *g.stream));
-      TL_CUDA(cudaEventSynchronize(*g.ev1));
-      float ms = 0.f;
-      TL_CUDA(cudaEventElapsedTime(&ms, *g.ev0, *g.ev1));
-      for (int j : g.jobs) plans[j]->total_ms = ms;   // the fits of a group share its launches
-    }
-    for (int j = 0; j < n_jobs; ++j) {
-      if (!plans[j]) continue;
-      if (!grouped[j]) {
-        TL_CUDA(cudaEventRecord(plans[j]->ev1, plans[j]->stream));
-        TL_CUDA(cudaEventSynchronize(plans[j]->ev1));
-        float ms = 0.f;
-        TL_CUDA(cudaEventElapsedTime(&ms, plans[j]->ev0, plans[j]->ev1));
-        plans[j]->total_ms = ms;
-      }
-      fill_result(*plans[j], results[j], false);
-    }
-    if (dbg) std::fprintf(stderr, "[topolow] batch results read: %.3f s\n", since());
-    plans.clear();
-    if (dbg) std::fprintf(stderr, "[topolow] batch plans destroyed: %.3f s\n", since());
-  } catch (const CudaError& e) {
-    for (int j = 0; j < n_jobs; ++j)
-      if (plans[j]) { results[j].status = TOPOLOW_ERR_CUDA; set_msg(results[j].message, sizeof results[j].message, e.what()); }
-    cudaGetLastError();
-    return TOPOLOW_ERR_CUDA;
-  }
-  return TOPOLOW_OK;
 }
 
 int topolow_plan_create(const topolow_problem* problem, const topolow_params* params, topolow_plan** plan_out,
