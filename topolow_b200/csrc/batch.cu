@@ -37,8 +37,8 @@ void launch_group(const std::vector<topolow_plan*>& members, const std::vector<i
   // (pageable source: the call returns once the source has been staged, so `jobs` may go out of scope)
   TL_CUDA(cudaMemcpyAsync(d_jobs, jobs.data(), jobs.size() * sizeof(BatchJob<real>), cudaMemcpyHostToDevice, stream));
   const topolow_plan& p0 = *members[0];
-  if (sizeof(real) == 8) launch_tile_batch_f64(p0.D, p0.geo.P, (const BatchJob<double>*)(const void*)d_jobs, (int)jobs.size(), p0.geo.W, smem, stream);
-  else launch_tile_batch_f32(p0.D, p0.geo.P, (const BatchJob<float>*)(const void*)d_jobs, (int)jobs.size(), p0.geo.W, smem, stream);
+  if constexpr (sizeof(real) == 8) launch_tile_batch_f64(p0.D, p0.geo.P, d_jobs, (int)jobs.size(), p0.geo.W, smem, stream);
+  else launch_tile_batch_f32(p0.D, p0.geo.P, d_jobs, (int)jobs.size(), p0.geo.W, smem, stream);
 }
 // Tile size of the one-CTA-per-fit path (TOPOLOW_BATCH_TILE overrides: measurement aid).
 int batch_tile_points() {

@@ -66,6 +66,13 @@ inline void pool_alloc(T*& p, size_t bytes) {
 }
 inline void pool_ready() { TL_CUDA(cudaStreamSynchronize(cudaStreamPerThread)); }   // allocations usable on any stream
 inline void pool_free(void* p) { if (p) cudaFreeAsync(p, cudaStreamPerThread); }
+// Makes `device` current for the lifetime of the object (destructors free on the device that owns the memory).
+struct DeviceScope {
+  int prev = -1;
+  explicit DeviceScope(int device) { if (cudaGetDevice(&prev) != cudaSuccess) prev = -1; if (prev != device) cudaSetDevice(device); else prev = -1; }
+  DeviceScope(const DeviceScope&) = delete;
+  ~DeviceScope() { if (prev >= 0) cudaSetDevice(prev); }
+};
 inline void keep_pool_memory(int device) {
   cudaMemPool_t pool;
   if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {

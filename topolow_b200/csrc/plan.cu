@@ -249,6 +249,7 @@ std::shared_ptr<EdgeStore> make_store(const topolow_problem& pb, int T, int P, i
   TL_CUDA(cudaSetDevice(device));
   keep_pool_memory(device);
   auto st = std::make_shared<EdgeStore>();
+  st->device = device;
   st->slot_of_point = random_permutation(pb.n, kLayoutSeed);
   st->point_of_slot.assign((size_t)T * 32 * P, -1);
   for (int64_t i = 0; i < pb.n; ++i) st->point_of_slot[st->slot_of_point[i]] = (int32_t)i;

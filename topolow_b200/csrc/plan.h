@@ -20,7 +20,8 @@ struct EdgeStore {
   std::vector<int32_t> slot_of_point;
   EdgeRec* edges = nullptr;
   uint32_t* bucket_off = nullptr;
-  ~EdgeStore() { pool_free(edges); pool_free(bucket_off); }
+  int device = 0;
+  ~EdgeStore() { DeviceScope on(device); pool_free(edges); pool_free(bucket_off); }
 };
 
 }  // namespace tl
@@ -48,6 +49,8 @@ struct topolow_plan {
   size_t smem = 0;
 
   ~topolow_plan() {
+    tl::DeviceScope on(device);
+    if (stream) cudaStreamSynchronize(stream);   // the buffers go back to the pool in another stream's order
     tl::pool_free(pos); tl::pool_free(best); tl::pool_free(dp1);
     tl::pool_free(state); tl::pool_free(partials); tl::pool_free(barrier); tl::pool_free(trace);
     tl::pool_free(hold_si); tl::pool_free(hold_sj); tl::pool_free(hold_truth);
