@@ -26,7 +26,7 @@
 #error "define TL_KP (points per lane: 1, 2 or 3) before including tilepass.cuh"
 #endif
 #ifndef TL_RING_UNROLL
-#define TL_RING_UNROLL 2   // ring steps per loop trip: the shuffles of one step overlap the first wave of the next
+#define TL_RING_UNROLL 0   // ring steps per loop trip; 0 = the measured default per tile size (kRingUnroll)
 #endif
 #define TL_PNS_CAT2(a, b) a##b
 #define TL_PNS_CAT(a, b) TL_PNS_CAT2(a, b)
@@ -37,7 +37,11 @@ namespace TL_PNS {   // one copy of everything below per tile size
 
 constexpr int kP = TL_KP;        // points of a tile held by one lane
 constexpr int kTile = 32 * kP;   // points per tile
-constexpr int kRingUnroll = TL_RING_UNROLL;
+// Ring steps per loop trip.  Inside an unrolled trip the shuffles of a step are scheduled between the
+// FMAs of the next one; only the last step of a trip has nothing after it.  Measured on B200 (ms per
+// iteration at N = 100k, d = 16, 96-point tiles): 1 -> 25.3, 2 -> 23.7, 4 -> 22.7, 8 -> 22.7; the smaller
+// bodies of the 32- and 64-point kernels gain a little more from 8.
+constexpr int kRingUnroll = TL_RING_UNROLL ? TL_RING_UNROLL : (kP == 3 ? 4 : 8);
 
 // ---------------------------------------------------------------------------------------
 // Math policies.  A policy owns the register image of a point (`Point<D>`: coordinates + the
