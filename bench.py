@@ -179,7 +179,6 @@ def cfg5_jobs(n, missing, samples, fit_iters, seed):
     """`samples` parameter draws x 4 CV folds on one synthetic matrix: the unit of work of
     initial_parameter_optimization (R/adaptive_sampling.R:419-425,516-528)."""
     from tools import synth
-    from topolow_b200 import cv
     rng = np.random.default_rng(seed)
     prob = synth.make_problem(n, 5, missing, seed=0, thresholds=False)
     ei, ej, ed = prob["edge_i"], prob["edge_j"], prob["edge_dist"]

@@ -1,7 +1,6 @@
 """Quick GPU check: smoke parity + throughput at cfg3/cfg4 sizes (synthetic generator of bench.py)."""
-import os, sys, time, json
+import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np
 import __graft_entry__ as ge
 from tools import synth
 from topolow_b200 import _lib

@@ -1,9 +1,8 @@
 """Per-job kernel times of the sharded schedule (emulated on one GPU): where does an iteration go?"""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np, torch
+import torch
 from tools import synth
-from topolow_b200 import _lib
 from topolow_b200.sharded import ShardedMap
 world = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 tp = int(sys.argv[2]) if len(sys.argv) > 2 else 0
