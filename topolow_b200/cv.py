@@ -106,6 +106,13 @@ def likelihood_batch(dissimilarity_matrix, samples, mapping_max_iter, relative_e
     cooling_rate, c_repulsion; returns one likelihood_function() result per sample.  All
     len(samples) x folds fits run in a single topolow_fit_batch call.
 
+    The folds are drawn ONCE for the whole batch (or taken from `fold_indices`): every sample is scored on
+    the same hold-out cells, and topolow_fit_batch builds the device records of a fold once.  The
+    reference draws fresh folds inside every likelihood_function call (R/adaptive_sampling.R:2568-2598);
+    the distribution of a sample's score is the same, the scores of different samples are no longer
+    independent (common random numbers - which is what comparing samples wants).  Call
+    likelihood_function per sample for the reference's behaviour.
+
     preserve_order defaults to True here because fold residuals are aligned by position; the
     reference re-aligns by row names (R/error_metrics.R:76-87) which an unnamed matrix lacks."""
     rng = rng or np.random.default_rng(seed)
