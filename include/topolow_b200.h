@@ -154,7 +154,11 @@ TOPOLOW_API int topolow_optimize_layout_exact(
 
 /* ---- batch of independent fits ----------------------------------------- */
 /* Jobs run concurrently on `device` (params[j].device is ignored); results[j].status is
- * per job and the call itself only fails for argument / CUDA set-up errors. */
+ * per job and the call itself only fails for argument / CUDA set-up errors.
+ * With 16 or more jobs every fit runs on one CTA (64-point tiles unless tile_points is set) and the fits
+ * are launched many per kernel.  Jobs whose edge_i / edge_j / edge_dist / edge_thresh POINTERS (and n,
+ * n_edges) are equal share one set of device records: hand the parameter samples of a CV grid the same
+ * arrays per fold.  A batch is not interruptible. */
 TOPOLOW_API int topolow_fit_batch(int32_t n_jobs, const topolow_problem* problems, const topolow_params* params,
                       topolow_result* results, int32_t device);
 
