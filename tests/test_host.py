@@ -228,3 +228,36 @@ def test_sharding_across_two_ranks_with_gloo(tmp_path):
         out, err = p.communicate(timeout=120)
         assert p.returncode == 0, err[-2000:]
         assert "ok" in out
+
+
+def test_likelihood_batch_holdout_cells_follow_the_reordering(monkeypatch):
+    """likelihood_batch hands every fit its hold-out cells in the row numbering of the fold's training
+    problem (which euclidean_embedding-style reordering permutes unless preserve_order).  A stub "fit"
+    that returns its initial positions makes the expected residuals computable by hand."""
+    m = random_r_matrix(30, 0.6, 11)
+    value, code, is_na = core.parse_dissimilarity(m)
+    folds = cv.make_folds(m, 3, np.random.default_rng(2))
+    G = np.random.default_rng(5).normal(size=(30, 2)) * 4          # "embedding" in the caller's row numbering
+
+    def stub_fit_batch(jobs, device=0):
+        out = []
+        for j in jobs:
+            pos = np.asarray(j["initial_positions"], dtype=float)
+            hi, hj, ht = j["holdout"]
+            ok = ~np.isnan(ht)
+            d = np.linalg.norm(pos[hi] - pos[hj], axis=1)
+            out.append(dict(status=_lib.OK, positions=pos, holdout_sum_abs=float(np.abs(ht[ok] - d[ok]).sum()),
+                            holdout_count=int(ok.sum()), iterations=1, converged=True))
+        return out
+
+    monkeypatch.setattr(_lib, "fit_batch", stub_fit_batch)
+    for preserve in (True, False):
+        inits, want = [], []
+        for h in folds:
+            prob, ci, cj, tr = cv._fold_job(value, code, is_na, np.asarray(h), preserve)
+            inits.append(G if prob["order"] is None else G[prob["order"]])
+            want.append(np.abs(tr - np.linalg.norm(G[ci] - G[cj], axis=1)).mean())
+        assert preserve or any(cv._fold_job(value, code, is_na, np.asarray(h), False)[0]["order"] is not None for h in folds)
+        got = cv.likelihood_batch(m, [dict(N=2, k0=1.0, cooling_rate=0.01, c_repulsion=0.01)], 5, 1e-4, folds=3,
+                                  preserve_order=preserve, fold_indices=folds, init_list=[inits])
+        assert [f["Holdout_MAE"] for f in got[0]["folds"]] == pytest.approx(want, rel=1e-12)
