@@ -348,7 +348,7 @@ def main():
     fa = synth.fit_args(prob)
     E = int(len(prob["edge_i"]))
     pairs = n * (n - 1) // 2
-    total_iters = args.steps + args.warmup
+    total_iters = args.steps + (max(args.warmup, 3) if args.warmup else 0)   # every iteration run is inside n_iter
     nw = total_iters + 1  # convergence window > n_iter: no early stop
 
     sharded = world > 1 and args.multi == "sharded"

@@ -173,7 +173,8 @@ TOPOLOW_API int topolow_plan_run(topolow_plan* plan, int32_t n_iters, void* stre
 TOPOLOW_API int topolow_plan_result(topolow_plan* plan, topolow_result* result);
 /* Geometry of the schedule: fills up to `cap` int64 values
  * {tiles, super_blocks, warps_per_cta, ctas, tasks_per_cta, rounds, pairs_per_iter, smem_bytes,
- * iterations_per_launch, kernel_launches_so_far, tile_points}. */
+ * iterations_per_launch, kernel_launches_so_far, tile_points, iterations_done, stopped} (the last two as of
+ * the last FINISHED launch: synchronise the stream first). */
 TOPOLOW_API int topolow_plan_info(const topolow_plan* plan, int64_t* out, int32_t cap);
 TOPOLOW_API void topolow_plan_destroy(topolow_plan* plan);
 

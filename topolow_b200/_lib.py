@@ -311,10 +311,10 @@ class Plan:
         return result_dict(res, out, tr)
 
     def info(self):
-        v = (C.c_int64 * 11)()
-        self._L.topolow_plan_info(self._h, v, 11)
+        v = (C.c_int64 * 13)()
+        self._L.topolow_plan_info(self._h, v, 13)
         keys = ["tiles", "super_blocks", "warps_per_cta", "ctas", "tasks_per_cta", "rounds", "pairs_per_iter",
-                "smem_bytes", "iters_per_launch", "launches", "tile_points"]
+                "smem_bytes", "iters_per_launch", "launches", "tile_points", "iterations_done", "stopped"]
         return dict(zip(keys, [int(x) for x in v]))
 
     def enumerate(self, it):

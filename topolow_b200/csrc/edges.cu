@@ -62,8 +62,10 @@ __global__ void scatter_kernel(const int32_t* __restrict__ ei, const int32_t* __
   }
 }
 
-// One warp per bucket: out[rank] = in[e], rank = number of records of the bucket that precede e
-// in (slot_lo, slot_hi) order (pairs are unique, so ranks are a permutation).
+// One warp per bucket: out[rank] = in[e], rank = number of records of the bucket that precede e in
+// (slot_lo, slot_hi, target bits, type) order.  A pair listed twice (also as (j, i)) is legal input: records
+// with equal keys are ordered by their remaining bits, fully equal records by their position, so the ranks
+// are a permutation and the result does not depend on the order the scatter left.
 __global__ void bucket_sort_kernel(const EdgeRec* __restrict__ in, EdgeRec* __restrict__ out,
                                    const uint32_t* __restrict__ off, size_t nkeys) {
   const int lane = threadIdx.x & 31;
@@ -74,10 +76,14 @@ __global__ void bucket_sort_kernel(const EdgeRec* __restrict__ in, EdgeRec* __re
     for (uint32_t x = b + lane; x < e; x += 32) {
       const EdgeRec r = in[x];
       const unsigned long long mine = ((unsigned long long)r.slot_lo << 32) | (r.slot_hi_type & 0x3fffffffu);
+      const unsigned long long mine2 = ((unsigned long long)__double_as_longlong(r.target) << 2) ^ (r.slot_hi_type >> 30);
       uint32_t rank = 0;
       for (uint32_t y = b; y < e; ++y) {
-        const unsigned long long other = ((unsigned long long)in[y].slot_lo << 32) | (in[y].slot_hi_type & 0x3fffffffu);
-        rank += other < mine ? 1u : 0u;
+        const EdgeRec o = in[y];
+        const unsigned long long other = ((unsigned long long)o.slot_lo << 32) | (o.slot_hi_type & 0x3fffffffu);
+        const unsigned long long other2 = ((unsigned long long)__double_as_longlong(o.target) << 2) ^ (o.slot_hi_type >> 30);
+        const bool before = other < mine || (other == mine && (other2 < mine2 || (other2 == mine2 && y < x)));
+        rank += before ? 1u : 0u;
       }
       out[b + rank] = r;
     }

@@ -381,7 +381,9 @@ double run_plan(topolow_plan& pl, int n_iters, cudaStream_t stream_in, topolow_i
   TL_CUDA(cudaSetDevice(pl.device));
   cudaStream_t s = stream_in ? stream_in : pl.stream;
   TL_CUDA(cudaEventRecord(pl.ev0, s));
-  int left = n_iters;
+  // never past n_iter (h_flag[1] = iterations done; every run_plan ends synchronised, so it is current here;
+  // the kernel clamps as well)
+  int left = std::min(n_iters, std::max(0, pl.prm.n_iter - (int)pl.h_flag[1]));
   while (left > 0) {
     if (pl.h_flag[0]) break;
     if (poll && poll(user)) { if (interrupted) *interrupted = true; break; }
@@ -623,9 +625,10 @@ int topolow_plan_result(topolow_plan* plan, topolow_result* result) {
 int topolow_plan_info(const topolow_plan* plan, int64_t* out, int32_t cap) {
   if (!plan || !out) return TOPOLOW_ERR_BAD_ARG;
   const Geometry& g = plan->geo;
-  const int64_t v[11] = {g.T, g.S, g.W, g.G, g.m, g.S, (int64_t)plan->n * (plan->n - 1) / 2, (int64_t)plan->smem,
-                         plan->chunk_iters, plan->launches, 32 * g.P};
-  for (int i = 0; i < cap && i < 11; ++i) out[i] = v[i];
+  const int64_t v[13] = {g.T, g.S, g.W, g.G, g.m, g.S, (int64_t)plan->n * (plan->n - 1) / 2, (int64_t)plan->smem,
+                         plan->chunk_iters, plan->launches, 32 * g.P,
+                         plan->h_flag ? plan->h_flag[1] : 0, plan->h_flag ? plan->h_flag[0] : 0};   // as of the last finished launch
+  for (int i = 0; i < cap && i < 13; ++i) out[i] = v[i];
   return TOPOLOW_OK;
 }
 

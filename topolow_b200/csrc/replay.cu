@@ -214,6 +214,7 @@ void run_replay(const topolow_problem& pb, const topolow_params& pr, topolow_res
   std::vector<int> h_ei(E), h_ej(E);
   for (int64_t e = 0; e < E; ++e) {
     int a = pb.edge_i[e], b = pb.edge_j[e];
+    if (a < 0 || b < 0 || a >= n || b >= n || a == b) throw std::invalid_argument("edge index out of range");
     h_ei[e] = a; h_ej[e] = b;
     if (a > b) std::swap(a, b);
     h_dist[(size_t)a * n + b] = pb.edge_dist[e];
@@ -307,6 +308,7 @@ void run_replay(const topolow_problem& pb, const topolow_params& pr, topolow_res
         for (int64_t p = 0; p < ppi; ++p) {
           int i = src[2 * p], j = src[2 * p + 1];
           if (i < 0) continue;
+          if (j < 0 || i >= n || j >= n || i == j) throw std::invalid_argument("pair_order entry out of range");
           if (i > j) std::swap(i, j);
           tmp.push_back({i, j});
         }

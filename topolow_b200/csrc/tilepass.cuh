@@ -822,7 +822,7 @@ TL_D void tile_body(const TileDev<typename M::real>& dv, const Geometry& geo, co
   }
 
   for (int it = 0; it < n_iters; ++it) {
-    if (st.stop) break;
+    if (st.stop || st.iter >= prm.n_iter) break;   // never past n_iter: trace[] holds n_iter entries, the forced last check is iter == n_iter - 1
     const int iter = st.iter;
     const typename M::Ctx ctx = M::make_ctx(st.k, prm.c_repulsion);
     if (tid < kIterKeys) s_key[tid] = iter_key(geo, iter, (uint32_t)tid);

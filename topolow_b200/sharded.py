@@ -56,6 +56,9 @@ class ShardedMap:
         assert self.Tm * self.M == lay["total_tiles"]
         self.block_elems = self.Tm * lay["tile_points"] * lay["ndim"]
         self.iteration = 0
+        self.n_iter = int(n_iter)
+        self.check_freq = int(convergence_check_freq) if int(convergence_check_freq) >= 1 else 10
+        self.stopped = False
         self._pos = None
         if not self.emulate:
             import torch
@@ -110,6 +113,8 @@ class ShardedMap:
             import torch
             stream = torch.cuda.current_stream().cuda_stream
         for _ in range(n_iters):
+            if self.stopped or self.iteration >= self.n_iter:
+                return False
             it = self.iteration
             for row in self.jobs(it):
                 if self.emulate:
@@ -128,7 +133,21 @@ class ShardedMap:
                 self._exchange([(2 * r, 2 * r + 1) for r in range(self.R)])
             self.plan.end_iteration(stream=stream)
             self.iteration += 1
-        return True
+            # the controller may only stop the fit on a check iteration (src/optimization.cpp:294): read the
+            # plan's mapped flag there, so that self.iteration never runs ahead of the device's iteration
+            if self.iteration % self.check_freq == 0 or self.iteration % 10 == 0 or self.iteration >= self.n_iter:
+                self._sync(stream)
+                if self.plan.info()["stopped"]:
+                    self.stopped = True
+                    return False
+        return not self.stopped and self.iteration < self.n_iter
+
+    def _sync(self, stream):
+        if self.emulate:
+            self.plan.run(0)      # no iterations: records and waits for an event on the plan's own stream
+        else:
+            import torch
+            torch.cuda.current_stream().synchronize()
 
     def result(self, trace=False):
         if not self.emulate:
