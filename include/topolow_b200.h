@@ -59,8 +59,11 @@ enum {
 enum {
   TOPOLOW_MODE_COLOURED = 0, /* production: hierarchical tournament of matchings (every pair once
                                 per iteration, updates within a matching commute) */
-  TOPOLOW_MODE_REPLAY = 1    /* FP64, consumes a given / seeded std::mt19937 pair permutation and
+  TOPOLOW_MODE_REPLAY = 1,   /* FP64, consumes a given / seeded std::mt19937 pair permutation and
                                 executes it by dependency levels: exactly the sequential loop */
+  TOPOLOW_MODE_ROWBLOCK = 2  /* relaxed, for large maps: every point's update is computed by the owner of its row
+                                against a replica of all positions (Gauss-Seidel along a row, Jacobi across
+                                rows); FP32; the scheme topolow_shard_* spreads over several GPUs */
 };
 /* precision (coloured mode) */
 enum {
@@ -195,6 +198,46 @@ TOPOLOW_API void* topolow_plan_positions(topolow_plan* plan);
 /* The sequential pair order one job is equivalent to (cf. topolow_plan_enumerate). */
 TOPOLOW_API int64_t topolow_plan_enumerate_job(const topolow_plan* plan, int32_t iter, int32_t kind, int32_t t0,
                                                int32_t tc, int32_t y0, int32_t yc, int32_t* out, int64_t cap_pairs);
+
+/* ---- one large map, row-block sharded (mode TOPOLOW_MODE_ROWBLOCK) ----------------
+ * Rank r of n_ranks (one process per GPU, or several shards in one process) owns a contiguous block of
+ * rows and a replica of all positions.  Per iteration it computes the one-sided updates of its rows
+ * (src/optimization.cpp:199-282 seen from the row's endpoint), stores the new rows straight into every
+ * replica over NVLink and raises one flag per peer; nothing goes through the host.  Protocol:
+ *   every rank: topolow_shard_create(same problem, same params, rank, n_ranks)  -> topolow_shard_export(handle)
+ *   all-gather the handles (topolow_shard_handle_bytes() each; any transport: torch.distributed, MPI, a file)
+ *   every rank: topolow_shard_attach(all handles in rank order)     [CUDA IPC; or topolow_shard_attach_local
+ *                                                                    for shards that live in one process]
+ *   every rank: topolow_shard_run(n_iters) with the same n_iters, as often as wanted; topolow_shard_result
+ *   on any rank returns the whole map (replicas are identical).  Synchronise the ranks (a host barrier)
+ *   before topolow_shard_destroy: peers store into a shard's memory until their last iteration ends.
+ * The result does not depend on n_ranks (fixed summation trees), n_ranks = 1 is topolow_fit with
+ * mode = TOPOLOW_MODE_ROWBLOCK.  A peer that does not arrive within 20 s ends the fit with TOPOLOW_ERR_CUDA. */
+typedef struct topolow_shard topolow_shard;
+TOPOLOW_API int topolow_shard_create(const topolow_problem* problem, const topolow_params* params, int32_t rank,
+                                     int32_t n_ranks, topolow_shard** shard_out, char* message, int32_t message_len);
+TOPOLOW_API int64_t topolow_shard_handle_bytes(void);
+TOPOLOW_API int topolow_shard_export(topolow_shard* shard, void* handle_out);
+TOPOLOW_API int topolow_shard_attach(topolow_shard* shard, const void* handles, int32_t n_handles, char* message,
+                                     int32_t message_len);
+TOPOLOW_API int topolow_shard_attach_local(topolow_shard* const* shards, int32_t n, char* message, int32_t message_len);
+/* Up to n_iters further iterations on `stream` (cudaStream_t, NULL = the shard's own); ms_out = CUDA-event time. */
+TOPOLOW_API int topolow_shard_run(topolow_shard* shard, int32_t n_iters, void* stream, double* ms_out);
+/* All shards of a map that live in this process.  Shards on one device run in lock step on one stream
+ * (how a single GPU checks the multi-GPU path: every wait finds its flag already raised), shards on
+ * distinct devices run concurrently. */
+TOPOLOW_API int topolow_shard_run_local(topolow_shard* const* shards, int32_t n, int32_t n_iters, double* ms_out);
+/* Runs n_iters iterations with CUDA events around every launch; out (up to 6 values) = average milliseconds
+ * of {repulsion, springs, edge MAE, controller, snapshot} and the number of MAE launches seen. */
+TOPOLOW_API int topolow_shard_time_kernels(topolow_shard* shard, int32_t n_iters, double* out, int32_t cap);
+TOPOLOW_API int topolow_shard_result(topolow_shard* shard, topolow_result* result);
+/* out (up to 16 values): {slots, ndim, stride, n_ranks, rank, row0, own_rows, partner_chunks, spring_records,
+ * mae_records, kernel_launches, iterations_done, stopped, peer_store_bytes_per_iteration, repulsion_items,
+ * repulsion_ctas}. */
+TOPOLOW_API int topolow_shard_info(const topolow_shard* shard, int64_t* out, int32_t cap);
+/* slot_of_point of the row-block layout (a pure function of n). */
+TOPOLOW_API int topolow_shard_slot_order(int64_t n, int32_t* slot_of_point_out);
+TOPOLOW_API void topolow_shard_destroy(topolow_shard* shard);
 
 /* The sequential pair order that is equivalent to iteration `iter` of a coloured-mode plan
  * (host-side walk of the same schedule functions the kernel executes).  out = [pairs][2]

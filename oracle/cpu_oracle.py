@@ -197,3 +197,53 @@ def edge_error(positions, edge_i, edge_j, edge_dist, edge_thresh):
                              ej.ctypes.data_as(_ip), ed.ctypes.data_as(_dp), et.ctypes.data_as(_ip),
                              C.byref(tot), C.byref(cnt))
     return tot.value, cnt.value
+
+
+def _relaxed_lib() -> C.CDLL:
+    if "relaxed" in _LIBS:
+        return _LIBS["relaxed"]
+    path = os.path.join(_HERE, "librelaxed.so")
+    if not os.path.exists(path):
+        build(ref=False)
+    lib = C.CDLL(path)
+    lib.relaxed_optimize_layout.restype = C.c_int
+    lib.relaxed_optimize_layout.argtypes = [
+        C.c_int64, C.c_int, _dp, _ip, C.c_int64, _ip, _ip, _dp, _ip, C.c_int, C.c_double, C.c_double, C.c_double,
+        C.c_double, C.c_int, C.c_int, _i32p, C.c_int, C.c_uint64, _dp, _ip, _ip, _dp, _dp, _dp, _ip]
+    _LIBS["relaxed"] = lib
+    return lib
+
+
+def relaxed_optimize_layout(initial_positions, degrees, edge_i, edge_j, edge_dist, edge_thresh, n_iter, k0,
+                            cooling_rate, c_repulsion, relative_epsilon=1e-4, convergence_window=5,
+                            convergence_check_freq=3, *, seed=0, slot_of_point=None, rotate=True, trace=False):
+    """oracle/relaxed_oracle.cpp: the row-block scheme of topolow_b200/csrc/rowblock.cu in FP64.
+    slot_of_point (optional): the relabelling the GPU uses (topolow_b200.rowblock.slot_order(n))."""
+    lib = _relaxed_lib()
+    init = np.asfortranarray(np.asarray(initial_positions, dtype=np.float64))
+    n, dim = init.shape
+    ei, ej, ed, et, deg = _i32(edge_i), _i32(edge_j), _f64(edge_dist), _i32(edge_thresh), _i32(degrees)
+    pos = None
+    if slot_of_point is not None:
+        sop = np.asarray(slot_of_point, dtype=np.int64)
+        pos = np.empty(n, dtype=np.int32)
+        pos[sop] = np.arange(n, dtype=np.int32)          # point_of_slot
+    out = np.empty((n, dim), dtype=np.float64, order="F")
+    conv, iters, run = C.c_int(0), C.c_int(0), C.c_int(0)
+    fmae, fk = C.c_double(0), C.c_double(0)
+    tr = np.full(max(int(n_iter), 1), np.nan) if trace else None
+    rc = lib.relaxed_optimize_layout(
+        n, dim, init.ctypes.data_as(_dp), deg.ctypes.data_as(_ip), len(ei), ei.ctypes.data_as(_ip),
+        ej.ctypes.data_as(_ip), ed.ctypes.data_as(_dp), et.ctypes.data_as(_ip), int(n_iter), float(k0),
+        float(cooling_rate), float(c_repulsion), float(relative_epsilon), int(convergence_window),
+        int(convergence_check_freq), _p(pos, _i32p), int(bool(rotate)), int(seed) & 0xFFFFFFFFFFFFFFFF,
+        out.ctypes.data_as(_dp), C.byref(conv), C.byref(iters), C.byref(fmae), C.byref(fk), _p(tr, _dp), C.byref(run))
+    if rc == 1:
+        raise OracleError("Need at least 2 points for embedding")
+    if rc == 2:
+        raise OracleError("Numerical instability at iteration %d. Reduce k0 or c_repulsion." % iters.value)
+    res = dict(positions=np.ascontiguousarray(out), converged=bool(conv.value), iterations=iters.value,
+               final_mae=fmae.value, final_k=fk.value, iterations_run=run.value)
+    if trace:
+        res["trace_mae"] = tr
+    return res

@@ -2,7 +2,7 @@
 //
 // TEST INFRASTRUCTURE ONLY.  CPU restatement (FP64) of the ROW-BLOCK ("relaxed", owner-computes)
 // iteration that topolow_b200/csrc/rowblock.cu runs on the GPU - the partitioning SURVEY.md section 8e
-// describes for one large map: every point's update is computed by its owner against a gathered copy
+// describes for one large map: every point's update is computed by the owner of its row against a copy
 // of all other points.  Used by tests/ to check the CUDA kernels (same arithmetic, FP64 here) and to
 // compare the scheme statistically with the reference's sequential loop (oracle/topolow_oracle.cpp).
 // Nothing under topolow_b200/ may import, link or execute this file.
@@ -10,10 +10,10 @@
 // One iteration on the snapshot P of all positions (citations: /root/reference/src/optimization.cpp):
 //   1. repulsion, Jacobi over all ordered pairs (:269-281 applied from the snapshot):
 //        R_i = - sum_{j != i} (P_j - P_i) * c / (2 (|P_j - P_i| + 0.01)^3) / (deg_i + 1)
-//   2. springs, Gauss-Seidel along the point's own measured pairs (:226-256), partners frozen at the
-//      snapshot ("groups" > 1: partners of an earlier group are read at their NEW position):
-//        x = P_i + R_i;  for every record (j, target, type) of row i, starting at a per-iteration offset:
-//          delta = Q_j - x, dist = |delta|, ds = dist + 0.01
+//   2. springs, Gauss-Seidel along the point's own measured pairs (:226-256), partners at the snapshot:
+//        x = P_i + R_i;  for every record (j, target, type) of row i (partners ascending by slot; the rows
+//        of a slice of 32 slots share a start offset drawn per iteration and walk the slice's width cyclically):
+//          delta = P_j - x, dist = |delta|, ds = dist + 0.01
 //          spring iff type == 0, or '>' and dist < target, or '<' and dist > target   (:237-243)
 //          if spring:  x -= delta * (2 k (target - dist) / ds) / (4 (deg_i + 1) + k)   (:246-253, own endpoint)
 //                      x += (P_j - P_i) * c / (2 (|P_j - P_i| + 0.01)^3) / (deg_i + 1)   (takes back what
@@ -29,6 +29,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <thread>
 #include <vector>
 
 namespace {
@@ -42,25 +43,38 @@ inline uint64_t mix64(uint64_t x) {
   return x;
 }
 
+// body(i) for i in [0, n) on all host cores; iterations are independent.
+template <class F>
+void parallel_for(int64_t n, F body) {
+  unsigned nt = std::thread::hardware_concurrency();
+  if (nt < 1) nt = 1;
+  if (nt > 64) nt = 64;
+  if ((int64_t)nt > n) nt = (unsigned)(n > 0 ? n : 1);
+  if (nt == 1) { for (int64_t i = 0; i < n; ++i) body(i); return; }
+  std::vector<std::thread> pool;
+  for (unsigned t = 0; t < nt; ++t)
+    pool.emplace_back([=] { for (int64_t i = t; i < n; i += nt) body(i); });
+  for (auto& th : pool) th.join();
+}
+
 }  // namespace
 
 extern "C" {
 
 // positions: column-major n x dim (like an R matrix) in and out.  slot_order (optional, length n):
 // slot_order[s] = point held by slot s - the order rows are grouped and (within a row) partners are
-// visited in; NULL = identity.  groups >= 1.  rotate != 0: the walk over a row starts at
-// mix64(seed, iter, slot) % len.  Returns 0, or 2 on non-finite positions (fail_iter in *iterations).
+// visited in; NULL = identity.  rotate != 0: the walk over the rows of slice s / 32 starts at
+// mix64(seed ^ mix64(iter << 32 | slice)) % width(slice).  Returns 0, or 2 on non-finite positions
+// (fail_iter in *iterations).
 int relaxed_optimize_layout(int64_t n, int dim, const double* init, const int* degrees, int64_t n_edges,
                             const int* edge_i, const int* edge_j, const double* edge_dist, const int* edge_thresh,
                             int n_iter, double k0, double cooling_rate, double c_repulsion, double relative_epsilon,
                             int convergence_window, int convergence_check_freq, const int32_t* slot_order,
-                            int groups, int group_rows, int rotate, uint64_t seed, int jacobi_full,
+                            int rotate, uint64_t seed,
                             double* out_positions, int* out_converged, int* out_iterations, double* out_final_mae,
                             double* out_final_k, double* trace, int* out_iterations_run) {
   if (n < 2) return 1;
   if (convergence_check_freq < 1) convergence_check_freq = 10;
-  if (groups < 1) groups = 1;
-  if (group_rows < 1) group_rows = 1;
   std::vector<int32_t> point_of_slot(n), slot_of_point(n);
   for (int64_t s = 0; s < n; ++s) point_of_slot[s] = slot_order ? slot_order[s] : (int32_t)s;
   for (int64_t s = 0; s < n; ++s) slot_of_point[point_of_slot[s]] = (int32_t)s;
@@ -77,8 +91,15 @@ int relaxed_optimize_layout(int64_t n, int dim, const double* init, const int* d
       recs[cur[b]++] = Rec{a, edge_thresh[e], edge_dist[e]};
     }
     for (int64_t s = 0; s < n; ++s)
-      std::sort(recs.begin() + off[s], recs.begin() + off[s + 1], [](const Rec& x, const Rec& y) { return x.j < y.j; });
+      std::sort(recs.begin() + off[s], recs.begin() + off[s + 1], [](const Rec& x, const Rec& y) {
+        if (x.j != y.j) return x.j < y.j;
+        const int tx = x.type == 0 ? 0 : (x.type == 1 ? 1 : 2), ty = y.type == 0 ? 0 : (y.type == 1 ? 1 : 2);
+        if (tx != ty) return tx < ty;
+        return x.target < y.target;
+      });
   }
+  std::vector<int64_t> slice_width((n + 31) / 32, 0);
+  for (int64_t s = 0; s < n; ++s) slice_width[s / 32] = std::max(slice_width[s / 32], off[s + 1] - off[s]);
   // slot-major AoS positions
   std::vector<double> P((size_t)n * dim), Pn((size_t)n * dim), best((size_t)n * dim), dp1(n);
   for (int64_t s = 0; s < n; ++s) {
@@ -95,8 +116,7 @@ int relaxed_optimize_layout(int64_t n, int dim, const double* init, const int* d
 
   for (int iter = 0; iter < n_iter; ++iter) {
     // ---- 1. repulsion from the snapshot ----
-#pragma omp parallel for schedule(static)
-    for (int64_t i = 0; i < n; ++i) {
+    parallel_for(n, [&](int64_t i) {
       double acc[64];
       for (int d = 0; d < dim; ++d) acc[d] = 0.0;
       const double* pi = &P[i * dim];
@@ -109,42 +129,36 @@ int relaxed_optimize_layout(int64_t n, int dim, const double* init, const int* d
         for (int d = 0; d < dim; ++d) acc[d] += delta[d] * w;   // j == i contributes delta = 0
       }
       for (int d = 0; d < dim; ++d) R[i * dim + d] = -acc[d] * c_half / dp1[i];
-    }
+    });
     // ---- 2. springs ----
-    for (int g = 0; g < groups; ++g) {
-#pragma omp parallel for schedule(dynamic, 16)
-      for (int64_t i = 0; i < n; ++i) {
-        if ((int)((i / group_rows) % groups) != g) continue;
-        double x[64];
-        const double* pi = &P[i * dim];
-        for (int d = 0; d < dim; ++d) x[d] = pi[d] + R[i * dim + d];
-        const int64_t len = off[i + 1] - off[i];
-        const int64_t start = (rotate && len > 0) ? (int64_t)(mix64(seed ^ mix64(((uint64_t)iter << 32) | (uint64_t)i)) % (uint64_t)len) : 0;
-        const double rnorm = 1.0 / (4.0 * dp1[i] + k), rdeg = c_half / dp1[i];
-        double jx[64];
-        if (jacobi_full) for (int d = 0; d < dim; ++d) jx[d] = x[d];
-        for (int64_t t = 0; t < len; ++t) {
-          int64_t at = start + t; if (at >= len) at -= len;
-          const Rec& r = recs[off[i] + at];
-          const int gj = (int)((r.j / group_rows) % groups);
-          const double* pj = &P[(size_t)r.j * dim];
-          const double* qj = gj < g ? &Pn[(size_t)r.j * dim] : pj;
-          double d2 = 0.0, delta[64];
-          const double* xs = jacobi_full ? jx : x;
-          for (int d = 0; d < dim; ++d) { delta[d] = qj[d] - xs[d]; d2 += delta[d] * delta[d]; }
-          const double dist = std::sqrt(d2), ds = dist + 0.01;
-          const bool spring = r.type == 0 || (r.type > 0 ? dist < r.target : dist > r.target);
-          if (!spring) continue;
-          const double f = 2.0 * k * (r.target - dist) / ds * rnorm;
-          double e2 = 0.0, d0[64];
-          for (int d = 0; d < dim; ++d) { d0[d] = pj[d] - pi[d]; e2 += d0[d] * d0[d]; }
-          const double ds0 = std::sqrt(e2) + 0.01;
-          const double w0 = rdeg / (ds0 * ds0 * ds0);
-          for (int d = 0; d < dim; ++d) x[d] += -delta[d] * f + d0[d] * w0;
-        }
-        for (int d = 0; d < dim; ++d) Pn[i * dim + d] = x[d];
+    parallel_for(n, [&](int64_t i) {
+      double x[64];
+      const double* pi = &P[i * dim];
+      for (int d = 0; d < dim; ++d) x[d] = pi[d] + R[i * dim + d];
+      const int64_t len = off[i + 1] - off[i];
+      const int64_t width = slice_width[i / 32];
+      const int64_t start = (rotate && width > 0)
+          ? (int64_t)(mix64(seed ^ mix64(((uint64_t)(uint32_t)iter << 32) | (uint64_t)(i / 32))) % (uint64_t)width) : 0;
+      const double rnorm = 1.0 / (4.0 * dp1[i] + k), rdeg = c_half / dp1[i];
+      for (int64_t t = 0; t < width; ++t) {
+        int64_t at = start + t; if (at >= width) at -= width;
+        if (at >= len) continue;                       // padding of the slice
+        const Rec& r = recs[off[i] + at];
+        const double* pj = &P[(size_t)r.j * dim];
+        double d2 = 0.0, delta[64];
+        for (int d = 0; d < dim; ++d) { delta[d] = pj[d] - x[d]; d2 += delta[d] * delta[d]; }
+        const double dist = std::sqrt(d2), ds = dist + 0.01;
+        const bool spring = r.type == 0 || (r.type > 0 ? dist < r.target : dist > r.target);
+        if (!spring) continue;
+        const double f = 2.0 * k * (r.target - dist) / ds * rnorm;
+        double e2 = 0.0, d0[64];
+        for (int d = 0; d < dim; ++d) { d0[d] = pj[d] - pi[d]; e2 += d0[d] * d0[d]; }
+        const double ds0 = std::sqrt(e2) + 0.01;
+        const double w0 = rdeg / (ds0 * ds0 * ds0);
+        for (int d = 0; d < dim; ++d) x[d] += -delta[d] * f + d0[d] * w0;
       }
-    }
+      for (int d = 0; d < dim; ++d) Pn[i * dim + d] = x[d];
+    });
     P.swap(Pn);
     k *= (1.0 - cooling_rate);
     iters_run = iter + 1;
@@ -152,7 +166,6 @@ int relaxed_optimize_layout(int64_t n, int dim, const double* init, const int* d
     const bool check = ((iter + 1) % convergence_check_freq == 0) || (iter == n_iter - 1);
     if (check) {
       double tot = 0.0; int64_t cnt = 0;
-#pragma omp parallel for schedule(static) reduction(+ : tot, cnt)
       for (int64_t i = 0; i < n; ++i)
         for (int64_t t = off[i]; t < off[i + 1]; ++t) {
           const Rec& r = recs[t];

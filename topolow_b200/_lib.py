@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("TOPOLOW_B200_LIB") or os.path.join(_HERE, "lib", "libtopolow_b200.so")
 
 OK, ERR_BAD_ARG, ERR_NONFINITE, ERR_CUDA, ERR_TOO_FEW_POINTS, ERR_INTERRUPTED = range(6)
-MODE_COLOURED, MODE_REPLAY = 0, 1
+MODE_COLOURED, MODE_REPLAY, MODE_ROWBLOCK = 0, 1, 2
 PREC_F32, PREC_F64_EXACT = 0, 1
 
 _dp = C.POINTER(C.c_double)
@@ -56,6 +56,9 @@ EXPORTS = [
     "topolow_plan_end_iteration", "topolow_plan_layout", "topolow_plan_positions", "topolow_plan_enumerate_job",
     "topolow_est_distances", "topolow_holdout_errors", "topolow_microbench", "topolow_device_info",
     "topolow_version", "topolow_abi_sizes",
+    "topolow_shard_create", "topolow_shard_handle_bytes", "topolow_shard_export", "topolow_shard_attach",
+    "topolow_shard_attach_local", "topolow_shard_run", "topolow_shard_run_local", "topolow_shard_time_kernels",
+    "topolow_shard_result", "topolow_shard_info", "topolow_shard_slot_order", "topolow_shard_destroy",
 ]
 
 _lib = None
@@ -127,6 +130,31 @@ def lib() -> C.CDLL:
     L.topolow_version.argtypes = []
     L.topolow_abi_sizes.restype = None
     L.topolow_abi_sizes.argtypes = [C.POINTER(C.c_int64 * 3)]
+    L.topolow_shard_create.restype = C.c_int
+    L.topolow_shard_create.argtypes = [C.POINTER(Problem), C.POINTER(Params), C.c_int32, C.c_int32,
+                                       C.POINTER(C.c_void_p), C.c_char_p, C.c_int32]
+    L.topolow_shard_handle_bytes.restype = C.c_int64
+    L.topolow_shard_handle_bytes.argtypes = []
+    L.topolow_shard_export.restype = C.c_int
+    L.topolow_shard_export.argtypes = [C.c_void_p, C.c_void_p]
+    L.topolow_shard_attach.restype = C.c_int
+    L.topolow_shard_attach.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_char_p, C.c_int32]
+    L.topolow_shard_attach_local.restype = C.c_int
+    L.topolow_shard_attach_local.argtypes = [C.POINTER(C.c_void_p), C.c_int32, C.c_char_p, C.c_int32]
+    L.topolow_shard_run.restype = C.c_int
+    L.topolow_shard_run.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, _dp]
+    L.topolow_shard_run_local.restype = C.c_int
+    L.topolow_shard_run_local.argtypes = [C.POINTER(C.c_void_p), C.c_int32, C.c_int32, _dp]
+    L.topolow_shard_time_kernels.restype = C.c_int
+    L.topolow_shard_time_kernels.argtypes = [C.c_void_p, C.c_int32, _dp, C.c_int32]
+    L.topolow_shard_result.restype = C.c_int
+    L.topolow_shard_result.argtypes = [C.c_void_p, C.POINTER(Result)]
+    L.topolow_shard_info.restype = C.c_int
+    L.topolow_shard_info.argtypes = [C.c_void_p, _i64p, C.c_int32]
+    L.topolow_shard_slot_order.restype = C.c_int
+    L.topolow_shard_slot_order.argtypes = [C.c_int64, _i32p]
+    L.topolow_shard_destroy.restype = None
+    L.topolow_shard_destroy.argtypes = [C.c_void_p]
     sizes = (C.c_int64 * 3)()
     L.topolow_abi_sizes(C.byref(sizes))
     if list(sizes) != [C.sizeof(Problem), C.sizeof(Params), C.sizeof(Result)]:

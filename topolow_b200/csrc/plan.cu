@@ -23,6 +23,7 @@
 #include "edges.h"
 #include "replay.h"
 #include "plan.h"
+#include "rowblock.h"
 
 using namespace tl;
 
@@ -484,6 +485,11 @@ int fit_impl(const topolow_problem* pb, const topolow_params* pr, topolow_result
       if (res->status == TOPOLOW_ERR_NONFINITE)
         std::snprintf(res->message, sizeof res->message,
                       "Numerical instability at iteration %d. Reduce k0 or c_repulsion.", res->fail_iter);
+    } else if (pr->mode == TOPOLOW_MODE_ROWBLOCK) {
+      struct Holder { RowPlan* p; ~Holder() { row_destroy(p); } } h{row_create(*pb, *pr, 0, 1)};
+      bool interrupted = false;
+      row_run(*h.p, pr->n_iter, nullptr, poll, user, &interrupted);
+      row_result(*h.p, *res, interrupted);
     } else {
       auto pl = make_plan(*pb, *pr);
       bool interrupted = false;

@@ -1,0 +1,1187 @@
+// topolow_b200/csrc/rowblock.cu
+//
+// Row-block ("owner computes") mode of the embedding loop - the partitioning of one large map that
+// SURVEY.md section 8e / BASELINE.json's north_star describe: the points are cut into G contiguous row
+// blocks, GPU g owns the updates of its rows and computes them against a replica of ALL positions;
+// within an iteration a point's own springs are applied one after another (Gauss-Seidel along the row),
+// other points are read at their position of the iteration's start (Jacobi across points and across
+// GPUs); the new rows are stored straight into every replica over NVLink (peer stores) and one
+// flag exchange per iteration is the only synchronisation.  G = 1 is the same code on one GPU.
+//
+// One iteration on the replica P of all positions (reference: /root/reference/src/optimization.cpp):
+//   repulse_kernel  R_i = -sum_{j != i} (P_j - P_i) * c / (2 (|P_j - P_i| + 0.01)^3) / (deg_i + 1)   (:269-281
+//                   seen from i's side), a tiled one-sided N-body pass in packed FP32: a work item is
+//                   256 own rows x one chunk of 2048 partners streamed through shared memory by cp.async.
+//   spring_kernel   x = P_i + R_i, then for every measured pair (i, j) of row i in turn (:226-256, i's side):
+//                   spring iff exact, or '>' and dist < target, or '<' and dist > target (:237-243);
+//                   x -= (P_j - x) * 2k (target - dist) / (dist + 0.01) / (4 (deg_i + 1) + k)  (:246-253) and the
+//                   repulsion R_i contains for this pair is taken back (a pair in spring state is not
+//                   repelled); a satisfied threshold keeps its repulsion (:257-267).  P'_i = x goes to every
+//                   replica.  One thread per row, records in degree-padded slices of 32 rows (SELL-32) so
+//                   that a warp's record loads are one contiguous 256-byte line.
+//   mae_kernel      on check iterations: sum |target - dist| and count over the measured pairs that are exact
+//                   or violated (:54-81) on P', FP64 sums, fixed summation tree; partial sums go to every replica.
+//   ctl_kernel      cooling happened in the spring kernel (:289); three-way controller with best-state snapshot
+//                   (:303-357, common.cuh::controller_check), finite check every 10 iterations (:359-361).
+// Every unordered pair is visited once from each side per iteration and each side moves only its own
+// endpoint, by what the reference's visit of the pair would move it.  Results do not depend on G (the
+// summation trees are fixed), which is what the tests check; the scheme is compared with the reference's
+// sequential loop statistically (tests/test_gpu_rowblock.py) and with its own CPU restatement
+// (oracle/relaxed_oracle.cpp) numerically.
+#include <algorithm>
+#include <cstring>
+#include <memory>
+#include <vector>
+
+#include "plan.h"
+#include "rowblock.h"
+
+namespace tl {
+
+std::vector<int32_t> random_permutation(int64_t n, uint64_t seed);   // plan.cu
+
+namespace {
+
+constexpr uint64_t kRowLayoutSeed = 0x726f77626c6f636bULL;
+constexpr int kStageJ = 128;   // partners per shared-memory stage
+constexpr int kStages = 3;
+constexpr int kRepThreads = 128;
+constexpr int kFlagStride = 32;   // 32-bit words between the flag words of two ranks (128 bytes)
+constexpr unsigned long long kWaitNs = 20ull * 1000ull * 1000ull * 1000ull;
+
+struct RowDev {
+  int n, slots, D, Dp, G, rank, row0, rows, chunks;
+  unsigned long long cap_rows;       // rows of one position buffer (slots rounded up to a chunk)
+  float* pos[kMaxShards];            // replica q: [2][cap_rows][Dp]
+  double* red[kMaxShards];           // replica q: [slots / 128][4]  {sum |err|, count, non-finite, -}
+  unsigned* flags[kMaxShards];       // replica q: [kMaxShards][kFlagStride], word r = epoch reached by rank r
+  float* best;                       // [cap_rows][Dp]
+  const float* dp1;                  // [slots] degree + 1 (0 = padding row)
+  float* rpart;                      // [chunks][rows][Dp] repulsion sums per partner chunk
+  const uint2* recs;                 // spring records of the own rows, SELL-32: {partner | type << 30, target}
+  const unsigned long long* soff;    // [rows / 32] first record of a slice
+  const int* swidth;                 // [rows / 32] records per row of a slice
+  const uint2* mrecs;                // the records this rank counts in the MAE (every pair once over all ranks)
+  const unsigned long long* moff;
+  const int* mwidth;
+  FitState* state;
+  double* trace;
+  unsigned* counters;                // [4] tickets of the "last CTA" of a launch
+  volatile int* host_flag;           // mapped: [0] stop, [1] iterations done
+  unsigned long long pairs_per_iter;
+  unsigned long long seed;
+};
+
+// ---------------------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------------------
+TL_D float sqrt_approx(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+TL_D float rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+TL_D unsigned ld_acquire_sys(const unsigned* p) {
+  unsigned v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
+}
+TL_D void st_release_sys(unsigned* p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+TL_D unsigned long long global_ns() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+TL_D void cp_async16(void* smem, const void* gmem) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+}
+TL_D void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> TL_D void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// H packed pairs of one point from (shared or global) memory; 16-byte loads when the stride allows.
+template <int H>
+TL_D void ld_point(const float* __restrict__ p, float2 (&v)[H]) {
+  if constexpr (H % 2 == 0) {
+#pragma unroll
+    for (int k = 0; k < H / 2; ++k) {
+      const float4 t = reinterpret_cast<const float4*>(p)[k];
+      v[2 * k] = make_float2(t.x, t.y); v[2 * k + 1] = make_float2(t.z, t.w);
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < H; ++k) v[k] = reinterpret_cast<const float2*>(p)[k];
+  }
+}
+template <int H>
+TL_D void st_point(float* __restrict__ p, const float2 (&v)[H]) {
+  if constexpr (H % 2 == 0) {
+#pragma unroll
+    for (int k = 0; k < H / 2; ++k)
+      reinterpret_cast<float4*>(p)[k] = make_float4(v[2 * k].x, v[2 * k].y, v[2 * k + 1].x, v[2 * k + 1].y);
+  } else {
+#pragma unroll
+    for (int k = 0; k < H; ++k) reinterpret_cast<float2*>(p)[k] = v[k];
+  }
+}
+
+// |q + np|^2 (np = -p); delta is kept for the caller.  kChains = 2 halves the dependent FMA chain (the
+// spring walk is one long dependency chain), 1 saves the packed add that joins the chains (the repulsion
+// pass has enough independent interactions in flight and is bound by the FMA pipe).
+template <int H, int kChains = 2>
+TL_D float dist2(const float2 (&np)[H], const float2 (&q)[H], float2 (&dl)[H]) {
+#pragma unroll
+  for (int k = 0; k < H; ++k) dl[k] = __fadd2_rn(q[k], np[k]);
+  float2 s0 = __fmul2_rn(dl[0], dl[0]);
+  if constexpr (kChains == 1 || H == 1) {
+#pragma unroll
+    for (int k = 1; k < H; ++k) s0 = __ffma2_rn(dl[k], dl[k], s0);
+  } else {
+    float2 s1 = __fmul2_rn(dl[1], dl[1]);
+#pragma unroll
+    for (int k = 2; k < H; ++k) {
+      if (k & 1) s1 = __ffma2_rn(dl[k], dl[k], s1);
+      else s0 = __ffma2_rn(dl[k], dl[k], s0);
+    }
+    s0 = __fadd2_rn(s0, s1);
+  }
+  return s0.x + s0.y;
+}
+
+// One-sided repulsion of partner q on the point -np: acc += (q - p) / (|q - p| + 0.01)^3.
+template <int H>
+TL_D void repel(const float2 (&np)[H], const float2 (&q)[H], float2 (&acc)[H]) {
+  float2 dl[H];
+  const float d2 = dist2<H, 1>(np, q, dl);
+  const float ds = sqrt_approx(d2) + 0.01f;
+  const float w = rcp_approx(ds * ds * ds);
+  const float2 ww = make_float2(w, w);
+#pragma unroll
+  for (int k = 0; k < H; ++k) acc[k] = __ffma2_rn(dl[k], ww, acc[k]);
+}
+
+// Every thread of the CTA calls this; returns false when the peers did not arrive in time (the fit is
+// then stopped with an error instead of hanging the device).
+TL_D bool wait_epoch(const RowDev& dv, unsigned epoch) {
+  if (dv.G <= 1 || epoch == 0) return true;
+  __shared__ int ok_s;
+  if (threadIdx.x < 32) {
+    const unsigned* f = dv.flags[dv.rank] + (size_t)(threadIdx.x < (unsigned)dv.G ? threadIdx.x : dv.rank) * kFlagStride;
+    const unsigned long long t0 = global_ns();
+    bool ok = true;
+    for (;;) {
+      const unsigned v = ld_acquire_sys(f);
+      if (__all_sync(0xffffffffu, v >= epoch)) break;
+      if (global_ns() - t0 > kWaitNs) { ok = false; break; }
+      __nanosleep(200);
+    }
+    ok = __all_sync(0xffffffffu, ok);
+    if (threadIdx.x == 0) ok_s = ok ? 1 : 0;
+  }
+  __syncthreads();
+  const bool ok = ok_s != 0;
+  __syncthreads();
+  return ok;
+}
+TL_D void peer_timeout(const RowDev& dv) {   // one thread
+  dv.state->status = 3; dv.state->stop = 1;
+  if (dv.host_flag) { __threadfence_system(); dv.host_flag[0] = 1; }
+}
+// One thread, after a __threadfence_system() that covers the data: tell every replica that this rank reached `epoch`.
+TL_D void signal_epoch(const RowDev& dv, unsigned epoch) {
+  for (int q = 0; q < dv.G; ++q) st_release_sys(dv.flags[q] + (size_t)dv.rank * kFlagStride, epoch);
+}
+// All threads call; true in every thread of the CTA that finished last.
+TL_D bool last_cta(unsigned* counter) {
+  __shared__ int last_s;
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned t = atomicAdd(counter, 1u);
+    last_s = (t == gridDim.x - 1) ? 1 : 0;
+    if (last_s) { *counter = 0u; __threadfence_system(); }
+  }
+  __syncthreads();
+  return last_s != 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// repulsion: one work item = 256 own rows (2 per thread) x one chunk of <= 2048 partners
+// ---------------------------------------------------------------------------------------------------
+template <int H, int R>
+__global__ void __launch_bounds__(kRepThreads, 4) repulse_kernel(RowDev dv, int cur, unsigned epoch) {
+  extern __shared__ float4 smem4[];
+  float* sm = reinterpret_cast<float*>(smem4);
+  constexpr int Dp = 2 * H;
+  constexpr int kStageFloats = kStageJ * Dp;
+  static_assert(R * kRepThreads == kRowTile, "a work item is one row tile");
+  if (__ldcg(&dv.state->stop)) return;
+  if (!wait_epoch(dv, epoch)) { if (blockIdx.x == 0 && threadIdx.x == 0) peer_timeout(dv); return; }
+  const int tid = threadIdx.x;
+  const float* __restrict__ P = dv.pos[dv.rank] + (size_t)cur * dv.cap_rows * Dp;
+  const int tiles = dv.rows / kRowTile;
+  const long long items = (long long)tiles * dv.chunks;
+  for (long long item = blockIdx.x; item < items; item += gridDim.x) {
+    const int c = (int)(item / tiles), tile = (int)(item % tiles);
+    const int lrow0 = tile * kRowTile;
+    float2 np[R][H], acc[R][H];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      float2 p[H];
+      ld_point<H>(P + (size_t)(dv.row0 + lrow0 + tid + r * kRepThreads) * Dp, p);
+#pragma unroll
+      for (int k = 0; k < H; ++k) { np[r][k] = make_float2(-p[k].x, -p[k].y); acc[r][k] = make_float2(0.f, 0.f); }
+    }
+    const int j0 = c * kChunk;
+    const int cnt = min(kChunk, dv.n - j0);
+    const int nst = (cnt + kStageJ - 1) / kStageJ;
+    const float* __restrict__ src = P + (size_t)j0 * Dp;
+    auto prefetch = [&](int s) {
+      if (s < nst) {
+        const float4* g = reinterpret_cast<const float4*>(src + (size_t)s * kStageFloats);
+        float4* d = reinterpret_cast<float4*>(sm + (size_t)(s % kStages) * kStageFloats);
+        for (int x = tid; x < kStageFloats / 4; x += kRepThreads) cp_async16(d + x, g + x);
+      }
+      cp_async_commit();
+    };
+#pragma unroll
+    for (int s = 0; s < kStages - 1; ++s) prefetch(s);
+    for (int s = 0; s < nst; ++s) {
+      cp_async_wait<kStages - 2>();
+      __syncthreads();
+      prefetch(s + kStages - 1);
+      const float* __restrict__ q_s = sm + (size_t)(s % kStages) * kStageFloats;
+      const int m = min(kStageJ, cnt - s * kStageJ);
+#pragma unroll 2
+      for (int j = 0; j < m; ++j) {
+        float2 q[H];
+        ld_point<H>(q_s + j * Dp, q);
+#pragma unroll
+        for (int r = 0; r < R; ++r) repel<H>(np[r], q, acc[r]);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+      st_point<H>(dv.rpart + ((size_t)c * dv.rows + lrow0 + tid + r * kRepThreads) * Dp, acc[r]);
+    __syncthreads();   // the stages are refilled by the next item's prologue
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// springs: one thread per own row, Gauss-Seidel along the row
+// ---------------------------------------------------------------------------------------------------
+template <int H>
+__global__ void __launch_bounds__(kBlockRows) spring_kernel(RowDev dv, FitParams prm, int cur, unsigned epoch) {
+  constexpr int Dp = 2 * H;
+  if (__ldcg(&dv.state->stop)) return;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int lrow = blockIdx.x * kBlockRows + tid;          // row inside the own block
+  const int row = dv.row0 + lrow;                          // slot
+  const float* __restrict__ P = dv.pos[dv.rank] + (size_t)cur * dv.cap_rows * Dp;
+  const double kd = __ldcg(&dv.state->k);
+  const int iter = __ldcg(&dv.state->iter);
+  const float k = (float)kd;
+  const float dp1 = dv.dp1[row];
+  if (dp1 > 0.f) {
+    float2 p0n[H], xn[H];   // -P_i and -x (the running position, negated: deltas are q + (-x))
+    {
+      float2 p[H], rs[H];
+      ld_point<H>(P + (size_t)row * Dp, p);
+#pragma unroll
+      for (int kk = 0; kk < H; ++kk) rs[kk] = make_float2(0.f, 0.f);
+      for (int c = 0; c < dv.chunks; ++c) {
+        float2 t[H];
+        ld_point<H>(dv.rpart + ((size_t)c * dv.rows + lrow) * Dp, t);
+#pragma unroll
+        for (int kk = 0; kk < H; ++kk) rs[kk] = __fadd2_rn(rs[kk], t[kk]);
+      }
+      const float rdeg0 = (float)(0.5 * prm.c_repulsion) / dp1;
+      const float2 rr = make_float2(rdeg0, rdeg0);
+#pragma unroll
+      for (int kk = 0; kk < H; ++kk) {
+        p0n[kk] = make_float2(-p[kk].x, -p[kk].y);
+        xn[kk] = __ffma2_rn(rs[kk], rr, p0n[kk]);          // -(p - rs * rdeg)
+      }
+    }
+    const float rdeg = (float)(0.5 * prm.c_repulsion) / dp1;
+    const float two_k_rnorm = 2.0f * k / (4.0f * dp1 + k);
+    const int slice = lrow >> 5;
+    const int width = dv.swidth[slice];
+    const uint2* __restrict__ rec = dv.recs + dv.soff[slice] + lane;
+    int at = 0;
+    if (width > 0) at = (int)(mix64(dv.seed ^ mix64(((unsigned long long)(unsigned)iter << 32) | (unsigned)(row >> 5))) % (unsigned long long)width);
+    auto next_at = [&]() { const int a = at; at = (at + 1 == width) ? 0 : at + 1; return a; };
+    uint2 r_n = make_uint2((unsigned)row | (3u << 30), 0u), r_nn = r_n;
+    float2 q_n[H];
+    if (width > 0) r_n = rec[(size_t)next_at() * 32];
+    if (width > 1) r_nn = rec[(size_t)next_at() * 32];
+    ld_point<H>(P + (size_t)(r_n.x & 0x3fffffffu) * Dp, q_n);
+    for (int t = 0; t < width; ++t) {
+      const uint2 r = r_n;
+      float2 q[H];
+#pragma unroll
+      for (int kk = 0; kk < H; ++kk) q[kk] = q_n[kk];
+      r_n = r_nn;
+      if (t + 1 < width) ld_point<H>(P + (size_t)(r_n.x & 0x3fffffffu) * Dp, q_n);
+      if (t + 2 < width) r_nn = rec[(size_t)next_at() * 32];
+      const unsigned type = r.x >> 30;
+      const float target = __uint_as_float(r.y);
+      float2 dl[H], d0[H];
+      const float d2 = dist2<H>(xn, q, dl);
+      const float e2 = dist2<H>(p0n, q, d0);
+      const float dist = sqrt_approx(d2);
+      const bool spring = type == 0u || (type == 1u ? dist < target : (type == 2u && dist > target));   // :237-243
+      const float f = spring ? two_k_rnorm * (target - dist) * rcp_approx(dist + 0.01f) : 0.f;
+      const float ds0 = sqrt_approx(e2) + 0.01f;
+      const float w0 = spring ? rdeg * rcp_approx(ds0 * ds0 * ds0) : 0.f;
+      // x += -delta f + d0 w0  <=>  (-x) += delta f - d0 w0
+      const float2 ff = make_float2(f, f), nw = make_float2(-w0, -w0);
+#pragma unroll
+      for (int kk = 0; kk < H; ++kk) xn[kk] = __ffma2_rn(d0[kk], nw, __ffma2_rn(dl[kk], ff, xn[kk]));
+    }
+    float2 x[H];
+#pragma unroll
+    for (int kk = 0; kk < H; ++kk) x[kk] = make_float2(-xn[kk].x, -xn[kk].y);
+    const size_t o = ((size_t)(cur ^ 1) * dv.cap_rows + row) * Dp;
+    for (int g = 0; g < dv.G; ++g) st_point<H>(dv.pos[g] + o, x);   // own replica and every peer (NVLink stores)
+  }
+  if (last_cta(&dv.counters[0])) {
+    if (tid == 0) {
+      FitState* st = dv.state;
+      st->k = kd * (1.0 - prm.cooling_rate);            // :289
+      st->iter = iter + 1;
+      st->pair_updates += dv.pairs_per_iter;
+      if (dv.host_flag) dv.host_flag[1] = iter + 1;
+      __threadfence_system();
+      signal_epoch(dv, epoch);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// edge MAE on the new positions: one thread per own row over the records this rank counts
+// ---------------------------------------------------------------------------------------------------
+template <int H>
+__global__ void __launch_bounds__(kBlockRows) mae_kernel(RowDev dv, int nxt, unsigned wait_for, unsigned epoch) {
+  constexpr int Dp = 2 * H;
+  constexpr int U = 4;
+  __shared__ double red_s[3][kBlockRows / 32];
+  if (__ldcg(&dv.state->stop)) return;
+  if (!wait_epoch(dv, wait_for)) { if (blockIdx.x == 0 && threadIdx.x == 0) peer_timeout(dv); return; }
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int lrow = blockIdx.x * kBlockRows + tid;
+  const int row = dv.row0 + lrow;
+  const float* __restrict__ P = dv.pos[dv.rank] + (size_t)nxt * dv.cap_rows * Dp;
+  double sum = 0.0, cnt = 0.0, bad = 0.0;
+  if (dv.dp1[row] > 0.f) {
+    float2 pn[H];
+    {
+      float2 p[H];
+      ld_point<H>(P + (size_t)row * Dp, p);
+#pragma unroll
+      for (int kk = 0; kk < H; ++kk) {
+        if (!isfinite(p[kk].x) || !isfinite(p[kk].y)) bad = 1.0;
+        pn[kk] = make_float2(-p[kk].x, -p[kk].y);
+      }
+    }
+    const int slice = lrow >> 5;
+    const int width = dv.mwidth[slice];
+    const uint2* __restrict__ rec = dv.mrecs + dv.moff[slice] + lane;
+    int t = 0;
+    for (; t + U <= width; t += U) {
+      uint2 r[U];
+      float2 q[U][H];
+#pragma unroll
+      for (int u = 0; u < U; ++u) r[u] = rec[(size_t)(t + u) * 32];
+#pragma unroll
+      for (int u = 0; u < U; ++u) ld_point<H>(P + (size_t)(r[u].x & 0x3fffffffu) * Dp, q[u]);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        float2 dl[H];
+        const float dist = __fsqrt_rn(dist2<H>(pn, q[u], dl));
+        const unsigned type = r[u].x >> 30;
+        const float target = __uint_as_float(r[u].y);
+        const bool on = type == 0u || (type == 1u ? dist < target : (type == 2u && dist > target));   // :72-75
+        if (on) { sum += fabs((double)target - (double)dist); cnt += 1.0; }
+      }
+    }
+    for (; t < width; ++t) {
+      const uint2 r = rec[(size_t)t * 32];
+      float2 q[H], dl[H];
+      ld_point<H>(P + (size_t)(r.x & 0x3fffffffu) * Dp, q);
+      const float dist = __fsqrt_rn(dist2<H>(pn, q, dl));
+      const unsigned type = r.x >> 30;
+      const float target = __uint_as_float(r.y);
+      const bool on = type == 0u || (type == 1u ? dist < target : (type == 2u && dist > target));
+      if (on) { sum += fabs((double)target - (double)dist); cnt += 1.0; }
+    }
+  }
+  // fixed tree: lanes, then warps
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    sum += __shfl_down_sync(0xffffffffu, sum, o);
+    cnt += __shfl_down_sync(0xffffffffu, cnt, o);
+    bad += __shfl_down_sync(0xffffffffu, bad, o);
+  }
+  if (lane == 0) { red_s[0][warp] = sum; red_s[1][warp] = cnt; red_s[2][warp] = bad; }
+  __syncthreads();
+  if (tid == 0) {
+    double s = 0.0, c = 0.0, b = 0.0;
+    for (int w = 0; w < kBlockRows / 32; ++w) { s += red_s[0][w]; c += red_s[1][w]; b += red_s[2][w]; }
+    const size_t e = (size_t)(row / kBlockRows) * 4;
+    for (int g = 0; g < dv.G; ++g) {
+      double* o = dv.red[g] + e;
+      o[0] = s; o[1] = c; o[2] = b;
+    }
+  }
+  if (last_cta(&dv.counters[1]) && tid == 0) signal_epoch(dv, epoch);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// controller (one CTA): pooled MAE, three-way classification, finite check
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ctl_kernel(RowDev dv, FitParams prm, int check, int fin, unsigned wait_for) {
+  __shared__ double red_s[3][256];
+  if (__ldcg(&dv.state->stop)) return;
+  if (!wait_epoch(dv, wait_for)) { if (threadIdx.x == 0) peer_timeout(dv); return; }
+  const int tid = threadIdx.x;
+  const int entries = dv.slots / kBlockRows;
+  const double* __restrict__ red = dv.red[dv.rank];
+  double s = 0.0, c = 0.0, b = 0.0;
+  for (int e = tid; e < entries; e += 256) { s += __ldcg(red + (size_t)e * 4); c += __ldcg(red + (size_t)e * 4 + 1); b += __ldcg(red + (size_t)e * 4 + 2); }
+  red_s[0][tid] = s; red_s[1][tid] = c; red_s[2][tid] = b;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (tid < o) { red_s[0][tid] += red_s[0][tid + o]; red_s[1][tid] += red_s[1][tid + o]; red_s[2][tid] += red_s[2][tid + o]; }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    FitState st = *dv.state;
+    const int iter = st.iter - 1;   // the iteration that just finished
+    st.snapshot = 0;
+    if (check) {
+      controller_check(st, prm, iter, red_s[0][0], (long long)red_s[1][0]);
+      if (dv.trace && iter >= 0 && iter < prm.n_iter) dv.trace[iter] = st.last_error;
+    }
+    if (!st.stop && fin && red_s[2][0] > 0.0) { st.status = 2; st.fail_iter = iter + 1; st.stop = 1; }
+    *dv.state = st;
+    if (dv.host_flag && st.stop) { __threadfence_system(); dv.host_flag[0] = 1; }
+  }
+}
+
+__global__ void __launch_bounds__(256) snap_kernel(RowDev dv, int nxt) {
+  if (!__ldcg(&dv.state->snapshot)) return;
+  const size_t total4 = (size_t)dv.slots * dv.Dp / 4;
+  const float4* __restrict__ src = reinterpret_cast<const float4*>(dv.pos[dv.rank] + (size_t)nxt * dv.cap_rows * dv.Dp);
+  float4* dst = reinterpret_cast<float4*>(dv.best);
+  for (size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x; x < total4; x += (size_t)gridDim.x * blockDim.x) dst[x] = src[x];
+}
+
+// ---------------------------------------------------------------------------------------------------
+// set-up kernels: COO edge list -> the two SELL-32 record arrays of the own rows
+// ---------------------------------------------------------------------------------------------------
+// A pair is counted in the MAE by exactly one of its endpoints, the two halves of every row about equal.
+TL_HD bool counts_here(uint32_t self, uint32_t other) { return (((self + other) & 1u) != 0u) == (self < other); }
+
+__global__ void count_kernel(const int32_t* __restrict__ ei, const int32_t* __restrict__ ej, long long E, long long n,
+                             const int32_t* __restrict__ slot_of_point, int row0, int rows, unsigned* len, unsigned* mlen, int* bad) {
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < E; e += (long long)gridDim.x * blockDim.x) {
+    const long long a = ei[e], b = ej[e];
+    if (a < 0 || b < 0 || a >= n || b >= n || a == b) { *bad = 1; continue; }
+    const uint32_t sa = (uint32_t)slot_of_point[a], sb = (uint32_t)slot_of_point[b];
+    const int la = (int)sa - row0, lb = (int)sb - row0;
+    if (la >= 0 && la < rows) { atomicAdd(&len[la], 1u); if (counts_here(sa, sb)) atomicAdd(&mlen[la], 1u); }
+    if (lb >= 0 && lb < rows) { atomicAdd(&len[lb], 1u); if (counts_here(sb, sa)) atomicAdd(&mlen[lb], 1u); }
+  }
+}
+__global__ void fill_kernel(const int32_t* __restrict__ ei, const int32_t* __restrict__ ej, const double* __restrict__ dist,
+                            const int32_t* __restrict__ thr, long long E, const int32_t* __restrict__ slot_of_point, int row0,
+                            int rows, const unsigned long long* __restrict__ off, unsigned* cursor, uint2* tmp) {
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < E; e += (long long)gridDim.x * blockDim.x) {
+    const uint32_t sa = (uint32_t)slot_of_point[ei[e]], sb = (uint32_t)slot_of_point[ej[e]];
+    const int t = thr[e];
+    const unsigned type = t == 0 ? 0u : (t == 1 ? 1u : 2u);   // src/optimization.cpp:237-243
+    const unsigned tb = __float_as_uint((float)dist[e]);
+    const int la = (int)sa - row0, lb = (int)sb - row0;
+    if (la >= 0 && la < rows) tmp[off[la] + atomicAdd(&cursor[la], 1u)] = make_uint2(sb | (type << 30), tb);
+    if (lb >= 0 && lb < rows) tmp[off[lb] + atomicAdd(&cursor[lb], 1u)] = make_uint2(sa | (type << 30), tb);
+  }
+}
+// One warp per own row: rank the row's records by (partner, type, target bits) - a fixed order whatever the
+// scatter left - and write them, transposed, into the slices; the tail of a row up to the slice width is
+// padding (type 3: never a spring, never counted; partner = the row itself).
+constexpr int kSortCap = 1024;
+__global__ void __launch_bounds__(128) sell_kernel(const uint2* __restrict__ tmp, const unsigned long long* __restrict__ off,
+                                                   const unsigned* __restrict__ len, int row0, int rows,
+                                                   const unsigned long long* __restrict__ soff, const int* __restrict__ swidth,
+                                                   const unsigned long long* __restrict__ moff, const int* __restrict__ mwidth,
+                                                   uint2* recs, uint2* mrecs) {
+  __shared__ uint2 stage[4][kSortCap];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lrow = blockIdx.x * 4 + warp;
+  if (lrow >= rows) return;
+  const unsigned n = len[lrow];
+  const uint2* __restrict__ in = tmp + off[lrow];
+  const bool staged = n <= (unsigned)kSortCap;
+  if (staged) for (unsigned x = lane; x < n; x += 32) stage[warp][x] = in[x];
+  __syncwarp();
+  const uint2* src = staged ? stage[warp] : in;
+  const uint32_t self = (uint32_t)(row0 + lrow);
+  const int slice = lrow >> 5, rl = lrow & 31;
+  uint2* out = recs + soff[slice] + rl;
+  uint2* mout = mrecs + moff[slice] + rl;
+  unsigned mcount = 0;
+  for (unsigned x0 = 0; x0 < n; x0 += 32) {
+    const unsigned x = x0 + lane;
+    if (x < n) {
+      const uint2 r = src[x];
+      const unsigned long long mkey = ((unsigned long long)(r.x & 0x3fffffffu) << 34) | ((unsigned long long)(r.x >> 30) << 32) | r.y;
+      const bool mcounted = counts_here(self, r.x & 0x3fffffffu);
+      unsigned rank = 0, mrank = 0;
+      for (unsigned y = 0; y < n; ++y) {
+        const uint2 o = src[y];
+        const unsigned long long okey = ((unsigned long long)(o.x & 0x3fffffffu) << 34) | ((unsigned long long)(o.x >> 30) << 32) | o.y;
+        const bool before = okey < mkey || (okey == mkey && y < x);
+        rank += before ? 1u : 0u;
+        mrank += (before && counts_here(self, o.x & 0x3fffffffu)) ? 1u : 0u;
+      }
+      out[(size_t)rank * 32] = r;
+      if (mcounted) mout[(size_t)mrank * 32] = r;
+    }
+  }
+  for (unsigned y = lane; y < n; y += 32) mcount += counts_here(self, src[y].x & 0x3fffffffu) ? 1u : 0u;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mcount += __shfl_xor_sync(0xffffffffu, mcount, o);
+  const uint2 pad = make_uint2(self | (3u << 30), 0u);
+  for (unsigned x = n + lane; x < (unsigned)swidth[slice]; x += 32) out[(size_t)x * 32] = pad;
+  for (unsigned x = mcount + lane; x < (unsigned)mwidth[slice]; x += 32) mout[(size_t)x * 32] = pad;
+}
+
+template <class F>
+void dispatch_h(int H, F&& f) {
+  switch (H) {
+    case 1: f(std::integral_constant<int, 1>()); break;
+    case 2: f(std::integral_constant<int, 2>()); break;
+    case 3: f(std::integral_constant<int, 3>()); break;
+    case 4: f(std::integral_constant<int, 4>()); break;
+    case 5: f(std::integral_constant<int, 5>()); break;
+    case 6: f(std::integral_constant<int, 6>()); break;
+    case 7: f(std::integral_constant<int, 7>()); break;
+    case 8: f(std::integral_constant<int, 8>()); break;
+    default: throw BadArg("row-block mode supports ndim <= 16");
+  }
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------
+struct RowHandle {            // what a rank publishes: its shared block and the geometry the others must agree with
+  cudaIpcMemHandle_t mem;
+  int32_t rank, n_ranks, slots, Dp;
+  uint64_t layout;            // byte size of the shared block
+};
+
+struct RowPlan {
+  int device = 0;
+  int64_t n = 0, E = 0;
+  RowDev dv{};
+  FitParams prm{};
+  std::vector<int32_t> slot_of_point;
+  // shared block (cudaMalloc: exportable): positions [2][cap_rows][Dp] | red [slots/128][4] | flags
+  char* shared = nullptr;
+  size_t shared_bytes = 0, off_red = 0, off_flags = 0;
+  void* peer_base[kMaxShards] = {};   // mapped blocks of the other ranks (IPC) - closed on destroy
+  bool peer_ipc[kMaxShards] = {};
+  // local
+  float* best = nullptr; float* dp1 = nullptr; float* rpart = nullptr;
+  uint2* recs = nullptr; uint2* mrecs = nullptr;
+  unsigned long long* soff = nullptr; unsigned long long* moff = nullptr; int* swidth = nullptr; int* mwidth = nullptr;
+  FitState* state = nullptr; double* trace = nullptr; unsigned* counters = nullptr;
+  volatile int* h_flag = nullptr; int* d_flag = nullptr;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int64_t n_holdout = 0;
+  std::vector<int32_t> hold_i, hold_j; std::vector<double> hold_truth;
+  int iter_launched = 0;      // iterations enqueued so far
+  unsigned epoch = 0;         // signals enqueued so far (the same number on every rank)
+  int64_t launches = 0;
+  int64_t n_recs = 0, n_mrecs = 0;
+  int rep_ctas = 0;
+  size_t rep_smem = 0;
+  double total_ms = 0.0;
+  bool attached = false;
+
+  ~RowPlan() {
+    DeviceScope on(device);
+    if (stream) cudaStreamSynchronize(stream);
+    for (int q = 0; q < kMaxShards; ++q) if (peer_base[q] && peer_ipc[q]) cudaIpcCloseMemHandle(peer_base[q]);
+    if (shared) cudaFree(shared);
+    pool_free(best); pool_free(dp1); pool_free(rpart); pool_free(recs); pool_free(mrecs);
+    pool_free(soff); pool_free(moff); pool_free(swidth); pool_free(mwidth);
+    pool_free(state); pool_free(trace); pool_free(counters);
+    if (h_flag) cudaFreeHost((void*)h_flag);
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
+    if (stream) cudaStreamDestroy(stream);
+  }
+};
+
+namespace {
+
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+void set_self_pointers(RowPlan& rp) {
+  RowDev& dv = rp.dv;
+  dv.pos[dv.rank] = reinterpret_cast<float*>(rp.shared);
+  dv.red[dv.rank] = reinterpret_cast<double*>(rp.shared + rp.off_red);
+  dv.flags[dv.rank] = reinterpret_cast<unsigned*>(rp.shared + rp.off_flags);
+}
+void set_peer_pointers(RowPlan& rp, int q, char* base) {
+  rp.dv.pos[q] = reinterpret_cast<float*>(base);
+  rp.dv.red[q] = reinterpret_cast<double*>(base + rp.off_red);
+  rp.dv.flags[q] = reinterpret_cast<unsigned*>(base + rp.off_flags);
+}
+
+// Builds the record arrays of the own rows on the device.
+void build_records(RowPlan& rp, const topolow_problem& pb) {
+  RowDev& dv = rp.dv;
+  cudaStream_t s = rp.stream;
+  const long long E = pb.n_edges;
+  const int rows = dv.rows, slices = rows / 32;
+  AsyncBuf<int32_t> d_ei(E, s), d_ej(E, s), d_thr(E, s), d_slot(rp.slot_of_point.size(), s);
+  AsyncBuf<double> d_dist(E, s);
+  AsyncBuf<unsigned> d_len(rows, s), d_mlen(rows, s), d_cur(rows, s);
+  AsyncBuf<unsigned long long> d_off(rows + 1, s);
+  AsyncBuf<int> d_bad(1, s);
+  PhaseTimer pt(s);
+  TL_CUDA(cudaMemcpyAsync(d_slot, rp.slot_of_point.data(), rp.slot_of_point.size() * 4, cudaMemcpyHostToDevice, s));
+  if (E > 0) {
+    TL_CUDA(cudaMemcpyAsync(d_ei, pb.edge_i, E * 4, cudaMemcpyHostToDevice, s));
+    TL_CUDA(cudaMemcpyAsync(d_ej, pb.edge_j, E * 4, cudaMemcpyHostToDevice, s));
+    TL_CUDA(cudaMemcpyAsync(d_dist, pb.edge_dist, E * 8, cudaMemcpyHostToDevice, s));
+    TL_CUDA(cudaMemcpyAsync(d_thr, pb.edge_thresh, E * 4, cudaMemcpyHostToDevice, s));
+  }
+  TL_CUDA(cudaMemsetAsync(d_len, 0, rows * 4, s));
+  TL_CUDA(cudaMemsetAsync(d_mlen, 0, rows * 4, s));
+  TL_CUDA(cudaMemsetAsync(d_cur, 0, rows * 4, s));
+  TL_CUDA(cudaMemsetAsync(d_bad, 0, 4, s));
+  pt.mark("rows: host to device");
+  const int blocks = 148 * 8, threads = 256;
+  if (E > 0) {
+    count_kernel<<<blocks, threads, 0, s>>>(d_ei, d_ej, E, pb.n, d_slot, dv.row0, rows, d_len, d_mlen, d_bad);
+    TL_CUDA(cudaGetLastError());
+  }
+  std::vector<unsigned> len(rows), mlen(rows);
+  int bad = 0;
+  TL_CUDA(cudaMemcpyAsync(len.data(), d_len, rows * 4, cudaMemcpyDeviceToHost, s));
+  TL_CUDA(cudaMemcpyAsync(mlen.data(), d_mlen, rows * 4, cudaMemcpyDeviceToHost, s));
+  TL_CUDA(cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, s));
+  TL_CUDA(cudaStreamSynchronize(s));
+  if (bad) throw BadArg("edge index out of range");
+  std::vector<unsigned long long> off(rows + 1, 0), soff(slices), moff(slices);
+  std::vector<int> swidth(slices), mwidth(slices);
+  for (int r = 0; r < rows; ++r) off[r + 1] = off[r] + len[r];
+  unsigned long long so = 0, mo = 0;
+  for (int sl = 0; sl < slices; ++sl) {
+    unsigned w = 0, mw = 0;
+    for (int r = 0; r < 32; ++r) { w = std::max(w, len[sl * 32 + r]); mw = std::max(mw, mlen[sl * 32 + r]); }
+    soff[sl] = so; moff[sl] = mo; swidth[sl] = (int)w; mwidth[sl] = (int)mw;
+    so += (unsigned long long)w * 32; mo += (unsigned long long)mw * 32;
+  }
+  rp.n_recs = (int64_t)so; rp.n_mrecs = (int64_t)mo;
+  pool_alloc(rp.recs, (size_t)so * sizeof(uint2));
+  pool_alloc(rp.mrecs, (size_t)mo * sizeof(uint2));
+  pool_alloc(rp.soff, slices * sizeof(unsigned long long));
+  pool_alloc(rp.moff, slices * sizeof(unsigned long long));
+  pool_alloc(rp.swidth, slices * sizeof(int));
+  pool_alloc(rp.mwidth, slices * sizeof(int));
+  pool_ready();
+  AsyncBuf<uint2> d_tmp((size_t)off[rows], s);
+  TL_CUDA(cudaMemcpyAsync(d_off, off.data(), (rows + 1) * 8, cudaMemcpyHostToDevice, s));
+  TL_CUDA(cudaMemcpyAsync(rp.soff, soff.data(), slices * 8, cudaMemcpyHostToDevice, s));
+  TL_CUDA(cudaMemcpyAsync(rp.moff, moff.data(), slices * 8, cudaMemcpyHostToDevice, s));
+  TL_CUDA(cudaMemcpyAsync(rp.swidth, swidth.data(), slices * 4, cudaMemcpyHostToDevice, s));
+  TL_CUDA(cudaMemcpyAsync(rp.mwidth, mwidth.data(), slices * 4, cudaMemcpyHostToDevice, s));
+  pt.mark("rows: lengths + offsets");
+  if (E > 0) {
+    fill_kernel<<<blocks, threads, 0, s>>>(d_ei, d_ej, d_dist, d_thr, E, d_slot, dv.row0, rows, d_off, d_cur, d_tmp);
+    TL_CUDA(cudaGetLastError());
+  }
+  sell_kernel<<<(rows + 3) / 4, 128, 0, s>>>(d_tmp, d_off, d_len, dv.row0, rows, rp.soff, rp.swidth, rp.moff, rp.mwidth,
+                                              rp.recs, rp.mrecs);
+  TL_CUDA(cudaGetLastError());
+  TL_CUDA(cudaStreamSynchronize(s));   // the host vectors above go out of scope
+  pt.mark("rows: fill + sort + transpose");
+  dv.recs = rp.recs; dv.mrecs = rp.mrecs; dv.soff = rp.soff; dv.moff = rp.moff; dv.swidth = rp.swidth; dv.mwidth = rp.mwidth;
+}
+
+template <int H>
+void launch_iteration(RowPlan& rp, cudaStream_t s, cudaEvent_t* ev /* 6 events or null */) {
+  RowDev& dv = rp.dv;
+  const int t = rp.iter_launched;
+  const int cur = t & 1, nxt = cur ^ 1;
+  const bool check = is_check_iter(t, rp.prm), fin = ((t + 1) % 10 == 0);
+  if (ev) TL_CUDA(cudaEventRecord(ev[0], s));
+  repulse_kernel<H, 2><<<rp.rep_ctas, kRepThreads, rp.rep_smem, s>>>(dv, cur, rp.epoch);
+  if (ev) TL_CUDA(cudaEventRecord(ev[1], s));
+  const unsigned e_spring = ++rp.epoch;
+  spring_kernel<H><<<dv.rows / kBlockRows, kBlockRows, 0, s>>>(dv, rp.prm, cur, e_spring);
+  if (ev) TL_CUDA(cudaEventRecord(ev[2], s));
+  rp.launches += 2;
+  if (check || fin) {
+    const unsigned e_mae = ++rp.epoch;
+    mae_kernel<H><<<dv.rows / kBlockRows, kBlockRows, 0, s>>>(dv, nxt, e_spring, e_mae);
+    if (ev) TL_CUDA(cudaEventRecord(ev[3], s));
+    ctl_kernel<<<1, 256, 0, s>>>(dv, rp.prm, check ? 1 : 0, fin ? 1 : 0, e_mae);
+    if (ev) TL_CUDA(cudaEventRecord(ev[4], s));
+    snap_kernel<<<148, 256, 0, s>>>(dv, nxt);
+    if (ev) TL_CUDA(cudaEventRecord(ev[5], s));
+    rp.launches += 3;
+  }
+  TL_CUDA(cudaGetLastError());
+  rp.iter_launched = t + 1;
+}
+
+void launch_one(RowPlan& rp, cudaStream_t s, cudaEvent_t* ev = nullptr) {
+  dispatch_h(rp.dv.Dp / 2, [&](auto h) { launch_iteration<decltype(h)::value>(rp, s, ev); });
+}
+
+template <int H>
+void configure_repulse(RowPlan& rp, int sms) {
+  const size_t smem = (size_t)kStages * kStageJ * 2 * H * sizeof(float);
+  TL_CUDA(cudaFuncSetAttribute(repulse_kernel<H, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  TL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, repulse_kernel<H, 2>, kRepThreads, smem));
+  if (per_sm < 1) per_sm = 1;
+  const long long items = (long long)(rp.dv.rows / kRowTile) * rp.dv.chunks;
+  rp.rep_ctas = (int)std::min<long long>((long long)sms * per_sm, std::max<long long>(items, 1));
+  rp.rep_smem = smem;
+}
+
+}  // namespace
+
+RowPlan* row_create(const topolow_problem& pb, const topolow_params& pr, int rank, int n_ranks) {
+  validate(pb, pr);
+  if (n_ranks < 1 || n_ranks > kMaxShards || rank < 0 || rank >= n_ranks) throw BadArg("rank / n_ranks out of range");
+  if (pb.ndim > 16) throw BadArg("row-block mode supports ndim <= 16");
+  if (pb.n >= (1ll << 30)) throw BadArg("n out of range");
+  TL_CUDA(cudaSetDevice(pr.device));
+  keep_pool_memory(pr.device);
+  cudaDeviceProp prop;
+  TL_CUDA(cudaGetDeviceProperties(&prop, pr.device));
+  std::unique_ptr<RowPlan> rp(new RowPlan());
+  rp->device = pr.device;
+  rp->n = pb.n; rp->E = pb.n_edges;
+  rp->prm = FitParams{pr.n_iter, pr.k0, pr.cooling_rate, pr.c_repulsion, pr.relative_epsilon, pr.convergence_window,
+                      pr.convergence_check_freq};
+  RowDev& dv = rp->dv;
+  dv.n = (int)pb.n; dv.D = pb.ndim; dv.Dp = (pb.ndim + 1) / 2 * 2;
+  dv.G = n_ranks; dv.rank = rank;
+  const int tiles = (int)((pb.n + kRowTile - 1) / kRowTile);
+  dv.slots = tiles * kRowTile;
+  const int t0 = (int)((long long)tiles * rank / n_ranks), t1 = (int)((long long)tiles * (rank + 1) / n_ranks);
+  dv.row0 = t0 * kRowTile; dv.rows = (t1 - t0) * kRowTile;
+  if (tiles < n_ranks) throw BadArg("too few points for this many ranks (every rank needs at least 256 rows)");
+  dv.chunks = (int)((pb.n + kChunk - 1) / kChunk);
+  dv.cap_rows = align_up((size_t)dv.slots, kChunk);
+  dv.pairs_per_iter = (unsigned long long)pb.n * (unsigned long long)(pb.n - 1) / 2ull;
+  dv.seed = pr.seed;
+  TL_CUDA(cudaStreamCreate(&rp->stream));
+  TL_CUDA(cudaEventCreate(&rp->ev0));
+  TL_CUDA(cudaEventCreate(&rp->ev1));
+  // relabelling: a fixed pseudo-random permutation (decorrelates the caller's row order from the row
+  // blocks and from the order a row visits its partners in)
+  rp->slot_of_point = random_permutation(pb.n, kRowLayoutSeed);
+
+  // ---- shared block ----
+  const size_t pos_bytes = 2 * dv.cap_rows * dv.Dp * sizeof(float);
+  rp->off_red = align_up(pos_bytes, 256);
+  rp->off_flags = align_up(rp->off_red + (size_t)(dv.slots / kBlockRows) * 4 * sizeof(double), 256);
+  rp->shared_bytes = align_up(rp->off_flags + (size_t)kMaxShards * kFlagStride * sizeof(unsigned), 256);
+  TL_CUDA(cudaMalloc((void**)&rp->shared, rp->shared_bytes));
+  TL_CUDA(cudaMemset(rp->shared, 0, rp->shared_bytes));
+  set_self_pointers(*rp);
+
+  // ---- points ----
+  {
+    std::vector<float> hp(dv.cap_rows * dv.Dp, 0.f), hd(dv.slots, 0.f);
+    for (int64_t i = 0; i < pb.n; ++i) {
+      const size_t sl = rp->slot_of_point[i];
+      for (int d = 0; d < pb.ndim; ++d) hp[sl * dv.Dp + d] = (float)pb.initial_positions[(size_t)d * pb.n + i];
+      hd[sl] = (float)((double)pb.degrees[i] + 1.0);
+    }
+    pool_alloc(rp->best, hp.size() * sizeof(float));
+    pool_alloc(rp->dp1, hd.size() * sizeof(float));
+    pool_alloc(rp->rpart, (size_t)dv.chunks * std::max(dv.rows, 1) * dv.Dp * sizeof(float));
+    pool_alloc(rp->state, sizeof(FitState));
+    pool_alloc(rp->trace, sizeof(double) * std::max(pr.n_iter, 1));
+    pool_alloc(rp->counters, 4 * sizeof(unsigned));
+    pool_ready();
+    TL_CUDA(cudaMemcpy(rp->shared, hp.data(), hp.size() * sizeof(float), cudaMemcpyHostToDevice));
+    TL_CUDA(cudaMemcpy(rp->best, hp.data(), hp.size() * sizeof(float), cudaMemcpyHostToDevice));
+    TL_CUDA(cudaMemcpy(rp->dp1, hd.data(), hd.size() * sizeof(float), cudaMemcpyHostToDevice));
+    std::vector<double> tr(std::max(pr.n_iter, 1), NAN);
+    TL_CUDA(cudaMemcpy(rp->trace, tr.data(), tr.size() * sizeof(double), cudaMemcpyHostToDevice));
+    TL_CUDA(cudaMemset(rp->counters, 0, 4 * sizeof(unsigned)));
+    FitState st;
+    state_init(st, rp->prm);
+    TL_CUDA(cudaMemcpy(rp->state, &st, sizeof st, cudaMemcpyHostToDevice));
+  }
+  dv.best = rp->best; dv.dp1 = rp->dp1; dv.rpart = rp->rpart; dv.state = rp->state; dv.trace = rp->trace;
+  dv.counters = rp->counters;
+  TL_CUDA(cudaHostAlloc((void**)&rp->h_flag, 2 * sizeof(int), cudaHostAllocMapped));
+  rp->h_flag[0] = 0; rp->h_flag[1] = 0;
+  TL_CUDA(cudaHostGetDevicePointer((void**)&rp->d_flag, (void*)rp->h_flag, 0));
+  dv.host_flag = rp->d_flag;
+
+  if (dv.rows > 0) build_records(*rp, pb);
+  if (pb.n_holdout > 0) {
+    if (!pb.holdout_i || !pb.holdout_j || !pb.holdout_truth) throw BadArg("hold-out arrays are required when n_holdout > 0");
+    rp->n_holdout = pb.n_holdout;
+    rp->hold_i.assign(pb.holdout_i, pb.holdout_i + pb.n_holdout);
+    rp->hold_j.assign(pb.holdout_j, pb.holdout_j + pb.n_holdout);
+    rp->hold_truth.assign(pb.holdout_truth, pb.holdout_truth + pb.n_holdout);
+  }
+  if (dv.rows > 0) dispatch_h(dv.Dp / 2, [&](auto h) { configure_repulse<decltype(h)::value>(*rp, prop.multiProcessorCount); });
+  TL_CUDA(cudaDeviceSynchronize());
+  rp->attached = (n_ranks == 1);
+  return rp.release();
+}
+
+void row_destroy(RowPlan* rp) { delete rp; }
+
+size_t row_handle_bytes() { return sizeof(RowHandle); }
+
+void row_export(RowPlan& rp, void* blob) {
+  DeviceScope on(rp.device);
+  RowHandle h{};
+  TL_CUDA(cudaIpcGetMemHandle(&h.mem, rp.shared));
+  h.rank = rp.dv.rank; h.n_ranks = rp.dv.G; h.slots = rp.dv.slots; h.Dp = rp.dv.Dp; h.layout = rp.shared_bytes;
+  std::memcpy(blob, &h, sizeof h);
+}
+
+void row_attach(RowPlan& rp, const void* blobs, int n_blobs) {
+  DeviceScope on(rp.device);
+  if (n_blobs != rp.dv.G) throw BadArg("one handle per rank is required");
+  const RowHandle* hs = static_cast<const RowHandle*>(blobs);
+  for (int q = 0; q < n_blobs; ++q) {
+    RowHandle h;
+    std::memcpy(&h, hs + q, sizeof h);
+    if (h.rank != q || h.n_ranks != rp.dv.G || h.slots != rp.dv.slots || h.Dp != rp.dv.Dp || h.layout != rp.shared_bytes)
+      throw BadArg("the ranks of a sharded map must be created from the same problem");
+    if (q == rp.dv.rank) continue;
+    void* base = nullptr;
+    TL_CUDA(cudaIpcOpenMemHandle(&base, h.mem, cudaIpcMemLazyEnablePeerAccess));
+    rp.peer_base[q] = base; rp.peer_ipc[q] = true;
+    set_peer_pointers(rp, q, static_cast<char*>(base));
+  }
+  rp.attached = true;
+}
+
+void row_attach_local(RowPlan* const* plans, int n) {
+  if (n < 1 || n > kMaxShards) throw BadArg("number of replicas out of range");
+  for (int a = 0; a < n; ++a) {
+    RowPlan& pa = *plans[a];
+    if (pa.dv.G != n || pa.dv.rank != a) throw BadArg("replicas must be passed in rank order");
+    if (pa.dv.slots != plans[0]->dv.slots || pa.dv.Dp != plans[0]->dv.Dp) throw BadArg("the ranks of a sharded map must be created from the same problem");
+    DeviceScope on(pa.device);
+    for (int b = 0; b < n; ++b) {
+      if (a == b) continue;
+      RowPlan& pb = *plans[b];
+      if (pb.device != pa.device) {
+        const cudaError_t e = cudaDeviceEnablePeerAccess(pb.device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) TL_CUDA(e);
+        cudaGetLastError();
+      }
+      pa.peer_base[b] = pb.shared; pa.peer_ipc[b] = false;
+      set_peer_pointers(pa, b, pb.shared);
+    }
+    pa.attached = true;
+  }
+}
+
+static void check_runnable(const RowPlan& rp) {
+  if (!rp.attached) throw BadArg("the replicas of a sharded map must be attached before it runs");
+}
+
+double row_run(RowPlan& rp, int n_iters, cudaStream_t stream_in, topolow_interrupt_fn poll, void* user, bool* interrupted) {
+  check_runnable(rp);
+  TL_CUDA(cudaSetDevice(rp.device));
+  cudaStream_t s = stream_in ? stream_in : rp.stream;
+  TL_CUDA(cudaEventRecord(rp.ev0, s));
+  int left = std::min(n_iters, std::max(0, rp.prm.n_iter - rp.iter_launched));
+  int since_sync = 0;
+  while (left > 0 && rp.dv.rows > 0) {
+    if (rp.h_flag[0]) break;
+    if (poll && since_sync == 0 && poll(user)) { if (interrupted) *interrupted = true; break; }
+    launch_one(rp, s);
+    --left;
+    if (++since_sync >= 50) {             // the reference's interrupt interval (src/optimization.cpp:364)
+      since_sync = 0;
+      if (poll) TL_CUDA(cudaStreamSynchronize(s));
+    }
+  }
+  TL_CUDA(cudaEventRecord(rp.ev1, s));
+  TL_CUDA(cudaEventSynchronize(rp.ev1));
+  float ms = 0.f;
+  TL_CUDA(cudaEventElapsedTime(&ms, rp.ev0, rp.ev1));
+  rp.total_ms += ms;
+  return ms;
+}
+
+double row_run_local(RowPlan* const* plans, int n, int n_iters) {
+  for (int a = 0; a < n; ++a) check_runnable(*plans[a]);
+  bool same_device = true;
+  for (int a = 1; a < n; ++a) same_device = same_device && plans[a]->device == plans[0]->device;
+  RowPlan& p0 = *plans[0];
+  int left = std::min(n_iters, std::max(0, p0.prm.n_iter - p0.iter_launched));
+  TL_CUDA(cudaSetDevice(p0.device));
+  TL_CUDA(cudaEventRecord(p0.ev0, p0.stream));
+  if (same_device) {
+    // lock step on ONE stream: rank after rank, phase after phase, so that every wait finds its epoch reached
+    cudaStream_t s = p0.stream;
+    for (int a = 1; a < n; ++a) TL_CUDA(cudaStreamSynchronize(plans[a]->stream));
+    while (left > 0) {
+      if (p0.h_flag[0]) break;
+      const int t = p0.iter_launched;
+      const int cur = t & 1, nxt = cur ^ 1;
+      const bool check = is_check_iter(t, p0.prm), fin = ((t + 1) % 10 == 0);
+      unsigned e_spring = 0, e_mae = 0;
+      for (int a = 0; a < n; ++a) {
+        RowPlan& rp = *plans[a];
+        if (rp.dv.rows == 0) { rp.iter_launched = t + 1; continue; }
+        dispatch_h(rp.dv.Dp / 2, [&](auto h) {
+          constexpr int H = decltype(h)::value;
+          repulse_kernel<H, 2><<<rp.rep_ctas, kRepThreads, rp.rep_smem, s>>>(rp.dv, cur, rp.epoch);
+          e_spring = ++rp.epoch;
+          spring_kernel<H><<<rp.dv.rows / kBlockRows, kBlockRows, 0, s>>>(rp.dv, rp.prm, cur, e_spring);
+        });
+        rp.launches += 2; rp.iter_launched = t + 1;
+      }
+      if (check || fin) {
+        for (int a = 0; a < n; ++a) {
+          RowPlan& rp = *plans[a];
+          if (rp.dv.rows == 0) continue;
+          dispatch_h(rp.dv.Dp / 2, [&](auto h) {
+            constexpr int H = decltype(h)::value;
+            e_mae = ++rp.epoch;
+            mae_kernel<H><<<rp.dv.rows / kBlockRows, kBlockRows, 0, s>>>(rp.dv, nxt, e_spring, e_mae);
+          });
+          rp.launches += 1;
+        }
+        for (int a = 0; a < n; ++a) {
+          RowPlan& rp = *plans[a];
+          if (rp.dv.rows == 0) continue;
+          ctl_kernel<<<1, 256, 0, s>>>(rp.dv, rp.prm, check ? 1 : 0, fin ? 1 : 0, e_mae);
+          snap_kernel<<<148, 256, 0, s>>>(rp.dv, nxt);
+          rp.launches += 2;
+        }
+      }
+      TL_CUDA(cudaGetLastError());
+      --left;
+      if ((t + 1) % 50 == 0) TL_CUDA(cudaStreamSynchronize(s));
+    }
+    TL_CUDA(cudaEventRecord(p0.ev1, s));
+  } else {
+    while (left > 0) {
+      if (p0.h_flag[0]) break;
+      for (int a = 0; a < n; ++a) {
+        TL_CUDA(cudaSetDevice(plans[a]->device));
+        if (plans[a]->dv.rows > 0) launch_one(*plans[a], plans[a]->stream);
+      }
+      --left;
+    }
+    for (int a = 1; a < n; ++a) { TL_CUDA(cudaSetDevice(plans[a]->device)); TL_CUDA(cudaStreamSynchronize(plans[a]->stream)); }
+    TL_CUDA(cudaSetDevice(p0.device));
+    TL_CUDA(cudaEventRecord(p0.ev1, p0.stream));
+  }
+  TL_CUDA(cudaEventSynchronize(p0.ev1));
+  float ms = 0.f;
+  TL_CUDA(cudaEventElapsedTime(&ms, p0.ev0, p0.ev1));
+  for (int a = 0; a < n; ++a) plans[a]->total_ms += ms;
+  return ms;
+}
+
+void row_time_kernels(RowPlan& rp, int n_iters, double* out, int cap) {
+  check_runnable(rp);
+  TL_CUDA(cudaSetDevice(rp.device));
+  double acc[6] = {0, 0, 0, 0, 0, 0};
+  int done = 0;
+  std::vector<EventGuard> evs(6);
+  cudaEvent_t ev[6];
+  for (int i = 0; i < 6; ++i) ev[i] = evs[i];
+  int left = std::min(n_iters, std::max(0, rp.prm.n_iter - rp.iter_launched));
+  while (left-- > 0 && !rp.h_flag[0] && rp.dv.rows > 0) {
+    const int t = rp.iter_launched;
+    const bool extra = is_check_iter(t, rp.prm) || ((t + 1) % 10 == 0);
+    launch_one(rp, rp.stream, ev);
+    TL_CUDA(cudaStreamSynchronize(rp.stream));
+    float ms = 0.f;
+    TL_CUDA(cudaEventElapsedTime(&ms, ev[0], ev[1])); acc[0] += ms;
+    TL_CUDA(cudaEventElapsedTime(&ms, ev[1], ev[2])); acc[1] += ms;
+    if (extra) {
+      TL_CUDA(cudaEventElapsedTime(&ms, ev[2], ev[3])); acc[2] += ms;
+      TL_CUDA(cudaEventElapsedTime(&ms, ev[3], ev[4])); acc[3] += ms;
+      TL_CUDA(cudaEventElapsedTime(&ms, ev[4], ev[5])); acc[4] += ms;
+      acc[5] += 1.0;
+    }
+    ++done;
+  }
+  const double v[6] = {done ? acc[0] / done : 0.0, done ? acc[1] / done : 0.0, acc[5] > 0 ? acc[2] / acc[5] : 0.0,
+                       acc[5] > 0 ? acc[3] / acc[5] : 0.0, acc[5] > 0 ? acc[4] / acc[5] : 0.0, acc[5]};
+  for (int i = 0; i < cap && i < 6; ++i) out[i] = v[i];
+}
+
+void row_result(RowPlan& rp, topolow_result& res, bool interrupted) {
+  TL_CUDA(cudaSetDevice(rp.device));
+  TL_CUDA(cudaStreamSynchronize(rp.stream));
+  FitState st;
+  TL_CUDA(cudaMemcpy(&st, rp.state, sizeof st, cudaMemcpyDeviceToHost));
+  const RowDev& dv = rp.dv;
+  if (res.positions) {
+    std::vector<float> hp((size_t)dv.slots * dv.Dp);
+    TL_CUDA(cudaMemcpy(hp.data(), rp.best, hp.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    for (int64_t i = 0; i < rp.n; ++i) {
+      const size_t sl = rp.slot_of_point[i];
+      for (int d = 0; d < dv.D; ++d) res.positions[(size_t)d * rp.n + i] = (double)hp[sl * dv.Dp + d];
+    }
+  }
+  res.converged = st.converged;
+  res.iterations = st.best_iter;     // src/optimization.cpp:368-381: always the best snapshot
+  res.final_mae = st.best_mae;
+  res.final_k = st.best_k;
+  res.iterations_run = st.iter;
+  res.pair_updates = (int64_t)st.pair_updates;
+  res.device_ms = rp.total_ms;
+  res.fail_iter = st.fail_iter;
+  res.status = TOPOLOW_OK;
+  res.message[0] = 0;
+  res.holdout_sum_abs = 0.0; res.holdout_count = 0;
+  if (st.status == 2) {
+    res.status = TOPOLOW_ERR_NONFINITE;
+    std::snprintf(res.message, sizeof res.message, "Numerical instability at iteration %d. Reduce k0 or c_repulsion.", st.fail_iter);
+  } else if (st.status == 3) {
+    res.status = TOPOLOW_ERR_CUDA;
+    std::snprintf(res.message, sizeof res.message, "a peer replica of the sharded map did not arrive within 20 s");
+  } else if (interrupted) {
+    res.status = TOPOLOW_ERR_INTERRUPTED;
+    std::snprintf(res.message, sizeof res.message, "interrupted");
+  }
+  if (res.status == TOPOLOW_OK && rp.n_holdout > 0 && res.positions &&
+      topolow_holdout_errors(res.positions, rp.n, dv.D, rp.n_holdout, rp.hold_i.data(), rp.hold_j.data(), rp.hold_truth.data(),
+                             &res.holdout_sum_abs, &res.holdout_count, rp.device) != TOPOLOW_OK)
+    throw BadArg("hold-out cells out of range");
+  if (res.trace_mae && rp.prm.n_iter > 0)
+    TL_CUDA(cudaMemcpy(res.trace_mae, rp.trace, sizeof(double) * rp.prm.n_iter, cudaMemcpyDeviceToHost));
+}
+
+void row_info(const RowPlan& rp, int64_t* out, int cap) {
+  const RowDev& dv = rp.dv;
+  const int64_t v[16] = {dv.slots, dv.D, dv.Dp, dv.G, dv.rank, dv.row0, dv.rows, dv.chunks, rp.n_recs, rp.n_mrecs, rp.launches,
+                         rp.h_flag ? rp.h_flag[1] : 0, rp.h_flag ? rp.h_flag[0] : 0,
+                         (int64_t)(dv.G - 1) * dv.rows * dv.Dp * 4,   // position bytes this rank stores into its peers per iteration
+                         (int64_t)(dv.rows / kRowTile) * dv.chunks, rp.rep_ctas};
+  for (int i = 0; i < cap && i < 16; ++i) out[i] = v[i];
+}
+
+}  // namespace tl
+
+// ---------------------------------------------------------------------------------------------------
+// C ABI (include/topolow_b200.h, topolow_shard_*)
+// ---------------------------------------------------------------------------------------------------
+struct topolow_shard { tl::RowPlan* rp; };
+
+using namespace tl;
+
+namespace {
+template <class F>
+int guarded(char* message, int32_t message_len, F&& f) {
+  try {
+    f();
+    return TOPOLOW_OK;
+  } catch (const BadArg& e) {
+    set_msg(message, message_len, e.what());
+    return TOPOLOW_ERR_BAD_ARG;
+  } catch (const std::invalid_argument& e) {
+    set_msg(message, message_len, e.what());
+    return TOPOLOW_ERR_BAD_ARG;
+  } catch (const CudaError& e) {
+    set_msg(message, message_len, e.what());
+    cudaGetLastError();
+    return TOPOLOW_ERR_CUDA;
+  } catch (const std::exception& e) {
+    set_msg(message, message_len, e.what());
+    return TOPOLOW_ERR_BAD_ARG;
+  }
+}
+}  // namespace
+
+extern "C" {
+
+int topolow_shard_create(const topolow_problem* problem, const topolow_params* params, int32_t rank, int32_t n_ranks,
+                         topolow_shard** shard_out, char* message, int32_t message_len) {
+  if (!problem || !params || !shard_out) return TOPOLOW_ERR_BAD_ARG;
+  *shard_out = nullptr;
+  if (problem->n < 2) { set_msg(message, message_len, "Need at least 2 points for embedding"); return TOPOLOW_ERR_TOO_FEW_POINTS; }
+  return guarded(message, message_len, [&] {
+    RowPlan* rp = row_create(*problem, *params, rank, n_ranks);
+    *shard_out = new topolow_shard{rp};
+  });
+}
+int64_t topolow_shard_handle_bytes(void) { return (int64_t)row_handle_bytes(); }
+int topolow_shard_export(topolow_shard* shard, void* handle_out) {
+  if (!shard || !handle_out) return TOPOLOW_ERR_BAD_ARG;
+  return guarded(nullptr, 0, [&] { row_export(*shard->rp, handle_out); });
+}
+int topolow_shard_attach(topolow_shard* shard, const void* handles, int32_t n_handles, char* message, int32_t message_len) {
+  if (!shard || !handles) return TOPOLOW_ERR_BAD_ARG;
+  return guarded(message, message_len, [&] { row_attach(*shard->rp, handles, n_handles); });
+}
+int topolow_shard_attach_local(topolow_shard* const* shards, int32_t n, char* message, int32_t message_len) {
+  if (!shards || n < 1 || n > kMaxShards) return TOPOLOW_ERR_BAD_ARG;
+  return guarded(message, message_len, [&] {
+    RowPlan* plans[kMaxShards];
+    for (int a = 0; a < n; ++a) { if (!shards[a]) throw BadArg("null shard"); plans[a] = shards[a]->rp; }
+    row_attach_local(plans, n);
+  });
+}
+int topolow_shard_run(topolow_shard* shard, int32_t n_iters, void* stream, double* ms_out) {
+  if (!shard) return TOPOLOW_ERR_BAD_ARG;
+  return guarded(nullptr, 0, [&] {
+    const double ms = row_run(*shard->rp, n_iters, (cudaStream_t)stream, nullptr, nullptr, nullptr);
+    if (ms_out) *ms_out = ms;
+  });
+}
+int topolow_shard_run_local(topolow_shard* const* shards, int32_t n, int32_t n_iters, double* ms_out) {
+  if (!shards || n < 1 || n > kMaxShards) return TOPOLOW_ERR_BAD_ARG;
+  return guarded(nullptr, 0, [&] {
+    RowPlan* plans[kMaxShards];
+    for (int a = 0; a < n; ++a) { if (!shards[a]) throw BadArg("null shard"); plans[a] = shards[a]->rp; }
+    const double ms = row_run_local(plans, n, n_iters);
+    if (ms_out) *ms_out = ms;
+  });
+}
+int topolow_shard_time_kernels(topolow_shard* shard, int32_t n_iters, double* out, int32_t cap) {
+  if (!shard || !out) return TOPOLOW_ERR_BAD_ARG;
+  return guarded(nullptr, 0, [&] { row_time_kernels(*shard->rp, n_iters, out, cap); });
+}
+int topolow_shard_result(topolow_shard* shard, topolow_result* result) {
+  if (!shard || !result) return TOPOLOW_ERR_BAD_ARG;
+  const int rc = guarded(result->message, sizeof result->message, [&] { row_result(*shard->rp, *result, false); });
+  if (rc != TOPOLOW_OK) { result->status = rc; return rc; }
+  return result->status;
+}
+int topolow_shard_info(const topolow_shard* shard, int64_t* out, int32_t cap) {
+  if (!shard || !out) return TOPOLOW_ERR_BAD_ARG;
+  row_info(*shard->rp, out, cap);
+  return TOPOLOW_OK;
+}
+// slot_of_point of the row-block layout (a pure function of n): lets a checker restate the order rows
+// are grouped and partners are visited in.
+int topolow_shard_slot_order(int64_t n, int32_t* slot_of_point_out) {
+  if (n < 1 || !slot_of_point_out) return TOPOLOW_ERR_BAD_ARG;
+  const std::vector<int32_t> p = random_permutation(n, kRowLayoutSeed);
+  std::memcpy(slot_of_point_out, p.data(), (size_t)n * sizeof(int32_t));
+  return TOPOLOW_OK;
+}
+void topolow_shard_destroy(topolow_shard* shard) {
+  if (!shard) return;
+  row_destroy(shard->rp);
+  delete shard;
+}
+
+}  // extern "C"
