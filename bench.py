@@ -138,6 +138,18 @@ def cpu_sample(prob, n, d, sample_pairs, kind="O2", seed=0):
                                      "set-up time subtracted")
 
 
+def map_config(workload, n, d, missing, E):
+    """The workload, named the same way by both arms (ours and --impl reference)."""
+    pairs = n * (n - 1) // 2
+    return {"workload": workload,
+            "description": f"synthetic low-rank dissimilarities (tools/synth.py, seed 0): {n} points, {missing:.0%} missing, ndim={d}, "
+                           "5 % '>' and 5 % '<' thresholds; k0=5, cooling_rate=0.01, c_repulsion=0.02, check every 3 iterations",
+            "n_points": n, "ndim": d, "missing": missing, "n_edges": int(E), "pairs_per_iteration": pairs,
+            "early_stop": "disabled (convergence_counter = n_iter + 1): every step is one full iteration",
+            "l2": "inputs larger than L2: the edge records streamed every iteration (%.0f MB over all ranks) exceed the 126 MB L2; "
+                  "the %.1f MB position replica is the resident working set, as in production" % (E * 16 / 1e6, n * d * 4 / 1e6)}
+
+
 def run_reference(args, n, d, missing):
     """--impl reference: the CPU implementation of the path on this box's host cores."""
     from tools import synth
@@ -163,8 +175,7 @@ def run_reference(args, n, d, missing):
         "impl": "reference", "metric": "pair-updates/s", "value": value, "unit": "pair-updates/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall / args.steps * 1e3 * (pairs / sample),
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": args.workload, "n_points": n, "ndim": d, "missing": missing, "n_edges": int(len(prob["edge_i"])),
-                   "pairs_per_iteration": pairs},
+        "config": map_config(args.workload, n, d, missing, len(prob["edge_i"])),
         "cpu_baseline": {"value": value, "unit": "pair-updates/s", "cores": 1, "kind": "port",
                          "sample": f"per step: {desc} (oracle = CPU restatement of src/optimization.cpp, g++ -O2, "
                                    "1 thread: a fit is single-threaded in the reference); ms_per_step is scaled to a full iteration"},
@@ -172,7 +183,6 @@ def run_reference(args, n, d, missing):
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
-
 
 
 def cfg5_jobs(n, missing, samples, fit_iters, seed):
@@ -208,94 +218,131 @@ def cfg5_jobs(n, missing, samples, fit_iters, seed):
     return prob, jobs, meta
 
 
-def main_cfg5(args, n, missing):
+def _cpu_fit_iters(job, iters):
+    """Worker of the CV-grid CPU baseline: `iters` iterations of one fold fit on one core; returns seconds."""
+    from oracle import cpu_oracle
+    t0 = time.perf_counter()
+    cpu_oracle.optimize_layout_exact(job["initial_positions"], job["degrees"], job["edge_i"], job["edge_j"], job["edge_dist"],
+                                     job["edge_thresh"], iters, job["k0"], job["cooling_rate"], job["c_repulsion"], 1e-4,
+                                     iters + 1, 3, seed=0, dense=True)
+    return time.perf_counter() - t0
+
+
+def cv_grid_cpu_baseline(jobs, mean_iters_run, fit_iters):
+    """The host-core baseline of the CV grid, like for like: one fold fit per core on ALL cores at once (what
+    parallel::mclapply does, R/adaptive_sampling.R:645-672), each timed for 0 and for 2 iterations (the difference
+    is the per-iteration cost under full-socket contention), scaled to the MEAN NUMBER OF ITERATIONS THE GPU
+    ARM'S FITS ACTUALLY RAN (same early-stopping rule, same work)."""
+    import multiprocessing as mp
+    from oracle import cpu_oracle
+    cpu_oracle.build(ref=False)
+    cores = os.cpu_count() or 1
+    pick = [jobs[(i * 7) % len(jobs)] for i in range(cores)]          # a stratified handful: different ndim / folds
+    pick = [{k: v for k, v in j.items() if k != "holdout"} for j in pick]
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        t0 = time.perf_counter()
+        setup = pool.starmap(_cpu_fit_iters, [(j, 0) for j in pick])
+        two = pool.starmap(_cpu_fit_iters, [(j, 2) for j in pick])
+        busy = time.perf_counter() - t0
+    per_iter = max(float(np.mean([b - a for a, b in zip(setup, two)])) / 2.0, 1e-9)
+    per_fit = per_iter * mean_iters_run + float(np.mean(setup))
+    return {"value": 60.0 / per_fit * cores, "unit": "CV embeddings/min", "cores": cores, "kind": "port",
+            "sample": f"{cores} fold fits at once, one per core (oracle, g++ -O2): {per_iter:.2f} s per iteration and "
+                      f"{np.mean(setup):.2f} s set-up per fit under full-socket load; scaled to the {mean_iters_run:.1f} iterations the "
+                      f"GPU arm's fits ran on average (mapping_max_iter={fit_iters}, same early stopping); {busy:.0f} s of wall time"}
+
+
+def cv_grid_measure(local, rank, world, samples, fit_iters, steps, warmup, n, missing, with_cpu):
+    """BASELINE.json configs[4]: `samples` parameter draws x 4 folds of independent fits PER GPU and step, through
+    topolow_fit_batch on host buffers (set-up, upload, fits, hold-out residuals, download: the path IS end to
+    end).  Weak scaling: every rank runs its own share, no collective on the data path."""
     import torch
     import torch.distributed as dist
     from topolow_b200 import _lib
-
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    prob, jobs, meta = cfg5_jobs(n, missing, args.samples, args.fit_iters, seed=rank)
+    prob, jobs, meta = cfg5_jobs(n, missing, samples, fit_iters, seed=rank)
     warm = [dict(j, n_iter=2) for j in jobs[:: max(1, len(jobs) // 18)]]   # loads every ndim variant of the kernel
-    _lib.fit_batch(warm, device=local)
-    for _ in range(max(args.warmup - 1, 0)):
+    for _ in range(max(warmup, 1)):
         _lib.fit_batch(warm, device=local)
-    barrier()
-    t0 = time.perf_counter()
-    done, pair_updates, dev_ms, held_mae = 0, 0, 0.0, []
     held_cells = {}   # the hold-out cells of a fold (fixed for the whole grid), scored on the device inside the batch
     for (_s, f, held) in meta:
         if f not in held_cells:
             held_cells[f] = (np.ascontiguousarray(prob["edge_i"][held]), np.ascontiguousarray(prob["edge_j"][held]),
                              np.ascontiguousarray(prob["edge_dist"][held]))
     jobs = [dict(j, holdout=held_cells[f]) for j, (_s, f, _h) in zip(jobs, meta)]
+    barrier()
+    t0 = time.perf_counter()
+    done, pair_updates, iters_run, flop, held_mae = 0, 0, 0, 0.0, []
     with ClockSampler(local) as clk:
-        for _ in range(args.steps):
-            # fits + hold-out residuals (R/error_metrics.R:95-114, R/adaptive_sampling.R:2642-2647) in one call
+        for _ in range(steps):
             out = _lib.fit_batch(jobs, device=local)
             held_mae.extend(r["holdout_sum_abs"] / max(r["holdout_count"], 1) for r in out)
             done += len(out)
             pair_updates += sum(r["pair_updates"] for r in out)
-            dev_ms = max(dev_ms, max(r["device_ms"] for r in out))
+            iters_run += sum(r["iterations_run"] for r in out)
+            flop += sum(r["pair_updates"] * (7.0 * j["initial_positions"].shape[1] + 8.0) for r, j in zip(out, jobs))
+            kernel_ms = max(r["device_ms"] for r in out)
         barrier()
     wall = time.perf_counter() - t0
     t = torch.tensor([wall], dtype=torch.float64, device="cuda")
-    tot = torch.tensor([done, pair_updates], dtype=torch.float64, device="cuda")
+    tot = torch.tensor([done, pair_updates, iters_run, flop], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        return None
     wall = float(t[0])
-    fits = float(tot[0])
-    cpu = None
-    if not args.no_cpu:
-        from oracle import cpu_oracle
-        from tools import synth
-        cpu_oracle.build(ref=False)
-        j = jobs[0]
-        t1 = time.perf_counter()
-        res = cpu_oracle.optimize_layout_exact(j["initial_positions"], j["degrees"], j["edge_i"], j["edge_j"], j["edge_dist"],
-                                               j["edge_thresh"], 2, j["k0"], j["cooling_rate"], j["c_repulsion"], 1e-4, 5, 3,
-                                               seed=0, dense=True)
-        dt = time.perf_counter() - t1
-        per_fit_s = dt / 2 * args.fit_iters
-        cores = os.cpu_count() or 1
-        cpu = {"value": 60.0 / per_fit_s * cores, "unit": "CV embeddings/min", "cores": cores, "kind": "port",
-               "sample": f"2 iterations of one fold fit on 1 core ({dt:.1f} s incl. set-up), scaled to {args.fit_iters} iterations "
-                         f"and to one fit per core on {cores} cores (mclapply, R/adaptive_sampling.R:645-672); no early stopping assumed"}
-    line = {
-        "metric": "CV embeddings/min", "value": fits / wall * 60.0, "unit": "CV embeddings/min", "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall / args.steps * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"cfg5: Euclidify grid, {args.samples} parameter samples x 4 folds per GPU per step, {n}-point synthetic "
-                               f"matrix ({missing:.0%} missing), ndim sampled in 2..10, mapping_max_iter={args.fit_iters}, early stopping on",
-                   "fits_per_step_per_gpu": len(jobs), "parallelism": "independent fits, one CTA per fit, no collective",
-                   "l2": "each fit streams its own edge list (about 9 MB per iteration); 128 fits in flight exceed L2"},
-        "pair_updates_per_s": float(tot[1]) / wall, "mean_holdout_mae": float(np.mean(held_mae)),
-        "clocks": clk.summary(),
-        "e2e": {"value": fits / wall * 60.0, "unit": "CV embeddings/min",
-                "h2d_bytes_per_step": int(sum(j["initial_positions"].nbytes + len(j["edge_i"]) * 20 + n * 4 for j in jobs)),
-                "d2h_bytes_per_step": int(sum(j["initial_positions"].nbytes for j in jobs)),
-                "note": "the measured path IS end to end: topolow_fit_batch on host buffers (set-up, upload, fits, download) "
-                        "including the hold-out residual kernel of every fit"},
-        # per step: one tile_batch_kernel launch per ndim group (one CTA per fit) + one hold-out kernel per fit
-        "gpu_launches": int(args.steps * (len({j["initial_positions"].shape[1] for j in jobs}) + len(jobs))),
-        "roofline": None, "cpu_baseline": cpu,
-    }
-    print(json.dumps(line), flush=True)
+    fits, mean_iters = float(tot[0]), float(tot[2]) / max(float(tot[0]), 1.0)
+    ffma_peak = _lib.microbench(0, local)
+    ach = float(tot[3]) / wall / world          # algorithmic flop/s per GPU over the whole end-to-end step
+    res = {"metric": "CV embeddings/min", "value": fits / wall * 60.0, "unit": "CV embeddings/min", "scaling": "weak",
+           "fits_per_gpu_per_step": len(jobs), "steps": steps, "ms_per_step": wall / steps * 1e3,
+           "workload": f"cfg5: Euclidify grid, 512 parameter samples x 4 folds = 2048 fits on 8 GPUs, i.e. {samples} samples x 4 folds "
+                       f"= {len(jobs)} independent fits per GPU and step; {n}-point synthetic matrix ({missing:.0%} missing), ndim sampled "
+                       f"in 2..10, mapping_max_iter={fit_iters}, early stopping on; hold-out residuals scored on the device",
+           "mean_iterations_run": mean_iters, "pair_updates_per_s": float(tot[1]) / wall,
+           "mean_holdout_mae": float(np.mean(held_mae)), "clocks": clk.summary(),
+           "h2d_bytes_per_step": int(sum(j["initial_positions"].nbytes + len(j["edge_i"]) * 20 + n * 4 for j in jobs)),
+           "d2h_bytes_per_step": int(sum(j["initial_positions"].nbytes for j in jobs)),
+           # per step: one tile_batch_kernel launch per ndim group (one CTA per fit) + one hold-out kernel per fit
+           "gpu_launches": int(steps * (len({j["initial_positions"].shape[1] for j in jobs}) + len(jobs))),
+           "roofline": {"bound": "fp32", "kernel": "tile_batch_kernel<D,FastF32> (one CTA per fit)", "achieved": ach / 1e12,
+                        "peak": ffma_peak / 1e12, "unit": "TFLOP/s", "frac": ach / ffma_peak,
+                        "note": "algorithmic flop (7 ndim + 8 per executed pair update, summed over the fits) / END-TO-END wall time "
+                                "of the step per GPU (set-up, upload and hold-out scoring included); peak = FFMA rate measured live"},
+           "cpu_baseline": cv_grid_cpu_baseline(jobs, mean_iters, fit_iters) if with_cpu else None}
+    if res["cpu_baseline"]:
+        res["speedup_vs_host_cores"] = res["value"] / res["cpu_baseline"]["value"]
+    return res
+
+
+def main_cfg5(args, n, missing):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    res = cv_grid_measure(local, rank, world, args.samples, args.fit_iters, args.steps, args.warmup, n, missing, not args.no_cpu)
+    if rank == 0:
+        line = {"metric": res["metric"], "value": res["value"], "unit": res["unit"], "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": res["workload"]},
+                "clocks": res["clocks"],
+                "e2e": {"value": res["value"], "unit": res["unit"], "h2d_bytes_per_step": res["h2d_bytes_per_step"],
+                        "d2h_bytes_per_step": res["d2h_bytes_per_step"],
+                        "note": "the measured path IS end to end: topolow_fit_batch on host buffers"},
+                "gpu_launches": res["gpu_launches"], "roofline": res["roofline"], "cpu_baseline": res["cpu_baseline"],
+                "cv_grid": res}
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
@@ -307,27 +354,33 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg4", choices=sorted(WORKLOADS))
+    ap.add_argument("--mode", default="rowblock", choices=["rowblock", "exact"],
+                    help="rowblock: owner-computes row blocks (one map over all GPUs, the mode that scales); exact: the coloured "
+                         "schedule with the reference's sequential semantics (1 GPU; with --gpus > 1 independent replicas)")
     ap.add_argument("--precision", default="f32", choices=["f32", "f64"])
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--multi", default="sharded", choices=["sharded", "replicas"],
-                    help="cfg4 with --gpus > 1: one map sharded over the GPUs (exact, position all-gather between rounds) "
-                         "or one independent replica per GPU")
-    ap.add_argument("--samples", type=int, default=74, help="cfg5: parameter samples per GPU per step (x 4 folds)")
-    ap.add_argument("--fit-iters", type=int, default=250, help="cfg5: mapping_max_iter of every fit (R/core.R:945)")
+    ap.add_argument("--no-cv", action="store_true", help="skip the cv_grid block (Metric 2) of the default line")
+    ap.add_argument("--no-exact", action="store_true", help="skip the short exact-mode comparison run at 1 GPU")
+    ap.add_argument("--samples", type=int, default=64, help="CV grid: parameter samples per GPU per step (x 4 folds); 64 = 512 / 8")
+    ap.add_argument("--fit-iters", type=int, default=250, help="CV grid: mapping_max_iter of every fit (R/core.R:945)")
+    ap.add_argument("--cv-steps", type=int, default=1)
     args = ap.parse_args()
     n, d, missing = WORKLOADS[args.workload]
     if args.workload == "cfg5":
         return main_cfg5(args, n, missing)
-
     if args.impl == "reference":
         run_reference(args, n, d, missing)
         return
+    main_map(args, n, d, missing)
 
+
+def main_map(args, n, d, missing):
     import torch
     import torch.distributed as dist
     from tools import synth
     from topolow_b200 import _lib
+    from topolow_b200.rowblock import RowBlockMap
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -343,41 +396,47 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(*vals):
+        t = torch.tensor(list(vals), dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(x) for x in t]
+
     prec = {"f32": _lib.PREC_F32, "f64": _lib.PREC_F64_EXACT}[args.precision]
     prob = synth.make_problem(n, d, missing, seed=0)
     fa = synth.fit_args(prob)
     E = int(len(prob["edge_i"]))
     pairs = n * (n - 1) // 2
-    total_iters = args.steps + (max(args.warmup, 3) if args.warmup else 0)   # every iteration run is inside n_iter
-    nw = total_iters + 1  # convergence window > n_iter: no early stop
-
-    sharded = world > 1 and args.multi == "sharded"
+    warm = max(args.warmup, 3) if args.warmup else 0
+    probe_iters = 6                                       # per-kernel event timing after the timed region
+    total_iters = warm + args.steps + probe_iters         # every iteration run is inside n_iter
+    nw = total_iters + 1                                  # convergence window > n_iter: no early stop
     hp = (HYPER["k0"], HYPER["cooling_rate"], HYPER["c_repulsion"], HYPER["relative_epsilon"])
+    freq = HYPER["convergence_check_freq"]
+    rowblock = args.mode == "rowblock"
+    one_map = rowblock or world == 1
+
     # ---- device-resident leg -------------------------------------------------------------------
-    if sharded:
-        from topolow_b200.sharded import ShardedMap
-        sm = ShardedMap(*fa, total_iters, *hp, nw, HYPER["convergence_check_freq"], world_size=world, rank=rank,
-                        device=local, precision=prec, seed=0)
-        info0 = dict(sm.plan.info(), mega_blocks=sm.M, tiles_per_mega_block=sm.Tm)
-        sm.step(max(args.warmup, 3) if args.warmup else 0)
-        launches_before = sm.plan.info()["launches"]
+    kt = None
+    if rowblock:
+        m = RowBlockMap(*fa, total_iters, *hp, nw, freq, rank=rank, world_size=world, device=local, seed=0)
+        info0 = m.info()
+        m.step(warm)
+        launches_before = m.info()["launches"]
         barrier()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         with ClockSampler(local) as clk:
             t0 = time.perf_counter()
-            ev0.record()                      # jobs and NCCL exchanges all run on torch's current stream
-            sm.step(args.steps)
-            ev1.record()
+            ms = m.step(args.steps)                       # CUDA events on the launching stream around the K iterations
             barrier()
             wall_ms = (time.perf_counter() - t0) * 1e3
-        ms = ev0.elapsed_time(ev1)
-        info1 = sm.plan.info()
-        res = sm.result()
-        sm.close()
+        launches = m.info()["launches"] - launches_before
+        kt = m.time_kernels(probe_iters)                  # events around every launch (all ranks step together)
+        res = m.result()
+        m.close()
     else:
-        plan = _lib.Plan(*fa, total_iters, *hp, nw, HYPER["convergence_check_freq"], precision=prec, seed=0, device=local)
+        plan = _lib.Plan(*fa, total_iters, *hp, nw, freq, precision=prec, seed=0, device=local)
         info0 = plan.info()
-        plan.run(max(args.warmup, 3) if args.warmup else 0)
+        plan.run(warm)
         launches_before = plan.info()["launches"]
         barrier()
         with ClockSampler(local) as clk:
@@ -385,47 +444,64 @@ def main():
             ms = plan.run(args.steps)
             barrier()
             wall_ms = (time.perf_counter() - t0) * 1e3
-        info1 = plan.info()
+        launches = plan.info()["launches"] - launches_before
         res = plan.result()
         plan.close()
-    launches = info1["launches"] - launches_before
-    t = torch.tensor([ms, wall_ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max, wall_max = float(t[0]), float(t[1])
-    # sharded: ONE map, every unordered pair once per iteration whatever the rank count (strong scaling);
-    # replicas: `world` independent maps (weak scaling)
-    value = (1 if sharded else world) * pairs * args.steps / (ms_max * 1e-3)
+    ms_max, wall_max = max_over_ranks(ms, wall_ms)
+    # one map: every unordered pair once per iteration whatever the rank count (strong scaling);
+    # exact mode on several GPUs: `world` independent maps (weak scaling)
+    maps = 1 if one_map else world
+    value = maps * pairs * args.steps / (ms_max * 1e-3)
 
     # ---- end-to-end leg: host buffers through the public call -----------------------------------
     e2e = None
     if not args.no_e2e:
-        # the step's inputs wait in pinned host memory (page-locked views handed to the C ABI as plain pointers)
+        def one_call(arrays):
+            barrier()
+            t0 = time.perf_counter()
+            if rowblock and world > 1:
+                mm = RowBlockMap(*arrays, args.steps, *hp, args.steps + 1, freq, rank=rank, world_size=world, device=local, seed=0)
+                mm.step(args.steps)
+                r2 = mm.result()
+                mm.close()
+            else:
+                r2 = _lib.fit(*arrays, args.steps, *hp, args.steps + 1, freq, precision=prec, seed=0, device=local,
+                              mode=_lib.MODE_ROWBLOCK if rowblock else _lib.MODE_COLOURED)
+            barrier()
+            return max_over_ranks(time.perf_counter() - t0)[0], r2
+        # the step's inputs wait in pinned host memory (page-locked views handed to the C ABI as plain pointers) ...
         keep_pinned = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in fa[1:]]
-        fa = (fa[0],) + tuple(t.numpy() for t in keep_pinned)
-        barrier()
-        t0 = time.perf_counter()
-        if sharded:
-            sm = ShardedMap(*fa, args.steps, *hp, args.steps + 1, HYPER["convergence_check_freq"], world_size=world,
-                            rank=rank, device=local, precision=prec, seed=0)
-            sm.step(args.steps)
-            r2 = sm.result()
-            sm.close()
-        else:
-            r2 = _lib.fit(*fa, args.steps, *hp, args.steps + 1, HYPER["convergence_check_freq"], precision=prec, seed=0,
-                          device=local)
-        barrier()
-        wall = time.perf_counter() - t0
-        tt = torch.tensor([wall], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        wall_pin, r2 = one_call((fa[0],) + tuple(t.numpy() for t in keep_pinned))
+        # ... and, as an R caller would hand them over, in ordinary pageable memory
+        wall_page, _ = one_call(fa)
         h2d = n * d * 8 + n * 4 + E * (4 + 4 + 8 + 4)
         d2h = n * d * 8
-        e2e = {"value": (1 if sharded else world) * pairs * r2["iterations_run"] / float(tt[0]), "unit": "pair-updates/s",
+        e2e = {"value": maps * pairs * r2["iterations_run"] / wall_pin, "unit": "pair-updates/s",
                "h2d_bytes_per_step": h2d // max(args.steps, 1), "d2h_bytes_per_step": d2h // max(args.steps, 1),
-               "note": "one fit of K iterations from pinned host buffers (per rank when sharded): upload, bucket build, "
-                       "K iterations, download; bytes are the call's totals divided by K",
-               "wall_s": float(tt[0]), "kernel_ms": r2["device_ms"]}
+               "note": "one fit of K iterations from pinned host buffers through the C ABI (topolow_fit; per rank topolow_shard_* "
+                       "when sharded: every rank uploads the edge list and keeps its rows): upload, record build, K iterations, "
+                       "download; bytes are the call's totals (per rank) divided by K",
+               "wall_s": wall_pin, "kernel_ms": r2["device_ms"],
+               "pageable": {"value": maps * pairs * r2["iterations_run"] / wall_page, "wall_s": wall_page,
+                            "note": "the same call with the caller's arrays in pageable memory (what R hands over)"}}
+
+    # ---- the exact (coloured) mode beside it, 1 GPU: the reference's sequential semantics -----------
+    exact = None
+    if rowblock and world == 1 and not args.no_exact and prec == _lib.PREC_F32:
+        ex_iters = 9
+        plan = _lib.Plan(*fa, ex_iters, *hp, ex_iters + 1, freq, precision=prec, seed=0, device=local)
+        plan.run(3)
+        ex_ms = plan.run(6)
+        plan.close()
+        exact = {"ms_per_step": ex_ms / 6, "value": pairs * 6 / (ex_ms * 1e-3), "unit": "pair-updates/s",
+                 "note": "mode=coloured (tile_kernel): matchings of commuting pair updates, one sequential order of the reference's "
+                         "loop per iteration; 6 iterations after 3 warm-up"}
+
+    # ---- Metric 2 in the same line ---------------------------------------------------------------------
+    cv = None
+    if not args.no_cv:
+        cn, _cd, cmiss = WORKLOADS["cfg5"]
+        cv = cv_grid_measure(local, rank, world, args.samples, args.fit_iters, args.cv_steps, 1, cn, cmiss, not args.no_cpu)
 
     if rank != 0:
         if world > 1:
@@ -436,43 +512,65 @@ def main():
     peaks, peak_src = measured_peaks()
     ffma_peak = _lib.microbench(0, local)      # flop/s, measured now on this GPU
     flop = flop_per_iter(n, d, E)
-    kernel_s = ms_max * 1e-3 / args.steps        # device time of one iteration (all of it is tile_kernel launches)
-    ach = flop / kernel_s / (world if sharded else 1)   # per GPU
-    roofline = {"bound": "fp32", "kernel": "tile_kernel<D,%s>" % ("FastF32" if prec == 0 else "ExactF64"),
-                "achieved": ach / 1e12, "peak": ffma_peak / 1e12, "unit": "TFLOP/s", "frac": ach / ffma_peak,
-                "peak_source": "topolow_microbench FFMA, measured live on this GPU (not in MEASURED_PEAKS.json)",
-                "flop_per_iteration": flop,
-                # dram__bytes_read + dram__bytes_write of one launch (= one iteration) of this kernel on this
-                # workload, from the ncu --set full capture summarised in profiles/r1_ncu_tile_kernel_cfg4.md
-                "traffic": 878.6e6 if (args.workload == "cfg4" and prec == 0) else None,
-                "traffic_unit": "bytes per launch (one iteration); algorithmic edge stream is bytes_per_iteration below",
-                "hbm": {"achieved": edge_bytes_per_iter(n, d, E) / kernel_s / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                        "frac": edge_bytes_per_iter(n, d, E) / kernel_s / 1e9 / peaks["hbm_gbs"], "peak_source": peak_src,
-                        "bytes_per_iteration": edge_bytes_per_iter(n, d, E)}}
+    if rowblock:
+        # the dominant kernel: repulse_kernel, one launch per iteration and rank, rows/world x (n - 1) one-sided
+        # interactions = that many HALF pair updates of SURVEY 8d's 7d + 8 flop
+        rep_flop = (7 * d + 8) * pairs / world
+        rep_s = kt["repulse"] * 1e-3
+        edge_b = edge_bytes_per_iter(n, d, E) / world
+        roofline = {"bound": "fp32", "kernel": "repulse_kernel<ndim/2, 2 rows per thread> (one launch per iteration and rank)",
+                    "achieved": rep_flop / rep_s / 1e12, "peak": ffma_peak / 1e12, "unit": "TFLOP/s",
+                    "frac": rep_flop / rep_s / ffma_peak,
+                    "peak_source": "topolow_microbench FFMA, measured live on this GPU (FP32 is not in MEASURED_PEAKS.json)",
+                    "algorithmic_flop_per_launch": rep_flop, "launch_ms": kt["repulse"],
+                    "note": "algorithmic = (7 ndim + 8) flop per unordered pair (SURVEY 8d); the kernel visits every pair from both "
+                            "sides (one-sided updates) and executes 54 FMA-pipe cycles per side at ndim 16, so 1.0 is not reachable: "
+                            "100 % FMA-pipe occupancy reads as 0.56 here",
+                    "traffic": None,
+                    "kernels_ms": kt,
+                    "edge_pass": {"bound": "hbm", "kernel": "mae_kernel (edge MAE on check iterations)",
+                                  "achieved": edge_b / (kt["mae"] * 1e-3) / 1e9 if kt["mae"] > 0 else None, "peak": peaks["hbm_gbs"],
+                                  "unit": "GB/s", "frac": edge_b / (kt["mae"] * 1e-3) / 1e9 / peaks["hbm_gbs"] if kt["mae"] > 0 else None,
+                                  "peak_source": peak_src, "algorithmic_bytes_per_launch": edge_b, "launch_ms": kt["mae"],
+                                  "note": "SURVEY 8d: 16 bytes per measured pair + every FP32 position read and written once, per rank"},
+                    "spring_pass": {"launch_ms": kt["spring"],
+                                    "achieved_gbs": (2 * E * 8 / world + 2 * n * d * 4 / world) / (kt["spring"] * 1e-3) / 1e9,
+                                    "note": "walks both directions of every measured pair (8-byte records) and gathers one 64-byte "
+                                            "partner row per record from the L2-resident replica"}}
+    else:
+        kernel_s = ms_max * 1e-3 / args.steps        # device time of one iteration (all of it is tile_kernel launches)
+        ach = flop / kernel_s
+        roofline = {"bound": "fp32", "kernel": "tile_kernel<D,%s>" % ("FastF32" if prec == 0 else "ExactF64"),
+                    "achieved": ach / 1e12, "peak": ffma_peak / 1e12, "unit": "TFLOP/s", "frac": ach / ffma_peak,
+                    "peak_source": "topolow_microbench FFMA, measured live on this GPU (not in MEASURED_PEAKS.json)",
+                    "flop_per_iteration": flop, "traffic": None}
 
     cpu = None
     if not args.no_cpu:
         from oracle import cpu_oracle
         cpu_oracle.build(ref=False)
-        sample = int(min(pairs, 2e8))
+        sample = int(min(pairs, 1e8))
         rate, dt, desc = cpu_sample(prob, n, d, sample)
+        rate3, dt3, _ = cpu_sample(prob, n, d, sample, kind="fast")
         cpu = {"value": rate, "unit": "pair-updates/s", "cores": 1, "kind": "port",
-               "sample": f"{desc}; {dt:.1f} s of CPU work (oracle = CPU restatement of src/optimization.cpp, g++ -O2, 1 thread)"}
+               "sample": f"{desc}; {dt:.1f} s of CPU work (oracle = CPU restatement of src/optimization.cpp, g++ -O2 = R's package "
+                         "default, 1 thread: a fit is single-threaded in the reference)",
+               "value_O3": rate3, "O3_note": f"the same sample built with g++ -O3 -march=x86-64-v3 ({dt3:.1f} s)"}
 
+    if rowblock:
+        par = ("1 GPU, row-block mode" if world == 1 else
+               f"one map, {world} row blocks (one per GPU): every rank computes the one-sided updates of its rows against a replica of all "
+               f"positions and stores its new rows into every replica over NVLink inside the spring kernel ({info0['peer_store_bytes_per_iteration']} "
+               "bytes per rank and iteration), one flag per peer and iteration; no host code, NCCL call or torch op in the loop")
+    else:
+        par = "1 GPU, exact coloured mode" if world == 1 else f"{world} independent replicas of the exact mode (no collective)"
     line = {
         "metric": "pair-updates/s", "value": value, "unit": "pair-updates/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
-        "scaling": "weak" if (world > 1 and not sharded) else "strong", "vs_baseline": None,
+        "scaling": "strong" if one_map else "weak", "vs_baseline": None,
         "dtype": "f32" if prec == 0 else "f64", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: synthetic low-rank, {n} points, {missing:.0%} missing, ndim={d}",
-                   "n_points": n, "ndim": d, "n_edges": E, "pairs_per_iteration": pairs, "schedule": info0,
-                   "parallelism": "1 GPU" if world == 1 else (
-                       f"one map row-sharded over {world} GPUs: tournament over {2 * world} mega-blocks, NCCL all-gather of the "
-                       "changed position blocks after each of its rounds, exact sequential semantics" if sharded
-                       else f"{world} independent replicas (no collective)"),
-                   "l2": "edge stream (%.0f MB/iteration) exceeds L2; the %.1f MB position array is the resident working set"
-                         % (E * 16 / 1e6, n * d * 4 / 1e6),
-                   "early_stop": "disabled (convergence_counter = n_iter + 1)"},
+        "config": map_config(args.workload, n, d, missing, E),
+        "mode": args.mode, "parallelism": par, "layout": info0,
         "wall_ms_per_step": wall_max / args.steps,
         "final_mae": res["final_mae"],
         "clocks": clk.summary(),
@@ -480,6 +578,8 @@ def main():
         "gpu_launches": int(launches),
         "roofline": roofline,
         "cpu_baseline": cpu,
+        "exact_mode": exact,
+        "cv_grid": cv,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

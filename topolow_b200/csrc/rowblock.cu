@@ -45,7 +45,6 @@ namespace {
 constexpr uint64_t kRowLayoutSeed = 0x726f77626c6f636bULL;
 constexpr int kStageJ = 128;   // partners per shared-memory stage
 constexpr int kStages = 3;
-constexpr int kRepThreads = 128;
 constexpr int kFlagStride = 32;   // 32-bit words between the flag words of two ranks (128 bytes)
 constexpr unsigned long long kWaitNs = 20ull * 1000ull * 1000ull * 1000ull;
 
@@ -72,6 +71,8 @@ struct RowDev {
   unsigned long long seed;
 };
 
+typedef void (*RepulseFn)(RowDev, int, unsigned);
+
 // ---------------------------------------------------------------------------------------------------
 // device helpers
 // ---------------------------------------------------------------------------------------------------
@@ -91,30 +92,26 @@ TL_D void cp_async16(void* smem, const void* gmem) {
 TL_D void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> TL_D void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// H packed pairs of one point from (shared or global) memory; 16-byte loads when the stride allows.
+// Rows are stored with a stride of kStride<H> floats (a multiple of 4: every row starts on a 16-byte boundary,
+// odd H leaves two pad floats that are never computed on).
+template <int H> struct Row { static constexpr int kStride = (2 * H + 3) / 4 * 4; };
+
+// H packed pairs of one point from (shared or global) memory: 16-byte loads, one 8-byte tail when H is odd.
 template <int H>
 TL_D void ld_point(const float* __restrict__ p, float2 (&v)[H]) {
-  if constexpr (H % 2 == 0) {
 #pragma unroll
-    for (int k = 0; k < H / 2; ++k) {
-      const float4 t = reinterpret_cast<const float4*>(p)[k];
-      v[2 * k] = make_float2(t.x, t.y); v[2 * k + 1] = make_float2(t.z, t.w);
-    }
-  } else {
-#pragma unroll
-    for (int k = 0; k < H; ++k) v[k] = reinterpret_cast<const float2*>(p)[k];
+  for (int k = 0; k < H / 2; ++k) {
+    const float4 t = reinterpret_cast<const float4*>(p)[k];
+    v[2 * k] = make_float2(t.x, t.y); v[2 * k + 1] = make_float2(t.z, t.w);
   }
+  if constexpr (H % 2 == 1) v[H - 1] = reinterpret_cast<const float2*>(p)[H - 1];
 }
 template <int H>
 TL_D void st_point(float* __restrict__ p, const float2 (&v)[H]) {
-  if constexpr (H % 2 == 0) {
 #pragma unroll
-    for (int k = 0; k < H / 2; ++k)
-      reinterpret_cast<float4*>(p)[k] = make_float4(v[2 * k].x, v[2 * k].y, v[2 * k + 1].x, v[2 * k + 1].y);
-  } else {
-#pragma unroll
-    for (int k = 0; k < H; ++k) reinterpret_cast<float2*>(p)[k] = v[k];
-  }
+  for (int k = 0; k < H / 2; ++k)
+    reinterpret_cast<float4*>(p)[k] = make_float4(v[2 * k].x, v[2 * k].y, v[2 * k + 1].x, v[2 * k + 1].y);
+  if constexpr (H % 2 == 1) reinterpret_cast<float2*>(p)[H - 1] = v[H - 1];
 }
 
 // |q + np|^2 (np = -p); delta is kept for the caller.  kChains = 2 halves the dependent FMA chain (the
@@ -140,13 +137,18 @@ TL_D float dist2(const float2 (&np)[H], const float2 (&q)[H], float2 (&dl)[H]) {
   return s0.x + s0.y;
 }
 
+TL_D float lg2_approx(float x) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+TL_D float ex2_approx(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+
 // One-sided repulsion of partner q on the point -np: acc += (q - p) / (|q - p| + 0.01)^3.
-template <int H>
+// kPow: the cube and its reciprocal as 2^(-3 log2(ds)) on the special-function unit (two MUFU + one multiply)
+// instead of two multiplies + MUFU.RCP: one FMA-pipe slot less in a loop that is bound by that pipe.
+template <int H, bool kPow = false>
 TL_D void repel(const float2 (&np)[H], const float2 (&q)[H], float2 (&acc)[H]) {
   float2 dl[H];
   const float d2 = dist2<H, 1>(np, q, dl);
   const float ds = sqrt_approx(d2) + 0.01f;
-  const float w = rcp_approx(ds * ds * ds);
+  const float w = kPow ? ex2_approx(-3.0f * lg2_approx(ds)) : rcp_approx(ds * ds * ds);
   const float2 ww = make_float2(w, w);
 #pragma unroll
   for (int k = 0; k < H; ++k) acc[k] = __ffma2_rn(dl[k], ww, acc[k]);
@@ -198,29 +200,36 @@ TL_D bool last_cta(unsigned* counter) {
 }
 
 // ---------------------------------------------------------------------------------------------------
-// repulsion: one work item = 256 own rows (2 per thread) x one chunk of <= 2048 partners
+// repulsion: one work item = 256 own rows (R per thread) x one chunk of <= 2048 partners
 // ---------------------------------------------------------------------------------------------------
-template <int H, int R>
-__global__ void __launch_bounds__(kRepThreads, 4) repulse_kernel(RowDev dv, int cur, unsigned epoch) {
+// Items are handed out by an atomic counter (reset by the spring kernel's last CTA): the partial sums of an
+// item do not depend on which CTA computed it, so the result is the same whatever the residency pattern.
+template <int H, int R, int U, int MAXR, bool kPow>
+__global__ void __maxnreg__(MAXR) repulse_kernel(RowDev dv, int cur, unsigned epoch) {
   extern __shared__ float4 smem4[];
+  __shared__ long long item_s;
   float* sm = reinterpret_cast<float*>(smem4);
-  constexpr int Dp = 2 * H;
+  constexpr int T = kRowTile / R;
+  constexpr int Dp = Row<H>::kStride;
   constexpr int kStageFloats = kStageJ * Dp;
-  static_assert(R * kRepThreads == kRowTile, "a work item is one row tile");
   if (__ldcg(&dv.state->stop)) return;
   if (!wait_epoch(dv, epoch)) { if (blockIdx.x == 0 && threadIdx.x == 0) peer_timeout(dv); return; }
   const int tid = threadIdx.x;
   const float* __restrict__ P = dv.pos[dv.rank] + (size_t)cur * dv.cap_rows * Dp;
   const int tiles = dv.rows / kRowTile;
   const long long items = (long long)tiles * dv.chunks;
-  for (long long item = blockIdx.x; item < items; item += gridDim.x) {
+  for (;;) {
+    if (tid == 0) item_s = (long long)atomicAdd(&dv.counters[2], 1u);
+    __syncthreads();
+    const long long item = item_s;
+    if (item >= items) break;
     const int c = (int)(item / tiles), tile = (int)(item % tiles);
     const int lrow0 = tile * kRowTile;
     float2 np[R][H], acc[R][H];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       float2 p[H];
-      ld_point<H>(P + (size_t)(dv.row0 + lrow0 + tid + r * kRepThreads) * Dp, p);
+      ld_point<H>(P + (size_t)(dv.row0 + lrow0 + tid + r * T) * Dp, p);
 #pragma unroll
       for (int k = 0; k < H; ++k) { np[r][k] = make_float2(-p[k].x, -p[k].y); acc[r][k] = make_float2(0.f, 0.f); }
     }
@@ -232,7 +241,7 @@ __global__ void __launch_bounds__(kRepThreads, 4) repulse_kernel(RowDev dv, int 
       if (s < nst) {
         const float4* g = reinterpret_cast<const float4*>(src + (size_t)s * kStageFloats);
         float4* d = reinterpret_cast<float4*>(sm + (size_t)(s % kStages) * kStageFloats);
-        for (int x = tid; x < kStageFloats / 4; x += kRepThreads) cp_async16(d + x, g + x);
+        for (int x = tid; x < kStageFloats / 4; x += T) cp_async16(d + x, g + x);
       }
       cp_async_commit();
     };
@@ -244,93 +253,218 @@ __global__ void __launch_bounds__(kRepThreads, 4) repulse_kernel(RowDev dv, int 
       prefetch(s + kStages - 1);
       const float* __restrict__ q_s = sm + (size_t)(s % kStages) * kStageFloats;
       const int m = min(kStageJ, cnt - s * kStageJ);
-#pragma unroll 2
+#pragma unroll U
       for (int j = 0; j < m; ++j) {
         float2 q[H];
         ld_point<H>(q_s + j * Dp, q);
 #pragma unroll
-        for (int r = 0; r < R; ++r) repel<H>(np[r], q, acc[r]);
+        for (int r = 0; r < R; ++r) repel<H, kPow>(np[r], q, acc[r]);
       }
     }
 #pragma unroll
     for (int r = 0; r < R; ++r)
-      st_point<H>(dv.rpart + ((size_t)c * dv.rows + lrow0 + tid + r * kRepThreads) * Dp, acc[r]);
-    __syncthreads();   // the stages are refilled by the next item's prologue
+      st_point<H>(dv.rpart + ((size_t)c * dv.rows + lrow0 + tid + r * T) * Dp, acc[r]);
+    __syncthreads();   // the stages are refilled by the next item's prologue; item_s is rewritten
   }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// the walk over the records of the own rows (springs and edge MAE)
+// ---------------------------------------------------------------------------------------------------
+// One thread per row, one warp per slice of 32 rows; step s of a warp handles record at(s) of each of its 32
+// rows.  The partner rows are gathered into a per-warp shared-memory ring kRing steps ahead by cp.async, the
+// four lanes of a quad fetching the 16-byte pieces of each other's rows: a warp-wide gather instruction then
+// touches 8 cache lines instead of 32 (scattered 16-byte loads are bound by the L1 tag stage, one line per clock,
+// long before L2 bandwidth), nothing is held in registers while in flight, and the records themselves ride the
+// same ring (8 bytes per lane, one contiguous 256-byte line per warp and step).
+constexpr int kRecAhead = 32;   // steps the record stream is prefetched into L2 ahead of its use
+constexpr unsigned kSlotMask = 0x3fffffffu;
+
+// kRing = steps of partner rows in flight per warp: 4 when the chip is full of warps (throughput: more CTAs per
+// SM), 8 when a rank owns few rows (latency: a step then costs its dependent arithmetic, not an L2 round trip / 3).
+template <int H, int kRing>
+struct Ring {
+  static constexpr int kRecRing = 2 * kRing;
+  static constexpr int Dp = Row<H>::kStride;
+  static constexpr int NC = Dp / 4;                         // 16-byte pieces of a row
+  static constexpr int kRowBytes = NC * 16;
+  static constexpr int kSlotBytes = 32 * kRowBytes;
+  static constexpr int kWarpBytes = kRing * kSlotBytes + kRecRing * 32 * 8;
+  // piece c of the row staged for `lane`: 64-byte rows are swizzled so that the eight lanes of a 128-bit
+  // shared-memory phase hit eight different bank groups
+  static TL_D int piece(int lane, int c) {
+    return NC == 4 ? lane * 64 + ((c ^ ((lane >> 1) & 3)) << 4) : lane * kRowBytes + (c << 4);
+  }
+};
+
+TL_D void cp_async16_ca(unsigned smem_addr, const void* gmem) {
+  // through L1: the two 16-byte halves of a 32-byte sector are asked for by two lanes of the same instruction;
+  // the L1-bypassing form (.cg) fetches the sector once per lane (measured: twice the L2 traffic)
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gmem) : "memory");
+}
+
+TL_D void keep(unsigned& x) { asm volatile("" : "+r"(x)); }   // opaque to the compiler: computed once, not rematerialised in the loop
+TL_D uint4 lds128(unsigned a) { uint4 v; asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a)); return v; }
+TL_D uint2 lds64(unsigned a) { uint2 v; asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a)); return v; }
+
+// consume(record, partner row) is called for every step in order, by all lanes of the warp together.
+// Order inside a step (a lone warp per scheduler issues in order, so the order is the schedule): wait for the
+// step's data, read it (row pieces, own record, the four records of the quad for the gather) in one burst of
+// shared-memory loads, issue the gathers of step t + kRing - 1 and the record of step t + 2 kRing - 1, then the
+// arithmetic of step t, which the compiler is free to spread between the copy instructions.
+template <int H, int kRing, class F>
+TL_D void walk_rows(const float* __restrict__ P, const uint2* __restrict__ rec /* + lane */, int width, int start, char* wsm,
+                    F&& consume) {
+  typedef Ring<H, kRing> R;
+  constexpr int kRecRing = R::kRecRing;
+  constexpr unsigned kRowsBytes = kRing * R::kSlotBytes, kRecSlotBytes = 32 * 8;
+  const int lane = threadIdx.x & 31;
+  const unsigned rows_a = (unsigned)__cvta_generic_to_shared(wsm);
+  const unsigned recs_a = rows_a + kRowsBytes;
+  const int c = lane & 3, quad = lane & ~3;
+  // lane constants (byte offsets inside a ring slot)
+  unsigned dst_off[4], own_off[R::NC];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) { dst_off[u] = (unsigned)R::piece(quad + u, c); keep(dst_off[u]); }
+#pragma unroll
+  for (int k = 0; k < R::NC; ++k) { own_off[k] = (unsigned)R::piece(lane, k); keep(own_off[k]); }
+  unsigned rec_own = (unsigned)lane * 8u, rec_quad = (unsigned)quad * 8u;
+  keep(rec_own); keep(rec_quad);
+  const char* P_c = reinterpret_cast<const char*>(P) + c * 16;
+  asm volatile("" : "+l"(P_c));
+  asm volatile("" : "+l"(rec));
+  // cursors (warp-uniform)
+  int r_at = start, r_left = width;
+  unsigned r_slot_a = recs_a;                                  // record-ring slot the next record goes to
+  int pf_at = start + kRecAhead;                               // record line pulled into L2 this step (lanes 0, 1)
+  if (width > 0) pf_at %= width;
+  const uint2* rec_line = rec - lane + (lane & 1) * 16;
+  auto issue_rec = [&]() {
+    if (r_left > 0) {
+      if (lane < 2 && r_left > kRecAhead) asm volatile("prefetch.global.L2 [%0];" ::"l"(rec_line + (size_t)pf_at * 32));
+      pf_at = (pf_at + 1 == width) ? 0 : pf_at + 1;
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(r_slot_a + rec_own), "l"(rec + (size_t)r_at * 32) : "memory");
+      r_at = (r_at + 1 == width) ? 0 : r_at + 1;
+      --r_left;
+    }
+    r_slot_a = (r_slot_a + kRecSlotBytes == recs_a + kRecRing * kRecSlotBytes) ? recs_a : r_slot_a + kRecSlotBytes;
+  };
+  int g_left = width;
+  unsigned g_slot_a = rows_a, g_rslot_a = recs_a;               // row-ring slot gathered into, record slot it reads
+  auto issue_gather = [&](const uint4 ja, const uint4 jb) {     // the four records of the quad: (ja.x, ja.z, jb.x, jb.z) are the .x words
+    if (g_left > 0) {
+      if (c < R::NC) {
+        const unsigned j[4] = {ja.x & kSlotMask, ja.z & kSlotMask, jb.x & kSlotMask, jb.z & kSlotMask};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) cp_async16_ca(g_slot_a + dst_off[u], P_c + (size_t)j[u] * (R::Dp * 4));
+      }
+      --g_left;
+    }
+    g_slot_a = (g_slot_a + R::kSlotBytes == rows_a + kRowsBytes) ? rows_a : g_slot_a + R::kSlotBytes;
+    g_rslot_a = (g_rslot_a + kRecSlotBytes == recs_a + kRecRing * kRecSlotBytes) ? recs_a : g_rslot_a + kRecSlotBytes;
+  };
+  for (int st = 0; st < kRecRing - 1; ++st) issue_rec();
+  cp_async_commit();
+  cp_async_wait<0>();
+  __syncwarp();
+  for (int st = 0; st < kRing - 1; ++st) {
+    const uint4 ja = lds128(g_rslot_a + rec_quad), jb = lds128(g_rslot_a + rec_quad + 16);
+    issue_gather(ja, jb);
+    cp_async_commit();
+  }
+  unsigned slot_a = rows_a, rslot_a = recs_a;
+  for (int t = 0; t < width; ++t) {
+    cp_async_wait<kRing - 2>();
+    __syncwarp();
+    // ---- everything this step reads from shared memory ----
+    uint4 qv[R::NC];
+#pragma unroll
+    for (int k = 0; k < H / 2; ++k) qv[k] = lds128(slot_a + own_off[k]);
+    uint2 qt = make_uint2(0u, 0u);
+    if constexpr (H % 2 == 1) qt = lds64(slot_a + own_off[H / 2]);
+    const uint2 r = lds64(rslot_a + rec_own);
+    const uint4 ja = lds128(g_rslot_a + rec_quad), jb = lds128(g_rslot_a + rec_quad + 16);
+    // ---- copies for the steps ahead ----
+    issue_gather(ja, jb);
+    issue_rec();
+    cp_async_commit();
+    slot_a = (slot_a + R::kSlotBytes == rows_a + kRowsBytes) ? rows_a : slot_a + R::kSlotBytes;
+    rslot_a = (rslot_a + kRecSlotBytes == recs_a + kRecRing * kRecSlotBytes) ? recs_a : rslot_a + kRecSlotBytes;
+    // ---- this step ----
+    float2 q[H];
+#pragma unroll
+    for (int k = 0; k < H / 2; ++k) {
+      q[2 * k] = make_float2(__uint_as_float(qv[k].x), __uint_as_float(qv[k].y));
+      q[2 * k + 1] = make_float2(__uint_as_float(qv[k].z), __uint_as_float(qv[k].w));
+    }
+    if constexpr (H % 2 == 1) q[H - 1] = make_float2(__uint_as_float(qt.x), __uint_as_float(qt.y));
+    consume(r, q);
+  }
+  cp_async_wait<0>();
+  __syncwarp();
 }
 
 // ---------------------------------------------------------------------------------------------------
 // springs: one thread per own row, Gauss-Seidel along the row
 // ---------------------------------------------------------------------------------------------------
-template <int H>
+template <int H, int kRing>
 __global__ void __launch_bounds__(kBlockRows) spring_kernel(RowDev dv, FitParams prm, int cur, unsigned epoch) {
-  constexpr int Dp = 2 * H;
+  constexpr int Dp = Row<H>::kStride;
+  extern __shared__ float4 smem4[];
   if (__ldcg(&dv.state->stop)) return;
-  const int tid = threadIdx.x, lane = tid & 31;
+  const int tid = threadIdx.x;
   const int lrow = blockIdx.x * kBlockRows + tid;          // row inside the own block
   const int row = dv.row0 + lrow;                          // slot
   const float* __restrict__ P = dv.pos[dv.rank] + (size_t)cur * dv.cap_rows * Dp;
   const double kd = __ldcg(&dv.state->k);
   const int iter = __ldcg(&dv.state->iter);
   const float k = (float)kd;
-  const float dp1 = dv.dp1[row];
+  const float dp1 = dv.dp1[row];                           // 0 for a padding row: its lane walks along, stores nothing
+  const float safe = dp1 > 0.f ? dp1 : 1.f;
+  float2 p0n[H], xn[H];   // -P_i and -x (the running position, negated: deltas are q + (-x))
+  {
+    float2 p[H], rs[H];
+    ld_point<H>(P + (size_t)row * Dp, p);
+#pragma unroll
+    for (int kk = 0; kk < H; ++kk) rs[kk] = make_float2(0.f, 0.f);
+    for (int c = 0; c < dv.chunks; ++c) {
+      float2 t[H];
+      ld_point<H>(dv.rpart + ((size_t)c * dv.rows + lrow) * Dp, t);
+#pragma unroll
+      for (int kk = 0; kk < H; ++kk) rs[kk] = __fadd2_rn(rs[kk], t[kk]);
+    }
+    const float rdeg0 = (float)(0.5 * prm.c_repulsion) / safe;
+    const float2 rr = make_float2(rdeg0, rdeg0);
+#pragma unroll
+    for (int kk = 0; kk < H; ++kk) {
+      p0n[kk] = make_float2(-p[kk].x, -p[kk].y);
+      xn[kk] = __ffma2_rn(rs[kk], rr, p0n[kk]);          // -(p - rs * rdeg)
+    }
+  }
+  const float rdeg = (float)(0.5 * prm.c_repulsion) / safe;
+  const float two_k_rnorm = 2.0f * k / (4.0f * safe + k);
+  const int slice = lrow >> 5;
+  const int width = dv.swidth[slice];
+  int start = 0;
+  if (width > 0) start = (int)(mix64(dv.seed ^ mix64(((unsigned long long)(unsigned)iter << 32) | (unsigned)(row >> 5))) % (unsigned long long)width);
+  walk_rows<H, kRing>(P, dv.recs + dv.soff[slice] + (tid & 31), width, start,
+               reinterpret_cast<char*>(smem4) + (size_t)(tid >> 5) * Ring<H, kRing>::kWarpBytes, [&](const uint2 r, const float2 (&q)[H]) {
+    const unsigned type = r.x >> 30;
+    const float target = __uint_as_float(r.y);
+    float2 dl[H], d0[H];
+    const float d2 = dist2<H>(xn, q, dl);
+    const float e2 = dist2<H>(p0n, q, d0);
+    const float dist = sqrt_approx(d2);
+    const bool spring = type == 0u || (type == 1u ? dist < target : (type == 2u && dist > target));   // :237-243
+    const float f = spring ? two_k_rnorm * (target - dist) * rcp_approx(dist + 0.01f) : 0.f;
+    const float ds0 = sqrt_approx(e2) + 0.01f;
+    const float w0 = spring ? rdeg * rcp_approx(ds0 * ds0 * ds0) : 0.f;
+    // x += -delta f + d0 w0  <=>  (-x) += delta f - d0 w0
+    const float2 ff = make_float2(f, f), nw = make_float2(-w0, -w0);
+#pragma unroll
+    for (int kk = 0; kk < H; ++kk) xn[kk] = __ffma2_rn(d0[kk], nw, __ffma2_rn(dl[kk], ff, xn[kk]));
+  });
   if (dp1 > 0.f) {
-    float2 p0n[H], xn[H];   // -P_i and -x (the running position, negated: deltas are q + (-x))
-    {
-      float2 p[H], rs[H];
-      ld_point<H>(P + (size_t)row * Dp, p);
-#pragma unroll
-      for (int kk = 0; kk < H; ++kk) rs[kk] = make_float2(0.f, 0.f);
-      for (int c = 0; c < dv.chunks; ++c) {
-        float2 t[H];
-        ld_point<H>(dv.rpart + ((size_t)c * dv.rows + lrow) * Dp, t);
-#pragma unroll
-        for (int kk = 0; kk < H; ++kk) rs[kk] = __fadd2_rn(rs[kk], t[kk]);
-      }
-      const float rdeg0 = (float)(0.5 * prm.c_repulsion) / dp1;
-      const float2 rr = make_float2(rdeg0, rdeg0);
-#pragma unroll
-      for (int kk = 0; kk < H; ++kk) {
-        p0n[kk] = make_float2(-p[kk].x, -p[kk].y);
-        xn[kk] = __ffma2_rn(rs[kk], rr, p0n[kk]);          // -(p - rs * rdeg)
-      }
-    }
-    const float rdeg = (float)(0.5 * prm.c_repulsion) / dp1;
-    const float two_k_rnorm = 2.0f * k / (4.0f * dp1 + k);
-    const int slice = lrow >> 5;
-    const int width = dv.swidth[slice];
-    const uint2* __restrict__ rec = dv.recs + dv.soff[slice] + lane;
-    int at = 0;
-    if (width > 0) at = (int)(mix64(dv.seed ^ mix64(((unsigned long long)(unsigned)iter << 32) | (unsigned)(row >> 5))) % (unsigned long long)width);
-    auto next_at = [&]() { const int a = at; at = (at + 1 == width) ? 0 : at + 1; return a; };
-    uint2 r_n = make_uint2((unsigned)row | (3u << 30), 0u), r_nn = r_n;
-    float2 q_n[H];
-    if (width > 0) r_n = rec[(size_t)next_at() * 32];
-    if (width > 1) r_nn = rec[(size_t)next_at() * 32];
-    ld_point<H>(P + (size_t)(r_n.x & 0x3fffffffu) * Dp, q_n);
-    for (int t = 0; t < width; ++t) {
-      const uint2 r = r_n;
-      float2 q[H];
-#pragma unroll
-      for (int kk = 0; kk < H; ++kk) q[kk] = q_n[kk];
-      r_n = r_nn;
-      if (t + 1 < width) ld_point<H>(P + (size_t)(r_n.x & 0x3fffffffu) * Dp, q_n);
-      if (t + 2 < width) r_nn = rec[(size_t)next_at() * 32];
-      const unsigned type = r.x >> 30;
-      const float target = __uint_as_float(r.y);
-      float2 dl[H], d0[H];
-      const float d2 = dist2<H>(xn, q, dl);
-      const float e2 = dist2<H>(p0n, q, d0);
-      const float dist = sqrt_approx(d2);
-      const bool spring = type == 0u || (type == 1u ? dist < target : (type == 2u && dist > target));   // :237-243
-      const float f = spring ? two_k_rnorm * (target - dist) * rcp_approx(dist + 0.01f) : 0.f;
-      const float ds0 = sqrt_approx(e2) + 0.01f;
-      const float w0 = spring ? rdeg * rcp_approx(ds0 * ds0 * ds0) : 0.f;
-      // x += -delta f + d0 w0  <=>  (-x) += delta f - d0 w0
-      const float2 ff = make_float2(f, f), nw = make_float2(-w0, -w0);
-#pragma unroll
-      for (int kk = 0; kk < H; ++kk) xn[kk] = __ffma2_rn(d0[kk], nw, __ffma2_rn(dl[kk], ff, xn[kk]));
-    }
     float2 x[H];
 #pragma unroll
     for (int kk = 0; kk < H; ++kk) x[kk] = make_float2(-xn[kk].x, -xn[kk].y);
@@ -343,6 +477,7 @@ __global__ void __launch_bounds__(kBlockRows) spring_kernel(RowDev dv, FitParams
       st->k = kd * (1.0 - prm.cooling_rate);            // :289
       st->iter = iter + 1;
       st->pair_updates += dv.pairs_per_iter;
+      dv.counters[2] = 0u;                              // the repulsion pass of the next iteration starts at item 0
       if (dv.host_flag) dv.host_flag[1] = iter + 1;
       __threadfence_system();
       signal_epoch(dv, epoch);
@@ -353,10 +488,10 @@ __global__ void __launch_bounds__(kBlockRows) spring_kernel(RowDev dv, FitParams
 // ---------------------------------------------------------------------------------------------------
 // edge MAE on the new positions: one thread per own row over the records this rank counts
 // ---------------------------------------------------------------------------------------------------
-template <int H>
+template <int H, int kRing>
 __global__ void __launch_bounds__(kBlockRows) mae_kernel(RowDev dv, int nxt, unsigned wait_for, unsigned epoch) {
-  constexpr int Dp = 2 * H;
-  constexpr int U = 4;
+  constexpr int Dp = Row<H>::kStride;
+  extern __shared__ float4 smem4[];
   __shared__ double red_s[3][kBlockRows / 32];
   if (__ldcg(&dv.state->stop)) return;
   if (!wait_epoch(dv, wait_for)) { if (blockIdx.x == 0 && threadIdx.x == 0) peer_timeout(dv); return; }
@@ -365,49 +500,26 @@ __global__ void __launch_bounds__(kBlockRows) mae_kernel(RowDev dv, int nxt, uns
   const int row = dv.row0 + lrow;
   const float* __restrict__ P = dv.pos[dv.rank] + (size_t)nxt * dv.cap_rows * Dp;
   double sum = 0.0, cnt = 0.0, bad = 0.0;
-  if (dv.dp1[row] > 0.f) {
-    float2 pn[H];
-    {
-      float2 p[H];
-      ld_point<H>(P + (size_t)row * Dp, p);
+  float2 pn[H];
+  {
+    float2 p[H];
+    ld_point<H>(P + (size_t)row * Dp, p);
 #pragma unroll
-      for (int kk = 0; kk < H; ++kk) {
-        if (!isfinite(p[kk].x) || !isfinite(p[kk].y)) bad = 1.0;
-        pn[kk] = make_float2(-p[kk].x, -p[kk].y);
-      }
-    }
-    const int slice = lrow >> 5;
-    const int width = dv.mwidth[slice];
-    const uint2* __restrict__ rec = dv.mrecs + dv.moff[slice] + lane;
-    int t = 0;
-    for (; t + U <= width; t += U) {
-      uint2 r[U];
-      float2 q[U][H];
-#pragma unroll
-      for (int u = 0; u < U; ++u) r[u] = rec[(size_t)(t + u) * 32];
-#pragma unroll
-      for (int u = 0; u < U; ++u) ld_point<H>(P + (size_t)(r[u].x & 0x3fffffffu) * Dp, q[u]);
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        float2 dl[H];
-        const float dist = __fsqrt_rn(dist2<H>(pn, q[u], dl));
-        const unsigned type = r[u].x >> 30;
-        const float target = __uint_as_float(r[u].y);
-        const bool on = type == 0u || (type == 1u ? dist < target : (type == 2u && dist > target));   // :72-75
-        if (on) { sum += fabs((double)target - (double)dist); cnt += 1.0; }
-      }
-    }
-    for (; t < width; ++t) {
-      const uint2 r = rec[(size_t)t * 32];
-      float2 q[H], dl[H];
-      ld_point<H>(P + (size_t)(r.x & 0x3fffffffu) * Dp, q);
-      const float dist = __fsqrt_rn(dist2<H>(pn, q, dl));
-      const unsigned type = r.x >> 30;
-      const float target = __uint_as_float(r.y);
-      const bool on = type == 0u || (type == 1u ? dist < target : (type == 2u && dist > target));
-      if (on) { sum += fabs((double)target - (double)dist); cnt += 1.0; }
+    for (int kk = 0; kk < H; ++kk) {
+      if (!isfinite(p[kk].x) || !isfinite(p[kk].y)) bad = 1.0;
+      pn[kk] = make_float2(-p[kk].x, -p[kk].y);
     }
   }
+  const int slice = lrow >> 5;
+  walk_rows<H, kRing>(P, dv.mrecs + dv.moff[slice] + lane, dv.mwidth[slice], 0,
+               reinterpret_cast<char*>(smem4) + (size_t)warp * Ring<H, kRing>::kWarpBytes, [&](const uint2 r, const float2 (&q)[H]) {
+    float2 dl[H];
+    const float dist = __fsqrt_rn(dist2<H>(pn, q, dl));
+    const unsigned type = r.x >> 30;
+    const float target = __uint_as_float(r.y);
+    const bool on = type == 0u || (type == 1u ? dist < target : (type == 2u && dist > target));   // :72-75
+    if (on) { sum += fabs((double)target - (double)dist); cnt += 1.0; }
+  });
   // fixed tree: lanes, then warps
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -499,51 +611,83 @@ __global__ void fill_kernel(const int32_t* __restrict__ ei, const int32_t* __res
     if (lb >= 0 && lb < rows) tmp[off[lb] + atomicAdd(&cursor[lb], 1u)] = make_uint2(sa | (type << 30), tb);
   }
 }
-// One warp per own row: rank the row's records by (partner, type, target bits) - a fixed order whatever the
+// One warp per own row: sort the row's records by (partner, type, target bits) - a fixed order whatever the
 // scatter left - and write them, transposed, into the slices; the tail of a row up to the slice width is
-// padding (type 3: never a spring, never counted; partner = the row itself).
-constexpr int kSortCap = 1024;
+// padding (type 3: never a spring, never counted; partner = the row itself).  Rows of up to kSortCap records
+// are sorted in shared memory (bitonic network on the 64-bit keys, from which the record is rebuilt), longer
+// ones by counting ranks in global memory.
+constexpr int kSortCap = 2048;
+TL_D unsigned long long rec_key(uint2 r) {
+  return ((unsigned long long)(r.x & 0x3fffffffu) << 34) | ((unsigned long long)(r.x >> 30) << 32) | r.y;
+}
+TL_D uint2 key_rec(unsigned long long k) {
+  return make_uint2((unsigned)(k >> 34) | ((unsigned)((k >> 32) & 3ull) << 30), (unsigned)k);
+}
 __global__ void __launch_bounds__(128) sell_kernel(const uint2* __restrict__ tmp, const unsigned long long* __restrict__ off,
                                                    const unsigned* __restrict__ len, int row0, int rows,
                                                    const unsigned long long* __restrict__ soff, const int* __restrict__ swidth,
                                                    const unsigned long long* __restrict__ moff, const int* __restrict__ mwidth,
                                                    uint2* recs, uint2* mrecs) {
-  __shared__ uint2 stage[4][kSortCap];
+  extern __shared__ unsigned long long sort_s[];   // [4][kSortCap]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int lrow = blockIdx.x * 4 + warp;
   if (lrow >= rows) return;
   const unsigned n = len[lrow];
   const uint2* __restrict__ in = tmp + off[lrow];
-  const bool staged = n <= (unsigned)kSortCap;
-  if (staged) for (unsigned x = lane; x < n; x += 32) stage[warp][x] = in[x];
-  __syncwarp();
-  const uint2* src = staged ? stage[warp] : in;
   const uint32_t self = (uint32_t)(row0 + lrow);
   const int slice = lrow >> 5, rl = lrow & 31;
   uint2* out = recs + soff[slice] + rl;
   uint2* mout = mrecs + moff[slice] + rl;
   unsigned mcount = 0;
-  for (unsigned x0 = 0; x0 < n; x0 += 32) {
-    const unsigned x = x0 + lane;
-    if (x < n) {
-      const uint2 r = src[x];
-      const unsigned long long mkey = ((unsigned long long)(r.x & 0x3fffffffu) << 34) | ((unsigned long long)(r.x >> 30) << 32) | r.y;
-      const bool mcounted = counts_here(self, r.x & 0x3fffffffu);
-      unsigned rank = 0, mrank = 0;
-      for (unsigned y = 0; y < n; ++y) {
-        const uint2 o = src[y];
-        const unsigned long long okey = ((unsigned long long)(o.x & 0x3fffffffu) << 34) | ((unsigned long long)(o.x >> 30) << 32) | o.y;
-        const bool before = okey < mkey || (okey == mkey && y < x);
-        rank += before ? 1u : 0u;
-        mrank += (before && counts_here(self, o.x & 0x3fffffffu)) ? 1u : 0u;
+  if (n <= (unsigned)kSortCap) {
+    unsigned long long* ks = sort_s + (size_t)warp * kSortCap;
+    unsigned m = 32;
+    while (m < n) m <<= 1;
+    for (unsigned x = lane; x < m; x += 32) ks[x] = x < n ? rec_key(in[x]) : ~0ull;
+    __syncwarp();
+    for (unsigned k = 2; k <= m; k <<= 1)
+      for (unsigned j = k >> 1; j > 0; j >>= 1) {
+        for (unsigned i = lane; i < m; i += 32) {
+          const unsigned l = i ^ j;
+          if (l > i) {
+            const unsigned long long a = ks[i], b = ks[l];
+            if ((a > b) == ((i & k) == 0)) { ks[i] = b; ks[l] = a; }
+          }
+        }
+        __syncwarp();
       }
-      out[(size_t)rank * 32] = r;
-      if (mcounted) mout[(size_t)mrank * 32] = r;
+    for (unsigned x0 = 0; x0 < n; x0 += 32) {
+      const unsigned x = x0 + lane;
+      const uint2 r = x < n ? key_rec(ks[x]) : make_uint2(0u, 0u);
+      const bool counted = x < n && counts_here(self, r.x & 0x3fffffffu);
+      const unsigned vote = __ballot_sync(0xffffffffu, counted);
+      if (x < n) out[(size_t)x * 32] = r;
+      if (counted) mout[(size_t)(mcount + __popc(vote & ((1u << lane) - 1u))) * 32] = r;
+      mcount += __popc(vote);
     }
-  }
-  for (unsigned y = lane; y < n; y += 32) mcount += counts_here(self, src[y].x & 0x3fffffffu) ? 1u : 0u;
+  } else {
+    for (unsigned x0 = 0; x0 < n; x0 += 32) {
+      const unsigned x = x0 + lane;
+      if (x < n) {
+        const uint2 r = in[x];
+        const unsigned long long mkey = rec_key(r);
+        const bool mcounted = counts_here(self, r.x & 0x3fffffffu);
+        unsigned rank = 0, mrank = 0;
+        for (unsigned y = 0; y < n; ++y) {
+          const uint2 o = in[y];
+          const unsigned long long okey = rec_key(o);
+          const bool before = okey < mkey || (okey == mkey && y < x);
+          rank += before ? 1u : 0u;
+          mrank += (before && counts_here(self, o.x & 0x3fffffffu)) ? 1u : 0u;
+        }
+        out[(size_t)rank * 32] = r;
+        if (mcounted) mout[(size_t)mrank * 32] = r;
+      }
+    }
+    for (unsigned y = lane; y < n; y += 32) mcount += counts_here(self, in[y].x & 0x3fffffffu) ? 1u : 0u;
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) mcount += __shfl_xor_sync(0xffffffffu, mcount, o);
+    for (int o = 16; o > 0; o >>= 1) mcount += __shfl_xor_sync(0xffffffffu, mcount, o);
+  }
   const uint2 pad = make_uint2(self | (3u << 30), 0u);
   for (unsigned x = n + lane; x < (unsigned)swidth[slice]; x += 32) out[(size_t)x * 32] = pad;
   for (unsigned x = mcount + lane; x < (unsigned)mwidth[slice]; x += 32) mout[(size_t)x * 32] = pad;
@@ -600,7 +744,9 @@ struct RowPlan {
   unsigned epoch = 0;         // signals enqueued so far (the same number on every rank)
   int64_t launches = 0;
   int64_t n_recs = 0, n_mrecs = 0;
-  int rep_ctas = 0;
+  int rep_ctas = 0, rep_threads = 128;
+  bool deep_ring = false;
+  void* rep_fn = nullptr;
   size_t rep_smem = 0;
   double total_ms = 0.0;
   bool attached = false;
@@ -701,13 +847,23 @@ void build_records(RowPlan& rp, const topolow_problem& pb) {
     fill_kernel<<<blocks, threads, 0, s>>>(d_ei, d_ej, d_dist, d_thr, E, d_slot, dv.row0, rows, d_off, d_cur, d_tmp);
     TL_CUDA(cudaGetLastError());
   }
-  sell_kernel<<<(rows + 3) / 4, 128, 0, s>>>(d_tmp, d_off, d_len, dv.row0, rows, rp.soff, rp.swidth, rp.moff, rp.mwidth,
+  static const cudaError_t sort_attr = cudaFuncSetAttribute(sell_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * kSortCap * 8);
+  TL_CUDA(sort_attr);
+  sell_kernel<<<(rows + 3) / 4, 128, 4 * kSortCap * 8, s>>>(d_tmp, d_off, d_len, dv.row0, rows, rp.soff, rp.swidth, rp.moff, rp.mwidth,
                                               rp.recs, rp.mrecs);
   TL_CUDA(cudaGetLastError());
   TL_CUDA(cudaStreamSynchronize(s));   // the host vectors above go out of scope
   pt.mark("rows: fill + sort + transpose");
   dv.recs = rp.recs; dv.mrecs = rp.mrecs; dv.soff = rp.soff; dv.moff = rp.moff; dv.swidth = rp.swidth; dv.mwidth = rp.mwidth;
 }
+
+template <int H, int kRing> constexpr size_t kWalkSmem = (size_t)(kBlockRows / 32) * Ring<H, kRing>::kWarpBytes;
+
+// the spring / MAE launches of one rank (deep ring when the rank owns few rows)
+template <int H>
+void launch_spring(const RowPlan& rp, cudaStream_t s, int cur, unsigned e_spring);
+template <int H>
+void launch_mae(const RowPlan& rp, cudaStream_t s, int nxt, unsigned e_spring, unsigned e_mae);
 
 template <int H>
 void launch_iteration(RowPlan& rp, cudaStream_t s, cudaEvent_t* ev /* 6 events or null */) {
@@ -716,15 +872,15 @@ void launch_iteration(RowPlan& rp, cudaStream_t s, cudaEvent_t* ev /* 6 events o
   const int cur = t & 1, nxt = cur ^ 1;
   const bool check = is_check_iter(t, rp.prm), fin = ((t + 1) % 10 == 0);
   if (ev) TL_CUDA(cudaEventRecord(ev[0], s));
-  repulse_kernel<H, 2><<<rp.rep_ctas, kRepThreads, rp.rep_smem, s>>>(dv, cur, rp.epoch);
+  ((RepulseFn)rp.rep_fn)<<<rp.rep_ctas, rp.rep_threads, rp.rep_smem, s>>>(dv, cur, rp.epoch);
   if (ev) TL_CUDA(cudaEventRecord(ev[1], s));
   const unsigned e_spring = ++rp.epoch;
-  spring_kernel<H><<<dv.rows / kBlockRows, kBlockRows, 0, s>>>(dv, rp.prm, cur, e_spring);
+  launch_spring<H>(rp, s, cur, e_spring);
   if (ev) TL_CUDA(cudaEventRecord(ev[2], s));
   rp.launches += 2;
   if (check || fin) {
     const unsigned e_mae = ++rp.epoch;
-    mae_kernel<H><<<dv.rows / kBlockRows, kBlockRows, 0, s>>>(dv, nxt, e_spring, e_mae);
+    launch_mae<H>(rp, s, nxt, e_spring, e_mae);
     if (ev) TL_CUDA(cudaEventRecord(ev[3], s));
     ctl_kernel<<<1, 256, 0, s>>>(dv, rp.prm, check ? 1 : 0, fin ? 1 : 0, e_mae);
     if (ev) TL_CUDA(cudaEventRecord(ev[4], s));
@@ -736,20 +892,53 @@ void launch_iteration(RowPlan& rp, cudaStream_t s, cudaEvent_t* ev /* 6 events o
   rp.iter_launched = t + 1;
 }
 
-void launch_one(RowPlan& rp, cudaStream_t s, cudaEvent_t* ev = nullptr) {
-  dispatch_h(rp.dv.Dp / 2, [&](auto h) { launch_iteration<decltype(h)::value>(rp, s, ev); });
+template <int H>
+void launch_spring(const RowPlan& rp, cudaStream_t s, int cur, unsigned e_spring) {
+  const int ctas = rp.dv.rows / kBlockRows;
+  if (rp.deep_ring) spring_kernel<H, 8><<<ctas, kBlockRows, kWalkSmem<H, 8>, s>>>(rp.dv, rp.prm, cur, e_spring);
+  else spring_kernel<H, 4><<<ctas, kBlockRows, kWalkSmem<H, 4>, s>>>(rp.dv, rp.prm, cur, e_spring);
+}
+template <int H>
+void launch_mae(const RowPlan& rp, cudaStream_t s, int nxt, unsigned e_spring, unsigned e_mae) {
+  const int ctas = rp.dv.rows / kBlockRows;
+  if (rp.deep_ring) mae_kernel<H, 8><<<ctas, kBlockRows, kWalkSmem<H, 8>, s>>>(rp.dv, nxt, e_spring, e_mae);
+  else mae_kernel<H, 4><<<ctas, kBlockRows, kWalkSmem<H, 4>, s>>>(rp.dv, nxt, e_spring, e_mae);
 }
 
+void launch_one(RowPlan& rp, cudaStream_t s, cudaEvent_t* ev = nullptr) {
+  dispatch_h((rp.dv.D + 1) / 2, [&](auto h) { launch_iteration<decltype(h)::value>(rp, s, ev); });
+}
+
+// Shapes of the repulsion kernel: {rows per thread, partner unroll, register cap, cube on the SFU}.
+// 0 is the production shape; the others stay selectable (TOPOLOW_REP_VARIANT) for measurements.
+template <int H>
+void repulse_variant(int v, RepulseFn* fn, int* threads) {
+  switch (v) {
+    case 1: *fn = repulse_kernel<H, 2, 2, 128, false>; *threads = kRowTile / 2; break;
+    case 2: *fn = repulse_kernel<H, 2, 2, 120, false>; *threads = kRowTile / 2; break;
+    case 3: *fn = repulse_kernel<H, 2, 2, 120, true>; *threads = kRowTile / 2; break;
+    default: *fn = repulse_kernel<H, 2, 2, 128, true>; *threads = kRowTile / 2; break;
+  }
+}
 template <int H>
 void configure_repulse(RowPlan& rp, int sms) {
-  const size_t smem = (size_t)kStages * kStageJ * 2 * H * sizeof(float);
-  TL_CUDA(cudaFuncSetAttribute(repulse_kernel<H, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const size_t smem = (size_t)kStages * kStageJ * Row<H>::kStride * sizeof(float);
+  const char* ev = std::getenv("TOPOLOW_REP_VARIANT");
+  RepulseFn fn; int threads;
+  repulse_variant<H>(ev ? std::atoi(ev) : 0, &fn, &threads);
   int per_sm = 0;
-  TL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, repulse_kernel<H, 2>, kRepThreads, smem));
+  TL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, smem));
   if (per_sm < 1) per_sm = 1;
+  if (const char* ec = std::getenv("TOPOLOW_REP_CTAS")) per_sm = std::max(1, std::atoi(ec));
   const long long items = (long long)(rp.dv.rows / kRowTile) * rp.dv.chunks;
   rp.rep_ctas = (int)std::min<long long>((long long)sms * per_sm, std::max<long long>(items, 1));
   rp.rep_smem = smem;
+  rp.rep_fn = (void*)fn; rp.rep_threads = threads;
+  // spring / MAE walk: the deep ring needs more than the default 48 KB of dynamic shared memory
+  rp.deep_ring = rp.dv.rows / kBlockRows <= 2 * sms;
+  if (const char* er = std::getenv("TOPOLOW_DEEP_RING")) rp.deep_ring = std::atoi(er) != 0;
+  TL_CUDA(cudaFuncSetAttribute(spring_kernel<H, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWalkSmem<H, 8>));
+  TL_CUDA(cudaFuncSetAttribute(mae_kernel<H, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWalkSmem<H, 8>));
 }
 
 }  // namespace
@@ -761,15 +950,15 @@ RowPlan* row_create(const topolow_problem& pb, const topolow_params& pr, int ran
   if (pb.n >= (1ll << 30)) throw BadArg("n out of range");
   TL_CUDA(cudaSetDevice(pr.device));
   keep_pool_memory(pr.device);
-  cudaDeviceProp prop;
-  TL_CUDA(cudaGetDeviceProperties(&prop, pr.device));
+  int sm_count = 0;
+  TL_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, pr.device));   // (cudaGetDeviceProperties costs milliseconds)
   std::unique_ptr<RowPlan> rp(new RowPlan());
   rp->device = pr.device;
   rp->n = pb.n; rp->E = pb.n_edges;
   rp->prm = FitParams{pr.n_iter, pr.k0, pr.cooling_rate, pr.c_repulsion, pr.relative_epsilon, pr.convergence_window,
                       pr.convergence_check_freq};
   RowDev& dv = rp->dv;
-  dv.n = (int)pb.n; dv.D = pb.ndim; dv.Dp = (pb.ndim + 1) / 2 * 2;
+  dv.n = (int)pb.n; dv.D = pb.ndim; dv.Dp = (pb.ndim + 3) / 4 * 4;
   dv.G = n_ranks; dv.rank = rank;
   const int tiles = (int)((pb.n + kRowTile - 1) / kRowTile);
   dv.slots = tiles * kRowTile;
@@ -783,9 +972,11 @@ RowPlan* row_create(const topolow_problem& pb, const topolow_params& pr, int ran
   TL_CUDA(cudaStreamCreate(&rp->stream));
   TL_CUDA(cudaEventCreate(&rp->ev0));
   TL_CUDA(cudaEventCreate(&rp->ev1));
+  PhaseTimer pt(rp->stream);
   // relabelling: a fixed pseudo-random permutation (decorrelates the caller's row order from the row
   // blocks and from the order a row visits its partners in)
   rp->slot_of_point = random_permutation(pb.n, kRowLayoutSeed);
+  pt.mark("rows: relabelling");
 
   // ---- shared block ----
   const size_t pos_bytes = 2 * dv.cap_rows * dv.Dp * sizeof(float);
@@ -795,6 +986,7 @@ RowPlan* row_create(const topolow_problem& pb, const topolow_params& pr, int ran
   TL_CUDA(cudaMalloc((void**)&rp->shared, rp->shared_bytes));
   TL_CUDA(cudaMemset(rp->shared, 0, rp->shared_bytes));
   set_self_pointers(*rp);
+  pt.mark("rows: shared block");
 
   // ---- points ----
   {
@@ -821,6 +1013,7 @@ RowPlan* row_create(const topolow_problem& pb, const topolow_params& pr, int ran
     state_init(st, rp->prm);
     TL_CUDA(cudaMemcpy(rp->state, &st, sizeof st, cudaMemcpyHostToDevice));
   }
+  pt.mark("rows: points");
   dv.best = rp->best; dv.dp1 = rp->dp1; dv.rpart = rp->rpart; dv.state = rp->state; dv.trace = rp->trace;
   dv.counters = rp->counters;
   TL_CUDA(cudaHostAlloc((void**)&rp->h_flag, 2 * sizeof(int), cudaHostAllocMapped));
@@ -836,8 +1029,11 @@ RowPlan* row_create(const topolow_problem& pb, const topolow_params& pr, int ran
     rp->hold_j.assign(pb.holdout_j, pb.holdout_j + pb.n_holdout);
     rp->hold_truth.assign(pb.holdout_truth, pb.holdout_truth + pb.n_holdout);
   }
-  if (dv.rows > 0) dispatch_h(dv.Dp / 2, [&](auto h) { configure_repulse<decltype(h)::value>(*rp, prop.multiProcessorCount); });
+  pt.mark("rows: records + hold-out");
+  if (dv.rows > 0) dispatch_h((dv.D + 1) / 2, [&](auto h) { configure_repulse<decltype(h)::value>(*rp, sm_count); });
+  pt.mark("rows: kernel attributes");
   TL_CUDA(cudaDeviceSynchronize());
+  pt.mark("rows: device synchronize");
   rp->attached = (n_ranks == 1);
   return rp.release();
 }
@@ -944,11 +1140,11 @@ double row_run_local(RowPlan* const* plans, int n, int n_iters) {
       for (int a = 0; a < n; ++a) {
         RowPlan& rp = *plans[a];
         if (rp.dv.rows == 0) { rp.iter_launched = t + 1; continue; }
-        dispatch_h(rp.dv.Dp / 2, [&](auto h) {
+        dispatch_h((rp.dv.D + 1) / 2, [&](auto h) {
           constexpr int H = decltype(h)::value;
-          repulse_kernel<H, 2><<<rp.rep_ctas, kRepThreads, rp.rep_smem, s>>>(rp.dv, cur, rp.epoch);
+          ((RepulseFn)rp.rep_fn)<<<rp.rep_ctas, rp.rep_threads, rp.rep_smem, s>>>(rp.dv, cur, rp.epoch);
           e_spring = ++rp.epoch;
-          spring_kernel<H><<<rp.dv.rows / kBlockRows, kBlockRows, 0, s>>>(rp.dv, rp.prm, cur, e_spring);
+          launch_spring<H>(rp, s, cur, e_spring);
         });
         rp.launches += 2; rp.iter_launched = t + 1;
       }
@@ -956,10 +1152,10 @@ double row_run_local(RowPlan* const* plans, int n, int n_iters) {
         for (int a = 0; a < n; ++a) {
           RowPlan& rp = *plans[a];
           if (rp.dv.rows == 0) continue;
-          dispatch_h(rp.dv.Dp / 2, [&](auto h) {
+          dispatch_h((rp.dv.D + 1) / 2, [&](auto h) {
             constexpr int H = decltype(h)::value;
             e_mae = ++rp.epoch;
-            mae_kernel<H><<<rp.dv.rows / kBlockRows, kBlockRows, 0, s>>>(rp.dv, nxt, e_spring, e_mae);
+            launch_mae<H>(rp, s, nxt, e_spring, e_mae);
           });
           rp.launches += 1;
         }
