@@ -138,14 +138,14 @@ def cpu_sample(prob, n, d, sample_pairs, kind="O2", seed=0):
                                      "set-up time subtracted")
 
 
-def map_config(workload, n, d, missing, E):
+def map_config(workload, n, d, missing, E, early_stop=None):
     """The workload, named the same way by both arms (ours and --impl reference)."""
     pairs = n * (n - 1) // 2
     return {"workload": workload,
             "description": f"synthetic low-rank dissimilarities (tools/synth.py, seed 0): {n} points, {missing:.0%} missing, ndim={d}, "
                            "5 % '>' and 5 % '<' thresholds; k0=5, cooling_rate=0.01, c_repulsion=0.02, check every 3 iterations",
             "n_points": n, "ndim": d, "missing": missing, "n_edges": int(E), "pairs_per_iteration": pairs,
-            "early_stop": "disabled (convergence_counter = n_iter + 1): every step is one full iteration",
+            "early_stop": early_stop or "disabled (convergence_counter = n_iter + 1): every step is one full iteration",
             "l2": "inputs larger than L2: the edge records streamed every iteration (%.0f MB over all ranks) exceed the 126 MB L2; "
                   "the %.1f MB position replica is the resident working set, as in production" % (E * 16 / 1e6, n * d * 4 / 1e6)}
 
@@ -267,7 +267,7 @@ def cv_grid_measure(local, rank, world, samples, fit_iters, steps, warmup, n, mi
         torch.cuda.synchronize()
 
     prob, jobs, meta = cfg5_jobs(n, missing, samples, fit_iters, seed=rank)
-    warm = [dict(j, n_iter=2) for j in jobs[:: max(1, len(jobs) // 18)]]   # loads every ndim variant of the kernel
+    warm = [dict(j, n_iter=2) for j in jobs]   # loads every ndim variant of the kernel, grows every pool the steps use
     for _ in range(max(warmup, 1)):
         _lib.fit_batch(warm, device=local)
     held_cells = {}   # the hold-out cells of a fold (fixed for the whole grid), scored on the device inside the batch
@@ -364,7 +364,12 @@ def main():
     ap.add_argument("--no-exact", action="store_true", help="skip the short exact-mode comparison run at 1 GPU")
     ap.add_argument("--samples", type=int, default=64, help="CV grid: parameter samples per GPU per step (x 4 folds); 64 = 512 / 8")
     ap.add_argument("--fit-iters", type=int, default=250, help="CV grid: mapping_max_iter of every fit (R/core.R:945)")
-    ap.add_argument("--cv-steps", type=int, default=1)
+    ap.add_argument("--cv-steps", type=int, default=2)
+    ap.add_argument("--converge", action="store_true",
+                    help="the north-star target run instead of the throughput bench: the map fitted to convergence "
+                         "(mapping_max_iter 1000, early stopping on) with 10 %% of the exact cells held out; prints held-out MAE, "
+                         "iterations and wall time, and the same fit against the CPU reference loop at --oracle-n points")
+    ap.add_argument("--oracle-n", type=int, default=4000, help="--converge: size of the CPU comparison (0 = skip)")
     args = ap.parse_args()
     n, d, missing = WORKLOADS[args.workload]
     if args.workload == "cfg5":
@@ -372,7 +377,93 @@ def main():
     if args.impl == "reference":
         run_reference(args, n, d, missing)
         return
+    if args.converge:
+        return main_converge(args, n, d, missing)
     main_map(args, n, d, missing)
+
+
+def heldout_split(prob, n, frac, seed):
+    """Hold `frac` of the exact (non-threshold) cells out of the fit: training arrays with recomputed degrees
+    (R/adaptive_sampling.R:2605-2616 masks the cells to NA before euclidean_embedding counts them) + the held cells."""
+    ei, ej, ed, et = prob["edge_i"], prob["edge_j"], prob["edge_dist"], prob["edge_thresh"]
+    held = (np.random.default_rng(seed).random(len(ei)) < frac) & (et == 0)
+    tr = ~held
+    deg = (np.bincount(ei[tr], minlength=n) + np.bincount(ej[tr], minlength=n) + 1).astype(np.int32)
+    train = (prob["initial_positions"], deg, np.ascontiguousarray(ei[tr]), np.ascontiguousarray(ej[tr]),
+             np.ascontiguousarray(ed[tr]), np.ascontiguousarray(et[tr]))
+    return train, (np.ascontiguousarray(ei[held]), np.ascontiguousarray(ej[held]), np.ascontiguousarray(ed[held]))
+
+
+def main_converge(args, n, d, missing):
+    """BASELINE.json north_star target: the cfg4 map converged to the reference's held-out MAE.  The held-out MAE is
+    the pooled |truth - distance| over cells the fit never saw (R/adaptive_sampling.R:2639-2656)."""
+    import torch
+    import torch.distributed as dist
+    from tools import synth
+    from topolow_b200 import _lib
+    from topolow_b200.rowblock import RowBlockMap
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    hp = (HYPER["k0"], HYPER["cooling_rate"], HYPER["c_repulsion"], HYPER["relative_epsilon"], 5, HYPER["convergence_check_freq"])
+    max_iter = 1000
+
+    def fit_map(nn, dd, miss, seed):
+        prob = synth.make_problem(nn, dd, miss, seed=seed)
+        train, held = heldout_split(prob, nn, 0.10, seed + 1)
+        barrier()
+        t0 = time.perf_counter()
+        m = RowBlockMap(*train, max_iter, *hp, rank=rank, world_size=world, device=local, seed=0, holdout=held)
+        ms = m.step(max_iter)
+        res = m.result(trace=True)
+        barrier()
+        wall = time.perf_counter() - t0
+        m.close()
+        out = {"n_points": nn, "ndim": dd, "missing": miss, "train_edges": int(len(train[2])), "heldout_cells": int(len(held[0])),
+               "mapping_max_iter": max_iter, "iterations_run": res["iterations_run"], "best_iteration": res["iterations"],
+               "converged": res["converged"], "edge_mae_train": res["final_mae"],
+               "heldout_mae": res["holdout_sum_abs"] / max(res["holdout_count"], 1), "wall_s": wall, "device_s": ms * 1e-3,
+               "ms_per_iteration": ms / max(res["iterations_run"], 1)}
+        tr = res["trace_mae"]
+        out["mae_trace_every_30"] = [round(float(x), 4) for x in tr[~np.isnan(tr)][::10]]
+        return out, train, held
+
+    big, _, _ = fit_map(n, d, missing, 0)
+    small, cpu = None, None
+    if args.oracle_n > 0:
+        # the same generator, hyper-parameters and hold-out rule at a size the dense CPU loop finishes in minutes
+        on, omiss = args.oracle_n, 0.90
+        if world == 1 or on >= 256 * world:
+            small, train, held = fit_map(on, d, omiss, 7)
+        if rank == 0 and small is not None:
+            from oracle import cpu_oracle
+            cpu_oracle.build(ref=False)
+            t0 = time.perf_counter()
+            c = cpu_oracle.optimize_layout_exact(*train, max_iter, *hp, seed=0)
+            dist_h = np.linalg.norm(c["positions"][held[0]] - c["positions"][held[1]], axis=1)
+            cpu = {"iterations": c["iterations"], "converged": c["converged"], "edge_mae_train": c["final_mae"],
+                   "heldout_mae": float(np.abs(held[2] - dist_h).mean()), "wall_s": time.perf_counter() - t0,
+                   "what": "oracle/topolow_oracle.cpp = the reference's sequential std::shuffle loop (src/optimization.cpp:108-382), 1 core"}
+    if rank == 0:
+        line = {"metric": "held-out MAE of the converged map", "n_gpus": world, "mode": "rowblock", "target": big,
+                "comparison": {"gpu": small, "cpu_reference_loop": cpu,
+                               "heldout_mae_ratio_gpu_over_cpu": (small["heldout_mae"] / cpu["heldout_mae"]) if (small and cpu) else None},
+                "config": map_config(args.workload, n, d, missing, big["train_edges"] + big["heldout_cells"],
+                                     early_stop="on: relative_epsilon 1e-4, convergence_counter 5, checked every 3 iterations "
+                                                "(the package defaults, R/core.R:184-199)")}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def main_map(args, n, d, missing):
