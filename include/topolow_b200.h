@@ -227,8 +227,9 @@ TOPOLOW_API int topolow_shard_run(topolow_shard* shard, int32_t n_iters, void* s
  * (how a single GPU checks the multi-GPU path: every wait finds its flag already raised), shards on
  * distinct devices run concurrently. */
 TOPOLOW_API int topolow_shard_run_local(topolow_shard* const* shards, int32_t n, int32_t n_iters, double* ms_out);
-/* Runs n_iters iterations with CUDA events around every launch; out (up to 6 values) = average milliseconds
- * of {repulsion, springs, edge MAE, controller, snapshot} and the number of MAE launches seen. */
+/* Runs n_iters iterations with every kernel in order on one stream and CUDA events around every launch (the
+ * production path overlaps the spring walk with the repulsion pass); out (up to 7 values) = average milliseconds
+ * of {repulsion, springs, edge MAE, controller, snapshot}, the number of MAE launches seen, {combine}. */
 TOPOLOW_API int topolow_shard_time_kernels(topolow_shard* shard, int32_t n_iters, double* out, int32_t cap);
 TOPOLOW_API int topolow_shard_result(topolow_shard* shard, topolow_result* result);
 /* out (up to 16 values): {slots, ndim, stride, n_ranks, rank, row0, own_rows, partner_chunks, spring_records,

@@ -11,7 +11,7 @@
 //   1. repulsion, Jacobi over all ordered pairs (:269-281 applied from the snapshot):
 //        R_i = - sum_{j != i} (P_j - P_i) * c / (2 (|P_j - P_i| + 0.01)^3) / (deg_i + 1)
 //   2. springs, Gauss-Seidel along the point's own measured pairs (:226-256), partners at the snapshot:
-//        x = P_i + R_i;  for every record (j, target, type) of row i (partners ascending by slot; the rows
+//        x = P_i;  for every record (j, target, type) of row i (partners ascending by slot; the rows
 //        of a slice of 32 slots share a start offset drawn per iteration and walk the slice's width cyclically):
 //          delta = P_j - x, dist = |delta|, ds = dist + 0.01
 //          spring iff type == 0, or '>' and dist < target, or '<' and dist > target   (:237-243)
@@ -19,7 +19,7 @@
 //                      x += (P_j - P_i) * c / (2 (|P_j - P_i| + 0.01)^3) / (deg_i + 1)   (takes back what
 //                           step 1 applied to this pair: a pair in spring state gets no repulsion, :226-256)
 //          else: nothing (a satisfied threshold is repelled like an unmeasured pair, :257-267: step 1 did it)
-//      P'_i = x
+//      P'_i = x + R_i   (steps 1 and 2 both read only the snapshot: the GPU runs them side by side)
 //   3. k *= 1 - cooling_rate (:289); every check_freq iterations and on the last one the edge MAE
 //      (:54-81) on P' and the three-way controller with best-state snapshot (:303-357,368-374).
 // Every unordered pair is visited once from each side per iteration; each side moves only its own
@@ -134,7 +134,7 @@ int relaxed_optimize_layout(int64_t n, int dim, const double* init, const int* d
     parallel_for(n, [&](int64_t i) {
       double x[64];
       const double* pi = &P[i * dim];
-      for (int d = 0; d < dim; ++d) x[d] = pi[d] + R[i * dim + d];
+      for (int d = 0; d < dim; ++d) x[d] = pi[d];
       const int64_t len = off[i + 1] - off[i];
       const int64_t width = slice_width[i / 32];
       const int64_t start = (rotate && width > 0)
@@ -157,7 +157,7 @@ int relaxed_optimize_layout(int64_t n, int dim, const double* init, const int* d
         const double w0 = rdeg / (ds0 * ds0 * ds0);
         for (int d = 0; d < dim; ++d) x[d] += -delta[d] * f + d0[d] * w0;
       }
-      for (int d = 0; d < dim; ++d) Pn[i * dim + d] = x[d];
+      for (int d = 0; d < dim; ++d) Pn[i * dim + d] = x[d] + R[i * dim + d];
     });
     P.swap(Pn);
     k *= (1.0 - cooling_rate);

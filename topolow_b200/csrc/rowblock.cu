@@ -12,13 +12,14 @@
 //   repulse_kernel  R_i = -sum_{j != i} (P_j - P_i) * c / (2 (|P_j - P_i| + 0.01)^3) / (deg_i + 1)   (:269-281
 //                   seen from i's side), a tiled one-sided N-body pass in packed FP32: a work item is
 //                   256 own rows x one chunk of 2048 partners streamed through shared memory by cp.async.
-//   spring_kernel   x = P_i + R_i, then for every measured pair (i, j) of row i in turn (:226-256, i's side):
+//   spring_kernel   x = P_i, then for every measured pair (i, j) of row i in turn (:226-256, i's side):
 //                   spring iff exact, or '>' and dist < target, or '<' and dist > target (:237-243);
 //                   x -= (P_j - x) * 2k (target - dist) / (dist + 0.01) / (4 (deg_i + 1) + k)  (:246-253) and the
 //                   repulsion R_i contains for this pair is taken back (a pair in spring state is not
-//                   repelled); a satisfied threshold keeps its repulsion (:257-267).  P'_i = x goes to every
-//                   replica.  One thread per row, records in degree-padded slices of 32 rows (SELL-32) so
-//                   that a warp's record loads are one contiguous 256-byte line.
+//                   repelled); a satisfied threshold keeps its repulsion (:257-267).  One thread per row, records
+//                   in degree-padded slices of 32 rows (SELL-32) so that a warp's record loads are one contiguous
+//                   256-byte line.  Runs on a second stream NEXT TO the repulsion pass (both read only P).
+//   combine_kernel  P'_i = x + R_i goes to every replica (peer stores), cooling (:289), one flag per peer.
 //   mae_kernel      on check iterations: sum |target - dist| and count over the measured pairs that are exact
 //                   or violated (:54-81) on P', FP64 sums, fixed summation tree; partial sums go to every replica.
 //   ctl_kernel      cooling happened in the spring kernel (:289); three-way controller with best-state snapshot
@@ -50,6 +51,7 @@ constexpr unsigned long long kWaitNs = 20ull * 1000ull * 1000ull * 1000ull;
 
 struct RowDev {
   int n, slots, D, Dp, G, rank, row0, rows, chunks;
+  int no_wait;                       // measurement only (TOPOLOW_IGNORE_PEERS): one rank of a sharded map timed without its peers
   unsigned long long cap_rows;       // rows of one position buffer (slots rounded up to a chunk)
   float* pos[kMaxShards];            // replica q: [2][cap_rows][Dp]
   double* red[kMaxShards];           // replica q: [slots / 128][4]  {sum |err|, count, non-finite, -}
@@ -57,6 +59,7 @@ struct RowDev {
   float* best;                       // [cap_rows][Dp]
   const float* dp1;                  // [slots] degree + 1 (0 = padding row)
   float* rpart;                      // [chunks][rows][Dp] repulsion sums per partner chunk
+  float* xs;                         // [rows][Dp] positions of the own rows after the spring walk (before the repulsion is added)
   const uint2* recs;                 // spring records of the own rows, SELL-32: {partner | type << 30, target}
   const unsigned long long* soff;    // [rows / 32] first record of a slice
   const int* swidth;                 // [rows / 32] records per row of a slice
@@ -157,7 +160,7 @@ TL_D void repel(const float2 (&np)[H], const float2 (&q)[H], float2 (&acc)[H]) {
 // Every thread of the CTA calls this; returns false when the peers did not arrive in time (the fit is
 // then stopped with an error instead of hanging the device).
 TL_D bool wait_epoch(const RowDev& dv, unsigned epoch) {
-  if (dv.G <= 1 || epoch == 0) return true;
+  if (dv.G <= 1 || epoch == 0 || dv.no_wait) return true;
   __shared__ int ok_s;
   if (threadIdx.x < 32) {
     const unsigned* f = dv.flags[dv.rank] + (size_t)(threadIdx.x < (unsigned)dv.G ? threadIdx.x : dv.rank) * kFlagStride;
@@ -290,10 +293,14 @@ struct Ring {
   static constexpr int kRowBytes = NC * 16;
   static constexpr int kSlotBytes = 32 * kRowBytes;
   static constexpr int kWarpBytes = kRing * kSlotBytes + kRecRing * 32 * 8;
-  // piece c of the row staged for `lane`: 64-byte rows are swizzled so that the eight lanes of a 128-bit
-  // shared-memory phase hit eight different bank groups
+  // piece c of the row staged for `lane`.  Rows are stored lane-transposed ((lane & 3) * 8 + lane / 4): the 32
+  // copies of one gather instruction (fixed quad member u, all quads, all pieces) then fill one contiguous
+  // 8-row block - no bank conflict on the write side (the natural order gave 8-way conflicts: the L1 data pipe
+  // was the limiter of the walk) - and 64-byte rows rotate their pieces by lane & 3 so that the eight lanes of a
+  // 128-bit read phase hit eight different bank groups.
   static TL_D int piece(int lane, int c) {
-    return NC == 4 ? lane * 64 + ((c ^ ((lane >> 1) & 3)) << 4) : lane * kRowBytes + (c << 4);
+    const int row = (lane & 3) * 8 + (lane >> 2);
+    return NC == 4 ? row * 64 + ((c ^ (lane & 3)) << 4) : row * kRowBytes + (c << 4);
   }
 };
 
@@ -411,35 +418,24 @@ template <int H, int kRing>
 __global__ void __launch_bounds__(kBlockRows) spring_kernel(RowDev dv, FitParams prm, int cur, unsigned epoch) {
   constexpr int Dp = Row<H>::kStride;
   extern __shared__ float4 smem4[];
+  asm volatile("griddepcontrol.launch_dependents;");   // a repulsion pass launched as programmatic dependent may start now
   if (__ldcg(&dv.state->stop)) return;
+  if (!wait_epoch(dv, epoch)) { if (blockIdx.x == 0 && threadIdx.x == 0) peer_timeout(dv); return; }
   const int tid = threadIdx.x;
-  const int lrow = blockIdx.x * kBlockRows + tid;          // row inside the own block
-  const int row = dv.row0 + lrow;                          // slot
   const float* __restrict__ P = dv.pos[dv.rank] + (size_t)cur * dv.cap_rows * Dp;
-  const double kd = __ldcg(&dv.state->k);
+  const float k = (float)__ldcg(&dv.state->k);
   const int iter = __ldcg(&dv.state->iter);
-  const float k = (float)kd;
+  for (int blk = blockIdx.x; blk < dv.rows / kBlockRows; blk += gridDim.x) {
+  const int lrow = blk * kBlockRows + tid;                 // row inside the own block
+  const int row = dv.row0 + lrow;                          // slot
   const float dp1 = dv.dp1[row];                           // 0 for a padding row: its lane walks along, stores nothing
   const float safe = dp1 > 0.f ? dp1 : 1.f;
   float2 p0n[H], xn[H];   // -P_i and -x (the running position, negated: deltas are q + (-x))
   {
-    float2 p[H], rs[H];
+    float2 p[H];
     ld_point<H>(P + (size_t)row * Dp, p);
 #pragma unroll
-    for (int kk = 0; kk < H; ++kk) rs[kk] = make_float2(0.f, 0.f);
-    for (int c = 0; c < dv.chunks; ++c) {
-      float2 t[H];
-      ld_point<H>(dv.rpart + ((size_t)c * dv.rows + lrow) * Dp, t);
-#pragma unroll
-      for (int kk = 0; kk < H; ++kk) rs[kk] = __fadd2_rn(rs[kk], t[kk]);
-    }
-    const float rdeg0 = (float)(0.5 * prm.c_repulsion) / safe;
-    const float2 rr = make_float2(rdeg0, rdeg0);
-#pragma unroll
-    for (int kk = 0; kk < H; ++kk) {
-      p0n[kk] = make_float2(-p[kk].x, -p[kk].y);
-      xn[kk] = __ffma2_rn(rs[kk], rr, p0n[kk]);          // -(p - rs * rdeg)
-    }
+    for (int kk = 0; kk < H; ++kk) { p0n[kk] = make_float2(-p[kk].x, -p[kk].y); xn[kk] = p0n[kk]; }
   }
   const float rdeg = (float)(0.5 * prm.c_repulsion) / safe;
   const float two_k_rnorm = 2.0f * k / (4.0f * safe + k);
@@ -456,25 +452,61 @@ __global__ void __launch_bounds__(kBlockRows) spring_kernel(RowDev dv, FitParams
     const float e2 = dist2<H>(p0n, q, d0);
     const float dist = sqrt_approx(d2);
     const bool spring = type == 0u || (type == 1u ? dist < target : (type == 2u && dist > target));   // :237-243
-    const float f = spring ? two_k_rnorm * (target - dist) * rcp_approx(dist + 0.01f) : 0.f;
     const float ds0 = sqrt_approx(e2) + 0.01f;
     const float w0 = spring ? rdeg * rcp_approx(ds0 * ds0 * ds0) : 0.f;
-    // x += -delta f + d0 w0  <=>  (-x) += delta f - d0 w0
+    const float f = spring ? two_k_rnorm * (target - dist) * rcp_approx(dist + 0.01f) : 0.f;
+    // x += -delta f + d0 w0  <=>  (-x) += delta f - d0 w0; the take-back term does not wait for f
     const float2 ff = make_float2(f, f), nw = make_float2(-w0, -w0);
 #pragma unroll
-    for (int kk = 0; kk < H; ++kk) xn[kk] = __ffma2_rn(d0[kk], nw, __ffma2_rn(dl[kk], ff, xn[kk]));
+    for (int kk = 0; kk < H; ++kk) xn[kk] = __ffma2_rn(dl[kk], ff, __ffma2_rn(d0[kk], nw, xn[kk]));
   });
   if (dp1 > 0.f) {
     float2 x[H];
 #pragma unroll
     for (int kk = 0; kk < H; ++kk) x[kk] = make_float2(-xn[kk].x, -xn[kk].y);
+    st_point<H>(dv.xs + (size_t)lrow * Dp, x);
+  }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// combine: P'_i = (position after the springs) + (repulsion of the iteration), stored into every replica
+// ---------------------------------------------------------------------------------------------------
+// The spring walk (a long dependent chain per row: latency) and the repulsion pass (FMA throughput) both read
+// only the iteration's snapshot, so they run side by side (the repulsion pass is a programmatic dependent launch of
+// the walk: it starts as soon as the walk's CTAs are resident); this kernel, a normal launch, joins them.  The
+// repulsion sums of a row are added chunk by chunk in a fixed order (the result does not depend on the rank count).
+template <int H>
+__global__ void __launch_bounds__(kBlockRows) combine_kernel(RowDev dv, FitParams prm, int cur, unsigned epoch) {
+  constexpr int Dp = Row<H>::kStride;
+  if (__ldcg(&dv.state->stop)) return;
+  const int tid = threadIdx.x;
+  const int lrow = blockIdx.x * kBlockRows + tid;
+  const int row = dv.row0 + lrow;
+  const float dp1 = dv.dp1[row];
+  if (dp1 > 0.f) {
+    float2 x[H], rs[H];
+    ld_point<H>(dv.xs + (size_t)lrow * Dp, x);
+#pragma unroll
+    for (int kk = 0; kk < H; ++kk) rs[kk] = make_float2(0.f, 0.f);
+    for (int c = 0; c < dv.chunks; ++c) {
+      float2 t[H];
+      ld_point<H>(dv.rpart + ((size_t)c * dv.rows + lrow) * Dp, t);
+#pragma unroll
+      for (int kk = 0; kk < H; ++kk) rs[kk] = __fadd2_rn(rs[kk], t[kk]);
+    }
+    const float nrdeg = -(float)(0.5 * prm.c_repulsion) / dp1;     // R_i = -sum * (c / 2) / (deg_i + 1)
+    const float2 rr = make_float2(nrdeg, nrdeg);
+#pragma unroll
+    for (int kk = 0; kk < H; ++kk) x[kk] = __ffma2_rn(rs[kk], rr, x[kk]);
     const size_t o = ((size_t)(cur ^ 1) * dv.cap_rows + row) * Dp;
     for (int g = 0; g < dv.G; ++g) st_point<H>(dv.pos[g] + o, x);   // own replica and every peer (NVLink stores)
   }
   if (last_cta(&dv.counters[0])) {
     if (tid == 0) {
       FitState* st = dv.state;
-      st->k = kd * (1.0 - prm.cooling_rate);            // :289
+      const int iter = st->iter;
+      st->k = st->k * (1.0 - prm.cooling_rate);         // :289
       st->iter = iter + 1;
       st->pair_updates += dv.pairs_per_iter;
       dv.counters[2] = 0u;                              // the repulsion pass of the next iteration starts at item 0
@@ -731,7 +763,7 @@ struct RowPlan {
   void* peer_base[kMaxShards] = {};   // mapped blocks of the other ranks (IPC) - closed on destroy
   bool peer_ipc[kMaxShards] = {};
   // local
-  float* best = nullptr; float* dp1 = nullptr; float* rpart = nullptr;
+  float* best = nullptr; float* dp1 = nullptr; float* rpart = nullptr; float* xs = nullptr;
   uint2* recs = nullptr; uint2* mrecs = nullptr;
   unsigned long long* soff = nullptr; unsigned long long* moff = nullptr; int* swidth = nullptr; int* mwidth = nullptr;
   FitState* state = nullptr; double* trace = nullptr; unsigned* counters = nullptr;
@@ -746,6 +778,8 @@ struct RowPlan {
   int64_t n_recs = 0, n_mrecs = 0;
   int rep_ctas = 0, rep_threads = 128;
   bool deep_ring = false;
+  bool overlap = true;        // repulsion pass launched as programmatic dependent of the spring walk (TOPOLOW_OVERLAP=0: in order)
+  int sm_count = 148;
   void* rep_fn = nullptr;
   size_t rep_smem = 0;
   double total_ms = 0.0;
@@ -756,7 +790,7 @@ struct RowPlan {
     if (stream) cudaStreamSynchronize(stream);
     for (int q = 0; q < kMaxShards; ++q) if (peer_base[q] && peer_ipc[q]) cudaIpcCloseMemHandle(peer_base[q]);
     if (shared) cudaFree(shared);
-    pool_free(best); pool_free(dp1); pool_free(rpart); pool_free(recs); pool_free(mrecs);
+    pool_free(best); pool_free(dp1); pool_free(rpart); pool_free(xs); pool_free(recs); pool_free(mrecs);
     pool_free(soff); pool_free(moff); pool_free(swidth); pool_free(mwidth);
     pool_free(state); pool_free(trace); pool_free(counters);
     if (h_flag) cudaFreeHost((void*)h_flag);
@@ -865,27 +899,49 @@ void launch_spring(const RowPlan& rp, cudaStream_t s, int cur, unsigned e_spring
 template <int H>
 void launch_mae(const RowPlan& rp, cudaStream_t s, int nxt, unsigned e_spring, unsigned e_mae);
 
+// One iteration of one rank.  overlap: the repulsion pass starts while the spring walk is still running (ranks
+// with few rows: the walk is a latency chain on a few warps); otherwise the kernels run one after another.
 template <int H>
-void launch_iteration(RowPlan& rp, cudaStream_t s, cudaEvent_t* ev /* 6 events or null */) {
+void launch_iteration(RowPlan& rp, cudaStream_t s, cudaEvent_t* ev /* 7 events or null */, bool overlap) {
   RowDev& dv = rp.dv;
   const int t = rp.iter_launched;
   const int cur = t & 1, nxt = cur ^ 1;
   const bool check = is_check_iter(t, rp.prm), fin = ((t + 1) % 10 == 0);
-  if (ev) TL_CUDA(cudaEventRecord(ev[0], s));
-  ((RepulseFn)rp.rep_fn)<<<rp.rep_ctas, rp.rep_threads, rp.rep_smem, s>>>(dv, cur, rp.epoch);
-  if (ev) TL_CUDA(cudaEventRecord(ev[1], s));
-  const unsigned e_spring = ++rp.epoch;
-  launch_spring<H>(rp, s, cur, e_spring);
-  if (ev) TL_CUDA(cudaEventRecord(ev[2], s));
-  rp.launches += 2;
+  const unsigned e_prev = rp.epoch;          // the epoch every rank reached when iteration t - 1 (and its check) ended
+  const int row_ctas = dv.rows / kBlockRows;
+  if (overlap) {
+    // The walk first: its CTAs announce themselves at once (griddepcontrol.launch_dependents), which lets the
+    // repulsion grid - launched as a programmatic dependent, it has no data dependence on the walk - fill the
+    // rest of the chip while the walk's few warps are already resident.  (Launched from two streams the
+    // repulsion grid usually won the race for the SMs and the walk ran after it.)
+    launch_spring<H>(rp, s, cur, e_prev);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)rp.rep_ctas); cfg.blockDim = dim3((unsigned)rp.rep_threads);
+    cfg.dynamicSmemBytes = rp.rep_smem; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    TL_CUDA(cudaLaunchKernelEx(&cfg, (RepulseFn)rp.rep_fn, dv, cur, e_prev));
+  } else {
+    if (ev) TL_CUDA(cudaEventRecord(ev[0], s));
+    ((RepulseFn)rp.rep_fn)<<<rp.rep_ctas, rp.rep_threads, rp.rep_smem, s>>>(dv, cur, e_prev);
+    if (ev) TL_CUDA(cudaEventRecord(ev[1], s));
+    launch_spring<H>(rp, s, cur, e_prev);
+    if (ev) TL_CUDA(cudaEventRecord(ev[2], s));
+  }
+  const unsigned e_iter = ++rp.epoch;
+  combine_kernel<H><<<row_ctas, kBlockRows, 0, s>>>(dv, rp.prm, cur, e_iter);
+  if (ev) TL_CUDA(cudaEventRecord(ev[3], s));
+  rp.launches += 3;
   if (check || fin) {
     const unsigned e_mae = ++rp.epoch;
-    launch_mae<H>(rp, s, nxt, e_spring, e_mae);
-    if (ev) TL_CUDA(cudaEventRecord(ev[3], s));
-    ctl_kernel<<<1, 256, 0, s>>>(dv, rp.prm, check ? 1 : 0, fin ? 1 : 0, e_mae);
+    launch_mae<H>(rp, s, nxt, e_iter, e_mae);
     if (ev) TL_CUDA(cudaEventRecord(ev[4], s));
-    snap_kernel<<<148, 256, 0, s>>>(dv, nxt);
+    ctl_kernel<<<1, 256, 0, s>>>(dv, rp.prm, check ? 1 : 0, fin ? 1 : 0, e_mae);
     if (ev) TL_CUDA(cudaEventRecord(ev[5], s));
+    snap_kernel<<<148, 256, 0, s>>>(dv, nxt);
+    if (ev) TL_CUDA(cudaEventRecord(ev[6], s));
     rp.launches += 3;
   }
   TL_CUDA(cudaGetLastError());
@@ -906,7 +962,7 @@ void launch_mae(const RowPlan& rp, cudaStream_t s, int nxt, unsigned e_spring, u
 }
 
 void launch_one(RowPlan& rp, cudaStream_t s, cudaEvent_t* ev = nullptr) {
-  dispatch_h((rp.dv.D + 1) / 2, [&](auto h) { launch_iteration<decltype(h)::value>(rp, s, ev); });
+  dispatch_h((rp.dv.D + 1) / 2, [&](auto h) { launch_iteration<decltype(h)::value>(rp, s, ev, rp.overlap && !ev); });
 }
 
 // Shapes of the repulsion kernel: {rows per thread, partner unroll, register cap, cube on the SFU}.
@@ -934,6 +990,9 @@ void configure_repulse(RowPlan& rp, int sms) {
   rp.rep_ctas = (int)std::min<long long>((long long)sms * per_sm, std::max<long long>(items, 1));
   rp.rep_smem = smem;
   rp.rep_fn = (void*)fn; rp.rep_threads = threads;
+  rp.sm_count = sms;
+  rp.overlap = true;   // measured on B200 at cfg4: one rank of 8 2.61 -> 2.38 ms, of 2 9.11 -> 8.99, one GPU 18.29 -> 18.11; cfg3 0.47 -> 0.29
+  if (const char* eo = std::getenv("TOPOLOW_OVERLAP")) rp.overlap = std::atoi(eo) != 0;
   // spring / MAE walk: the deep ring needs more than the default 48 KB of dynamic shared memory
   rp.deep_ring = rp.dv.rows / kBlockRows <= 2 * sms;
   if (const char* er = std::getenv("TOPOLOW_DEEP_RING")) rp.deep_ring = std::atoi(er) != 0;
@@ -969,6 +1028,7 @@ RowPlan* row_create(const topolow_problem& pb, const topolow_params& pr, int ran
   dv.cap_rows = align_up((size_t)dv.slots, kChunk);
   dv.pairs_per_iter = (unsigned long long)pb.n * (unsigned long long)(pb.n - 1) / 2ull;
   dv.seed = pr.seed;
+  dv.no_wait = std::getenv("TOPOLOW_IGNORE_PEERS") ? 1 : 0;
   TL_CUDA(cudaStreamCreate(&rp->stream));
   TL_CUDA(cudaEventCreate(&rp->ev0));
   TL_CUDA(cudaEventCreate(&rp->ev1));
@@ -999,6 +1059,7 @@ RowPlan* row_create(const topolow_problem& pb, const topolow_params& pr, int ran
     pool_alloc(rp->best, hp.size() * sizeof(float));
     pool_alloc(rp->dp1, hd.size() * sizeof(float));
     pool_alloc(rp->rpart, (size_t)dv.chunks * std::max(dv.rows, 1) * dv.Dp * sizeof(float));
+    pool_alloc(rp->xs, (size_t)std::max(dv.rows, 1) * dv.Dp * sizeof(float));
     pool_alloc(rp->state, sizeof(FitState));
     pool_alloc(rp->trace, sizeof(double) * std::max(pr.n_iter, 1));
     pool_alloc(rp->counters, 4 * sizeof(unsigned));
@@ -1014,7 +1075,7 @@ RowPlan* row_create(const topolow_problem& pb, const topolow_params& pr, int ran
     TL_CUDA(cudaMemcpy(rp->state, &st, sizeof st, cudaMemcpyHostToDevice));
   }
   pt.mark("rows: points");
-  dv.best = rp->best; dv.dp1 = rp->dp1; dv.rpart = rp->rpart; dv.state = rp->state; dv.trace = rp->trace;
+  dv.best = rp->best; dv.dp1 = rp->dp1; dv.rpart = rp->rpart; dv.xs = rp->xs; dv.state = rp->state; dv.trace = rp->trace;
   dv.counters = rp->counters;
   TL_CUDA(cudaHostAlloc((void**)&rp->h_flag, 2 * sizeof(int), cudaHostAllocMapped));
   rp->h_flag[0] = 0; rp->h_flag[1] = 0;
@@ -1101,7 +1162,7 @@ double row_run(RowPlan& rp, int n_iters, cudaStream_t stream_in, topolow_interru
   TL_CUDA(cudaEventRecord(rp.ev0, s));
   int left = std::min(n_iters, std::max(0, rp.prm.n_iter - rp.iter_launched));
   int since_sync = 0;
-  while (left > 0 && rp.dv.rows > 0) {
+  while (left > 0) {
     if (rp.h_flag[0]) break;
     if (poll && since_sync == 0 && poll(user)) { if (interrupted) *interrupted = true; break; }
     launch_one(rp, s);
@@ -1130,39 +1191,36 @@ double row_run_local(RowPlan* const* plans, int n, int n_iters) {
   if (same_device) {
     // lock step on ONE stream: rank after rank, phase after phase, so that every wait finds its epoch reached
     cudaStream_t s = p0.stream;
-    for (int a = 1; a < n; ++a) TL_CUDA(cudaStreamSynchronize(plans[a]->stream));
+    for (int a = 0; a < n; ++a) TL_CUDA(cudaStreamSynchronize(plans[a]->stream));
     while (left > 0) {
       if (p0.h_flag[0]) break;
       const int t = p0.iter_launched;
       const int cur = t & 1, nxt = cur ^ 1;
       const bool check = is_check_iter(t, p0.prm), fin = ((t + 1) % 10 == 0);
-      unsigned e_spring = 0, e_mae = 0;
       for (int a = 0; a < n; ++a) {
         RowPlan& rp = *plans[a];
-        if (rp.dv.rows == 0) { rp.iter_launched = t + 1; continue; }
         dispatch_h((rp.dv.D + 1) / 2, [&](auto h) {
           constexpr int H = decltype(h)::value;
-          ((RepulseFn)rp.rep_fn)<<<rp.rep_ctas, rp.rep_threads, rp.rep_smem, s>>>(rp.dv, cur, rp.epoch);
-          e_spring = ++rp.epoch;
-          launch_spring<H>(rp, s, cur, e_spring);
+          const unsigned e_prev = rp.epoch;
+          ((RepulseFn)rp.rep_fn)<<<rp.rep_ctas, rp.rep_threads, rp.rep_smem, s>>>(rp.dv, cur, e_prev);
+          launch_spring<H>(rp, s, cur, e_prev);
+          combine_kernel<H><<<rp.dv.rows / kBlockRows, kBlockRows, 0, s>>>(rp.dv, rp.prm, cur, ++rp.epoch);
         });
-        rp.launches += 2; rp.iter_launched = t + 1;
+        rp.launches += 3; rp.iter_launched = t + 1;
       }
       if (check || fin) {
         for (int a = 0; a < n; ++a) {
           RowPlan& rp = *plans[a];
-          if (rp.dv.rows == 0) continue;
           dispatch_h((rp.dv.D + 1) / 2, [&](auto h) {
             constexpr int H = decltype(h)::value;
-            e_mae = ++rp.epoch;
-            launch_mae<H>(rp, s, nxt, e_spring, e_mae);
+            const unsigned e_iter = rp.epoch;
+            launch_mae<H>(rp, s, nxt, e_iter, ++rp.epoch);
           });
           rp.launches += 1;
         }
         for (int a = 0; a < n; ++a) {
           RowPlan& rp = *plans[a];
-          if (rp.dv.rows == 0) continue;
-          ctl_kernel<<<1, 256, 0, s>>>(rp.dv, rp.prm, check ? 1 : 0, fin ? 1 : 0, e_mae);
+          ctl_kernel<<<1, 256, 0, s>>>(rp.dv, rp.prm, check ? 1 : 0, fin ? 1 : 0, rp.epoch);
           snap_kernel<<<148, 256, 0, s>>>(rp.dv, nxt);
           rp.launches += 2;
         }
@@ -1177,7 +1235,7 @@ double row_run_local(RowPlan* const* plans, int n, int n_iters) {
       if (p0.h_flag[0]) break;
       for (int a = 0; a < n; ++a) {
         TL_CUDA(cudaSetDevice(plans[a]->device));
-        if (plans[a]->dv.rows > 0) launch_one(*plans[a], plans[a]->stream);
+        launch_one(*plans[a], plans[a]->stream);
       }
       --left;
     }
@@ -1195,31 +1253,33 @@ double row_run_local(RowPlan* const* plans, int n, int n_iters) {
 void row_time_kernels(RowPlan& rp, int n_iters, double* out, int cap) {
   check_runnable(rp);
   TL_CUDA(cudaSetDevice(rp.device));
-  double acc[6] = {0, 0, 0, 0, 0, 0};
+  double acc[7] = {0, 0, 0, 0, 0, 0, 0};
   int done = 0;
-  std::vector<EventGuard> evs(6);
-  cudaEvent_t ev[6];
-  for (int i = 0; i < 6; ++i) ev[i] = evs[i];
+  std::vector<EventGuard> evs(7);
+  cudaEvent_t ev[7];
+  for (int i = 0; i < 7; ++i) ev[i] = evs[i];
   int left = std::min(n_iters, std::max(0, rp.prm.n_iter - rp.iter_launched));
-  while (left-- > 0 && !rp.h_flag[0] && rp.dv.rows > 0) {
+  while (left-- > 0 && !rp.h_flag[0]) {
     const int t = rp.iter_launched;
     const bool extra = is_check_iter(t, rp.prm) || ((t + 1) % 10 == 0);
-    launch_one(rp, rp.stream, ev);
+    launch_one(rp, rp.stream, ev);     // in order on one stream: every kernel is timed alone
     TL_CUDA(cudaStreamSynchronize(rp.stream));
     float ms = 0.f;
     TL_CUDA(cudaEventElapsedTime(&ms, ev[0], ev[1])); acc[0] += ms;
     TL_CUDA(cudaEventElapsedTime(&ms, ev[1], ev[2])); acc[1] += ms;
+    TL_CUDA(cudaEventElapsedTime(&ms, ev[2], ev[3])); acc[6] += ms;
     if (extra) {
-      TL_CUDA(cudaEventElapsedTime(&ms, ev[2], ev[3])); acc[2] += ms;
-      TL_CUDA(cudaEventElapsedTime(&ms, ev[3], ev[4])); acc[3] += ms;
-      TL_CUDA(cudaEventElapsedTime(&ms, ev[4], ev[5])); acc[4] += ms;
+      TL_CUDA(cudaEventElapsedTime(&ms, ev[3], ev[4])); acc[2] += ms;
+      TL_CUDA(cudaEventElapsedTime(&ms, ev[4], ev[5])); acc[3] += ms;
+      TL_CUDA(cudaEventElapsedTime(&ms, ev[5], ev[6])); acc[4] += ms;
       acc[5] += 1.0;
     }
     ++done;
   }
-  const double v[6] = {done ? acc[0] / done : 0.0, done ? acc[1] / done : 0.0, acc[5] > 0 ? acc[2] / acc[5] : 0.0,
-                       acc[5] > 0 ? acc[3] / acc[5] : 0.0, acc[5] > 0 ? acc[4] / acc[5] : 0.0, acc[5]};
-  for (int i = 0; i < cap && i < 6; ++i) out[i] = v[i];
+  const double v[7] = {done ? acc[0] / done : 0.0, done ? acc[1] / done : 0.0, acc[5] > 0 ? acc[2] / acc[5] : 0.0,
+                       acc[5] > 0 ? acc[3] / acc[5] : 0.0, acc[5] > 0 ? acc[4] / acc[5] : 0.0, acc[5],
+                       done ? acc[6] / done : 0.0};
+  for (int i = 0; i < cap && i < 7; ++i) out[i] = v[i];
 }
 
 void row_result(RowPlan& rp, topolow_result& res, bool interrupted) {

@@ -68,12 +68,13 @@ class Shard:
         return ms.value
 
     def time_kernels(self, n_iters):
-        v = (C.c_double * 6)()
-        rc = self._L.topolow_shard_time_kernels(self._h, int(n_iters), v, 6)
+        v = (C.c_double * 7)()
+        rc = self._L.topolow_shard_time_kernels(self._h, int(n_iters), v, 7)
         if rc != OK:
             raise TopolowError(rc, f"topolow_shard_time_kernels failed with status {rc}")
         out = dict(zip(KERNELS, [float(x) for x in v[:5]]))
         out["mae_launches"] = int(v[5])
+        out["combine"] = float(v[6])
         return out
 
     def result(self, trace=False):
