@@ -244,9 +244,10 @@ def mask_fold(dissimilarity_matrix, holdout_indices):
 
 def likelihood_function(dissimilarity_matrix, mapping_max_iter, relative_epsilon, N, k0, cooling_rate,
                         c_repulsion, folds=20, preserve_order=True, *, fold_indices=None, rng=None,
-                        init_list=None, seed=0):
+                        init_list=None, seed=0, pair_orders=None):
     """R/adaptive_sampling.R:2552-2726, sequential branch.  `fold_indices` / `init_list` inject
-    the two R-RNG dependent inputs (fold hold-out index lists; per-fold initial positions)."""
+    the two R-RNG dependent inputs (fold hold-out index lists; per-fold initial positions); `pair_orders[f]`
+    (optional, [n_iter][pairs][2]) replaces the shuffle of fold f's fit by an explicit pair order."""
     rng = rng or np.random.default_rng(seed)
     if fold_indices is None:
         fold_indices = make_folds(dissimilarity_matrix, folds, rng)
@@ -256,7 +257,8 @@ def likelihood_function(dissimilarity_matrix, mapping_max_iter, relative_epsilon
         try:
             res = euclidean_embedding(train, N, mapping_max_iter, k0, cooling_rate, c_repulsion,
                                       relative_epsilon, 5, None if init_list is None else init_list[f],
-                                      preserve_order=preserve_order, seed=seed + f, rng=rng)
+                                      preserve_order=preserve_order, seed=seed + f, rng=rng,
+                                      pair_order=None if pair_orders is None else pair_orders[f])
         except Exception:
             rows.append(dict(Holdout_MAE=math.nan, n_samples=0, sum_abs_errors=0.0, iter=math.nan, converged=0))
             continue

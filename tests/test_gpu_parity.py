@@ -317,6 +317,22 @@ def test_holdout_errors_and_likelihood_function():
     assert [f["n_samples"] for f in got["folds"]] == [f["n_samples"] for f in want["folds"]]
     assert got["Holdout_MAE"] == pytest.approx(want["Holdout_MAE"], rel=0.25)   # different pair orders
     assert got["NLL"] == pytest.approx(sum(f["n_samples"] for f in got["folds"]) * (1 + np.log(2 * got["Holdout_MAE"])))
+    # the same comparison with the pair order taken out of it: the CPU side replays, fold by fold, the sequential
+    # order the GPU schedule is equivalent to (FP64 both sides) - every pooled number then agrees to rounding
+    value, code, is_na = core.parse_dissimilarity(m)
+    orders = []
+    for f, hold in enumerate(folds):
+        prob = cv._fold_job(value, code, is_na, np.asarray(hold), True)[0]
+        plan = _lib.Plan(inits[0][f], prob["degrees"], prob["edge_i"], prob["edge_j"], prob["edge_dist"], prob["edge_thresh"],
+                         60, 2.0, 0.02, 0.01, 1e-4, 5, 3, precision=_lib.PREC_F64_EXACT, seed=f)
+        orders.append(np.stack([plan.enumerate(it) for it in range(60)]))
+        plan.close()
+    want2 = r_glue.likelihood_function(m, 60, 1e-4, 2, 2.0, 0.02, 0.01, folds=4, fold_indices=folds, init_list=inits[0],
+                                       pair_orders=orders)
+    assert got["Holdout_MAE"] == pytest.approx(want2["Holdout_MAE"], rel=1e-9)
+    assert got["NLL"] == pytest.approx(want2["NLL"], rel=1e-9)
+    assert [f["iter"] for f in got["folds"]] == [f["iter"] for f in want2["folds"]]
+    assert [f["sum_abs_errors"] for f in got["folds"]] == pytest.approx([f["sum_abs_errors"] for f in want2["folds"]], rel=1e-9)
 
 
 def test_batch_equals_individual_fits():
