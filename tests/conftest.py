@@ -80,3 +80,30 @@ def random_r_matrix(n, density, seed, thresholds=True):
                 m[i, j] = s
                 m[j, i] = s
     return m
+
+
+# ---- the .Call shim (integration/r_shim.c) built against the stand-in R headers of integration/r_stub/ ----
+def build_r_shim_harness(out_path, real_library):
+    """Compile shim + stand-in runtime + harness; linked with the recording fake (CPU) or with libtopolow_b200.so."""
+    import subprocess
+    stub = os.path.join(ROOT, "integration", "r_stub")
+    cmd = ["gcc", "-std=gnu11", "-O1", "-Wall", "-Werror=implicit-function-declaration", "-Werror=incompatible-pointer-types",
+           "-I", stub, "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "integration", "r_shim.c"),
+           os.path.join(stub, "r_stub.c"), os.path.join(stub, "harness.c"), "-o", out_path]
+    if real_library:
+        libdir = os.path.join(ROOT, "topolow_b200", "lib")
+        cmd += ["-L", libdir, "-ltopolow_b200", "-Wl,-rpath," + libdir]
+    else:
+        cmd.insert(-2, os.path.join(stub, "fake_topolow.c"))
+    subprocess.run(cmd, check=True, capture_output=True, text=True)
+    return out_path
+
+
+def write_problem_bin(path, init, deg, ei, ej, ed, et, holdout=None):
+    hi, hj, ht = holdout if holdout is not None else (np.zeros(0, np.int32),) * 2 + (np.zeros(0),)
+    with open(path, "wb") as f:
+        np.array([init.shape[0], init.shape[1], len(ei), len(hi)], dtype=np.int64).tofile(f)
+        np.asfortranarray(init, dtype=np.float64).T.tofile(f)            # column-major, like an R matrix
+        for a, t in ((deg, np.int32), (ei, np.int32), (ej, np.int32), (ed, np.float64), (et, np.int32), (hi, np.int32),
+                     (hj, np.int32), (ht, np.float64)):
+            np.ascontiguousarray(a, dtype=t).tofile(f)

@@ -1,6 +1,7 @@
 """CPU tests of the host side: C-ABI surface, schedule coverage, the Python mirror of the R glue
 (against oracle/r_glue.py), fold construction, sharding over ranks (gloo, world size 2)."""
 import ctypes as C
+import json
 import os
 import re
 import subprocess
@@ -261,3 +262,83 @@ def test_likelihood_batch_holdout_cells_follow_the_reordering(monkeypatch):
         got = cv.likelihood_batch(m, [dict(N=2, k0=1.0, cooling_rate=0.01, c_repulsion=0.01)], 5, 1e-4, folds=3,
                                   preserve_order=preserve, fold_indices=folds, init_list=[inits])
         assert [f["Holdout_MAE"] for f in got[0]["folds"]] == pytest.approx(want, rel=1e-12)
+
+
+# ------------------------------------------------------------------ the .Call shim ---------------
+@pytest.fixture(scope="module")
+def shim_cpu(tmp_path_factory):
+    from conftest import build_r_shim_harness
+    return build_r_shim_harness(str(tmp_path_factory.mktemp("shim") / "harness_cpu"), real_library=False)
+
+
+def _harness(exe, *args):
+    out = subprocess.run([exe] + [str(a) for a in args], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    return json.loads(out.stdout.strip().splitlines()[-1])
+
+
+def _clean(r):
+    assert r["protect_depth"] == 0 and r["type_errors"] == 0 and r["rng_violations"] == 0 and r["rng_open"] == 0
+    assert r["raw_interrupt_jumps"] == 0
+
+
+def test_r_shim_registers_both_entries(shim_cpu):
+    r = _harness(shim_cpu, "register")
+    assert r["routines"] == {"_topolow_optimize_layout_b200": 16, "_topolow_fit_batch_b200": 3}    # src/RcppExports.cpp:41-49
+    assert r["dynamic_symbols"] == 0
+
+
+def test_r_shim_single_call_marshals_every_field(shim_cpu, tmp_path):
+    from conftest import write_problem_bin
+    init, deg, ei, ej, ed, et = small_problem(40, 3, 0.3, 1)
+    write_problem_bin(tmp_path / "p.bin", init, deg, ei, ej, ed, et)
+    r = _harness(shim_cpu, "single", tmp_path / "p.bin", tmp_path / "o.bin", 100, 5.0, 0.01, 0.02, 1e-4, 5, 3, "rowblock")
+    _clean(r)
+    assert r["names"] == ["positions", "converged", "iterations", "final_mae", "final_k"]      # src/optimization.cpp:375-381
+    assert r["types"] == [14, 10, 13, 14, 14] and r["dim"] == [40, 3]                          # REALSXP, LGLSXP, INTSXP, REALSXP x 2
+    out = np.fromfile(tmp_path / "o.bin")
+    # the recording fake answers with functions of what it was handed (integration/r_stub/fake_topolow.c)
+    assert out[0] == 1 and out[1] == 100 - 3
+    assert out[2] == pytest.approx(float(np.sum(ed * (1 + et) + ei - ej)), rel=1e-12)
+    assert out[3] == pytest.approx(5.0 * 0.99 + 0.02 + 1e-4, rel=1e-15)
+    pos = out[4:].reshape(3, 40).T
+    np.testing.assert_allclose(pos, 2 * init + deg[:, None], rtol=0, atol=0)
+    # a second scenario in the default mode: seed drawn inside GetRNGstate / PutRNGstate (two draws of the fixed stream)
+    r2 = _harness(shim_cpu, "single", tmp_path / "p.bin", tmp_path / "o2.bin", 50, 1.0, 0.5, 0.0, 0.0, 4, 1)
+    _clean(r2)
+    assert np.fromfile(tmp_path / "o2.bin")[0] == 0          # convergence_window reached the library as 4
+
+
+def test_r_shim_errors_and_interrupts_leave_through_the_shim(shim_cpu, tmp_path):
+    from conftest import write_problem_bin
+    r = _harness(shim_cpu, "too_few")
+    assert r["left_by"] == "Rf_error" and r["message"] == "Need at least 2 points for embedding"   # src/optimization.cpp:131
+    _clean(r)
+    write_problem_bin(tmp_path / "p.bin", *small_problem(30, 2, 0.3, 2))
+    r = _harness(shim_cpu, "interrupt", tmp_path / "p.bin", 3)
+    # the interrupt is caught inside R_ToplevelExec, reported to the library as a return value, and only after the
+    # library has returned TOPOLOW_ERR_INTERRUPTED does the shim raise the R condition - never a jump through it
+    assert r["left_by"] == "Rf_onintr" and r["onintr_calls"] == 1 and r["interrupt_checks"] == 3
+    _clean(r)
+    r = _harness(shim_cpu, "interrupt", tmp_path / "p.bin", 0)      # no interrupt: polled between chunks, returns normally
+    assert r["left_by"] == "return" and r["interrupt_checks"] == 4
+    _clean(r)
+
+
+def test_r_shim_batch_shares_fold_arrays_and_reports_per_job_status(shim_cpu, tmp_path):
+    from conftest import write_problem_bin
+    init, deg, ei, ej, ed, et = small_problem(50, 4, 0.2, 3)
+    hold = (np.array([0, 3, 7], np.int32), np.array([5, 9, 11], np.int32), np.array([1.5, 2.5, 0.25]))
+    write_problem_bin(tmp_path / "p.bin", init, deg, ei, ej, ed, et, hold)
+    r = _harness(shim_cpu, "batch", tmp_path / "p.bin", tmp_path / "o.bin", 5, 250, 4.0, 0.01, 0.02, 1e-4, 5, 3, 1)
+    _clean(r)
+    assert r["n"] == 5 and r["names"][:8] == ["converged", "iterations", "final_mae", "final_k", "holdout_sum_abs",
+                                               "holdout_count", "status", "message"]
+    assert "shared=4" in r["jobs"][0]["message"]             # the four other jobs carried the same edge vectors
+    assert [j["status"] for j in r["jobs"]] == [0] * 5 and all(j["pos_len"] == 200 for j in r["jobs"])
+    out = np.fromfile(tmp_path / "o.bin").reshape(5, 7 + 200)
+    for j in range(5):
+        assert out[j, 1] == 247 and out[j, 3] == pytest.approx(4.0 * (1 + 0.25 * j) * 0.99 + 0.02 + 1e-4, rel=1e-15)
+        assert out[j, 4] == pytest.approx(hold[2].sum() + hold[0].sum() + 2 * hold[1].sum()) and out[j, 5] == 3
+    r = _harness(shim_cpu, "batch", tmp_path / "p.bin", tmp_path / "o.bin", 2, 250, 4.0, 0.01, 0.02, 1e-4, 5, 3, 0)
+    assert all(j["pos_len"] == 0 for j in r["jobs"])         # positions stay on the device side unless asked for

@@ -60,6 +60,9 @@ struct RowDev {
   const float* dp1;                  // [slots] degree + 1 (0 = padding row)
   float* rpart;                      // [chunks][rows][Dp] repulsion sums per partner chunk
   float* xs;                         // [rows][Dp] positions of the own rows after the spring walk (before the repulsion is added)
+  float* img;                        // [cap_rows][Img<H>::kStride] partner image of the iteration: -2 (P_j - centre) | |P_j - centre|^2 / 2 twice
+  float* hmax;                       // [2] max over all points of |P_j - centre|^2 / 2, per position buffer
+  float centre[16];                  // centroid of the initial positions (fixed for the fit, the same on every rank)
   const uint2* recs;                 // spring records of the own rows, SELL-32: {partner | type << 30, target}
   const unsigned long long* soff;    // [rows / 32] first record of a slice
   const int* swidth;                 // [rows / 32] records per row of a slice
@@ -267,6 +270,224 @@ __global__ void __maxnreg__(MAXR) repulse_kernel(RowDev dv, int cur, unsigned ep
 #pragma unroll
     for (int r = 0; r < R; ++r)
       st_point<H>(dv.rpart + ((size_t)c * dv.rows + lrow0 + tid + r * T) * Dp, acc[r]);
+    __syncthreads();   // the stages are refilled by the next item's prologue; item_s is rewritten
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// repulsion, inner-product form (ndim >= 5): |q - p|^2 = |p|^2 + |q|^2 - 2 p.q
+// ---------------------------------------------------------------------------------------------------
+// The difference form above spends 3 packed FMA-pipe instructions per coordinate pair and interaction
+// (q - p, its square, the accumulation of w (q - p)); the pass is bound by that pipe (ncu: 82 % busy).  Written
+// with inner products an interaction needs 2: p.q~ (q~ = -2 (q - centre), its half norm rides in the accumulator's
+// start value) and A += w q~, plus W += w; the sum over the partners comes out as -A / 2 - p W at the end of the
+// item.  image_kernel prepares q~ and the half norms once per iteration (6 MB read, 8 MB written).
+// Cancellation: the rounding error of the inner-product distance is about (H + 1) 2^-24 (|p|^2 + |q|^2), harmless for
+// a pair that is far apart and fatal for one that is not.  Pairs with d^2 < thr = (H + 1) 2^-13 (|p|^2 / 2 + max_j |q_j|^2 / 2)
+// ("near": relative error of d^2 could exceed 1e-3; a handful per point in 5 dimensions, none in 16, always the
+// point itself) get weight 0 in the main loop, raise a flag, and the stage is walked again for them in the
+// difference form into a thread-private accumulator in shared memory - the same arithmetic as repulse_kernel.
+template <int H> struct Img { static constexpr int kStride = (2 * H + 2 + 3) / 4 * 4; };
+
+template <int NF4>
+TL_D float f4_elem(const float4 (&t)[NF4], int e) {
+  const float4& x = t[e >> 2];
+  switch (e & 3) { case 0: return x.x; case 1: return x.y; case 2: return x.z; default: return x.w; }
+}
+// image row: H packed pairs of q~ and the half norm (in both lanes of hh)
+template <int H>
+TL_D void ld_image(const float* __restrict__ p, float2 (&v)[H], float2& hh) {
+  constexpr int NF4 = Img<H>::kStride / 4;
+  float4 t[NF4];
+#pragma unroll
+  for (int k = 0; k < NF4; ++k) t[k] = reinterpret_cast<const float4*>(p)[k];
+#pragma unroll
+  for (int k = 0; k < H; ++k) v[k] = make_float2(f4_elem<NF4>(t, 2 * k), f4_elem<NF4>(t, 2 * k + 1));
+  hh = make_float2(f4_elem<NF4>(t, 2 * H), f4_elem<NF4>(t, 2 * H + 1));
+}
+// d^2 by inner product and the near test.  Explicit roundings: the main loop and the second walk must agree bit for bit.
+template <int H>
+TL_D bool near_test(const float2 (&p)[H], float sp, float thr, const float2 (&q)[H], float2 hh, float& d2) {
+  float2 s = __ffma2_rn(p[0], q[0], hh);
+#pragma unroll
+  for (int k = 1; k < H; ++k) s = __ffma2_rn(p[k], q[k], s);
+  d2 = __fadd_rn(__fadd_rn(s.x, s.y), sp);
+  return d2 < thr;
+}
+// kSeries: (dist + 0.01)^-3 = (r (1 - x + x^2 - x^3))^3 (1 + O(x^4)) with r = 1 / dist (one MUFU.RSQ) and x = 0.01 r -
+// seven FMA-pipe instructions instead of three MUFU (sqrt, lg2, ex2), each of which holds the quarter's
+// special-function unit for 8 cycles.  Only pairs that pass the near test get here: the threshold is never below
+// kSeriesFloor = 0.1 (dist > 0.316, x < 0.0316, x^4 < 1e-6), the others take the exact formula in the second walk.
+constexpr float kSeriesFloor = 0.1f;
+TL_D float rsqrt_approx(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+template <int H, bool kSeries>
+TL_D bool repel_dot(const float2 (&p)[H], float sp, float thr, const float2 (&q)[H], float2 hh, float2 (&acc)[H], float& W) {
+  float d2;
+  const bool nr = near_test<H>(p, sp, thr, q, hh, d2);
+  float w;
+  if constexpr (kSeries) {
+    const float r = rsqrt_approx(d2);
+    const float a = fmaf(-0.01f, r, 1.0f);
+    const float b = (r * r) * 1e-4f;
+    const float u = r * fmaf(b, a, a);
+    w = u * u * u;
+  } else {
+    const float ds = sqrt_approx(d2) + 0.01f;
+    w = ex2_approx(-3.0f * lg2_approx(ds));
+  }
+  w = nr ? 0.f : w;                      // also swallows the NaN of a slightly negative d2
+  const float2 ww = make_float2(w, w);
+#pragma unroll
+  for (int k = 0; k < H; ++k) acc[k] = __ffma2_rn(q[k], ww, acc[k]);
+  W += w;
+  return nr;
+}
+
+template <int H>
+__global__ void __launch_bounds__(kBlockRows) image_kernel(RowDev dv, int cur, unsigned epoch) {
+  constexpr int Dp = Row<H>::kStride, Dq = Img<H>::kStride;
+  if (__ldcg(&dv.state->stop)) return;
+  if (!wait_epoch(dv, epoch)) { if (blockIdx.x == 0 && threadIdx.x == 0) peer_timeout(dv); return; }
+  const int row = blockIdx.x * kBlockRows + threadIdx.x;
+  if (row == 0) dv.hmax[cur ^ 1] = 0.f;          // the other buffer's maximum: its readers (the previous iteration) are done
+  const float* __restrict__ P = dv.pos[dv.rank] + (size_t)cur * dv.cap_rows * Dp;
+  float2 p[H];
+  ld_point<H>(P + (size_t)row * Dp, p);
+  float4 o[Dq / 4];
+  float* of = reinterpret_cast<float*>(o);
+  float2 s = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int k = 0; k < H; ++k) {
+    const float2 dl = __fadd2_rn(p[k], make_float2(-dv.centre[2 * k], -dv.centre[2 * k + 1]));
+    s = __ffma2_rn(dl, dl, s);
+    of[2 * k] = -2.0f * dl.x; of[2 * k + 1] = -2.0f * dl.y;
+  }
+  float h = 0.5f * __fadd_rn(s.x, s.y);
+  if (row >= dv.n) {                              // padding rows: never partners; keep them finite
+    h = 0.f;
+#pragma unroll
+    for (int k = 0; k < 2 * H; ++k) of[k] = 0.f;
+  }
+#pragma unroll
+  for (int k = 2 * H; k < Dq; ++k) of[k] = h;
+  float4* out = reinterpret_cast<float4*>(dv.img + (size_t)row * Dq);
+#pragma unroll
+  for (int k = 0; k < Dq / 4; ++k) out[k] = o[k];
+  float m = h;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, d));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(reinterpret_cast<int*>(dv.hmax + cur), __float_as_int(m));   // m >= 0: integer order = float order
+}
+
+template <int H, int R, int U, int MAXR, int SJ = kStageJ, bool kSeries = false>
+__global__ void __maxnreg__(MAXR) repulse_dot_kernel(RowDev dv, int cur, unsigned epoch) {
+  extern __shared__ float4 smem4[];
+  __shared__ long long item_s;
+  float* sm = reinterpret_cast<float*>(smem4);
+  constexpr int T = kRowTile / R;
+  constexpr int Dp = Row<H>::kStride, Dq = Img<H>::kStride;
+  constexpr int kStageFloats = SJ * Dq;
+  float2* fix_s = reinterpret_cast<float2*>(sm + kStages * kStageFloats);   // [R * H][T], written by the second walk only
+  if (__ldcg(&dv.state->stop)) return;
+  (void)epoch;                                     // image_kernel of this iteration waited for the peers
+  const int tid = threadIdx.x;
+  const float* __restrict__ I = dv.img;
+  const float hmax = __ldcg(dv.hmax + cur);
+  constexpr float kTau = (float)(H + 1) / 8192.0f;
+  const int tiles = dv.rows / kRowTile;
+  const long long items = (long long)tiles * dv.chunks;
+  for (;;) {
+    if (tid == 0) item_s = (long long)atomicAdd(&dv.counters[2], 1u);
+    __syncthreads();
+    const long long item = item_s;
+    if (item >= items) break;
+    const int c = (int)(item / tiles), tile = (int)(item % tiles);
+    const int lrow0 = tile * kRowTile;
+    float2 p[R][H], acc[R][H];
+    float sp[R], thr[R], W[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      float2 qt[H], hh;
+      ld_image<H>(I + (size_t)(dv.row0 + lrow0 + tid + r * T) * Dq, qt, hh);
+#pragma unroll
+      for (int k = 0; k < H; ++k) { p[r][k] = make_float2(-0.5f * qt[k].x, -0.5f * qt[k].y); acc[r][k] = make_float2(0.f, 0.f); }
+      sp[r] = 2.0f * hh.x; thr[r] = kTau * (hh.x + hmax); W[r] = 0.f;
+      if constexpr (kSeries) thr[r] = fmaxf(thr[r], kSeriesFloor);
+    }
+    bool fixed = false;
+    const int j0 = c * kChunk;
+    const int cnt = min(kChunk, dv.n - j0);
+    const int nst = (cnt + SJ - 1) / SJ;
+    const float* __restrict__ src = I + (size_t)j0 * Dq;
+    auto prefetch = [&](int s) {
+      if (s < nst) {
+        const float4* g = reinterpret_cast<const float4*>(src + (size_t)s * kStageFloats);
+        float4* d = reinterpret_cast<float4*>(sm + (size_t)(s % kStages) * kStageFloats);
+        for (int x = tid; x < kStageFloats / 4; x += T) cp_async16(d + x, g + x);
+      }
+      cp_async_commit();
+    };
+#pragma unroll
+    for (int s = 0; s < kStages - 1; ++s) prefetch(s);
+    for (int s = 0; s < nst; ++s) {
+      cp_async_wait<kStages - 2>();
+      __syncthreads();
+      prefetch(s + kStages - 1);
+      const float* __restrict__ q_s = sm + (size_t)(s % kStages) * kStageFloats;
+      const int m = min(SJ, cnt - s * SJ);
+      bool flag = false;
+#pragma unroll U
+      for (int j = 0; j < m; ++j) {
+        float2 q[H], hh;
+        ld_image<H>(q_s + j * Dq, q, hh);
+#pragma unroll
+        for (int r = 0; r < R; ++r) flag |= repel_dot<H, kSeries>(p[r], sp[r], thr[r], q, hh, acc[r], W[r]);
+      }
+      if (flag) {                                   // rare: the near pairs of this stage, in the difference form
+        if (!fixed) {
+#pragma unroll
+          for (int x = 0; x < R * H; ++x) fix_s[x * T + tid] = make_float2(0.f, 0.f);
+          fixed = true;
+        }
+        for (int j = 0; j < m; ++j) {
+          float2 q[H], hh;
+          ld_image<H>(q_s + j * Dq, q, hh);
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            float d2;
+            if (near_test<H>(p[r], sp[r], thr[r], q, hh, d2)) {
+              const float2 mh = make_float2(-0.5f, -0.5f);
+              float2 s2 = make_float2(0.f, 0.f);
+#pragma unroll
+              for (int k = 0; k < H; ++k) {
+                const float2 dl = __ffma2_rn(q[k], mh, make_float2(-p[r][k].x, -p[r][k].y));   // (q - centre) - (p - centre), exact halving
+                s2 = __ffma2_rn(dl, dl, s2);
+              }
+              const float ds = sqrt_approx(s2.x + s2.y) + 0.01f;
+              const float w = ex2_approx(-3.0f * lg2_approx(ds));
+              const float2 ww = make_float2(w, w);
+#pragma unroll
+              for (int k = 0; k < H; ++k) {
+                const float2 dl = __ffma2_rn(q[k], mh, make_float2(-p[r][k].x, -p[r][k].y));
+                float2* f = fix_s + (r * H + k) * T + tid;
+                *f = __ffma2_rn(dl, ww, *f);
+              }
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      float2 o[H];
+#pragma unroll
+      for (int k = 0; k < H; ++k) {
+        // sum_j w (q_j - p) = -A / 2 - p W  (A accumulated on q~ = -2 (q - centre))
+        o[k] = make_float2(fmaf(-p[r][k].x, W[r], -0.5f * acc[r][k].x), fmaf(-p[r][k].y, W[r], -0.5f * acc[r][k].y));
+        if (fixed) o[k] = __fadd2_rn(o[k], fix_s[(r * H + k) * T + tid]);
+      }
+      st_point<H>(dv.rpart + ((size_t)c * dv.rows + lrow0 + tid + r * T) * Dp, o);
+    }
     __syncthreads();   // the stages are refilled by the next item's prologue; item_s is rewritten
   }
 }
@@ -764,6 +985,8 @@ struct RowPlan {
   bool peer_ipc[kMaxShards] = {};
   // local
   float* best = nullptr; float* dp1 = nullptr; float* rpart = nullptr; float* xs = nullptr;
+  float* img = nullptr; float* hmax = nullptr;
+  bool dot_form = false;      // repulsion in the inner-product form (image_kernel + repulse_dot_kernel)
   uint2* recs = nullptr; uint2* mrecs = nullptr;
   unsigned long long* soff = nullptr; unsigned long long* moff = nullptr; int* swidth = nullptr; int* mwidth = nullptr;
   FitState* state = nullptr; double* trace = nullptr; unsigned* counters = nullptr;
@@ -790,7 +1013,7 @@ struct RowPlan {
     if (stream) cudaStreamSynchronize(stream);
     for (int q = 0; q < kMaxShards; ++q) if (peer_base[q] && peer_ipc[q]) cudaIpcCloseMemHandle(peer_base[q]);
     if (shared) cudaFree(shared);
-    pool_free(best); pool_free(dp1); pool_free(rpart); pool_free(xs); pool_free(recs); pool_free(mrecs);
+    pool_free(best); pool_free(dp1); pool_free(rpart); pool_free(xs); pool_free(img); pool_free(hmax); pool_free(recs); pool_free(mrecs);
     pool_free(soff); pool_free(moff); pool_free(swidth); pool_free(mwidth);
     pool_free(state); pool_free(trace); pool_free(counters);
     if (h_flag) cudaFreeHost((void*)h_flag);
@@ -909,6 +1132,8 @@ void launch_iteration(RowPlan& rp, cudaStream_t s, cudaEvent_t* ev /* 7 events o
   const bool check = is_check_iter(t, rp.prm), fin = ((t + 1) % 10 == 0);
   const unsigned e_prev = rp.epoch;          // the epoch every rank reached when iteration t - 1 (and its check) ended
   const int row_ctas = dv.rows / kBlockRows;
+  if (ev) TL_CUDA(cudaEventRecord(ev[0], s));
+  if (rp.dot_form) { image_kernel<H><<<dv.slots / kBlockRows, kBlockRows, 0, s>>>(dv, cur, e_prev); rp.launches += 1; }
   if (overlap) {
     // The walk first: its CTAs announce themselves at once (griddepcontrol.launch_dependents), which lets the
     // repulsion grid - launched as a programmatic dependent, it has no data dependence on the walk - fill the
@@ -924,7 +1149,6 @@ void launch_iteration(RowPlan& rp, cudaStream_t s, cudaEvent_t* ev /* 7 events o
     cfg.attrs = at; cfg.numAttrs = 1;
     TL_CUDA(cudaLaunchKernelEx(&cfg, (RepulseFn)rp.rep_fn, dv, cur, e_prev));
   } else {
-    if (ev) TL_CUDA(cudaEventRecord(ev[0], s));
     ((RepulseFn)rp.rep_fn)<<<rp.rep_ctas, rp.rep_threads, rp.rep_smem, s>>>(dv, cur, e_prev);
     if (ev) TL_CUDA(cudaEventRecord(ev[1], s));
     launch_spring<H>(rp, s, cur, e_prev);
@@ -967,21 +1191,43 @@ void launch_one(RowPlan& rp, cudaStream_t s, cudaEvent_t* ev = nullptr) {
 
 // Shapes of the repulsion kernel: {rows per thread, partner unroll, register cap, cube on the SFU}.
 // 0 is the production shape; the others stay selectable (TOPOLOW_REP_VARIANT) for measurements.
+// Variant 0 = policy = 5, the difference form.  The inner-product forms (4, 6-9) are kept selectable as the measured
+// record of why they are not the default (B200, cfg4 / cfg3 repulsion pass in ms; difference form 16.8 / 0.23):
+//   6  one partner per trip, no spill          16.6 / 0.30   issue port 79 % busy (a packed instruction holds it 2 cycles):
+//                                                            two dependency chains per warp cannot hide the MUFU chain
+//   4  two partners per trip, 128 registers    19.1 / 0.31   needs 159 registers; capped, ptxas spills W / sp / thr and shuffles p
+//   7  two partners per trip, 168 registers    18.1 / 0.30   3 warps per scheduler
+//   8  as 6, power by series (1 MUFU)          17.5 / 0.27   +6 FMA-pipe slots cost more than 2 MUFU saved
+//   9  as 4, power by series                   20.9 / 0.26
+// The difference form issues 24 packed + 8.75 other instructions per interaction (56.75 port cycles) and runs at 60.6
+// cycles: it is bound by the issue port, not by the FMA pipe's 51 cycles, and the inner-product form's 49 port cycles only
+// pay with four chains in flight, which do not fit beside 64 registers of own rows and accumulators.
 template <int H>
-void repulse_variant(int v, RepulseFn* fn, int* threads) {
+void repulse_variant(int v, RepulseFn* fn, int* threads, bool* dot, int* stage) {
+  *dot = false;
+  *stage = kStageJ;
+  *threads = kRowTile / 2;
   switch (v) {
-    case 1: *fn = repulse_kernel<H, 2, 2, 128, false>; *threads = kRowTile / 2; break;
-    case 2: *fn = repulse_kernel<H, 2, 2, 120, false>; *threads = kRowTile / 2; break;
-    case 3: *fn = repulse_kernel<H, 2, 2, 120, true>; *threads = kRowTile / 2; break;
-    default: *fn = repulse_kernel<H, 2, 2, 128, true>; *threads = kRowTile / 2; break;
+    case 1: *fn = repulse_kernel<H, 2, 2, 128, false>; break;
+    case 2: *fn = repulse_kernel<H, 2, 2, 120, false>; break;
+    case 3: *fn = repulse_kernel<H, 2, 2, 120, true>; break;
+    case 4: *fn = repulse_dot_kernel<H, 2, 2, 128>; *dot = true; break;
+    case 6: *fn = repulse_dot_kernel<H, 2, 1, 128>; *dot = true; break;
+    case 7: *fn = repulse_dot_kernel<H, 2, 2, 168>; *dot = true; break;
+    case 8: *fn = repulse_dot_kernel<H, 2, 1, 128, kStageJ, true>; *dot = true; break;
+    case 9: *fn = repulse_dot_kernel<H, 2, 2, 128, kStageJ, true>; *dot = true; break;
+    default: *fn = repulse_kernel<H, 2, 2, 128, true>; break;
   }
 }
 template <int H>
 void configure_repulse(RowPlan& rp, int sms) {
-  const size_t smem = (size_t)kStages * kStageJ * Row<H>::kStride * sizeof(float);
   const char* ev = std::getenv("TOPOLOW_REP_VARIANT");
   RepulseFn fn; int threads;
-  repulse_variant<H>(ev ? std::atoi(ev) : 0, &fn, &threads);
+  int stage = kStageJ;
+  repulse_variant<H>(ev ? std::atoi(ev) : 0, &fn, &threads, &rp.dot_form, &stage);
+  const size_t smem = rp.dot_form ? (size_t)kStages * stage * Img<H>::kStride * sizeof(float) + (size_t)2 * H * threads * sizeof(float2)
+                                  : (size_t)kStages * kStageJ * Row<H>::kStride * sizeof(float);
+  if (smem > 48 * 1024) TL_CUDA(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
   TL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, smem));
   if (per_sm < 1) per_sm = 1;
@@ -1060,6 +1306,8 @@ RowPlan* row_create(const topolow_problem& pb, const topolow_params& pr, int ran
     pool_alloc(rp->dp1, hd.size() * sizeof(float));
     pool_alloc(rp->rpart, (size_t)dv.chunks * std::max(dv.rows, 1) * dv.Dp * sizeof(float));
     pool_alloc(rp->xs, (size_t)std::max(dv.rows, 1) * dv.Dp * sizeof(float));
+    pool_alloc(rp->img, dv.cap_rows * (size_t)(((dv.D + 1) / 2 * 2 + 2 + 3) / 4 * 4) * sizeof(float));   // Img<H>::kStride floats per row
+    pool_alloc(rp->hmax, 2 * sizeof(float));
     pool_alloc(rp->state, sizeof(FitState));
     pool_alloc(rp->trace, sizeof(double) * std::max(pr.n_iter, 1));
     pool_alloc(rp->counters, 4 * sizeof(unsigned));
@@ -1070,12 +1318,24 @@ RowPlan* row_create(const topolow_problem& pb, const topolow_params& pr, int ran
     std::vector<double> tr(std::max(pr.n_iter, 1), NAN);
     TL_CUDA(cudaMemcpy(rp->trace, tr.data(), tr.size() * sizeof(double), cudaMemcpyHostToDevice));
     TL_CUDA(cudaMemset(rp->counters, 0, 4 * sizeof(unsigned)));
+    TL_CUDA(cudaMemset(rp->hmax, 0, 2 * sizeof(float)));
+    // centre of the inner-product form: the centroid of the initial positions, summed in point order (the same on
+    // every rank, fixed for the fit; the map stays about where it starts, and a map that wanders only makes more
+    // pairs take the difference form)
+    for (int d = 0; d < 16; ++d) dv.centre[d] = 0.f;
+    for (int d = 0; d < pb.ndim; ++d) {
+      double sum = 0.0;
+      for (int64_t i = 0; i < pb.n; ++i) sum += pb.initial_positions[(size_t)d * pb.n + i];
+      const double c = sum / (double)pb.n;
+      dv.centre[d] = std::isfinite(c) ? (float)c : 0.f;
+    }
     FitState st;
     state_init(st, rp->prm);
     TL_CUDA(cudaMemcpy(rp->state, &st, sizeof st, cudaMemcpyHostToDevice));
   }
   pt.mark("rows: points");
-  dv.best = rp->best; dv.dp1 = rp->dp1; dv.rpart = rp->rpart; dv.xs = rp->xs; dv.state = rp->state; dv.trace = rp->trace;
+  dv.best = rp->best; dv.dp1 = rp->dp1; dv.rpart = rp->rpart; dv.xs = rp->xs; dv.img = rp->img; dv.hmax = rp->hmax;
+  dv.state = rp->state; dv.trace = rp->trace;
   dv.counters = rp->counters;
   TL_CUDA(cudaHostAlloc((void**)&rp->h_flag, 2 * sizeof(int), cudaHostAllocMapped));
   rp->h_flag[0] = 0; rp->h_flag[1] = 0;
@@ -1202,6 +1462,7 @@ double row_run_local(RowPlan* const* plans, int n, int n_iters) {
         dispatch_h((rp.dv.D + 1) / 2, [&](auto h) {
           constexpr int H = decltype(h)::value;
           const unsigned e_prev = rp.epoch;
+          if (rp.dot_form) { image_kernel<H><<<rp.dv.slots / kBlockRows, kBlockRows, 0, s>>>(rp.dv, cur, e_prev); rp.launches += 1; }
           ((RepulseFn)rp.rep_fn)<<<rp.rep_ctas, rp.rep_threads, rp.rep_smem, s>>>(rp.dv, cur, e_prev);
           launch_spring<H>(rp, s, cur, e_prev);
           combine_kernel<H><<<rp.dv.rows / kBlockRows, kBlockRows, 0, s>>>(rp.dv, rp.prm, cur, ++rp.epoch);
