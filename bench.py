@@ -600,6 +600,15 @@ def main_map(args, n, d, missing):
         return
 
     # ---- roofline ---------------------------------------------------------------------------------
+    def tracked_traffic(kernel):
+        """DRAM bytes per launch of `kernel` from a tracked ncu capture of this workload at this GPU count, else None."""
+        try:
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                e = json.load(f).get("%s/%d/%s" % (args.workload, world, kernel))
+            return e["bytes"] if e else None
+        except (OSError, ValueError, KeyError):
+            return None
+
     peaks, peak_src = measured_peaks()
     ffma_peak = _lib.microbench(0, local)      # flop/s, measured now on this GPU
     flop = flop_per_iter(n, d, E)
@@ -616,14 +625,20 @@ def main_map(args, n, d, missing):
                     "algorithmic_flop_per_launch": rep_flop, "launch_ms": kt["repulse"],
                     "note": "algorithmic = (7 ndim + 8) flop per unordered pair (SURVEY 8d); the kernel visits every pair from both "
                             "sides (one-sided updates) and executes 54 FMA-pipe cycles per side at ndim 16, so 1.0 is not reachable: "
-                            "100 % FMA-pipe occupancy reads as 0.56 here",
-                    "traffic": None,
+                            "100 % FMA-pipe occupancy reads as 0.56 here; ncu (profiles/r2_ncu_rowblock_cfg4.md): FMA pipe 82 % of cycles, "
+                            "issue port 94 % (a packed FP32 instruction holds it for two cycles)",
+                    "traffic": tracked_traffic("repulse_kernel"),
                     "kernels_ms": kt,
                     "edge_pass": {"bound": "hbm", "kernel": "mae_kernel (edge MAE on check iterations)",
                                   "achieved": edge_b / (kt["mae"] * 1e-3) / 1e9 if kt["mae"] > 0 else None, "peak": peaks["hbm_gbs"],
                                   "unit": "GB/s", "frac": edge_b / (kt["mae"] * 1e-3) / 1e9 / peaks["hbm_gbs"] if kt["mae"] > 0 else None,
                                   "peak_source": peak_src, "algorithmic_bytes_per_launch": edge_b, "launch_ms": kt["mae"],
-                                  "note": "SURVEY 8d: 16 bytes per measured pair + every FP32 position read and written once, per rank"},
+                                  "traffic": tracked_traffic("mae_kernel"),
+                                  "gather_bytes_per_launch": info0["mae_records"] * (8 + 4 * ((d + 3) // 4 * 4)),
+                                  "note": "SURVEY 8d: 16 bytes per measured pair + every FP32 position read and written once, per rank. "
+                                          "The kernel streams 8-byte records (DRAM) and gathers one partner row per record from the "
+                                          "L2-resident replica (gather_bytes_per_launch): ncu shows it bound by the L1TEX gather path "
+                                          "(66 % of peak; L2 25 %, DRAM 8 %), not by HBM"},
                     "spring_pass": {"launch_ms": kt["spring"],
                                     "achieved_gbs": (2 * E * 8 / world + 2 * n * d * 4 / world) / (kt["spring"] * 1e-3) / 1e9,
                                     "note": "walks both directions of every measured pair (8-byte records) and gathers one 64-byte "

@@ -569,7 +569,14 @@ def test_cfg3_against_the_reference_loop_goldens(mode):
         maes.append(g["final_mae"]); holds.append(np.abs(ht - dist).mean())
         tr = g["trace_mae"][~np.isnan(g["trace_mae"])]
         assert len(tr) == len(ref_trace)
-        np.testing.assert_allclose(tr[4::5], ref_trace[4::5], rtol=0.02)     # iterations 15, 30, ... (the first checks are the steep part)
+        # iterations 15, 30, ..., 90 (the first checks are the steep part).  The row-block scheme is Jacobi across points and
+        # lags the sequential loop while the map unfolds (measured at iteration 15: 2.79 vs 2.51), from iteration 30 on
+        # it is the same curve
+        if mode == "rowblock":
+            np.testing.assert_allclose(tr[4], ref_trace[4], rtol=0.15)
+            np.testing.assert_allclose(tr[9::5], ref_trace[9::5], rtol=0.02)
+        else:
+            np.testing.assert_allclose(tr[4::5], ref_trace[4::5], rtol=0.02)
     assert np.mean(maes) == pytest.approx(ref_mae.mean(), rel=0.02), (maes, ref_mae)
     assert np.mean(holds) == pytest.approx(ref_hold.mean(), rel=0.02), (holds, ref_hold)
 
