@@ -261,6 +261,17 @@ TOPOLOW_API int topolow_holdout_errors(const double* positions, int64_t n, int32
                            const int32_t* cell_i, const int32_t* cell_j, const double* truth,
                            double* sum_abs_out, int64_t* count_out, int32_t device);
 
+/* ---- measurement graph ------------------------------------------------------ */
+/* Connected components of the graph whose edges are the non-NA off-diagonal cells (adjacency = !is.na,
+ * R/diagnostics.R:444-446), i.e. what check_matrix_connectivity gets from igraph::components()$no
+ * (R/utils.R:223-229) - for n_masks candidate point subsets at once: masks[m * n + v] != 0 selects point v in
+ * candidate m (the attempts of subsample_dissimilarity_matrix, R/utils.R:371-440); masks == NULL means one
+ * candidate with every point.  Per candidate: components among the selected points, selected points, and edges with
+ * both ends selected (n_measurements of R/diagnostics.R:462).  points_out / edges_out may be NULL. */
+TOPOLOW_API int topolow_components(int64_t n, int64_t n_edges, const int32_t* edge_i, const int32_t* edge_j, int32_t n_masks,
+                                   const uint8_t* masks, int64_t* components_out, int64_t* points_out, int64_t* edges_out,
+                                   int32_t device);
+
 /* ---- measurement helpers --------------------------------------------------- */
 /* which: 0 FFMA (FP32 flop/s), 1 packed fma.f32x2, 2 DFMA, 3 SHFL (warp-instr/s), 4 MUFU.RSQ,
  * 5 device copy (bytes/s read+write), 6/7/8 = milliseconds of a loop of 8 FFMA2 / 4 SHFL / both per trip

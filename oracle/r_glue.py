@@ -278,3 +278,145 @@ def likelihood_function(dissimilarity_matrix, mapping_max_iter, relative_epsilon
     nll = total_samples * (1 + math.log(2 * pooled)) if not math.isnan(pooled) else math.nan
     return dict(Holdout_MAE=pooled, NLL=nll, mean_iter=float(np.mean([r["iter"] for r in valid])),
                 pct_converged=float(np.mean([r["converged"] for r in valid]) * 100), folds=rows)
+
+
+# ---------------------------------------------------------------------------------------------
+# R/utils.R: create_cv_folds (:69-150), check_matrix_connectivity (:199-253),
+# subsample_dissimilarity_matrix (:321-463); R/diagnostics.R:434-472 (adjacency, completeness)
+# ---------------------------------------------------------------------------------------------
+def create_cv_folds(dissimilarity_matrix, n_folds, picks_per_fold):
+    """R/utils.R:103-147 with the sample() draws injected: `picks_per_fold[f]` are the 1-based positions, in
+    which(!is.na(sampling_pool)) order (column-major), is replaced by explicit 0-based linear indices."""
+    m = np.asarray(dissimilarity_matrix)
+    nrow, ncol = m.shape
+    pool = np.array([[not _is_na(x) for x in row] for row in m])
+    out = []
+    for f in range(n_folds):
+        train = np.array(m, dtype=object, copy=True)
+        for index in picks_per_fold[f]:                      # `index` here is 0-based: (index) %/% nrow, (index) %% ncol
+            row, col = int(index) // nrow, int(index) % ncol
+            train[row, col] = None
+            train[col, row] = None
+            pool[row, col] = False
+            pool[col, row] = False
+        out.append(train)
+    return out, pool
+
+
+def check_matrix_connectivity(dissimilarity_matrix):
+    """R/utils.R:199-253 + R/diagnostics.R:444-464.  igraph::components is replaced by scipy's connected_components
+    (declared substitution: only the component count is used)."""
+    from scipy.sparse import csr_matrix
+    from scipy.sparse.csgraph import connected_components
+    m = np.asarray(dissimilarity_matrix)
+    n = m.shape[0]
+    adj = np.array([[not _is_na(x) for x in row] for row in m])
+    for i in range(n):
+        adj[i, i] = False
+    ncomp, _ = connected_components(csr_matrix(adj | adj.T), directed=False)
+    return dict(is_connected=ncomp == 1, n_components=int(ncomp), completeness=adj.sum() / (n * (n - 1)), n_points=n,
+                n_measurements=adj.sum() / 2)
+
+
+def subsample_dissimilarity_matrix(dissimilarity_matrix, attempts):
+    """R/utils.R:371-440: the attempts one after another (`attempts[k]` = the indices sample() returned in attempt k,
+    already sorted when preserve_order); returns (attempt number, indices, connectivity) of the first connected one,
+    or None."""
+    m = np.asarray(dissimilarity_matrix)
+    for k, sel in enumerate(attempts):
+        sub = m[np.ix_(sel, sel)]
+        c = check_matrix_connectivity(sub)
+        if c["is_connected"]:
+            return k + 1, sel, c
+    return None
+
+
+# ---------------------------------------------------------------------------------------------
+# The sampler: R/adaptive_sampling.R weighted_kde (:1901-1935), calculate_weighted_marginals (:2457-2519),
+# generate_kde_samples (:1804-1885); R/data_preprocessing.R clean_data / detect_outliers_mad (:864-879, :956-996)
+# ---------------------------------------------------------------------------------------------
+def _median(v):
+    s = sorted(v)
+    k = len(s)
+    return s[k // 2] if k % 2 else 0.5 * (s[k // 2 - 1] + s[k // 2])
+
+
+def clean_data(x, k=3):
+    vals = [v for v in x if not math.isnan(v)]
+    med = _median(vals)
+    mad = 1.4826 * _median([abs(v - med) for v in vals])
+    return [math.nan if (not math.isnan(v) and abs(v - med) > k * mad) else v for v in x]
+
+
+def weighted_kde(x, weights, n=512):
+    tot = sum(weights)
+    w = [a / tot for a in weights]
+    m = sum(x) / len(x)
+    sd = math.sqrt(sum((a - m) ** 2 for a in x) / (len(x) - 1))
+    bw = 1.06 * sd * len(x) ** (-1 / 5)
+    lo, hi = min(x) - bw, max(x) + bw
+    by = (hi - lo) / (n - 1)
+    pts = [lo + i * by for i in range(n)]
+    dens = []
+    for z in pts:                       # compute_density(z) = sum(weights * dnorm(z, mean = x, sd = bw))
+        dens.append(sum(wi * math.exp(-0.5 * ((z - xi) / bw) ** 2) / (bw * math.sqrt(2 * math.pi)) for wi, xi in zip(w, x)))
+    return dict(x=pts, y=dens)
+
+
+def _weights(score, temperature=0.1):
+    lo, hi = min(score), max(score)
+    w = [math.exp(-((s - lo) / (hi - lo + 1e-10)) / temperature) for s in score]
+    tot = sum(w)
+    return [a / tot for a in w]
+
+
+def _filter_mae(table):
+    keep = [i for i, v in enumerate(table["Holdout_MAE"]) if not math.isnan(v) and v > 0]
+    t = {k: [table[k][i] for i in keep] for k in table}
+    t["Holdout_MAE"] = clean_data(t["Holdout_MAE"], 3)
+    keep = [i for i, v in enumerate(t["Holdout_MAE"]) if not math.isnan(v) and v > 0]
+    return {k: [t[k][i] for i in keep] for k in t}
+
+
+def calculate_weighted_marginals(table):
+    t = _filter_mae({k: [float(v) for v in vals] for k, vals in table.items()})
+    w = _weights([math.log(v) for v in t["Holdout_MAE"]])
+    return {v: weighted_kde(t[v], w) for v in ("log_N", "log_k0", "log_cooling_rate", "log_c_repulsion")}
+
+
+def approx_rule2(x, y, xout):
+    """stats::approx(x, y, xout, rule = 2) with the default ties = mean."""
+    groups = {}
+    for a, b in zip(x, y):
+        groups.setdefault(a, []).append(b)
+    ux = sorted(groups)
+    uy = [sum(groups[a]) / len(groups[a]) for a in ux]
+    out = []
+    for v in xout:
+        if v <= ux[0]:
+            out.append(uy[0])
+        elif v >= ux[-1]:
+            out.append(uy[-1])
+        else:
+            k = max(i for i in range(len(ux)) if ux[i] <= v)
+            out.append(uy[k] + (uy[k + 1] - uy[k]) * (v - ux[k]) / (ux[k + 1] - ux[k]))
+    return out
+
+
+def generate_kde_samples(table, n, uniforms):
+    """`uniforms[param]` = the n runif draws of the inverse-transform step (the epsilon draw changes nothing)."""
+    t = {k: [float(v) for v in vals] for k, vals in table.items()}
+    t["Holdout_MAE"] = clean_data(t["Holdout_MAE"], 3)
+    keep = [i for i, v in enumerate(t["Holdout_MAE"]) if not math.isnan(v) and v > 0]
+    t = {k: [t[k][i] for i in keep] for k in t}
+    w = _weights([-math.log(v) for v in t["Holdout_MAE"]])
+    out = {}
+    for param in ("log_N", "log_k0", "log_cooling_rate", "log_c_repulsion"):
+        kde = weighted_kde(t[param], w)
+        tot = sum(kde["y"])
+        cdf, run = [], 0.0
+        for v in kde["y"]:
+            run += v
+            cdf.append(run / tot)
+        out[param] = approx_rule2(cdf, kde["x"], uniforms[param])
+    return out

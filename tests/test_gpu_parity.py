@@ -609,3 +609,124 @@ def test_rowblock_inner_product_variant_tracks_the_restatement(monkeypatch):
         err = np.abs(got["positions"] - want["positions"])
         assert np.quantile(err, 0.99) <= 2e-4 * scale and err.max() <= 2e-3 * scale
         assert got["final_mae"] == pytest.approx(want["final_mae"], rel=1e-3)
+
+
+def test_sparse_table_entry_equals_the_matrix_entry():
+    """euclidean_embedding_coo (nothing n x n is built) returns the positions, convergence fields and mae of
+    euclidean_embedding on the matrix the table stands for; est_distances on the listed pairs and on extra
+    (held-out) pairs equal the dense est_distances there."""
+    m = random_r_matrix(90, 0.3, 5)
+    ii, jj = np.nonzero(np.frompyfunc(lambda x: x is not None, 1, 1)(m).astype(bool))
+    up = ii < jj
+    init = np.random.default_rng(2).normal(size=(90, 3))
+    for preserve in (True, False):
+        dense = core.euclidean_embedding(m, 3, 80, 4.0, 0.02, 0.01, initial_positions=init, preserve_order=preserve, seed=3)
+        sp = core.euclidean_embedding_coo(90, ii[up], jj[up], m[ii[up], jj[up]], 3, 80, 4.0, 0.02, 0.01, initial_positions=init,
+                                          preserve_order=preserve, seed=3, extra_pairs=(np.array([0, 5, 7]), np.array([9, 1, 8])))
+        assert np.array_equal(dense["positions"], sp["positions"])
+        assert dense["convergence"] == sp["convergence"] and dense["iter"] == sp["iter"]
+        assert sp["mae"] == pytest.approx(dense["mae"], rel=1e-9)
+        ci, cj = sp["pairs"]
+        np.testing.assert_allclose(sp["est_distances"], dense["est_distances"][ci, cj], rtol=1e-12)
+        order = dense["order"] if dense["order"] is not None else np.arange(90)
+        rank = np.empty(90, dtype=int); rank[order] = np.arange(90)
+        np.testing.assert_allclose(sp["est_extra"], dense["est_distances"][rank[[0, 5, 7]], rank[[9, 1, 8]]], rtol=1e-12)
+
+
+# ------------------------------------------------------------------ measurement graph, sparse CV --
+def test_device_components_equal_scipy():
+    """topolow_components (csrc/graph.cu) vs scipy's connected_components: component count, selected points and
+    selected edges for random graphs, every point / many candidate masks, isolated points, no edges at all."""
+    from scipy.sparse import coo_matrix
+    from scipy.sparse.csgraph import connected_components
+    rng = np.random.default_rng(0)
+    for n, dens, n_masks in ((50, 0.03, 7), (400, 0.004, 16), (3000, 0.0006, 5), (2000, 0.01, 3), (10, 0.0, 2)):
+        iu = np.triu_indices(n, 1)
+        keep = rng.random(len(iu[0])) < dens
+        ei, ej = iu[0][keep].astype(np.int32), iu[1][keep].astype(np.int32)
+        if len(ei) and rng.random() < 0.5:
+            ei, ej = np.r_[ei, ej[:5]], np.r_[ej, ei[:5]]           # duplicates and reversed orientation are legal
+        masks = rng.random((n_masks, n)) < 0.6
+        masks[0, :] = True
+        for mk_set in (None, masks):
+            comp, pts, edg = _lib.components(n, ei, ej, mk_set)
+            for a, mk in enumerate(np.ones((1, n), bool) if mk_set is None else mk_set):
+                k = mk[ei] & mk[ej]
+                lab = connected_components(coo_matrix((np.ones(k.sum()), (ei[k], ej[k])), shape=(n, n)), directed=False)[1]
+                assert comp[a] == len(set(lab[mk])) and pts[a] == mk.sum() and edg[a] == k.sum(), (n, a)
+    with pytest.raises(_lib.TopolowError):
+        _lib.components(5, [0, 9], [1, 2])
+
+
+def test_subsampling_on_the_device_follows_the_reference_loop():
+    from topolow_b200 import subsample
+    m = random_r_matrix(200, 0.03, 4, thresholds=False)
+    fm = np.array([[np.nan if x is None else float(x) for x in row] for row in m])
+    np.fill_diagonal(fm, 0.0)
+    import warnings as w
+    with w.catch_warnings():
+        w.simplefilter("ignore")
+        full = subsample.check_matrix_connectivity(fm)
+        assert full["n_components"] == r_glue.check_matrix_connectivity(fm)["n_components"]
+        found = 0
+        for seed in range(8):
+            rng = np.random.default_rng(seed)
+            attempts = [np.sort(rng.choice(200, size=120, replace=False)) for _ in range(5)]
+            want = r_glue.subsample_dissimilarity_matrix(fm, attempts)
+            try:
+                got = subsample.subsample_dissimilarity_matrix(fm, 120, rng=np.random.default_rng(seed), preserve_order=True)
+            except RuntimeError:
+                assert want is None
+                continue
+            found += 1
+            assert got["attempt_number"] == want[0] and np.array_equal(got["selected_indices"], want[1])
+            assert got["completeness"] == pytest.approx(want[2]["completeness"])
+    assert found > 0
+
+
+def test_likelihood_on_a_table_equals_likelihood_on_the_matrix():
+    """likelihood_batch_coo (folds drawn and masked on the cell list, nothing n x n) == likelihood_batch on the matrix
+    for the same drawn cells and initial positions: every pooled number and every fold row."""
+    n = 80
+    m = random_r_matrix(n, 0.3, 9)
+    value, code, is_na = core.parse_dissimilarity(m)
+    ii, jj = np.nonzero(np.triu(~is_na, 1))
+    full = core.build_problem_coo(n, ii, jj, m[ii, jj], preserve_order=True)
+    cells = cv.make_folds_cells(n, full["cell_i"], full["cell_j"], 4, np.random.default_rng(1))
+    lin = []
+    for picks in cells:
+        a = np.where(picks < n, picks, full["cell_i"][np.maximum(picks - n, 0) >> 1])
+        b = np.where(picks < n, picks, full["cell_j"][np.maximum(picks - n, 0) >> 1])
+        swap = (picks >= n) & (((picks - n) & 1) == 1)
+        a, b = np.where(swap, b, a), np.where(swap, a, b)
+        lin.append(a + b * n)
+    samples = [dict(N=2, k0=3.0, cooling_rate=0.02, c_repulsion=0.01), dict(N=4, k0=6.0, cooling_rate=0.01, c_repulsion=0.02)]
+    rng = np.random.default_rng(5)
+    inits = [[rng.normal(size=(n, s["N"])) for _ in range(4)] for s in samples]
+    dense = cv.likelihood_batch(m, samples, 60, 1e-4, folds=4, fold_indices=lin, init_list=inits, seed=2)
+    table = cv.likelihood_batch_coo(n, ii, jj, m[ii, jj], samples, 60, 1e-4, folds=4, fold_cells=cells, init_list=inits, seed=2)
+    for d, t in zip(dense, table):
+        assert d["Holdout_MAE"] == pytest.approx(t["Holdout_MAE"], rel=1e-12) and d["NLL"] == pytest.approx(t["NLL"], rel=1e-12)
+        assert [f["n_samples"] for f in d["folds"]] == [f["n_samples"] for f in t["folds"]]
+        assert [f["iter"] for f in d["folds"]] == [f["iter"] for f in t["folds"]]
+
+
+def test_batched_adaptive_chains_on_the_device():
+    """sampler.adaptive_mc_batch: 4 chains x 2 rounds, every round one likelihood_batch call of chains x folds fits on
+    the device; the table grows by valid rows whose MAE is that of the drawn parameters."""
+    from topolow_b200 import sampler
+    m = random_r_matrix(60, 0.4, 3, thresholds=False)
+    rng = np.random.default_rng(0)
+    design = sampler.lhs_design(12, (2, 4), (1.0, 8.0), (1e-3, 0.05), (0.005, 0.05), rng=rng)
+    sets = [dict(N=int(design["N"][i]), k0=design["k0"][i], cooling_rate=design["cooling_rate"][i], c_repulsion=design["c_repulsion"][i])
+            for i in range(12)]
+    first = cv.likelihood_batch(m, sets, 80, 1e-4, folds=4, rng=rng)
+    table = {"log_N": np.log(design["N"]), "log_k0": np.log(design["k0"]), "log_cooling_rate": np.log(design["cooling_rate"]),
+             "log_c_repulsion": np.log(design["c_repulsion"]), "Holdout_MAE": np.array([r["Holdout_MAE"] for r in first]),
+             "NLL": np.array([r["NLL"] for r in first]), "mean_iter": np.array([r["mean_iter"] for r in first]),
+             "pct_converged": np.array([r["pct_converged"] for r in first])}
+    assert np.all(np.isfinite(table["Holdout_MAE"]))
+    grown = sampler.adaptive_mc_batch(table, m, iterations=2, chains=4, mapping_max_iter=80, relative_epsilon=1e-4, folds=4, rng=rng)
+    assert len(grown["Holdout_MAE"]) == 12 + 8 and np.all(np.isfinite(grown["Holdout_MAE"])) and np.all(grown["Holdout_MAE"] > 0)
+    np.testing.assert_allclose(grown["NLL"][12:] / (1 + np.log(2 * grown["Holdout_MAE"][12:])),
+                               np.round(grown["NLL"][12:] / (1 + np.log(2 * grown["Holdout_MAE"][12:]))), atol=1e-6)   # NLL = n (1 + log 2 MAE)

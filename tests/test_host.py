@@ -2,6 +2,7 @@
 (against oracle/r_glue.py), fold construction, sharding over ranks (gloo, world size 2)."""
 import ctypes as C
 import json
+import math
 import os
 import re
 import subprocess
@@ -342,3 +343,240 @@ def test_r_shim_batch_shares_fold_arrays_and_reports_per_job_status(shim_cpu, tm
         assert out[j, 4] == pytest.approx(hold[2].sum() + hold[0].sum() + 2 * hold[1].sum()) and out[j, 5] == 3
     r = _harness(shim_cpu, "batch", tmp_path / "p.bin", tmp_path / "o.bin", 2, 250, 4.0, 0.01, 0.02, 1e-4, 5, 3, 0)
     assert all(j["pos_len"] == 0 for j in r["jobs"])         # positions stay on the device side unless asked for
+
+
+# ------------------------------------------------------------------ parsing and the sparse entry --
+def _odd_cells(m, seed):
+    if seed % 2:
+        m[3, 4] = m[4, 3] = "NA"; m[5, 6] = m[6, 5] = "abc"; m[7, 8] = m[8, 7] = ">"; m[1, 2] = "  3.5"; m[2, 1] = "3.5e0"
+        m[9, 10] = np.nan; m[10, 9] = float("nan"); m[11, 12] = 4; m[12, 11] = np.float32(4); m[13, 14] = "<1e-3"; m[14, 13] = "> 2"
+    return m
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_vectorised_parsing_equals_the_cell_by_cell_rule(seed):
+    """R/core.R:345-374 (startsWith / sub / as.numeric) without a Python loop over the cells: same value, threshold
+    code and NA mask as the cell-by-cell rule and as the R-glue restatement, for object and for string matrices."""
+    m = _odd_cells(random_r_matrix(60, 0.3, seed), seed)
+    got = core.parse_values(m)
+    want = core._parse_elementwise(np.asarray(m).ravel())
+    for a, b in zip(got, want):
+        assert np.array_equal(a, b, equal_nan=True)
+    ms = np.where(np.frompyfunc(lambda x: x is None, 1, 1)(m).astype(bool), "NA", m).astype(str)
+    for a, b in zip(core.parse_values(ms), core._parse_elementwise(ms.ravel())):
+        assert np.array_equal(a, b, equal_nan=True)
+    value, code, is_na = core.parse_dissimilarity(m)
+    rv, rc, rna = r_glue.parse_matrix(m)
+    assert np.array_equal(is_na, rna) and np.array_equal(code[~rna], rc[~rna])
+    assert np.array_equal(np.where(np.isnan(value) | is_na, np.inf, value), np.where(np.isnan(rv), np.inf, rv))
+
+
+@pytest.mark.parametrize("seed", range(4))
+@pytest.mark.parametrize("preserve", [True, False])
+def test_sparse_table_builds_the_same_problem_as_the_matrix(seed, preserve):
+    """build_problem_coo: degrees, order and the edge list (in which(arr.ind = TRUE) order) of the dense path,
+    from the non-NA cells listed in any order, in both or in one orientation."""
+    m = random_r_matrix(70, 0.25, seed)
+    dense = core.build_problem(m, preserve)
+    ii, jj = np.nonzero(np.frompyfunc(lambda x: x is not None, 1, 1)(m).astype(bool))
+    off = ii != jj
+    perm = np.random.default_rng(seed).permutation(int(off.sum()))
+    ii, jj = ii[off][perm], jj[off][perm]
+    for sel in (np.ones(len(ii), bool), ii < jj, ii > jj):
+        coo = core.build_problem_coo(70, ii[sel], jj[sel], m[ii[sel], jj[sel]], preserve)
+        for k in ("degrees", "edge_i", "edge_j", "edge_dist", "edge_thresh"):
+            assert np.array_equal(dense[k], coo[k]), k
+        assert (dense["order"] is None) == (coo["order"] is None)
+        assert dense["order"] is None or np.array_equal(dense["order"], coo["order"])
+    with pytest.raises(ValueError, match="out of range"):
+        core.build_problem_coo(70, [0, 70], [1, 2], [1.0, 2.0])
+
+
+# ------------------------------------------------------------------ folds, subsampling -----------
+def test_create_cv_folds_follows_the_reference_scheme():
+    """cv.create_cv_folds vs the loop restatement of R/utils.R:103-147 fed the same draws; sizes, symmetry,
+    disjoint folds, validation messages."""
+    m = random_r_matrix(40, 0.4, 7)
+
+    class Rec:                         # records what the product drew so that the restatement can replay it
+        def __init__(self, seed): self.rng, self.picks = np.random.default_rng(seed), []
+        def choice(self, a, size, replace): p = self.rng.choice(a, size=size, replace=replace); self.picks.append(p); return p
+
+    rec = Rec(3)
+    got = cv.create_cv_folds(m, n_folds=5, rng=rec)
+    want, pool = r_glue.create_cv_folds(m, 5, rec.picks)
+    assert len(got) == 5
+    non_na = sum(x is not None for x in m.ravel())
+    for f in range(5):
+        assert len(rec.picks[f]) == non_na // 10
+        g, w = got[f]["train"], want[f]
+        assert all((a is None) == (b is None) and (a is None or a == b) for a, b in zip(g.ravel(), w.ravel()))
+        na = np.frompyfunc(lambda x: x is None, 1, 1)(g).astype(bool)
+        assert np.array_equal(na, na.T) and got[f]["truth"] is m
+    held = [np.frompyfunc(lambda x: x is None, 1, 1)(got[f]["train"]).astype(bool) & ~np.frompyfunc(lambda x: x is None, 1, 1)(m).astype(bool) for f in range(5)]
+    assert not np.any(sum(h.astype(int) for h in held) > 1)            # no cell is held out twice
+    fm = np.where(np.frompyfunc(lambda x: x is None, 1, 1)(m).astype(bool), np.nan, 1.0)
+    assert len(cv.create_cv_folds(fm, n_folds=4, random_seed=1)) == 4 and np.isnan(cv.create_cv_folds(fm, None, 4, 1)[0]["train"]).sum() > np.isnan(fm).sum()
+    for kw, msg in ((dict(n_folds=1), "`n_folds` must be an integer greater than or equal to 2."),
+                    (dict(n_folds=41), "`n_folds` cannot be larger than the number of rows in the matrix."),
+                    (dict(random_seed=1.5), "`random_seed` must be an integer."),
+                    (dict(ground_truth_matrix=np.zeros((3, 3))), "must have the same dimensions")):
+        with pytest.raises(ValueError, match=re.escape(msg)):
+            cv.create_cv_folds(m, **kw)
+
+
+def test_folds_on_the_cell_list_equal_folds_on_the_matrix():
+    """make_folds_cells / fold_problem_cells (nothing n x n) give the training problem, degrees and out-of-sample
+    cells that masking the matrix gives (R/adaptive_sampling.R:2608-2647) for the same drawn cells."""
+    n = 50
+    m = random_r_matrix(n, 0.3, 2)
+    value, code, is_na = core.parse_dissimilarity(m)
+    ii, jj = np.nonzero(np.triu(~is_na, 1))
+    full = core.build_problem_coo(n, ii, jj, m[ii, jj], preserve_order=True)
+    folds = cv.make_folds_cells(n, full["cell_i"], full["cell_j"], 4, np.random.default_rng(0))
+    assert [len(p) for p in folds] == [(n + 2 * len(ii)) // 8] * 4
+    seen = np.zeros(n + 2 * len(ii), dtype=int)
+    for picks in folds:
+        seen[picks] += 1
+        pr = picks[picks >= n] - n
+        seen[n + (pr ^ 1)] += 1
+        a = np.where(picks < n, picks, full["cell_i"][np.maximum(picks - n, 0) >> 1])
+        b = np.where(picks < n, picks, full["cell_j"][np.maximum(picks - n, 0) >> 1])
+        swap = (picks >= n) & (((picks - n) & 1) == 1)
+        a, b = np.where(swap, b, a), np.where(swap, a, b)
+        pm, hi_m, hj_m, ht_m = cv._fold_job(value, code, is_na, a + b * n, True)
+        pc, hi_c, hj_c, ht_c = cv.fold_problem_cells(full, picks, n)
+        for k in ("degrees", "edge_i", "edge_j", "edge_dist", "edge_thresh"):
+            assert np.array_equal(pm[k], pc[k]), k
+        assert sorted(zip(hi_m.tolist(), hj_m.tolist(), ht_m.tolist())) == sorted(zip(hi_c.tolist(), hj_c.tolist(), ht_c.tolist()))
+    assert seen.max() <= 2 and np.all(seen[:n] <= 1)              # a pair leaves the pool with its mirror (drawn + mirrored at most once each way)
+
+
+def _scipy_components(n, ei, ej, masks):
+    """Stand-in for _lib.components on a box without a GPU (tests of the HOST logic only)."""
+    from scipy.sparse import coo_matrix
+    from scipy.sparse.csgraph import connected_components
+    masks = np.ones((1, n), bool) if masks is None else np.asarray(masks, bool)
+    comp, pts, edg = [], [], []
+    for mk in masks:
+        keep = mk[ei] & mk[ej]
+        g = coo_matrix((np.ones(keep.sum()), (ei[keep], ej[keep])), shape=(n, n))
+        lab = connected_components(g, directed=False)[1]
+        comp.append(len(set(lab[mk]))); pts.append(int(mk.sum())); edg.append(int(keep.sum()))
+    return np.array(comp), np.array(pts), np.array(edg)
+
+
+def test_subsampling_follows_the_reference_loop():
+    from topolow_b200 import subsample
+    m = random_r_matrix(60, 0.13, 11, thresholds=False)               # sparse: some attempts are disconnected
+    fm = np.where(np.frompyfunc(lambda x: x is None, 1, 1)(m).astype(bool), np.nan, 1.0) * np.array(
+        [[0.0 if x is None else float(x) for x in row] for row in m])
+    np.fill_diagonal(fm, 0.0)
+    want_full = r_glue.check_matrix_connectivity(fm)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        got_full = subsample.check_matrix_connectivity(fm, components_fn=_scipy_components)
+    assert got_full["n_components"] == want_full["n_components"] and got_full["is_connected"] == want_full["is_connected"]
+    assert got_full["completeness"] == pytest.approx(want_full["completeness"]) and got_full["n_measurements"] == want_full["n_measurements"]
+    hits = 0
+    for seed in range(12):
+        for preserve in (False, True):
+            rng = np.random.default_rng(seed)
+            attempts = [rng.choice(60, size=25, replace=False) for _ in range(5)]
+            if preserve:
+                attempts = [np.sort(a) for a in attempts]
+            want = r_glue.subsample_dissimilarity_matrix(fm, attempts)
+            try:
+                with warnings.catch_warnings():
+                    warnings.simplefilter("ignore")
+                    got = subsample.subsample_dissimilarity_matrix(fm, 25, rng=np.random.default_rng(seed), preserve_order=preserve,
+                                                                   components_fn=_scipy_components)
+            except RuntimeError as e:
+                assert want is None and "Failed to obtain a connected subsample after 5 attempts." in str(e)
+                continue
+            hits += 1
+            assert want is not None and got["attempt_number"] == want[0] and np.array_equal(got["selected_indices"], want[1])
+            assert got["completeness"] == pytest.approx(want[2]["completeness"]) and got["is_connected"]
+            assert np.array_equal(got["subsampled_matrix"], fm[np.ix_(want[1], want[1])], equal_nan=True)
+    assert hits > 0
+    whole = subsample.subsample_dissimilarity_matrix(fm, 60, components_fn=_scipy_components)
+    assert whole["attempt_number"] == 1 and np.array_equal(whole["selected_indices"], np.arange(60))
+    with pytest.raises(ValueError, match="sample_size must be a numeric value >= 2"):
+        subsample.subsample_dissimilarity_matrix(fm, 1, components_fn=_scipy_components)
+    chk = subsample.sanity_check_subsample(fm[:30, :30], folds=20, verbose=False)
+    assert not chk["checks"]["sufficient_points"] and "Very few points (30) for 20-fold CV." in chk["warnings"][0]
+    assert chk["diagnostics"]["n_measurements"] == int((~np.isnan(fm[:30, :30])).sum() / 2)
+
+
+# ------------------------------------------------------------------ the sampler between fits ------
+def _sample_table(rows, seed):
+    rng = np.random.default_rng(seed)
+    t = {"log_N": rng.uniform(0.7, 2.3, rows), "log_k0": rng.uniform(0, 3, rows), "log_cooling_rate": rng.uniform(-7, -3, rows),
+         "log_c_repulsion": rng.uniform(-8, -2, rows)}
+    t["Holdout_MAE"] = 0.8 + 0.3 * (t["log_N"] - 1.6) ** 2 + 0.1 * rng.random(rows)
+    t["Holdout_MAE"][::17] = np.nan
+    t["Holdout_MAE"][5] = 40.0                      # an outlier the MAD rule removes
+    t["NLL"] = 100 * (1 + np.log(2 * t["Holdout_MAE"]))
+    return t
+
+
+def test_weighted_marginals_and_kde_draws_follow_the_reference():
+    """sampler.weighted_kde / calculate_weighted_marginals / generate_kde_samples (one broadcast) vs the loop
+    restatement of R/adaptive_sampling.R:1901-1935, :2457-2519, :1804-1885 with the same uniform draws."""
+    from topolow_b200 import sampler
+    t = _sample_table(90, 1)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        got = sampler.calculate_weighted_marginals(t)
+    want = r_glue.calculate_weighted_marginals(t)
+    for v in sampler.PAR_NAMES:
+        np.testing.assert_allclose(got[v]["x"], want[v]["x"], rtol=1e-12, atol=1e-12)
+        np.testing.assert_allclose(got[v]["y"], want[v]["y"], rtol=1e-10, atol=1e-300)
+        assert len(got[v]["x"]) == 512
+    # the weights favour low MAE: the log_N marginal peaks near the minimum of the MAE parabola
+    assert abs(got["log_N"]["x"][np.argmax(got["log_N"]["y"])] - 1.6) < 0.35
+    assert np.array_equal(np.isnan(sampler.clean_data(t["Holdout_MAE"])), np.isnan(np.array(r_glue.clean_data(list(t["Holdout_MAE"])))))
+
+    class Rec:                                      # hands out recorded uniforms in the order the product asks for them
+        def __init__(self): self.rng, self.u = np.random.default_rng(4), []
+        def random(self, n=None):
+            v = self.rng.random(n)
+            if n is not None: self.u.append(v)
+            return v
+    rec = Rec()
+    new = sampler.generate_kde_samples(t, 25, epsilon=0.3, rng=rec)
+    ref = r_glue.generate_kde_samples(t, 25, dict(zip(sampler.PAR_NAMES, rec.u)))
+    for v in sampler.PAR_NAMES:
+        np.testing.assert_allclose(new[v], ref[v], rtol=1e-9)
+        assert new[v].min() >= got[v]["x"][0] - 1e-9 and new[v].max() <= got[v]["x"][-1] + 1e-9
+    with pytest.raises(ValueError, match="Missing required columns: log_k0"):
+        sampler.calculate_weighted_marginals({k: v for k, v in t.items() if k != "log_k0"})
+    with pytest.raises(ValueError, match="must contain a 'Holdout_MAE' column"):
+        sampler.generate_kde_samples({"log_N": np.zeros(3)}, 2)
+
+
+def test_lhs_design_and_batched_chains():
+    from topolow_b200 import sampler
+    d = sampler.lhs_design(40, (2, 10), (1.0, 20.0), (1e-4, 0.05), (1e-4, 0.05), rng=np.random.default_rng(0))
+    assert d["N"].min() >= 2 and d["N"].max() <= 10 and d["N"].dtype.kind == "i"
+    for k, (lo, hi) in (("k0", (1.0, 20.0)), ("c_repulsion", (1e-4, 0.05)), ("cooling_rate", (1e-4, 0.05))):
+        strata = np.floor((d[k] - lo) / (hi - lo) * 40).astype(int)
+        assert sorted(strata) == list(range(40))                     # one point per stratum: a Latin hypercube
+    t = _sample_table(60, 2)
+    calls = []
+
+    def evaluate(matrix, sets):
+        calls.append(len(sets))
+        out = []
+        for s in sets:
+            mae = 0.8 + 0.3 * (math.log(s["N"]) - 1.6) ** 2
+            out.append(dict(Holdout_MAE=mae if s["k0"] < 15 else math.nan, NLL=10.0, mean_iter=50.0, pct_converged=100.0))
+        return out
+    grown = sampler.adaptive_mc_batch(t, None, iterations=5, chains=8, mapping_max_iter=10, relative_epsilon=1e-4,
+                                      rng=np.random.default_rng(3), evaluate=evaluate)
+    assert calls == [8] * 5                                           # one batch per round, all chains in it
+    added = len(grown["Holdout_MAE"]) - 60
+    assert 0 < added <= 40 and all(len(v) == 60 + added for v in grown.values())
+    assert np.all(np.exp(grown["log_N"][60:]).round() >= 1)
+    with pytest.raises(ValueError, match="Samples file missing required columns: NLL"):
+        sampler.adaptive_mc_batch({k: v for k, v in t.items() if k != "NLL"}, None, 1, 2, 10, 1e-4, evaluate=evaluate)

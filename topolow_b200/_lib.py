@@ -54,7 +54,7 @@ EXPORTS = [
     "topolow_plan_create", "topolow_plan_run", "topolow_plan_result", "topolow_plan_info",
     "topolow_plan_destroy", "topolow_plan_enumerate", "topolow_schedule_enumerate", "topolow_plan_run_job",
     "topolow_plan_end_iteration", "topolow_plan_layout", "topolow_plan_positions", "topolow_plan_enumerate_job",
-    "topolow_est_distances", "topolow_holdout_errors", "topolow_microbench", "topolow_device_info",
+    "topolow_est_distances", "topolow_holdout_errors", "topolow_components", "topolow_microbench", "topolow_device_info",
     "topolow_version", "topolow_abi_sizes",
     "topolow_shard_create", "topolow_shard_handle_bytes", "topolow_shard_export", "topolow_shard_attach",
     "topolow_shard_attach_local", "topolow_shard_run", "topolow_shard_run_local", "topolow_shard_time_kernels",
@@ -119,6 +119,9 @@ def lib() -> C.CDLL:
                                              _i32p, C.c_int64]
     L.topolow_est_distances.restype = C.c_int
     L.topolow_est_distances.argtypes = [_dp, C.c_int64, C.c_int32, _dp, C.c_int32]
+    L.topolow_components.restype = C.c_int
+    L.topolow_components.argtypes = [C.c_int64, C.c_int64, _i32p, _i32p, C.c_int32, C.POINTER(C.c_uint8), _i64p, _i64p, _i64p,
+                                     C.c_int32]
     L.topolow_holdout_errors.restype = C.c_int
     L.topolow_holdout_errors.argtypes = [_dp, C.c_int64, C.c_int32, C.c_int64, _i32p, _i32p, _dp, _dp, _i64p,
                                          C.c_int32]
@@ -434,6 +437,26 @@ def holdout_errors(positions, cell_i, cell_j, truth, device=0):
     if rc != OK:
         raise TopolowError(rc, f"topolow_holdout_errors failed with status {rc}")
     return s.value, c.value
+
+
+def components(n, edge_i, edge_j, masks=None, device=0):
+    """Connected components of the measurement graph for every candidate point subset in `masks` ([n_masks][n] bool;
+    None = all points once).  -> (components, points, edges) int64 arrays of length n_masks."""
+    ei = np.ascontiguousarray(edge_i, dtype=np.int32)
+    ej = np.ascontiguousarray(edge_j, dtype=np.int32)
+    mk, n_masks = None, 1
+    if masks is not None:
+        mk = np.ascontiguousarray(np.atleast_2d(masks), dtype=np.uint8)
+        if mk.shape[1] != n:
+            raise ValueError("masks must be [n_masks][n]")
+        n_masks = mk.shape[0]
+    comp, pts, edg = (np.zeros(n_masks, dtype=np.int64) for _ in range(3))
+    rc = lib().topolow_components(int(n), len(ei), ei.ctypes.data_as(_i32p), ej.ctypes.data_as(_i32p), n_masks,
+                                  None if mk is None else mk.ctypes.data_as(C.POINTER(C.c_uint8)), comp.ctypes.data_as(_i64p),
+                                  pts.ctypes.data_as(_i64p), edg.ctypes.data_as(_i64p), device)
+    if rc != OK:
+        raise TopolowError(rc, f"topolow_components failed with status {rc}")
+    return comp, pts, edg
 
 
 def microbench(which, device=0) -> float:

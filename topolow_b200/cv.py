@@ -14,7 +14,7 @@ import warnings
 import numpy as np
 
 from . import _lib
-from .core import build_problem, parse_dissimilarity, random_initial_positions
+from .core import build_problem, build_problem_coo, parse_dissimilarity, random_initial_positions
 
 
 def error_calculator_comparison(predicted_dissimilarities, true_dissimilarities, input_dissimilarities=None):
@@ -78,6 +78,104 @@ def make_folds(dissimilarity_matrix, folds, rng):
     return out
 
 
+def create_cv_folds(dissimilarity_matrix, ground_truth_matrix=None, n_folds=10, random_seed=None, *, rng=None):
+    """R/utils.R:69-150: a list of {truth, train} matrices; every fold masks floor(#non-NA / (2 n_folds)) cells drawn
+    from the cells no earlier fold took, symmetrically.  `rng` (numpy Generator) stands in for R's sample();
+    `random_seed` seeds a fresh one.  Matrices are float arrays with NaN = NA or object arrays, as everywhere."""
+    if random_seed is not None:
+        if not isinstance(random_seed, (int, float, np.integer, np.floating)) or random_seed != round(random_seed):
+            raise ValueError("`random_seed` must be an integer.")
+        rng = np.random.default_rng(int(random_seed))
+    rng = rng or np.random.default_rng()
+    if not isinstance(dissimilarity_matrix, np.ndarray) or dissimilarity_matrix.ndim != 2:
+        raise ValueError("`dissimilarity_matrix` must be a matrix.")
+    if ground_truth_matrix is not None:
+        if not isinstance(ground_truth_matrix, np.ndarray) or ground_truth_matrix.ndim != 2:
+            raise ValueError("`ground_truth_matrix` must be NULL or a matrix.")
+        if ground_truth_matrix.shape != dissimilarity_matrix.shape:
+            raise ValueError("`dissimilarity_matrix` and `ground_truth_matrix` must have the same dimensions.")
+    if not isinstance(n_folds, (int, float, np.integer, np.floating)) or n_folds < 2 or n_folds != round(n_folds):
+        raise ValueError("`n_folds` must be an integer greater than or equal to 2.")
+    n_folds = int(n_folds)
+    nrow, ncol = dissimilarity_matrix.shape
+    if n_folds > nrow:
+        raise ValueError("`n_folds` cannot be larger than the number of rows in the matrix.")
+    truth = ground_truth_matrix if ground_truth_matrix is not None else dissimilarity_matrix
+    pool = ~parse_dissimilarity(dissimilarity_matrix)[2]
+    holdout_size = int(pool.sum()) // (n_folds * 2)
+    na_cell = None if dissimilarity_matrix.dtype.kind == "O" else np.nan
+    out = []
+    for _ in range(n_folds):
+        if int(pool.sum()) < holdout_size:
+            warnings.warn("Could not create all requested folds due to data sparsity. Returning fewer folds.")
+            break
+        lin = np.flatnonzero(pool.ravel(order="F"))                 # which(!is.na(sampling_pool)), column-major
+        pick = rng.choice(lin, size=holdout_size, replace=False)
+        # the reference turns the linear index into (row, col) with `%/% nrow` for the row and `%% ncol` for the
+        # column (R/utils.R:129-130) - transposed for a column-major index, harmless because the mask is symmetric
+        r, c = pick // nrow, pick % ncol
+        train = dissimilarity_matrix.copy()
+        train[r, c] = na_cell
+        train[c, r] = na_cell
+        pool[r, c] = False
+        pool[c, r] = False
+        out.append(dict(truth=truth, train=train))
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# The same folds on an edge list: nothing n x n
+# ---------------------------------------------------------------------------------------------
+def make_folds_cells(n, cell_i, cell_j, folds, rng, diagonal=True):
+    """R/adaptive_sampling.R:2568-2598 on the non-NA cells of a symmetric matrix given as its upper-triangle pairs
+    (cell_i < cell_j) + optionally the n diagonal cells.  The pool holds every non-NA cell: the diagonal ones and BOTH
+    orientations of every pair; a drawn cell takes its mirror out of the pool with it.  Returns one array of cell ids
+    per fold: id < n = diagonal cell (id, id); n + 2p = pair p as (i, j), n + 2p + 1 = pair p as (j, i).
+    Walking the pool in id order instead of column-major order changes which uniform draw maps to which cell, not
+    the distribution."""
+    base = n if diagonal else 0
+    total = base + 2 * len(cell_i)
+    pool = np.ones(total, dtype=bool)
+    holdout_size = total // (folds * 2)
+    out = []
+    for _ in range(folds):
+        if int(pool.sum()) < holdout_size:
+            warnings.warn("Could not create all folds due to data sparsity. Using fewer folds.")
+            break
+        pick = rng.choice(np.flatnonzero(pool), size=holdout_size, replace=False)
+        out.append(pick)
+        pool[pick] = False
+        pr = pick[pick >= base] - base
+        pool[base + (pr ^ 1)] = False                                # the mirror cell
+    return out
+
+
+def fold_problem_cells(full, picks, base):
+    """Training problem of one fold + its out-of-sample cells from the full problem (build_problem_coo with
+    preserve_order = TRUE) and the fold's drawn cell ids: what mask + build_problem + error_calculator_comparison
+    derive from matrices (R/adaptive_sampling.R:2608-2647)."""
+    n = full["n"]
+    ci, cj = full["cell_i"], full["cell_j"]
+    held_pair = np.zeros(len(ci), dtype=bool)
+    held_pair[(picks[picks >= base] - base) >> 1] = True
+    held_diag = picks[picks < base]
+    deg = full["degrees"].astype(np.int64).copy()
+    deg -= np.bincount(ci[held_pair], minlength=n) + np.bincount(cj[held_pair], minlength=n)
+    deg[held_diag] -= 1
+    keep = ~held_pair
+    measured = keep & ~np.isnan(full["cell_value"]) & (full["cell_value"] != np.inf)
+    prob = dict(n=n, order=None, degrees=deg.astype(np.int32), edge_i=ci[measured].astype(np.int32),
+                edge_j=cj[measured].astype(np.int32), edge_dist=full["cell_value"][measured].astype(np.float64),
+                edge_thresh=full["cell_code"][measured].astype(np.int32))
+    # out-of-sample cells: masked in the training matrix, numeric (not a threshold) in the truth; the flattened matrices
+    # list a pair in both orientations and a masked diagonal cell once (truth 0)
+    out = held_pair & full["plain"]
+    hi = np.concatenate([ci[out], cj[out], held_diag]).astype(np.int32)
+    hj = np.concatenate([cj[out], ci[out], held_diag]).astype(np.int32)
+    ht = np.concatenate([full["cell_value"][out], full["cell_value"][out], np.zeros(len(held_diag))])
+    return prob, hi, hj, ht
+
+
 def _fold_job(value, code, is_na, holdout, preserve_order):
     """Training problem of one fold (R/adaptive_sampling.R:2608-2616) + its held-out cells."""
     n = value.shape[0]
@@ -119,8 +217,40 @@ def likelihood_batch(dissimilarity_matrix, samples, mapping_max_iter, relative_e
     value, code, is_na = parse_dissimilarity(dissimilarity_matrix)
     if fold_indices is None:
         fold_indices = make_folds(dissimilarity_matrix, folds, rng)
-    prec_c = {"f32": _lib.PREC_F32, "f64": _lib.PREC_F64_EXACT}[precision]
     fold_jobs = [_fold_job(value, code, is_na, np.asarray(h), preserve_order) for h in fold_indices]
+    return _run_folds(fold_jobs, samples, mapping_max_iter, relative_epsilon, init_list, rng, seed, device, precision)
+
+
+def likelihood_batch_coo(n, rows, cols, values, samples, mapping_max_iter, relative_epsilon, folds=20, *, diagonal=True,
+                         fold_cells=None, init_list=None, rng=None, seed=0, device=0, precision="f32"):
+    """likelihood_batch for a dissimilarity table (0-based rows / cols, values numbers or threshold strings): the folds
+    are drawn and masked on the cell list (make_folds_cells / fold_problem_cells), nothing n x n is built, and the
+    hold-out cells are scored on the device inside each fit.  Row order is the table's (preserve_order = TRUE).
+    `fold_cells` injects the drawn cell ids (see make_folds_cells)."""
+    rng = rng or np.random.default_rng(seed)
+    full = build_problem_coo(n, rows, cols, values, preserve_order=True, diagonal=diagonal)
+    base = n if diagonal else 0
+    if fold_cells is None:
+        fold_cells = make_folds_cells(n, full["cell_i"], full["cell_j"], folds, rng, diagonal)
+    fold_jobs = []
+    for picks in fold_cells:
+        prob, hi, hj, ht = fold_problem_cells(full, np.asarray(picks), base)
+        kept = prob["edge_thresh"] == 0       # R/core.R:407-409: the largest plain number of the fold's TRAINING matrix
+        prob["init_step"] = (max(float(prob["edge_dist"][kept].max()), 0.0) if kept.any() else 0.0) / n
+        fold_jobs.append((prob, hi, hj, ht))
+    return _run_folds(fold_jobs, samples, mapping_max_iter, relative_epsilon, init_list, rng, seed, device, precision)
+
+
+def _initial_positions(prob, ndim, rng):
+    if "value" in prob:
+        return random_initial_positions(prob["value"], prob["code"], prob["is_na"], ndim, rng)
+    steps = rng.uniform(0.0, 2.0 * prob["init_step"], size=(prob["n"] - 1, ndim))          # R/core.R:407-415
+    return np.vstack([np.zeros((1, ndim)), np.cumsum(steps, axis=0)])
+
+
+def _run_folds(fold_jobs, samples, mapping_max_iter, relative_epsilon, init_list, rng, seed, device, precision):
+    """All len(samples) x len(fold_jobs) fits in one topolow_fit_batch call, pooled as R/adaptive_sampling.R:2695-2725."""
+    prec_c = {"f32": _lib.PREC_F32, "f64": _lib.PREC_F64_EXACT}[precision]
     # hold-out cells in the row numbering of the fold's training problem: they are scored on the device
     # at the end of each fit (topolow_problem.holdout_*), the positions need not come back for that
     fold_holdout = []
@@ -141,7 +271,7 @@ def likelihood_batch(dissimilarity_matrix, samples, mapping_max_iter, relative_e
             if init_list is not None:
                 init = init_list[s_idx][f_idx]
             else:
-                init = random_initial_positions(prob["value"], prob["code"], prob["is_na"], ndim, rng)
+                init = _initial_positions(prob, ndim, rng)
             jobs.append(dict(initial_positions=init, degrees=prob["degrees"], edge_i=prob["edge_i"],
                              edge_j=prob["edge_j"], edge_dist=prob["edge_dist"], edge_thresh=prob["edge_thresh"],
                              n_iter=int(mapping_max_iter), k0=s["k0"], cooling_rate=s["cooling_rate"],
