@@ -1104,8 +1104,8 @@ void build_records(RowPlan& rp, const topolow_problem& pb) {
     fill_kernel<<<blocks, threads, 0, s>>>(d_ei, d_ej, d_dist, d_thr, E, d_slot, dv.row0, rows, d_off, d_cur, d_tmp);
     TL_CUDA(cudaGetLastError());
   }
-  static const cudaError_t sort_attr = cudaFuncSetAttribute(sell_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * kSortCap * 8);
-  TL_CUDA(sort_attr);
+  // per device, so every time (a function-local static would configure only the device of the first call)
+  TL_CUDA(cudaFuncSetAttribute(sell_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * kSortCap * 8));
   sell_kernel<<<(rows + 3) / 4, 128, 4 * kSortCap * 8, s>>>(d_tmp, d_off, d_len, dv.row0, rows, rp.soff, rp.swidth, rp.moff, rp.mwidth,
                                               rp.recs, rp.mrecs);
   TL_CUDA(cudaGetLastError());
