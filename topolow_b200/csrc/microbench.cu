@@ -115,6 +115,38 @@ __global__ void __launch_bounds__(256) mix_kernel(float* out, float a, float b, 
   if (s == 123.456f) out[0] = s;
 }
 
+// Legacy warp-level tensor instruction (mma.sync m16n8k8, TF32 inputs, FP32 accumulate): kChains independent accumulator
+// tiles per warp.  n_mma / n_fma / n_mufu per trip let the probe mix it with FP32 and special-function work (do the
+// tensor pipe and the FMA / XU pipes overlap for a warp that issues in order?).
+__global__ void __launch_bounds__(256) mma_tf32_kernel(float* out, int n_mma, int n_fma, int n_mufu) {
+  float c[kChains][4];
+  float f[kChains];
+  unsigned a0 = __float_as_uint(1.0f + threadIdx.x * 1e-3f), a1 = a0 + 64, a2 = a0 + 128, a3 = a0 + 192;
+  unsigned b0 = __float_as_uint(0.5f), b1 = __float_as_uint(0.25f);
+#pragma unroll
+  for (int k = 0; k < kChains; ++k) { c[k][0] = c[k][1] = c[k][2] = c[k][3] = 0.f; f[k] = 1.0f + k; }
+  for (int i = 0; i < kInner; ++i) {
+#pragma unroll
+    for (int k = 0; k < kChains; ++k) {
+      if (k < n_mma)
+        asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                     : "+f"(c[k][0]), "+f"(c[k][1]), "+f"(c[k][2]), "+f"(c[k][3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int k = 0; k < kChains; ++k)
+        if (j * kChains + k < n_fma) f[k] = fmaf(f[k], 1.0001f, 0.5f);
+#pragma unroll
+    for (int k = 0; k < kChains; ++k)
+      if (k < n_mufu) asm volatile("rsqrt.approx.ftz.f32 %0, %0;" : "+f"(f[k]));
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < kChains; ++k) s += c[k][0] + c[k][1] + c[k][2] + c[k][3] + f[k];
+  if (s == 123.456f) out[0] = s;
+}
+
 __global__ void copy_kernel(const float4* __restrict__ in, float4* __restrict__ out, size_t n4) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) out[i] = in[i];
@@ -149,6 +181,11 @@ extern "C" int topolow_microbench(int32_t which, int32_t device, double* value_o
         case 6: mix_kernel<<<blocks, threads, 0, s>>>(d_out, 1.0001f, 0.5f, 8, 0); break;   // 8 FFMA2 per trip
         case 7: mix_kernel<<<blocks, threads, 0, s>>>(d_out, 1.0001f, 0.5f, 0, 4); break;   // 4 SHFL per trip
         case 8: mix_kernel<<<blocks, threads, 0, s>>>(d_out, 1.0001f, 0.5f, 8, 4); break;   // both
+        case 9: mma_tf32_kernel<<<blocks, threads, 0, s>>>(d_out, 8, 0, 0); break;                                  // tensor only, full occupancy
+        case 10: mma_tf32_kernel<<<prop.multiProcessorCount * 2, threads, 0, s>>>(d_out, 8, 0, 0); break;         // 4 warps per scheduler
+        case 11: mma_tf32_kernel<<<prop.multiProcessorCount * 2, threads, 0, s>>>(d_out, 5, 24, 6); break;        // the mix of one trip
+        case 12: mma_tf32_kernel<<<prop.multiProcessorCount * 2, threads, 0, s>>>(d_out, 0, 24, 6); break;        // its FP32 / MUFU part
+        case 13: mma_tf32_kernel<<<prop.multiProcessorCount * 2, threads, 0, s>>>(d_out, 5, 0, 0); break;         // its tensor part
         default: return TOPOLOW_ERR_BAD_ARG;
       }
       TL_CUDA(cudaGetLastError());
@@ -166,7 +203,9 @@ extern "C" int topolow_microbench(int32_t which, int32_t device, double* value_o
     else if (which == 3) v = thread_ops / 32.0 / sec;      // warp instructions / s
     else if (which == 4) v = thread_ops / 32.0 / sec;      // warp MUFU instructions / s
     else if (which == 5) v = 2.0 * copy_bytes / sec;       // bytes/s
-    else v = sec * 1e3;                                    // 6..8: milliseconds of the FFMA2 / SHFL / mixed loop
+    else if (which == 9) v = thread_ops / 32.0 * (2.0 * 16 * 8 * 8) / sec;                                        // flop/s
+    else if (which == 10) v = (double)prop.multiProcessorCount * 2 * threads * kInner * kChains / 32.0 * (2.0 * 16 * 8 * 8) / sec;
+    else v = sec * 1e3;                                    // 6..8, 11..13: milliseconds of the loop
     *value_out = v;
     cudaFree(d_out); if (d_a) cudaFree(d_a); if (d_b) cudaFree(d_b);
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaStreamDestroy(s);

@@ -51,6 +51,7 @@ constexpr unsigned long long kWaitNs = 20ull * 1000ull * 1000ull * 1000ull;
 
 struct RowDev {
   int n, slots, D, Dp, G, rank, row0, rows, chunks;
+  int rparts;                        // partial-sum entries per row in rpart: chunks (2 x chunks for the tensor-core pass)
   int no_wait;                       // measurement only (TOPOLOW_IGNORE_PEERS): one rank of a sharded map timed without its peers
   unsigned long long cap_rows;       // rows of one position buffer (slots rounded up to a chunk)
   float* pos[kMaxShards];            // replica q: [2][cap_rows][Dp]
@@ -492,6 +493,8 @@ __global__ void __maxnreg__(MAXR) repulse_dot_kernel(RowDev dv, int cur, unsigne
   }
 }
 
+#include "rowblock_tc.cuh"
+
 // ---------------------------------------------------------------------------------------------------
 // the walk over the records of the own rows (springs and edge MAE)
 // ---------------------------------------------------------------------------------------------------
@@ -710,7 +713,7 @@ __global__ void __launch_bounds__(kBlockRows) combine_kernel(RowDev dv, FitParam
     ld_point<H>(dv.xs + (size_t)lrow * Dp, x);
 #pragma unroll
     for (int kk = 0; kk < H; ++kk) rs[kk] = make_float2(0.f, 0.f);
-    for (int c = 0; c < dv.chunks; ++c) {
+    for (int c = 0; c < dv.rparts; ++c) {
       float2 t[H];
       ld_point<H>(dv.rpart + ((size_t)c * dv.rows + lrow) * Dp, t);
 #pragma unroll
@@ -986,6 +989,9 @@ struct RowPlan {
   // local
   float* best = nullptr; float* dp1 = nullptr; float* rpart = nullptr; float* xs = nullptr;
   float* img = nullptr; float* hmax = nullptr;
+  float* tc_buf = nullptr;    // the five arrays of TcImage in one allocation
+  bool tc_form = false;       // distances on the tensor cores (image_tc_kernel + repulse_tc_kernel)
+  int tc_cpi = 1;             // partner chunks per work item
   bool dot_form = false;      // repulsion in the inner-product form (image_kernel + repulse_dot_kernel)
   uint2* recs = nullptr; uint2* mrecs = nullptr;
   unsigned long long* soff = nullptr; unsigned long long* moff = nullptr; int* swidth = nullptr; int* mwidth = nullptr;
@@ -1013,7 +1019,7 @@ struct RowPlan {
     if (stream) cudaStreamSynchronize(stream);
     for (int q = 0; q < kMaxShards; ++q) if (peer_base[q] && peer_ipc[q]) cudaIpcCloseMemHandle(peer_base[q]);
     if (shared) cudaFree(shared);
-    pool_free(best); pool_free(dp1); pool_free(rpart); pool_free(xs); pool_free(img); pool_free(hmax); pool_free(recs); pool_free(mrecs);
+    pool_free(best); pool_free(dp1); pool_free(rpart); pool_free(xs); pool_free(img); pool_free(hmax); pool_free(tc_buf); pool_free(recs); pool_free(mrecs);
     pool_free(soff); pool_free(moff); pool_free(swidth); pool_free(mwidth);
     pool_free(state); pool_free(trace); pool_free(counters);
     if (h_flag) cudaFreeHost((void*)h_flag);
@@ -1114,6 +1120,29 @@ void build_records(RowPlan& rp, const topolow_problem& pb) {
   dv.recs = rp.recs; dv.mrecs = rp.mrecs; dv.soff = rp.soff; dv.moff = rp.moff; dv.swidth = rp.swidth; dv.mwidth = rp.mwidth;
 }
 
+TcImage tc_image(const RowPlan& rp) {
+  TcImage im;
+  const size_t cap = rp.dv.cap_rows;
+  im.xhi = rp.tc_buf; im.xlo = im.xhi + 16 * cap; im.aug_a = im.xlo + 16 * cap; im.aug_b = im.aug_a + 4 * cap; im.rows32 = im.aug_b + 4 * cap;
+  return im;
+}
+template <int H>
+void launch_image_tc(RowPlan& rp, cudaStream_t s, int cur, unsigned e_prev) {
+  image_tc_kernel<H><<<(unsigned)(rp.dv.cap_rows / kBlockRows), kBlockRows, 0, s>>>(rp.dv, tc_image(rp), cur, e_prev);
+  rp.launches += 1;
+}
+template <int H>
+void launch_repulse_tc(RowPlan& rp, cudaStream_t s, int cur, bool dependent) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)rp.rep_ctas); cfg.blockDim = dim3(kTcThreads);
+  cfg.dynamicSmemBytes = TcSmem::kTotal; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = dependent ? 1 : 0;
+  TL_CUDA(cudaLaunchKernelEx(&cfg, repulse_tc_kernel<H>, rp.dv, tc_image(rp), cur, rp.tc_cpi));
+}
+
 template <int H, int kRing> constexpr size_t kWalkSmem = (size_t)(kBlockRows / 32) * Ring<H, kRing>::kWarpBytes;
 
 // the spring / MAE launches of one rank (deep ring when the rank owns few rows)
@@ -1134,6 +1163,7 @@ void launch_iteration(RowPlan& rp, cudaStream_t s, cudaEvent_t* ev /* 7 events o
   const int row_ctas = dv.rows / kBlockRows;
   if (ev) TL_CUDA(cudaEventRecord(ev[0], s));
   if (rp.dot_form) { image_kernel<H><<<dv.slots / kBlockRows, kBlockRows, 0, s>>>(dv, cur, e_prev); rp.launches += 1; }
+  if (rp.tc_form) launch_image_tc<H>(rp, s, cur, e_prev);
   if (overlap) {
     // The walk first: its CTAs announce themselves at once (griddepcontrol.launch_dependents), which lets the
     // repulsion grid - launched as a programmatic dependent, it has no data dependence on the walk - fill the
@@ -1147,9 +1177,11 @@ void launch_iteration(RowPlan& rp, cudaStream_t s, cudaEvent_t* ev /* 7 events o
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    TL_CUDA(cudaLaunchKernelEx(&cfg, (RepulseFn)rp.rep_fn, dv, cur, e_prev));
+    if (rp.tc_form) launch_repulse_tc<H>(rp, s, cur, true);
+    else TL_CUDA(cudaLaunchKernelEx(&cfg, (RepulseFn)rp.rep_fn, dv, cur, e_prev));
   } else {
-    ((RepulseFn)rp.rep_fn)<<<rp.rep_ctas, rp.rep_threads, rp.rep_smem, s>>>(dv, cur, e_prev);
+    if (rp.tc_form) launch_repulse_tc<H>(rp, s, cur, false);
+    else ((RepulseFn)rp.rep_fn)<<<rp.rep_ctas, rp.rep_threads, rp.rep_smem, s>>>(dv, cur, e_prev);
     if (ev) TL_CUDA(cudaEventRecord(ev[1], s));
     launch_spring<H>(rp, s, cur, e_prev);
     if (ev) TL_CUDA(cudaEventRecord(ev[2], s));
@@ -1224,7 +1256,43 @@ void configure_repulse(RowPlan& rp, int sms) {
   const char* ev = std::getenv("TOPOLOW_REP_VARIANT");
   RepulseFn fn; int threads;
   int stage = kStageJ;
-  repulse_variant<H>(ev ? std::atoi(ev) : 0, &fn, &threads, &rp.dot_form, &stage);
+  const int variant = ev ? std::atoi(ev) : 0;
+  if (variant == 10) {          // distances on the tensor cores
+    rp.tc_form = true;
+    rp.dv.rparts = 2 * rp.dv.chunks;
+    TL_CUDA(cudaFuncSetAttribute(repulse_tc_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem::kTotal));
+    TL_CUDA(cudaFuncSetAttribute(repulse_tc_kernel<H>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    int per_sm = 0;
+    TL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, repulse_tc_kernel<H>, kTcThreads, TcSmem::kTotal));
+    if (std::getenv("TOPOLOW_DEBUG")) {
+      int sm_smem = 0, blk_smem = 0, regs_sm = 0, o0 = 0, o1 = 0, o2 = 0, o3 = 0;
+      cudaDeviceGetAttribute(&sm_smem, cudaDevAttrMaxSharedMemoryPerMultiprocessor, rp.device);
+      cudaDeviceGetAttribute(&blk_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, rp.device);
+      cudaDeviceGetAttribute(&regs_sm, cudaDevAttrMaxRegistersPerMultiprocessor, rp.device);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o0, repulse_tc_kernel<H>, kTcThreads, 0);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o1, repulse_tc_kernel<H>, kTcThreads, 65536);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o2, repulse_tc_kernel<H>, 256, TcSmem::kTotal);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o3, repulse_tc_kernel<H>, kTcThreads, 90000);
+      cudaFuncAttributes fa;
+      cudaFuncGetAttributes(&fa, repulse_tc_kernel<H>);
+      std::fprintf(stderr, "[topolow] repulse_tc: %d CTAs per SM by the occupancy API at %d bytes (0 B: %d, 64 KB: %d, 90000 B: %d, 256 threads: %d); "
+                   "SM smem %d, block optin %d, regs/SM %d; kernel regs %d static smem %d maxdyn %d carveout %d\n",
+                   per_sm, (int)TcSmem::kTotal, o0, o1, o3, o2, sm_smem, blk_smem, regs_sm, fa.numRegs, (int)fa.sharedSizeBytes,
+                   fa.maxDynamicSharedSizeBytes, fa.preferredShmemCarveout);
+    }
+    // The occupancy API answers 1 for a kernel that allocates tensor memory (it cannot know how many of the 512 columns
+    // tcgen05.alloc will ask for); registers, shared memory and the 256 columns a CTA takes all allow two, and the work
+    // split does not depend on how many CTAs are resident at once.
+    per_sm = 2;
+    if (const char* ec = std::getenv("TOPOLOW_TC_CTAS")) per_sm = std::max(1, std::atoi(ec));
+    const long long pairs = (long long)(rp.dv.rows / kRowTile) * rp.dv.chunks;
+    rp.tc_cpi = (int)std::max<long long>(1, std::min<long long>(rp.dv.chunks, pairs / (6ll * sms * per_sm)));
+    if (const char* ec = std::getenv("TOPOLOW_TC_CPI")) rp.tc_cpi = std::max(1, std::atoi(ec));
+    const long long items = (long long)(rp.dv.rows / kRowTile) * ((rp.dv.chunks + rp.tc_cpi - 1) / rp.tc_cpi);
+    rp.rep_ctas = (int)std::min<long long>((long long)sms * per_sm, std::max<long long>(items, 1));
+    rp.rep_threads = kTcThreads; rp.rep_smem = TcSmem::kTotal; rp.rep_fn = nullptr;
+  }
+  repulse_variant<H>(rp.tc_form ? 5 : variant, &fn, &threads, &rp.dot_form, &stage);
   const size_t smem = rp.dot_form ? (size_t)kStages * stage * Img<H>::kStride * sizeof(float) + (size_t)2 * H * threads * sizeof(float2)
                                   : (size_t)kStages * kStageJ * Row<H>::kStride * sizeof(float);
   if (smem > 48 * 1024) TL_CUDA(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1233,9 +1301,11 @@ void configure_repulse(RowPlan& rp, int sms) {
   if (per_sm < 1) per_sm = 1;
   if (const char* ec = std::getenv("TOPOLOW_REP_CTAS")) per_sm = std::max(1, std::atoi(ec));
   const long long items = (long long)(rp.dv.rows / kRowTile) * rp.dv.chunks;
-  rp.rep_ctas = (int)std::min<long long>((long long)sms * per_sm, std::max<long long>(items, 1));
-  rp.rep_smem = smem;
-  rp.rep_fn = (void*)fn; rp.rep_threads = threads;
+  if (!rp.tc_form) {
+    rp.rep_ctas = (int)std::min<long long>((long long)sms * per_sm, std::max<long long>(items, 1));
+    rp.rep_smem = smem;
+    rp.rep_fn = (void*)fn; rp.rep_threads = threads;
+  }
   rp.sm_count = sms;
   rp.overlap = true;   // measured on B200 at cfg4: one rank of 8 2.61 -> 2.38 ms, of 2 9.11 -> 8.99, one GPU 18.29 -> 18.11; cfg3 0.47 -> 0.29
   if (const char* eo = std::getenv("TOPOLOW_OVERLAP")) rp.overlap = std::atoi(eo) != 0;
@@ -1271,6 +1341,7 @@ RowPlan* row_create(const topolow_problem& pb, const topolow_params& pr, int ran
   dv.row0 = t0 * kRowTile; dv.rows = (t1 - t0) * kRowTile;
   if (tiles < n_ranks) throw BadArg("too few points for this many ranks (every rank needs at least 256 rows)");
   dv.chunks = (int)((pb.n + kChunk - 1) / kChunk);
+  dv.rparts = dv.chunks;
   dv.cap_rows = align_up((size_t)dv.slots, kChunk);
   dv.pairs_per_iter = (unsigned long long)pb.n * (unsigned long long)(pb.n - 1) / 2ull;
   dv.seed = pr.seed;
@@ -1304,7 +1375,8 @@ RowPlan* row_create(const topolow_problem& pb, const topolow_params& pr, int ran
     }
     pool_alloc(rp->best, hp.size() * sizeof(float));
     pool_alloc(rp->dp1, hd.size() * sizeof(float));
-    pool_alloc(rp->rpart, (size_t)dv.chunks * std::max(dv.rows, 1) * dv.Dp * sizeof(float));
+    pool_alloc(rp->rpart, (size_t)2 * dv.chunks * std::max(dv.rows, 1) * dv.Dp * sizeof(float));
+    pool_alloc(rp->tc_buf, dv.cap_rows * (size_t)(16 + 16 + 4 + 4 + 16) * sizeof(float));
     pool_alloc(rp->xs, (size_t)std::max(dv.rows, 1) * dv.Dp * sizeof(float));
     pool_alloc(rp->img, dv.cap_rows * (size_t)(((dv.D + 1) / 2 * 2 + 2 + 3) / 4 * 4) * sizeof(float));   // Img<H>::kStride floats per row
     pool_alloc(rp->hmax, 2 * sizeof(float));
@@ -1463,7 +1535,8 @@ double row_run_local(RowPlan* const* plans, int n, int n_iters) {
           constexpr int H = decltype(h)::value;
           const unsigned e_prev = rp.epoch;
           if (rp.dot_form) { image_kernel<H><<<rp.dv.slots / kBlockRows, kBlockRows, 0, s>>>(rp.dv, cur, e_prev); rp.launches += 1; }
-          ((RepulseFn)rp.rep_fn)<<<rp.rep_ctas, rp.rep_threads, rp.rep_smem, s>>>(rp.dv, cur, e_prev);
+          if (rp.tc_form) { launch_image_tc<H>(rp, s, cur, e_prev); launch_repulse_tc<H>(rp, s, cur, false); }
+          else ((RepulseFn)rp.rep_fn)<<<rp.rep_ctas, rp.rep_threads, rp.rep_smem, s>>>(rp.dv, cur, e_prev);
           launch_spring<H>(rp, s, cur, e_prev);
           combine_kernel<H><<<rp.dv.rows / kBlockRows, kBlockRows, 0, s>>>(rp.dv, rp.prm, cur, ++rp.epoch);
         });
