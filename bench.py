@@ -618,15 +618,18 @@ def main_map(args, n, d, missing):
         rep_flop = (7 * d + 8) * pairs / world
         rep_s = kt["repulse"] * 1e-3
         edge_b = edge_bytes_per_iter(n, d, E) / world
-        roofline = {"bound": "fp32", "kernel": "repulse_kernel<ndim/2, 2 rows per thread> (one launch per iteration and rank)",
+        tc = d >= 9 and not os.environ.get("TOPOLOW_REP_VARIANT")
+        roofline = {"bound": "fp32", "kernel": ("image_tc_kernel + repulse_tc_kernel<ndim/2> (pair distances as a 3-pass TF32 GEMM on tcgen05 with TMEM "
+                                                "accumulators; weights and accumulation on the FP32 pipes)" if tc else
+                                                "repulse_kernel<ndim/2, 2 rows per thread>") + " (one launch per iteration and rank)",
                     "achieved": rep_flop / rep_s / 1e12, "peak": ffma_peak / 1e12, "unit": "TFLOP/s",
                     "frac": rep_flop / rep_s / ffma_peak,
                     "peak_source": "topolow_microbench FFMA, measured live on this GPU (FP32 is not in MEASURED_PEAKS.json)",
                     "algorithmic_flop_per_launch": rep_flop, "launch_ms": kt["repulse"],
-                    "note": "algorithmic = (7 ndim + 8) flop per unordered pair (SURVEY 8d); the kernel visits every pair from both "
-                            "sides (one-sided updates) and executes 54 FMA-pipe cycles per side at ndim 16, so 1.0 is not reachable: "
-                            "100 % FMA-pipe occupancy reads as 0.56 here; ncu (profiles/r2_ncu_rowblock_cfg4.md): FMA pipe 82 % of cycles, "
-                            "issue port 94 % (a packed FP32 instruction holds it for two cycles)",
+                    "note": "algorithmic = (7 ndim + 8) flop per unordered pair (SURVEY 8d) against the FP32 FFMA peak; the kernel visits "
+                            "every pair from both sides (one-sided updates). With the distances on the tensor cores the FP32 pipes "
+                            "execute ~33 issue-port cycles per side at ndim 16 (weights on the special-function unit + 8 packed FMA of the "
+                            "accumulation); the difference form (repulse_kernel, ndim < 9) needs 57 and ran at 0.51",
                     "traffic": tracked_traffic("repulse_kernel"),
                     "kernels_ms": kt,
                     "edge_pass": {"bound": "hbm", "kernel": "mae_kernel (edge MAE on check iterations)",

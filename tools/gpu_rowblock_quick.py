@@ -27,9 +27,9 @@ if os.environ.get("QUICK_TWICE"):      # a first shard pays for module loading a
     rowblock.Shard(*fa, 3, 5.0, 0.01, 0.02, 1e-4, 10 ** 6, 3, seed=0).close()
     print("---- second create ----", flush=True)
 t0 = time.time()
-sh = rowblock.Shard(*fa, 3 + 6 + iters, 5.0, 0.01, 0.02, 1e-4, 10 ** 6, 3, seed=0)
+sh = rowblock.Shard(*fa, int(os.environ.get('QUICK_WARM', '3')) + 6 + iters, 5.0, 0.01, 0.02, 1e-4, 10 ** 6, 3, seed=0)
 print("create %.2fs" % (time.time() - t0), sh.info(), flush=True)
-sh.run(3)
+sh.run(int(os.environ.get('QUICK_WARM', '3')))
 tk = sh.time_kernels(6)
 print("kernels ms:", {k: round(v, 4) if isinstance(v, float) else v for k, v in tk.items()}, flush=True)
 ms = sh.run(iters)

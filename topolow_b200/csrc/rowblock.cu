@@ -494,6 +494,7 @@ __global__ void __maxnreg__(MAXR) repulse_dot_kernel(RowDev dv, int cur, unsigne
 }
 
 #include "rowblock_tc.cuh"
+#include "rowblock_tc2.cuh"
 
 // ---------------------------------------------------------------------------------------------------
 // the walk over the records of the own rows (springs and edge MAE)
@@ -991,6 +992,7 @@ struct RowPlan {
   float* img = nullptr; float* hmax = nullptr;
   float* tc_buf = nullptr;    // the five arrays of TcImage in one allocation
   bool tc_form = false;       // distances on the tensor cores (image_tc_kernel + repulse_tc_kernel)
+  bool tc2_form = false;      // distances and accumulation on the tensor cores (+ image_t2_kernel, repulse_tc2_kernel)
   int tc_cpi = 1;             // partner chunks per work item
   bool dot_form = false;      // repulsion in the inner-product form (image_kernel + repulse_dot_kernel)
   uint2* recs = nullptr; uint2* mrecs = nullptr;
@@ -1126,10 +1128,20 @@ TcImage tc_image(const RowPlan& rp) {
   im.xhi = rp.tc_buf; im.xlo = im.xhi + 16 * cap; im.aug_a = im.xlo + 16 * cap; im.aug_b = im.aug_a + 4 * cap; im.rows32 = im.aug_b + 4 * cap;
   return im;
 }
+T2Image t2_image(const RowPlan& rp) {
+  T2Image im;
+  im.a = tc_image(rp);
+  im.yhi = im.a.rows32 + 16 * rp.dv.cap_rows; im.ylo = im.yhi + 32 * rp.dv.cap_rows;
+  return im;
+}
 template <int H>
 void launch_image_tc(RowPlan& rp, cudaStream_t s, int cur, unsigned e_prev) {
   image_tc_kernel<H><<<(unsigned)(rp.dv.cap_rows / kBlockRows), kBlockRows, 0, s>>>(rp.dv, tc_image(rp), cur, e_prev);
   rp.launches += 1;
+  if (rp.tc2_form) {
+    image_t2_kernel<<<(unsigned)(rp.dv.cap_rows / 4 * 32 / 256), 256, 0, s>>>(rp.dv, t2_image(rp));
+    rp.launches += 1;
+  }
 }
 template <int H>
 void launch_repulse_tc(RowPlan& rp, cudaStream_t s, int cur, bool dependent) {
@@ -1140,6 +1152,11 @@ void launch_repulse_tc(RowPlan& rp, cudaStream_t s, int cur, bool dependent) {
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at; cfg.numAttrs = dependent ? 1 : 0;
+  if (rp.tc2_form) {
+    cfg.blockDim = dim3(kT2Threads); cfg.dynamicSmemBytes = T2Smem::kTotal;
+    TL_CUDA(cudaLaunchKernelEx(&cfg, repulse_tc2_kernel<H>, rp.dv, t2_image(rp), cur, rp.tc_cpi));
+    return;
+  }
   TL_CUDA(cudaLaunchKernelEx(&cfg, repulse_tc_kernel<H>, rp.dv, tc_image(rp), cur, rp.tc_cpi));
 }
 
@@ -1223,8 +1240,9 @@ void launch_one(RowPlan& rp, cudaStream_t s, cudaEvent_t* ev = nullptr) {
 
 // Shapes of the repulsion kernel: {rows per thread, partner unroll, register cap, cube on the SFU}.
 // 0 is the production shape; the others stay selectable (TOPOLOW_REP_VARIANT) for measurements.
-// Variant 0 = policy = 5, the difference form.  The inner-product forms (4, 6-9) are kept selectable as the measured
-// record of why they are not the default (B200, cfg4 / cfg3 repulsion pass in ms; difference form 16.8 / 0.23):
+// Variant 0 = policy: 10 (rowblock_tc.cuh: distances on the tensor cores) from ndim 9 on, 5 (the difference form) below.
+// The FP32 inner-product forms (4, 6-9) are kept selectable as the measured record of why they are not used (B200, cfg4 /
+// cfg3 repulsion pass in ms; difference form 16.8 / 0.23, tensor-core form 13.4 / 0.19):
 //   6  one partner per trip, no spill          16.6 / 0.30   issue port 79 % busy (a packed instruction holds it 2 cycles):
 //                                                            two dependency chains per warp cannot hide the MUFU chain
 //   4  two partners per trip, 128 registers    19.1 / 0.31   needs 159 registers; capped, ptxas spills W / sp / thr and shuffles p
@@ -1256,10 +1274,17 @@ void configure_repulse(RowPlan& rp, int sms) {
   const char* ev = std::getenv("TOPOLOW_REP_VARIANT");
   RepulseFn fn; int threads;
   int stage = kStageJ;
-  const int variant = ev ? std::atoi(ev) : 0;
-  if (variant == 10) {          // distances on the tensor cores
+  int variant = ev ? std::atoi(ev) : 0;
+  if (variant == 0) variant = H >= 5 ? 10 : 5;   // policy, measured (ms per repulsion pass, 10 vs 5): ndim 16 / 100k: 13.4 vs 16.8; ndim 12 / 40k:
+                                                 // 1.82 vs 2.32; ndim 10 / 10k: 0.19 vs 0.23; ndim 6 / 30k: 0.84 vs 0.75
+  if (variant == 10 || variant == 11) {          // distances (10) / distances and accumulation (11) on the tensor cores
     rp.tc_form = true;
-    rp.dv.rparts = 2 * rp.dv.chunks;
+    rp.tc2_form = variant == 11;
+    rp.dv.rparts = (rp.tc2_form ? 3 : 2) * rp.dv.chunks;
+    if (rp.tc2_form) {
+      TL_CUDA(cudaFuncSetAttribute(repulse_tc2_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2Smem::kTotal));
+      TL_CUDA(cudaFuncSetAttribute(repulse_tc2_kernel<H>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    }
     TL_CUDA(cudaFuncSetAttribute(repulse_tc_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem::kTotal));
     TL_CUDA(cudaFuncSetAttribute(repulse_tc_kernel<H>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     int per_sm = 0;
@@ -1375,8 +1400,8 @@ RowPlan* row_create(const topolow_problem& pb, const topolow_params& pr, int ran
     }
     pool_alloc(rp->best, hp.size() * sizeof(float));
     pool_alloc(rp->dp1, hd.size() * sizeof(float));
-    pool_alloc(rp->rpart, (size_t)2 * dv.chunks * std::max(dv.rows, 1) * dv.Dp * sizeof(float));
-    pool_alloc(rp->tc_buf, dv.cap_rows * (size_t)(16 + 16 + 4 + 4 + 16) * sizeof(float));
+    pool_alloc(rp->rpart, (size_t)3 * dv.chunks * std::max(dv.rows, 1) * dv.Dp * sizeof(float));
+    pool_alloc(rp->tc_buf, dv.cap_rows * (size_t)(16 + 16 + 4 + 4 + 16 + 32 + 16) * sizeof(float));
     pool_alloc(rp->xs, (size_t)std::max(dv.rows, 1) * dv.Dp * sizeof(float));
     pool_alloc(rp->img, dv.cap_rows * (size_t)(((dv.D + 1) / 2 * 2 + 2 + 3) / 4 * 4) * sizeof(float));   // Img<H>::kStride floats per row
     pool_alloc(rp->hmax, 2 * sizeof(float));

@@ -11,9 +11,12 @@
 // special-function unit, and the accumulation A_i += w x_j, W_i += w (8 packed FMA) with partner rows broadcast from
 // shared memory; the sum over partners is A_i - x_i W_i.  About 30 issue-port cycles per interaction instead of 57.
 //
-// Pairs whose inner-product distance cannot be trusted (d^2 / 2 < 1e-3 (h_i + max_j h_j): relative error could pass 1e-3;
-// in 16 dimensions that is the point itself and hardly anything else) get weight 0 in the main loop and are re-done from
-// the coordinate differences; the point itself (difference exactly 0) contributes nothing, as in the difference form.
+// Pairs whose inner-product distance cannot be trusted get weight 0 in the main loop and are re-done from the coordinate
+// differences (the point itself, difference exactly 0, contributes nothing, as in the difference form).  The error of
+// d^2 / 2 is about 7e-7 (h_i + h_j), h = |x|^2 / 2; "near" means d^2 / 2 < tau (h_i + h_j) with tau = 1e-3 (relative error of
+// d^2 could pass 1e-3).  A near partner has |x_j| <= |x_i| + d, hence h_j <= 2 h_i + d^2, and the test
+// d^2 / 2 < 3.01 tau h_i - a per-row constant - catches every such pair whatever the rest of the map looks like.
+// In 16 dimensions that is the point itself and hardly anything else.
 //
 // Roles in a CTA of 9 warps: warp 8, one elected lane, is producer and MMA issuer (1-D bulk copies global -> shared
 // signalled on mbarriers, tcgen05.mma, tcgen05.commit); warps 0-7 consume: warp w reads TMEM lanes 32 (w % 4) .. + 31
@@ -122,7 +125,6 @@ __global__ void __launch_bounds__(kBlockRows) image_tc_kernel(RowDev dv, TcImage
   if (__ldcg(&dv.state->stop)) return;
   if (!wait_epoch(dv, epoch)) { if (blockIdx.x == 0 && threadIdx.x == 0) peer_timeout(dv); return; }
   const size_t row = (size_t)blockIdx.x * kBlockRows + threadIdx.x;     // grid covers cap_rows
-  if (row == 0) dv.hmax[cur ^ 1] = 0.f;
   float x[16];
 #pragma unroll
   for (int k = 0; k < 16; ++k) x[k] = 0.f;
@@ -150,10 +152,22 @@ __global__ void __launch_bounds__(kBlockRows) image_tc_kernel(RowDev dv, TcImage
   const float h_hi = tf32_round(h), hb_hi = tf32_round(hb);
   reinterpret_cast<float4*>(im.aug_a)[row] = make_float4(-h_hi, -(h - h_hi), -1.f, -1.f);
   reinterpret_cast<float4*>(im.aug_b)[row] = make_float4(1.f, 1.f, hb_hi, hb - hb_hi);
-  float m = real ? h : 0.f;
+}
+
+// A near pair, from the coordinate differences (the arithmetic of repulse_kernel).  Out of line and on accumulators in
+// local memory: it must not cost the main loop registers, and it is rare in a map that has spread out (the point
+// itself, once per row and iteration) but not in the first iterations of a tightly packed start.
+template <int H>
+__device__ __noinline__ void near_fix(const float* __restrict__ xi, const float* __restrict__ xj, float* __restrict__ facc) {
+  float d2 = 0.f;
 #pragma unroll
-  for (int d = 16; d > 0; d >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, d));
-  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(reinterpret_cast<int*>(dv.hmax + cur), __float_as_int(m));
+  for (int k = 0; k < 2 * H; ++k) { const float dl = xj[k] - __ldg(xi + k); d2 = fmaf(dl, dl, d2); }
+  if (d2 > 0.f) {                                 // the point itself (and exact duplicates) contribute nothing
+    const float ds = sqrt_approx(d2) + 0.01f;
+    const float w = ex2_approx(-3.0f * lg2_approx(ds));
+#pragma unroll
+    for (int k = 0; k < 2 * H; ++k) facc[k] = fmaf(xj[k] - __ldg(xi + k), w, facc[k]);
+  }
 }
 
 // ---- the pass ------------------------------------------------------------------------------------------
@@ -285,7 +299,6 @@ __global__ void __maxnreg__(80) repulse_tc_kernel(RowDev dv, TcImage im, int cur
     // ======================================= consumers =======================================
     const int quad = warp & 3, half = warp >> 2;
     const unsigned lane_sel = (unsigned)(quad * 32) << 16;
-    const float hmax = __ldcg(dv.hmax + cur);
     unsigned g = 0;
     for (long long item = blockIdx.x; item < items; item += gridDim.x) {
       const int tile = (int)(item / groups), grp = (int)(item % groups);
@@ -293,10 +306,14 @@ __global__ void __maxnreg__(80) repulse_tc_kernel(RowDev dv, TcImage im, int cur
       const int lrow[2] = {tile * kTcRows + quad * 32 + lane, tile * kTcRows + 128 + quad * 32 + lane};
       float thr[2];
 #pragma unroll
-      for (int r = 0; r < 2; ++r) thr[r] = 1e-3f * (-__ldg(im.aug_a + (size_t)(dv.row0 + lrow[r]) * 4) + hmax);   // aug_a.x = -h_hi
+      for (int r = 0; r < 2; ++r) thr[r] = -3.01e-3f * __ldg(im.aug_a + (size_t)(dv.row0 + lrow[r]) * 4);   // aug_a.x = -h_i (TF32-rounded)
       for (int c = c_lo; c < c_hi; ++c) {
         float2 acc[2][H];
         float W[2] = {0.f, 0.f};
+        float facc[32];                                         // sums of the near pairs (difference form), both rows
+        bool fixed = false;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) facc[k] = 0.f;
 #pragma unroll
         for (int r = 0; r < 2; ++r)
 #pragma unroll
@@ -325,7 +342,7 @@ __global__ void __maxnreg__(80) repulse_tc_kernel(RowDev dv, TcImage im, int cur
                 const float S = __uint_as_float(r == 0 ? s0[jj] : s1[jj]);          // d^2 / 2
                 const bool nr = S < thr[r];
                 // (d + 0.01)^-3 with d = sqrt(2 S): 2^(-1.5 - 3 log2(sqrt(S) + 0.01 / sqrt(2)))
-                const float ds = sqrt_approx(S) + 0.00707106781f;
+                const float ds = sqrt_approx(fabsf(S)) + 0.00707106781f;       // |.|: a rounding-negative S of a near pair must not make a NaN
                 float w = ex2_approx(fmaf(-3.0f, lg2_approx(ds), -1.5f));
                 w = nr ? 0.f : w;
                 flag |= nr;
@@ -335,27 +352,21 @@ __global__ void __maxnreg__(80) repulse_tc_kernel(RowDev dv, TcImage im, int cur
                 W[r] += w;
               }
             }
-            if (__any_sync(0xffffffffu, flag)) {                // rare: some pair of this batch is near - redo those from differences
-              for (int jj = 0; jj < 8; ++jj) {
+            if (__any_sync(0xffffffffu, flag)) {                // some pair of this batch is near: redo those from differences
+              unsigned t0[8], t1[8];
+              tc_ld8(t_base + bt * 8, t0);
+              tc_ld8(t_base + kTcSJ + bt * 8, t1);
+              tc_wait_ld();
+              float sv[16];                                    // indexed in a loop: lives in local memory, on this path only
 #pragma unroll
-                for (int r = 0; r < 2; ++r) {
-                  const float S = __uint_as_float(tc_ld1(t_base + r * kTcSJ + bt * 8 + jj));
-                  tc_wait_ld();
-                  if (S < thr[r]) {
-                    const float* xi = im.rows32 + (size_t)(dv.row0 + lrow[r]) * 16;
-                    const float* xj = q_s + (bt * 8 + jj) * 16;
-                    float d2 = 0.f;
-                    for (int k = 0; k < 2 * H; ++k) { const float dl = xj[k] - __ldg(xi + k); d2 = fmaf(dl, dl, d2); }
-                    if (d2 > 0.f) {                             // the point itself (and exact duplicates) contribute nothing
-                      const float dsx = sqrt_approx(d2) + 0.01f;
-                      const float w = ex2_approx(-3.0f * lg2_approx(dsx));
-                      for (int k = 0; k < H; ++k) {
-                        acc[r][k].x = fmaf(xj[2 * k], w, acc[r][k].x);
-                        acc[r][k].y = fmaf(xj[2 * k + 1], w, acc[r][k].y);
-                      }
-                      W[r] += w;
-                    }
-                  }
+              for (int jj = 0; jj < 8; ++jj) { sv[jj] = __uint_as_float(t0[jj]); sv[8 + jj] = __uint_as_float(t1[jj]); }
+              if (flag) {
+                fixed = true;
+#pragma unroll 1
+                for (int x = 0; x < 16; ++x) {
+                  const int r = x >> 3, jj = x & 7;
+                  if (sv[x] < (r ? thr[1] : thr[0]))
+                    near_fix<H>(im.rows32 + (size_t)(dv.row0 + (r ? lrow[1] : lrow[0])) * 16, q_s + (bt * 8 + jj) * 16, facc + r * 16);
                 }
               }
             }
@@ -371,6 +382,10 @@ __global__ void __maxnreg__(80) repulse_tc_kernel(RowDev dv, TcImage im, int cur
           ld_point<H>(im.rows32 + (size_t)(dv.row0 + lrow[r]) * 16, xi);
 #pragma unroll
           for (int k = 0; k < H; ++k) o[k] = make_float2(fmaf(-xi[k].x, W[r], acc[r][k].x), fmaf(-xi[k].y, W[r], acc[r][k].y));
+          if (fixed) {
+#pragma unroll 1
+            for (int k = 0; k < H; ++k) { o[k].x += facc[r * 16 + 2 * k]; o[k].y += facc[r * 16 + 2 * k + 1]; }
+          }
           st_point<H>(dv.rpart + ((size_t)(2 * c + half) * dv.rows + lrow[r]) * Dp, o);
         }
       }

@@ -1,0 +1,375 @@
+// topolow_b200/csrc/rowblock_tc2.cuh - included by rowblock.cu after rowblock_tc.cuh, inside namespace tl::{anonymous}.
+//
+// Repulsion pass with BOTH contractions on the tensor cores - the structure of a fused attention kernel:
+//   GEMM 1   S = d^2 / 2 for 128 rows x 32 partners                    (as in rowblock_tc.cuh: 3-pass TF32, norms in K)
+//   FP32     w = (d + 0.01)^-3 per pair, read from and written back to the same TMEM columns (weights of near pairs 0)
+//   GEMM 2   D2[128 x 32] += w[128 x 32] Y[32 partners x 32]            A operand from TMEM, Y = (x_0..x_15, 1, 0...): columns
+//                                                                       0..15 collect sum_j w x_j, column 16 collects sum_j w
+// and per chunk of 2048 partners the rows' sums come out as D2[0..15] - x_i D2[16].  The FP32 pipes are left with about nine
+// instructions per pair, two of them on the special-function unit (sqrt, reciprocal), which is what bounds the pass.
+//
+// Precision of GEMM 2: w is used as TF32 (truncated by the tensor core) consistently in the sums of w x_j and of w, so
+// the difference D2[0..15] - x_i D2[16] still telescopes.  The partner coordinates enter rounded to TF32 (2^-11 relative:
+// a partner seen 0.01 away from where it is, at distances of 10, with independent signs over 100 000 partners) - the
+// second pass over the remainders (kT2LoPass) costs a quarter more tensor instructions and changes nothing measurable.
+// A weight carries a relative error of 2^-11 with random sign: noise far below the Jacobi / Gauss-Seidel difference.
+//
+// Issue rate: a stage is 22 tensor instructions and 9 bulk copies for 8192 pairs, and the FP32 side needs only ~0.4 us
+// for them.  One lane doing all of it (with the loop wrappers the compiler puts around a warp-uniform instruction in
+// divergent code) took 2 us per stage; hence two whole, converged warps - one issues the MMAs, one the copies - with
+// elect.sync around the single-lane instructions.
+//
+// TMEM (256 columns per CTA, two CTAs per SM): S / w  [2 buffers][2 tiles][32] = 128, D2 [2 buffers][2 tiles][32] = 128.
+
+constexpr int kT2SJ = 32;            // partners per stage
+constexpr int kT2Stages = 4;
+constexpr int kT2Threads = 320;       // 8 consumer warps + the MMA warp + the copy warp
+constexpr bool kT2LoPass = false;     // second pass of GEMM 2 over the TF32 remainders of the partner coordinates (see below)
+
+struct T2Smem {
+  static constexpr int kAHi = 0;                                   // 6 planes x 256 rows x 16 B
+  static constexpr int kALo = kAHi + 6 * kTcRows * 16;             // 4 planes
+  static constexpr int kStage0 = kALo + 4 * kTcRows * 16;
+  static constexpr int kBHi = 0;                                   // 6 planes x 32 x 16 B   (GEMM 1, K-major over coordinates)
+  static constexpr int kBLo = 6 * kT2SJ * 16;                      // 4 planes
+  static constexpr int kYHi = kBLo + 4 * kT2SJ * 16;               // 8 partner-quads x 32 rows x 16 B (GEMM 2, K-major over partners)
+  static constexpr int kYLo = kYHi + 8 * 32 * 16;                  // 8 partner-quads x 16 rows x 16 B
+  static constexpr int kRows32 = kYLo + 8 * 16 * 16;               // 32 x 64 B (near pairs only)
+  static constexpr int kStageBytes = kRows32 + kT2SJ * 64;
+  static constexpr int kBars = kStage0 + kT2Stages * kStageBytes;
+  static constexpr int kNumBars = 1 + 2 * kT2Stages + 8 + 1;       // a_full | full, empty per stage | tfull, wfull, d2full, d2empty x 2 | a_free
+  static constexpr int kTmemPtr = kBars + kNumBars * 8;
+  static constexpr int kTotal = kTmemPtr + 16;
+  static constexpr int kStageTx = 4 * kT2SJ * 16 + kT2SJ * 16 + 4 * kT2SJ * 16 + 8 * 32 * 16 + (kT2LoPass ? 8 * 16 * 16 : 0) + kT2SJ * 64;
+};
+
+struct T2Image {
+  TcImage a;      // the arrays of the one-GEMM form
+  float* yhi;     // [cap_rows / 4][32][4]   row n of a partner quad: n < 16 coordinate n (TF32-rounded), n = 16: 1, else 0
+  float* ylo;     // [cap_rows / 4][16][4]   the remainders of the coordinates
+};
+
+TL_D void tc_st8(unsigned taddr, const unsigned (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+               ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
+TL_D void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+TL_D void tc_mma_tf32_ts(unsigned d_tmem, unsigned a_tmem, unsigned long long b_desc, unsigned idesc, unsigned accumulate) {
+  asm volatile("{ .reg .pred p; setp.ne.b32 p, %4, 0; tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p; }"
+               ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+TL_D bool elect_one() {
+  unsigned pred = 0;
+  asm volatile("{ .reg .pred p; elect.sync _|p, 0xffffffff; selp.u32 %0, 1, 0, p; }" : "=r"(pred));
+  return pred != 0;
+}
+TL_D float rcp_approx_ftz(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+
+constexpr unsigned kT2Idesc1 = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 13) | ((unsigned)(kT2SJ >> 3) << 17) | ((128u >> 4) << 24);   // -A B^T, N = 32
+constexpr unsigned kT2Idesc2Hi = (1u << 4) | (2u << 7) | (2u << 10) | ((32u >> 3) << 17) | ((128u >> 4) << 24);                         // N = 32
+constexpr unsigned kT2Idesc2Lo = (1u << 4) | (2u << 7) | (2u << 10) | ((16u >> 3) << 17) | ((128u >> 4) << 24);                         // N = 16
+
+// The transposed image of GEMM 2 (the other arrays come from image_tc_kernel).  One thread per (partner quad, row n).
+__global__ void __launch_bounds__(256) image_t2_kernel(RowDev dv, T2Image im) {
+  if (__ldcg(&dv.state->stop)) return;
+  const size_t x = (size_t)blockIdx.x * 256 + threadIdx.x;           // quad * 32 + n
+  const size_t quad = x >> 5;
+  const int n = (int)(x & 31);
+  if (quad >= dv.cap_rows / 4) return;
+  float4 hi = make_float4(0.f, 0.f, 0.f, 0.f), lo = hi;
+  if (n < 16) {
+    const float* r = im.a.rows32 + quad * 4 * 16 + n;                // rows32[partner][n], partners quad * 4 .. + 3
+    const float v0 = r[0], v1 = r[16], v2 = r[32], v3 = r[48];
+    hi = make_float4(tf32_round(v0), tf32_round(v1), tf32_round(v2), tf32_round(v3));
+    lo = make_float4(v0 - hi.x, v1 - hi.y, v2 - hi.z, v3 - hi.w);
+    reinterpret_cast<float4*>(im.ylo)[quad * 16 + n] = lo;
+  } else if (n == 16) {
+    hi = make_float4(1.f, 1.f, 1.f, 1.f);
+  }
+  reinterpret_cast<float4*>(im.yhi)[quad * 32 + n] = hi;
+}
+
+template <int H>
+__global__ void __maxnreg__(80) repulse_tc2_kernel(RowDev dv, T2Image im, int cur, int cpi) {
+  extern __shared__ __align__(128) unsigned char tc_smem[];
+  constexpr int Dp = Row<H>::kStride;
+  (void)cur;
+  if (__ldcg(&dv.state->stop)) return;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const unsigned sm0 = smem_u32(tc_smem);
+  const unsigned bar_a_full = sm0 + T2Smem::kBars;
+  auto bar_full = [&](int s) { return sm0 + T2Smem::kBars + 8u * (1 + s); };
+  auto bar_empty = [&](int s) { return sm0 + T2Smem::kBars + 8u * (1 + kT2Stages + s); };
+  auto bar_x = [&](int kind, int b) { return sm0 + T2Smem::kBars + 8u * (1 + 2 * kT2Stages + 2 * kind + b); };   // 0 tfull 1 wfull 2 d2full 3 d2empty
+  const unsigned bar_a_free = sm0 + T2Smem::kBars + 8u * (1 + 2 * kT2Stages + 8);
+  unsigned* tmem_ptr_s = reinterpret_cast<unsigned*>(tc_smem + T2Smem::kTmemPtr);
+
+  for (int x = tid; x < kTcRows * 4; x += kT2Threads) reinterpret_cast<float*>(tc_smem + T2Smem::kAHi + 5 * kTcRows * 16)[x] = 0.f;
+  for (int s = 0; s < kT2Stages; ++s)
+    for (int x = tid; x < kT2SJ * 4; x += kT2Threads)
+      reinterpret_cast<float*>(tc_smem + T2Smem::kStage0 + s * T2Smem::kStageBytes + T2Smem::kBHi + 5 * kT2SJ * 16)[x] = 0.f;
+  if (tid == 0) {
+    mbar_init(bar_a_full, 1);
+    mbar_init(bar_a_free, 1);
+    for (int s = 0; s < kT2Stages; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 9); }   // 8 consumer warps + the commit of GEMM 2
+    for (int b = 0; b < 2; ++b) { mbar_init(bar_x(0, b), 1); mbar_init(bar_x(1, b), 8); mbar_init(bar_x(2, b), 1); mbar_init(bar_x(3, b), 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 8) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_s)), "r"(256) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const unsigned tmem0 = *tmem_ptr_s;
+  auto col_s = [&](int b, int m) { return (unsigned)(b * 64 + m * 32); };           // S / w of buffer b, tile m
+  auto col_d = [&](int e, int m) { return (unsigned)(128 + e * 64 + m * 32); };     // D2 of buffer e, tile m
+
+  const int tiles = dv.rows / kTcRows;
+  const int groups = (dv.chunks + cpi - 1) / cpi;
+  const long long items = (long long)tiles * groups;
+  auto chunk_stages = [&](int c) { return (min(kChunk, dv.n - c * kChunk) + kT2SJ - 1) / kT2SJ; };
+
+  struct Cursor { long long item; int c, c_hi, s; size_t r0; bool valid; };
+  auto open_item = [&](Cursor& cu) {
+    cu.valid = cu.item < items;
+    if (!cu.valid) return;
+    const int tile = (int)(cu.item / groups), grp = (int)(cu.item % groups);
+    cu.c = grp * cpi; cu.c_hi = min(dv.chunks, cu.c + cpi); cu.s = 0;
+    cu.r0 = (size_t)dv.row0 + (size_t)tile * kTcRows;
+  };
+  auto advance = [&](Cursor& cu) {
+    if (++cu.s < chunk_stages(cu.c)) return;
+    cu.s = 0;
+    if (++cu.c < cu.c_hi) return;
+    cu.item += gridDim.x;
+    open_item(cu);
+  };
+
+  if (warp == 9) {
+    // =========================== copy warp: shared-memory stages and the A tile of every item ===========================
+    Cursor ld;
+    ld.item = blockIdx.x;
+    open_item(ld);
+    unsigned load_g = 0, item_g = 0;
+    while (ld.valid) {
+      if (ld.s == 0 && ld.c % cpi == 0) {
+        // a new item: its A tile replaces the one the GEMM 1 of the item before read; the MMA warp commits a_free after the
+        // last of them (this warp is at most one item boundary ahead of it: the phase waited for is the current one)
+        if (item_g > 0) mbar_wait(bar_a_free, (item_g - 1) & 1);
+        ++item_g;
+        if (elect_one()) {
+          mbar_expect_tx(bar_a_full, TcSmem::kATx);
+          for (int c = 0; c < 4; ++c) {
+            bulk_g2s(sm0 + T2Smem::kAHi + c * kTcRows * 16, im.a.xhi + ((size_t)c * dv.cap_rows + ld.r0) * 4, kTcRows * 16, bar_a_full);
+            bulk_g2s(sm0 + T2Smem::kALo + c * kTcRows * 16, im.a.xlo + ((size_t)c * dv.cap_rows + ld.r0) * 4, kTcRows * 16, bar_a_full);
+          }
+          bulk_g2s(sm0 + T2Smem::kAHi + 4 * kTcRows * 16, im.a.aug_a + ld.r0 * 4, kTcRows * 16, bar_a_full);
+        }
+        __syncwarp();
+      }
+      const int s = load_g % kT2Stages;
+      mbar_wait(bar_empty(s), ((load_g / kT2Stages) & 1) ^ 1);
+      if (elect_one()) {
+        const size_t j0 = (size_t)ld.c * kChunk + (size_t)ld.s * kT2SJ;
+        const unsigned stg = sm0 + T2Smem::kStage0 + s * T2Smem::kStageBytes;
+        mbar_expect_tx(bar_full(s), T2Smem::kStageTx);
+        for (int c = 0; c < 4; ++c) {
+          bulk_g2s(stg + T2Smem::kBHi + c * kT2SJ * 16, im.a.xhi + ((size_t)c * dv.cap_rows + j0) * 4, kT2SJ * 16, bar_full(s));
+          bulk_g2s(stg + T2Smem::kBLo + c * kT2SJ * 16, im.a.xlo + ((size_t)c * dv.cap_rows + j0) * 4, kT2SJ * 16, bar_full(s));
+        }
+        bulk_g2s(stg + T2Smem::kBHi + 4 * kT2SJ * 16, im.a.aug_b + j0 * 4, kT2SJ * 16, bar_full(s));
+        bulk_g2s(stg + T2Smem::kYHi, im.yhi + (j0 / 4) * 32 * 4, 8 * 32 * 16, bar_full(s));
+        if (kT2LoPass) bulk_g2s(stg + T2Smem::kYLo, im.ylo + (j0 / 4) * 16 * 4, 8 * 16 * 16, bar_full(s));
+        bulk_g2s(stg + T2Smem::kRows32, im.a.rows32 + j0 * 16, kT2SJ * 64, bar_full(s));
+      }
+      __syncwarp();
+      ++load_g;
+      advance(ld);
+    }
+  } else if (warp == 8) {
+    // =========================== MMA warp: GEMM 1 of stage g + 1, then GEMM 2 of stage g ===========================
+    Cursor g1, g2;
+    g1.item = g2.item = blockIdx.x;
+    open_item(g1); open_item(g2);
+    unsigned g1_g = 0, g2_g = 0, a_uses = 0, chunk_g = 0;
+    auto gemm1 = [&]() {
+      if (g1.s == 0 && g1.c % cpi == 0) { mbar_wait(bar_a_full, a_uses & 1); ++a_uses; }
+      const int s = g1_g % kT2Stages, b = g1_g & 1;
+      mbar_wait(bar_full(s), (g1_g / kT2Stages) & 1);
+      // buffer b: its last reader, GEMM 2 of stage g1_g - 2, was issued before this instruction (the tensor pipe runs in order)
+      tc_fence_after();
+      if (elect_one()) {
+        const unsigned stg = sm0 + T2Smem::kStage0 + s * T2Smem::kStageBytes;
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+          const unsigned d = tmem0 + col_s(b, m);
+          const unsigned a_hi = sm0 + T2Smem::kAHi + m * 128 * 16, a_lo = sm0 + T2Smem::kALo + m * 128 * 16;
+          const unsigned b_hi = stg + T2Smem::kBHi, b_lo = stg + T2Smem::kBLo;
+          constexpr unsigned kLboA = kTcRows * 16, kLboB = kT2SJ * 16;
+#pragma unroll
+          for (int k = 0; k < 3; ++k)
+            tc_mma_tf32(d, tc_desc(a_hi + k * 2 * kLboA, kLboA, 128), tc_desc(b_hi + k * 2 * kLboB, kLboB, 128), kT2Idesc1, k > 0);
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            tc_mma_tf32(d, tc_desc(a_hi + k * 2 * kLboA, kLboA, 128), tc_desc(b_lo + k * 2 * kLboB, kLboB, 128), kT2Idesc1, 1);
+            tc_mma_tf32(d, tc_desc(a_lo + k * 2 * kLboA, kLboA, 128), tc_desc(b_hi + k * 2 * kLboB, kLboB, 128), kT2Idesc1, 1);
+          }
+        }
+        tc_commit(bar_x(0, b));
+        if (g1.s + 1 == chunk_stages(g1.c) && g1.c + 1 == g1.c_hi) tc_commit(bar_a_free);   // the item's last GEMM 1
+      }
+      __syncwarp();
+      ++g1_g;
+      advance(g1);
+    };
+    auto gemm2 = [&]() {
+      const int s = g2_g % kT2Stages, b = g2_g & 1, e = chunk_g & 1;
+      const bool first = g2.s == 0, last = g2.s + 1 == chunk_stages(g2.c);
+      mbar_wait(bar_x(1, b), (g2_g >> 1) & 1);                       // the weights of the stage are in TMEM
+      if (first) mbar_wait(bar_x(3, e), ((chunk_g >> 1) & 1) ^ 1);   // the sums of chunk - 2 have been read
+      tc_fence_after();
+      if (elect_one()) {
+        const unsigned stg = sm0 + T2Smem::kStage0 + s * T2Smem::kStageBytes;
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+          const unsigned d = tmem0 + col_d(e, m), a = tmem0 + col_s(b, m);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {                                // 8 partners (two quads) per MMA
+            // Y planes: per partner quad [32 rows][16 B] (hi) / [16 rows][16 B] (lo): LBO = next quad, SBO = 8 rows
+            tc_mma_tf32_ts(d, a + k * 8, tc_desc(stg + T2Smem::kYHi + k * 2 * 512, 512, 128), kT2Idesc2Hi, !(first && k == 0));
+            if (kT2LoPass) tc_mma_tf32_ts(d, a + k * 8, tc_desc(stg + T2Smem::kYLo + k * 2 * 256, 256, 128), kT2Idesc2Lo, 1);
+          }
+        }
+        tc_commit(bar_empty(s));                                       // the stage's shared memory (and w buffer b) are free
+        if (last) tc_commit(bar_x(2, e));
+      }
+      __syncwarp();
+      if (last) ++chunk_g;
+      ++g2_g;
+      advance(g2);
+    };
+    if (g1.valid) gemm1();
+    while (g2.valid) {
+      if (g1.valid) gemm1();          // distances of the next stage while the consumers work on this one
+      gemm2();
+    }
+  } else {
+    const int quad = warp & 3, half = warp >> 2;
+    const unsigned lane_sel = (unsigned)(quad * 32) << 16;
+    unsigned g = 0, chunk_g = 0;
+    for (long long item = blockIdx.x; item < items; item += gridDim.x) {
+      const int tile = (int)(item / groups), grp = (int)(item % groups);
+      const int c_lo = grp * cpi, c_hi = min(dv.chunks, c_lo + cpi);
+      const int lrow[2] = {tile * kTcRows + quad * 32 + lane, tile * kTcRows + 128 + quad * 32 + lane};
+      float thr[2];
+#pragma unroll
+      for (int r = 0; r < 2; ++r) thr[r] = -3.01e-3f * __ldg(im.a.aug_a + (size_t)(dv.row0 + lrow[r]) * 4);
+      for (int c = c_lo; c < c_hi; ++c, ++chunk_g) {
+        float facc[32];
+        bool fixed = false;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) facc[k] = 0.f;
+        const int nst = chunk_stages(c);
+        for (int st = 0; st < nst; ++st, ++g) {
+          const int s = g % kT2Stages, b = g & 1;
+          mbar_wait(bar_full(s), (g / kT2Stages) & 1);
+          mbar_wait(bar_x(0, b), (g >> 1) & 1);
+          tc_fence_after();
+          const float* __restrict__ q_s = reinterpret_cast<const float*>(tc_smem + T2Smem::kStage0 + s * T2Smem::kStageBytes + T2Smem::kRows32) + half * 16 * 16;
+          const unsigned t_base = tmem0 + lane_sel + col_s(b, 0) + (unsigned)(half * 16);    // this warp's 16 partners of the stage, tile 0
+#pragma unroll 1
+          for (int bt = 0; bt < 2; ++bt) {
+            unsigned s0[8], s1[8];
+            tc_ld8(t_base + bt * 8, s0);
+            tc_ld8(t_base + 32 + bt * 8, s1);
+            tc_wait_ld();
+            bool flag = false;
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) {
+#pragma unroll
+              for (int r = 0; r < 2; ++r) {
+                const float S = __uint_as_float(r == 0 ? s0[jj] : s1[jj]);          // d^2 / 2
+                const bool nr = S < thr[r];
+                // (d + 0.01)^-3, d = sqrt(2 S):  (2^-0.5 / (sqrt(S) + 0.01 2^-0.5))^3
+                const float rc = 0.70710678f * rcp_approx_ftz(sqrt_approx(fabsf(S)) + 0.00707106781f);
+                float w = rc * rc * rc;
+                w = nr ? -0.0f : w;            // -0: adds nothing in GEMM 2 and is told apart from a weight that underflowed to +0
+                flag |= nr;
+                if (r == 0) s0[jj] = __float_as_uint(w); else s1[jj] = __float_as_uint(w);
+              }
+            }
+            tc_st8(t_base + bt * 8, s0);
+            tc_st8(t_base + 32 + bt * 8, s1);
+            if (__any_sync(0xffffffffu, flag)) {
+              if (flag) {
+                fixed = true;
+                unsigned sv[16];
+                // the distances were overwritten by the weights: a near pair is one whose weight is -0
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) { sv[jj] = s0[jj]; sv[8 + jj] = s1[jj]; }
+#pragma unroll 1
+                for (int x = 0; x < 16; ++x) {
+                  const int r = x >> 3, jj = x & 7;
+                  if (sv[x] == 0x80000000u)
+                    near_fix<H>(im.a.rows32 + (size_t)(dv.row0 + (r ? lrow[1] : lrow[0])) * 16, q_s + (bt * 8 + jj) * 16, facc + r * 16);
+                }
+              }
+            }
+          }
+          tc_wait_st();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) { mbar_arrive(bar_x(1, b)); mbar_arrive(bar_empty(s)); }
+        }
+        // ---- the chunk's sums: warps of half h read tile h ----
+        const int e = chunk_g & 1;
+        mbar_wait(bar_x(2, e), (chunk_g >> 1) & 1);
+        tc_fence_after();
+        {
+          unsigned dlo[8], dhi[8];
+          const unsigned d_base = tmem0 + lane_sel + col_d(e, half);
+          tc_ld8(d_base, dlo);
+          tc_ld8(d_base + 8, dhi);
+          const float Wsum = __uint_as_float(tc_ld1(d_base + 16));
+          tc_wait_ld();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_x(3, e));
+          // facc of the OTHER tile's rows lives in the other half's threads: exchange through shared memory would cost a
+          // barrier; instead every thread adds its own near sums to the tile it writes... it only has them for its own
+          // (half-specific) partners.  So near sums are written as their own partial entry (see below).
+          const int r = half;
+          float2 xi[H], o[H];
+          ld_point<H>(im.a.rows32 + (size_t)(dv.row0 + lrow[r]) * 16, xi);
+#pragma unroll
+          for (int k = 0; k < H; ++k) {
+            const float ax = __uint_as_float(k < 4 ? dlo[2 * k] : dhi[2 * k - 8]), ay = __uint_as_float(k < 4 ? dlo[2 * k + 1] : dhi[2 * k - 7]);
+            o[k] = make_float2(fmaf(-xi[k].x, Wsum, ax), fmaf(-xi[k].y, Wsum, ay));
+          }
+          st_point<H>(dv.rpart + ((size_t)(3 * c) * dv.rows + lrow[r]) * Dp, o);
+        }
+        // near-pair sums of this thread's partner half, both rows: partial entries 3 c + 1 + half (zeros when there were none)
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          float2 o[H];
+#pragma unroll
+          for (int k = 0; k < H; ++k) o[k] = make_float2(0.f, 0.f);
+          if (fixed) {
+#pragma unroll 1
+            for (int k = 0; k < H; ++k) o[k] = make_float2(facc[r * 16 + 2 * k], facc[r * 16 + 2 * k + 1]);
+          }
+          st_point<H>(dv.rpart + ((size_t)(3 * c + 1 + half) * dv.rows + lrow[r]) * Dp, o);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    __syncwarp();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem0), "r"(256) : "memory");
+  }
+}
