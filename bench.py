@@ -618,19 +618,37 @@ def main_map(args, n, d, missing):
         rep_flop = (7 * d + 8) * pairs / world
         rep_s = kt["repulse"] * 1e-3
         edge_b = edge_bytes_per_iter(n, d, E) / world
-        tc = d >= 9 and not os.environ.get("TOPOLOW_REP_VARIANT")
-        roofline = {"bound": "fp32", "kernel": ("image_tc_kernel + repulse_tc_kernel<ndim/2> (pair distances as a 3-pass TF32 GEMM on tcgen05 with TMEM "
-                                                "accumulators; weights and accumulation on the FP32 pipes)" if tc else
-                                                "repulse_kernel<ndim/2, 2 rows per thread>") + " (one launch per iteration and rank)",
+        form = info0.get("repulsion_form", 5)
+        rep_names = {11: "image_tc_kernel + image_t2_kernel + repulse_tc2_kernel<ndim/2> (tcgen05: pair distances as a 3-pass TF32 GEMM into "
+                         "TMEM, weights computed in place by the FP32 / special-function pipes, sum w x_j and sum w as an A-from-TMEM GEMM)",
+                     10: "image_tc_kernel + repulse_tc_kernel<ndim/2> (pair distances as a 3-pass TF32 GEMM on tcgen05 with TMEM "
+                         "accumulators; weights and accumulation on the FP32 pipes)"}
+        rep_kernel = {11: "repulse_tc2_kernel", 10: "repulse_tc_kernel"}.get(form, "repulse_kernel")
+        one_sided = pairs * 2.0 / world                       # interactions one launch evaluates (every pair from both sides)
+        mufu_peak = _lib.microbench(4, local) * 32.0          # MUFU lane-operations / s, measured now on this GPU
+        mufu_per = 2.0 if form == 11 else 3.0                 # form 11: sqrt + reciprocal; forms 5 / 10: sqrt, lg2, ex2
+        roofline = {"bound": "fp32", "kernel": rep_names.get(form, "repulse_kernel<ndim/2, 2 rows per thread>") + " (one launch per iteration and rank)",
+                    "repulsion_form": form,
                     "achieved": rep_flop / rep_s / 1e12, "peak": ffma_peak / 1e12, "unit": "TFLOP/s",
                     "frac": rep_flop / rep_s / ffma_peak,
                     "peak_source": "topolow_microbench FFMA, measured live on this GPU (FP32 is not in MEASURED_PEAKS.json)",
                     "algorithmic_flop_per_launch": rep_flop, "launch_ms": kt["repulse"],
-                    "note": "algorithmic = (7 ndim + 8) flop per unordered pair (SURVEY 8d) against the FP32 FFMA peak; the kernel visits "
-                            "every pair from both sides (one-sided updates). With the distances on the tensor cores the FP32 pipes "
-                            "execute ~33 issue-port cycles per side at ndim 16 (weights on the special-function unit + 8 packed FMA of the "
-                            "accumulation); the difference form (repulse_kernel, ndim < 9) needs 57 and ran at 0.51",
-                    "traffic": tracked_traffic("repulse_kernel"),
+                    "note": "algorithmic = (7 ndim + 8) flop per unordered pair (SURVEY 8d) against the FP32 FFMA peak, the denominator the "
+                            "north-star names; the kernel visits every pair from both sides (one-sided updates). In form 11 both "
+                            "contractions (the 5 ndim flop of the distance and the accumulation) run on the tensor cores, so the fraction "
+                            "can exceed what the FP32 pipes alone could reach; what bounds the pass is the special-function unit "
+                            "(`special_function_unit`: sqrt + reciprocal per interaction). The FP32 difference form (ndim < 5) ran at 0.51",
+                    "special_function_unit": {"ops_per_launch": mufu_per * one_sided, "achieved": mufu_per * one_sided / rep_s / 1e12,
+                                              "peak": mufu_peak / 1e12, "unit": "T lane-ops/s",
+                                              "frac": mufu_per * one_sided / rep_s / mufu_peak,
+                                              "peak_source": "topolow_microbench MUFU.RSQ, measured live on this GPU"},
+                    "tensor": {"executed_flop_per_launch": (2.0 * 56 + 2.0 * 32) * one_sided if form == 11 else
+                                                           (2.0 * 56 * one_sided if form == 10 else 0.0),
+                               "achieved_tflops": ((2.0 * 56 + 2.0 * 32) if form == 11 else (2.0 * 56 if form == 10 else 0.0)) * one_sided / rep_s / 1e12,
+                               "note": "executed TF32 flop: GEMM 1 K = 24 + 16 + 16 (hi x hi, hi x lo, lo x hi with the half norms in K), "
+                                       "GEMM 2 K = 32 partners x N = 32 columns (17 used); TF32 dense peak is half of the bf16 figure in "
+                                       "MEASURED_PEAKS.json - the tensor pipe is not the bound"},
+                    "traffic": tracked_traffic(rep_kernel),
                     "kernels_ms": kt,
                     "edge_pass": {"bound": "hbm", "kernel": "mae_kernel (edge MAE on check iterations)",
                                   "achieved": edge_b / (kt["mae"] * 1e-3) / 1e9 if kt["mae"] > 0 else None, "peak": peaks["hbm_gbs"],

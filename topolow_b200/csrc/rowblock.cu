@@ -1008,6 +1008,7 @@ struct RowPlan {
   int64_t launches = 0;
   int64_t n_recs = 0, n_mrecs = 0;
   int rep_ctas = 0, rep_threads = 128;
+  int rep_form = 0;           // shape of the repulsion pass in use (repulse_variant / configure_repulse)
   bool deep_ring = false;
   bool overlap = true;        // repulsion pass launched as programmatic dependent of the spring walk (TOPOLOW_OVERLAP=0: in order)
   int sm_count = 148;
@@ -1240,7 +1241,8 @@ void launch_one(RowPlan& rp, cudaStream_t s, cudaEvent_t* ev = nullptr) {
 
 // Shapes of the repulsion kernel: {rows per thread, partner unroll, register cap, cube on the SFU}.
 // 0 is the production shape; the others stay selectable (TOPOLOW_REP_VARIANT) for measurements.
-// Variant 0 = policy: 10 (rowblock_tc.cuh: distances on the tensor cores) from ndim 9 on, 5 (the difference form) below.
+// Variant 0 = policy: 11 (rowblock_tc2.cuh: distances and accumulation on the tensor cores) from ndim 5 on, 5 (the difference
+// form) below; 10 (rowblock_tc.cuh: distances only on the tensor cores) stays selectable.
 // The FP32 inner-product forms (4, 6-9) are kept selectable as the measured record of why they are not used (B200, cfg4 /
 // cfg3 repulsion pass in ms; difference form 16.8 / 0.23, tensor-core form 13.4 / 0.19):
 //   6  one partner per trip, no spill          16.6 / 0.30   issue port 79 % busy (a packed instruction holds it 2 cycles):
@@ -1275,8 +1277,11 @@ void configure_repulse(RowPlan& rp, int sms) {
   RepulseFn fn; int threads;
   int stage = kStageJ;
   int variant = ev ? std::atoi(ev) : 0;
-  if (variant == 0) variant = H >= 5 ? 10 : 5;   // policy, measured (ms per repulsion pass, 10 vs 5): ndim 16 / 100k: 13.4 vs 16.8; ndim 12 / 40k:
-                                                 // 1.82 vs 2.32; ndim 10 / 10k: 0.19 vs 0.23; ndim 6 / 30k: 0.84 vs 0.75
+  // policy, measured on B200 (ms per repulsion pass, forms 11 / 10 / 5): ndim 16, 100k: 7.5 / 13.4 / 16.8; ndim 12, 40k: 1.24 / 1.82 /
+  // 2.32; ndim 10, 10k: 0.16 / 0.19 / 0.23; ndim 6, 30k: 0.69 / 0.84 / 0.75.  The two-GEMM form costs the same at every ndim (K is
+  // padded to 16 coordinates); the difference form's cost falls with ndim and takes over below ndim 5.
+  if (variant == 0) variant = H >= 3 ? 11 : 5;
+  rp.rep_form = variant;
   if (variant == 10 || variant == 11) {          // distances (10) / distances and accumulation (11) on the tensor cores
     rp.tc_form = true;
     rp.tc2_form = variant == 11;
@@ -1686,11 +1691,11 @@ void row_result(RowPlan& rp, topolow_result& res, bool interrupted) {
 
 void row_info(const RowPlan& rp, int64_t* out, int cap) {
   const RowDev& dv = rp.dv;
-  const int64_t v[16] = {dv.slots, dv.D, dv.Dp, dv.G, dv.rank, dv.row0, dv.rows, dv.chunks, rp.n_recs, rp.n_mrecs, rp.launches,
+  const int64_t v[17] = {dv.slots, dv.D, dv.Dp, dv.G, dv.rank, dv.row0, dv.rows, dv.chunks, rp.n_recs, rp.n_mrecs, rp.launches,
                          rp.h_flag ? rp.h_flag[1] : 0, rp.h_flag ? rp.h_flag[0] : 0,
                          (int64_t)(dv.G - 1) * dv.rows * dv.Dp * 4,   // position bytes this rank stores into its peers per iteration
-                         (int64_t)(dv.rows / kRowTile) * dv.chunks, rp.rep_ctas};
-  for (int i = 0; i < cap && i < 16; ++i) out[i] = v[i];
+                         (int64_t)(dv.rows / kRowTile) * dv.chunks, rp.rep_ctas, rp.rep_form};
+  for (int i = 0; i < cap && i < 17; ++i) out[i] = v[i];
 }
 
 }  // namespace tl

@@ -24,7 +24,7 @@ from ._lib import OK, TopolowError
 
 INFO_KEYS = ["slots", "ndim", "stride", "n_ranks", "rank", "row0", "own_rows", "partner_chunks", "spring_records",
              "mae_records", "launches", "iterations_done", "stopped", "peer_store_bytes_per_iteration",
-             "repulsion_items", "repulsion_ctas"]
+             "repulsion_items", "repulsion_ctas", "repulsion_form"]
 KERNELS = ["repulse", "spring", "mae", "controller", "snapshot"]
 
 
@@ -91,8 +91,8 @@ class Shard:
         return _lib.result_dict(res, out, tr)
 
     def info(self):
-        v = (C.c_int64 * 16)()
-        self._L.topolow_shard_info(self._h, v, 16)
+        v = (C.c_int64 * 17)()
+        self._L.topolow_shard_info(self._h, v, 17)
         return dict(zip(INFO_KEYS, [int(x) for x in v]))
 
     def close(self):
