@@ -1,5 +1,5 @@
 """End-to-end timing of one fit through topolow_fit on host buffers (cfg4 shape by default).
-TOPOLOW_DEBUG=1 prints the phase times of the native side.  usage: gpu_e2e.py [n d missing iters] [--pinned]"""
+TOPOLOW_DEBUG=1 prints the phase times of the native side.  usage: gpu_e2e.py [n d missing iters] [--pinned] [--rowblock]"""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -20,10 +20,11 @@ if "--pinned" in sys.argv:
         t = torch.from_numpy(np.ascontiguousarray(a) if a.flags.c_contiguous else np.asfortranarray(a).T.copy()).pin_memory()
         keep.append(t)
         fa[i] = t.numpy() if a.flags.c_contiguous else t.numpy().T
-_lib.fit(*fa, 2, 5.0, 0.01, 0.02, 1e-4, 3, 3)   # warm-up (context, module load)
+mode = _lib.MODE_ROWBLOCK if "--rowblock" in sys.argv else _lib.MODE_COLOURED
+_lib.fit(*fa, 2, 5.0, 0.01, 0.02, 1e-4, 3, 3, mode=mode)   # warm-up (context, module load)
 for rep in range(2):
     t0 = time.perf_counter()
-    r = _lib.fit(*fa, iters, 5.0, 0.01, 0.02, 1e-4, iters + 1, 3)
+    r = _lib.fit(*fa, iters, 5.0, 0.01, 0.02, 1e-4, iters + 1, 3, mode=mode)
     wall = time.perf_counter() - t0
     pairs = n * (n - 1) // 2
     print(f"e2e wall {wall*1e3:.1f} ms, device {r['device_ms']:.1f} ms, overhead {wall*1e3 - r['device_ms']:.1f} ms, "

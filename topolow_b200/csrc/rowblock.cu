@@ -52,6 +52,9 @@ constexpr unsigned long long kWaitNs = 20ull * 1000ull * 1000ull * 1000ull;
 struct RowDev {
   int n, slots, D, Dp, G, rank, row0, rows, chunks;
   int rparts;                        // partial-sum entries per row in rpart: chunks (2 x chunks for the tensor-core pass)
+  int adaptive;                      // 1: the repulsion form is chosen per iteration on the device (counters[6], set by image_tc_kernel)
+  int probe_k;                       // sampled partners per row of the near-pair probe
+  unsigned probe_limit;              // tensor form while the probe finds at most this many near pairs
   int no_wait;                       // measurement only (TOPOLOW_IGNORE_PEERS): one rank of a sharded map timed without its peers
   unsigned long long cap_rows;       // rows of one position buffer (slots rounded up to a chunk)
   float* pos[kMaxShards];            // replica q: [2][cap_rows][Dp]
@@ -72,13 +75,17 @@ struct RowDev {
   const int* mwidth;
   FitState* state;
   double* trace;
-  unsigned* counters;                // [4] tickets of the "last CTA" of a launch
+  unsigned* counters;                // [0..2] tickets of the "last CTA" of a launch / work items; [4] near pairs the probe found, [5] its
+                                     // ticket, [6] form of this iteration (1 = tensor cores), [7] iterations run in the tensor form
   volatile int* host_flag;           // mapped: [0] stop, [1] iterations done
   unsigned long long pairs_per_iter;
   unsigned long long seed;
 };
 
 typedef void (*RepulseFn)(RowDev, int, unsigned);
+
+// Adaptive runs launch both repulsion kernels every iteration; the one whose form was not chosen returns at once.
+TL_D bool form_is_tensor(const RowDev& dv) { return __ldcg(&dv.counters[6]) != 0u; }
 
 // ---------------------------------------------------------------------------------------------------
 // device helpers
@@ -220,6 +227,7 @@ __global__ void __maxnreg__(MAXR) repulse_kernel(RowDev dv, int cur, unsigned ep
   constexpr int Dp = Row<H>::kStride;
   constexpr int kStageFloats = kStageJ * Dp;
   if (__ldcg(&dv.state->stop)) return;
+  if (dv.adaptive && form_is_tensor(dv)) return;
   if (!wait_epoch(dv, epoch)) { if (blockIdx.x == 0 && threadIdx.x == 0) peer_timeout(dv); return; }
   const int tid = threadIdx.x;
   const float* __restrict__ P = dv.pos[dv.rank] + (size_t)cur * dv.cap_rows * Dp;
@@ -714,7 +722,8 @@ __global__ void __launch_bounds__(kBlockRows) combine_kernel(RowDev dv, FitParam
     ld_point<H>(dv.xs + (size_t)lrow * Dp, x);
 #pragma unroll
     for (int kk = 0; kk < H; ++kk) rs[kk] = make_float2(0.f, 0.f);
-    for (int c = 0; c < dv.rparts; ++c) {
+    const int nparts = (dv.adaptive && !form_is_tensor(dv)) ? dv.chunks : dv.rparts;   // the FP32 form writes one entry per chunk
+    for (int c = 0; c < nparts; ++c) {
       float2 t[H];
       ld_point<H>(dv.rpart + ((size_t)c * dv.rows + lrow) * Dp, t);
 #pragma unroll
@@ -1007,13 +1016,17 @@ struct RowPlan {
   unsigned epoch = 0;         // signals enqueued so far (the same number on every rank)
   int64_t launches = 0;
   int64_t n_recs = 0, n_mrecs = 0;
+  int64_t tensor_iters = -1;  // adaptive runs: iterations that ran the tensor form (read back by row_result; -1 = not adaptive / not read yet)
   int rep_ctas = 0, rep_threads = 128;
+  double near_limit = 0.0;    // adaptive runs: the tensor form while the probed near-pair fraction is at most this
   int rep_form = 0;           // shape of the repulsion pass in use (repulse_variant / configure_repulse)
   bool deep_ring = false;
   bool overlap = true;        // repulsion pass launched as programmatic dependent of the spring walk (TOPOLOW_OVERLAP=0: in order)
   int sm_count = 148;
   void* rep_fn = nullptr;
   size_t rep_smem = 0;
+  int f32_ctas = 0, f32_threads = 128;   // the FP32 difference form beside a tensor form (adaptive runs launch both)
+  size_t f32_smem = 0;
   double total_ms = 0.0;
   bool attached = false;
 
@@ -1195,11 +1208,18 @@ void launch_iteration(RowPlan& rp, cudaStream_t s, cudaEvent_t* ev /* 7 events o
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
+    if (!rp.tc_form || dv.adaptive) {
+      cfg.gridDim = dim3((unsigned)rp.f32_ctas); cfg.blockDim = dim3((unsigned)rp.f32_threads); cfg.dynamicSmemBytes = rp.f32_smem;
+      TL_CUDA(cudaLaunchKernelEx(&cfg, (RepulseFn)rp.rep_fn, dv, cur, e_prev));
+      rp.launches += dv.adaptive ? 1 : 0;
+    }
     if (rp.tc_form) launch_repulse_tc<H>(rp, s, cur, true);
-    else TL_CUDA(cudaLaunchKernelEx(&cfg, (RepulseFn)rp.rep_fn, dv, cur, e_prev));
   } else {
+    if (!rp.tc_form || dv.adaptive) {
+      ((RepulseFn)rp.rep_fn)<<<rp.f32_ctas, rp.f32_threads, rp.f32_smem, s>>>(dv, cur, e_prev);
+      rp.launches += dv.adaptive ? 1 : 0;
+    }
     if (rp.tc_form) launch_repulse_tc<H>(rp, s, cur, false);
-    else ((RepulseFn)rp.rep_fn)<<<rp.rep_ctas, rp.rep_threads, rp.rep_smem, s>>>(dv, cur, e_prev);
     if (ev) TL_CUDA(cudaEventRecord(ev[1], s));
     launch_spring<H>(rp, s, cur, e_prev);
     if (ev) TL_CUDA(cudaEventRecord(ev[2], s));
@@ -1331,11 +1351,21 @@ void configure_repulse(RowPlan& rp, int sms) {
   if (per_sm < 1) per_sm = 1;
   if (const char* ec = std::getenv("TOPOLOW_REP_CTAS")) per_sm = std::max(1, std::atoi(ec));
   const long long items = (long long)(rp.dv.rows / kRowTile) * rp.dv.chunks;
-  if (!rp.tc_form) {
-    rp.rep_ctas = (int)std::min<long long>((long long)sms * per_sm, std::max<long long>(items, 1));
-    rp.rep_smem = smem;
-    rp.rep_fn = (void*)fn; rp.rep_threads = threads;
-  }
+  rp.f32_ctas = (int)std::min<long long>((long long)sms * per_sm, std::max<long long>(items, 1));
+  rp.f32_smem = smem; rp.f32_threads = threads;
+  rp.rep_fn = (void*)fn;
+  if (!rp.tc_form) { rp.rep_ctas = rp.f32_ctas; rp.rep_smem = smem; rp.rep_threads = threads; }
+  // The policy's tensor form is adaptive: the device picks the form of every iteration (image_tc_kernel's probe) and
+  // the host launches both kernels.  A form asked for by name (TOPOLOW_REP_VARIANT) runs unconditionally.
+  rp.dv.adaptive = (rp.tc_form && !ev) ? 1 : 0;
+  if (const char* ea = std::getenv("TOPOLOW_ADAPTIVE")) rp.dv.adaptive = (rp.tc_form && std::atoi(ea) != 0) ? 1 : 0;
+  rp.dv.probe_k = (int)std::min<long long>(64, std::max<long long>(4, (262144 + rp.dv.n - 1) / std::max(rp.dv.n, 1)));
+  // Break-even, measured at cfg4 (ndim 16): the fix-ups cost about 4.7 s x (near fraction) per pass over 1e10 one-sided pairs,
+  // the difference form 9 ms more than the tensor form: near fraction 2e-3; half of that is the limit, scaled with ndim
+  // (the difference form's cost falls with ndim, the tensor form's does not).
+  const double p_lim = 1.25e-4 * H;
+  if (const char* el = std::getenv("TOPOLOW_NEAR_LIMIT")) { rp.near_limit = std::atof(el); } else rp.near_limit = p_lim;
+  rp.dv.probe_limit = (unsigned)((double)rp.dv.probe_k * (double)rp.dv.n * rp.near_limit);
   rp.sm_count = sms;
   rp.overlap = true;   // measured on B200 at cfg4: one rank of 8 2.61 -> 2.38 ms, of 2 9.11 -> 8.99, one GPU 18.29 -> 18.11; cfg3 0.47 -> 0.29
   if (const char* eo = std::getenv("TOPOLOW_OVERLAP")) rp.overlap = std::atoi(eo) != 0;
@@ -1412,14 +1442,14 @@ RowPlan* row_create(const topolow_problem& pb, const topolow_params& pr, int ran
     pool_alloc(rp->hmax, 2 * sizeof(float));
     pool_alloc(rp->state, sizeof(FitState));
     pool_alloc(rp->trace, sizeof(double) * std::max(pr.n_iter, 1));
-    pool_alloc(rp->counters, 4 * sizeof(unsigned));
+    pool_alloc(rp->counters, 8 * sizeof(unsigned));
     pool_ready();
     TL_CUDA(cudaMemcpy(rp->shared, hp.data(), hp.size() * sizeof(float), cudaMemcpyHostToDevice));
     TL_CUDA(cudaMemcpy(rp->best, hp.data(), hp.size() * sizeof(float), cudaMemcpyHostToDevice));
     TL_CUDA(cudaMemcpy(rp->dp1, hd.data(), hd.size() * sizeof(float), cudaMemcpyHostToDevice));
     std::vector<double> tr(std::max(pr.n_iter, 1), NAN);
     TL_CUDA(cudaMemcpy(rp->trace, tr.data(), tr.size() * sizeof(double), cudaMemcpyHostToDevice));
-    TL_CUDA(cudaMemset(rp->counters, 0, 4 * sizeof(unsigned)));
+    TL_CUDA(cudaMemset(rp->counters, 0, 8 * sizeof(unsigned)));
     TL_CUDA(cudaMemset(rp->hmax, 0, 2 * sizeof(float)));
     // centre of the inner-product form: the centroid of the initial positions, summed in point order (the same on
     // every rank, fixed for the fit; the map stays about where it starts, and a map that wanders only makes more
@@ -1565,8 +1595,12 @@ double row_run_local(RowPlan* const* plans, int n, int n_iters) {
           constexpr int H = decltype(h)::value;
           const unsigned e_prev = rp.epoch;
           if (rp.dot_form) { image_kernel<H><<<rp.dv.slots / kBlockRows, kBlockRows, 0, s>>>(rp.dv, cur, e_prev); rp.launches += 1; }
-          if (rp.tc_form) { launch_image_tc<H>(rp, s, cur, e_prev); launch_repulse_tc<H>(rp, s, cur, false); }
-          else ((RepulseFn)rp.rep_fn)<<<rp.rep_ctas, rp.rep_threads, rp.rep_smem, s>>>(rp.dv, cur, e_prev);
+          if (rp.tc_form) launch_image_tc<H>(rp, s, cur, e_prev);
+          if (!rp.tc_form || rp.dv.adaptive) {
+            ((RepulseFn)rp.rep_fn)<<<rp.f32_ctas, rp.f32_threads, rp.f32_smem, s>>>(rp.dv, cur, e_prev);
+            rp.launches += rp.dv.adaptive ? 1 : 0;
+          }
+          if (rp.tc_form) launch_repulse_tc<H>(rp, s, cur, false);
           launch_spring<H>(rp, s, cur, e_prev);
           combine_kernel<H><<<rp.dv.rows / kBlockRows, kBlockRows, 0, s>>>(rp.dv, rp.prm, cur, ++rp.epoch);
         });
@@ -1667,6 +1701,14 @@ void row_result(RowPlan& rp, topolow_result& res, bool interrupted) {
   res.iterations_run = st.iter;
   res.pair_updates = (int64_t)st.pair_updates;
   res.device_ms = rp.total_ms;
+  if (dv.adaptive) {
+    unsigned c[8];
+    TL_CUDA(cudaMemcpy(c, rp.counters, sizeof c, cudaMemcpyDeviceToHost));
+    rp.tensor_iters = (int64_t)c[7];
+    if (std::getenv("TOPOLOW_DEBUG"))
+      std::fprintf(stderr, "[topolow] rows: %lld of %d iterations ran the tensor form (probe: %d partners per row, limit %u near pairs)\n",
+                   (long long)rp.tensor_iters, st.iter, dv.probe_k, dv.probe_limit);
+  }
   res.fail_iter = st.fail_iter;
   res.status = TOPOLOW_OK;
   res.message[0] = 0;
@@ -1691,11 +1733,11 @@ void row_result(RowPlan& rp, topolow_result& res, bool interrupted) {
 
 void row_info(const RowPlan& rp, int64_t* out, int cap) {
   const RowDev& dv = rp.dv;
-  const int64_t v[17] = {dv.slots, dv.D, dv.Dp, dv.G, dv.rank, dv.row0, dv.rows, dv.chunks, rp.n_recs, rp.n_mrecs, rp.launches,
+  const int64_t v[18] = {dv.slots, dv.D, dv.Dp, dv.G, dv.rank, dv.row0, dv.rows, dv.chunks, rp.n_recs, rp.n_mrecs, rp.launches,
                          rp.h_flag ? rp.h_flag[1] : 0, rp.h_flag ? rp.h_flag[0] : 0,
                          (int64_t)(dv.G - 1) * dv.rows * dv.Dp * 4,   // position bytes this rank stores into its peers per iteration
-                         (int64_t)(dv.rows / kRowTile) * dv.chunks, rp.rep_ctas, rp.rep_form};
-  for (int i = 0; i < cap && i < 17; ++i) out[i] = v[i];
+                         (int64_t)(dv.rows / kRowTile) * dv.chunks, rp.rep_ctas, rp.rep_form, rp.tensor_iters};
+  for (int i = 0; i < cap && i < 18; ++i) out[i] = v[i];
 }
 
 }  // namespace tl

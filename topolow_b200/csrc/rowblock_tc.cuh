@@ -152,6 +152,44 @@ __global__ void __launch_bounds__(kBlockRows) image_tc_kernel(RowDev dv, TcImage
   const float h_hi = tf32_round(h), hb_hi = tf32_round(hb);
   reinterpret_cast<float4*>(im.aug_a)[row] = make_float4(-h_hi, -(h - h_hi), -1.f, -1.f);
   reinterpret_cast<float4*>(im.aug_b)[row] = make_float4(1.f, 1.f, hb_hi, hb - hb_hi);
+  if (dv.adaptive) {
+    // ---- which form runs this iteration ----
+    // The tensor form re-does every pair whose distance is small against the point's distance from the centre (the
+    // cancellation in |x|^2 / 2 + |y|^2 / 2 - x.y) in the difference form, one divergent call each: cheap in a map that has
+    // spread out, ruinous in the first iterations of the reference's start (R/core.R:407-415: cumulative steps along the
+    // diagonal, 3 % of all pairs are near: 136 ms instead of 7.5 at cfg4).  Every row tests a few pseudo-random partners
+    // against the same criterion; the count is a function of the replica alone, so every rank of a sharded map decides
+    // the same way and the result still does not depend on the rank count.
+    unsigned near = 0;
+    if (real) {
+      const unsigned it = (unsigned)__ldcg(&dv.state->iter);
+      for (int k = 0; k < dv.probe_k; ++k) {
+        unsigned long long z = ((unsigned long long)row * 64ull + (unsigned long long)k) * 0x9E3779B97F4A7C15ull + (unsigned long long)it * 0xD1B54A32D192ED03ull + dv.seed;
+        z ^= z >> 30; z *= 0xBF58476D1CE4E5B9ull; z ^= z >> 27; z *= 0x94D049BB133111EBull; z ^= z >> 31;
+        const size_t j = (size_t)(z % (unsigned long long)dv.n);
+        if (j == row) continue;
+        float2 q[H];
+        ld_point<H>(dv.pos[dv.rank] + ((size_t)cur * dv.cap_rows + j) * Dp, q);
+        float d2 = 0.f;
+#pragma unroll
+        for (int c = 0; c < H; ++c) {
+          const float dx = q[c].x - dv.centre[2 * c] - x[2 * c], dy = q[c].y - dv.centre[2 * c + 1] - x[2 * c + 1];
+          d2 = fmaf(dx, dx, d2); d2 = fmaf(dy, dy, d2);
+        }
+        near += (0.5f * d2 < 3.01e-3f * h_hi) ? 1u : 0u;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) near += __shfl_xor_sync(0xffffffffu, near, o);
+    if ((threadIdx.x & 31) == 0 && near) atomicAdd(&dv.counters[4], near);
+    if (last_cta(&dv.counters[5]) && threadIdx.x == 0) {
+      const unsigned found = atomicExch(&dv.counters[4], 0u);
+      const unsigned tensor = found <= dv.probe_limit ? 1u : 0u;
+      dv.counters[6] = tensor;
+      dv.counters[7] += tensor;
+      __threadfence();
+    }
+  }
 }
 
 // A near pair, from the coordinate differences (the arithmetic of repulse_kernel).  Out of line and on accumulators in
@@ -179,6 +217,7 @@ __global__ void __maxnreg__(80) repulse_tc_kernel(RowDev dv, TcImage im, int cur
   extern __shared__ __align__(128) unsigned char tc_smem[];
   constexpr int Dp = Row<H>::kStride;
   if (__ldcg(&dv.state->stop)) return;
+  if (dv.adaptive && !form_is_tensor(dv)) return;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const unsigned sm0 = smem_u32(tc_smem);
   const unsigned bar_a_full = sm0 + TcSmem::kBars;

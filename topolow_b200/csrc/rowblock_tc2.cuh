@@ -95,6 +95,7 @@ __global__ void __maxnreg__(80) repulse_tc2_kernel(RowDev dv, T2Image im, int cu
   constexpr int Dp = Row<H>::kStride;
   (void)cur;
   if (__ldcg(&dv.state->stop)) return;
+  if (dv.adaptive && !form_is_tensor(dv)) return;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const unsigned sm0 = smem_u32(tc_smem);
   const unsigned bar_a_full = sm0 + T2Smem::kBars;

@@ -24,7 +24,8 @@ from ._lib import OK, TopolowError
 
 INFO_KEYS = ["slots", "ndim", "stride", "n_ranks", "rank", "row0", "own_rows", "partner_chunks", "spring_records",
              "mae_records", "launches", "iterations_done", "stopped", "peer_store_bytes_per_iteration",
-             "repulsion_items", "repulsion_ctas", "repulsion_form"]
+             "repulsion_items", "repulsion_ctas", "repulsion_form",
+             "tensor_form_iterations"]
 KERNELS = ["repulse", "spring", "mae", "controller", "snapshot"]
 
 
@@ -91,8 +92,8 @@ class Shard:
         return _lib.result_dict(res, out, tr)
 
     def info(self):
-        v = (C.c_int64 * 17)()
-        self._L.topolow_shard_info(self._h, v, 17)
+        v = (C.c_int64 * 18)()
+        self._L.topolow_shard_info(self._h, v, 18)
         return dict(zip(INFO_KEYS, [int(x) for x in v]))
 
     def close(self):
