@@ -22,6 +22,10 @@ if "--pinned" in sys.argv:
         fa[i] = t.numpy() if a.flags.c_contiguous else t.numpy().T
 mode = _lib.MODE_ROWBLOCK if "--rowblock" in sys.argv else _lib.MODE_COLOURED
 _lib.fit(*fa, 2, 5.0, 0.01, 0.02, 1e-4, 3, 3, mode=mode)   # warm-up (context, module load)
+t0 = time.perf_counter()
+_pa = _lib.ProblemArrays(*fa)
+print(f"ProblemArrays (host marshalling alone): {(time.perf_counter() - t0) * 1e3:.1f} ms", flush=True)
+del _pa
 for rep in range(2):
     t0 = time.perf_counter()
     r = _lib.fit(*fa, iters, 5.0, 0.01, 0.02, 1e-4, iters + 1, 3, mode=mode)

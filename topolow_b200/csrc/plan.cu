@@ -486,10 +486,25 @@ int fit_impl(const topolow_problem* pb, const topolow_params* pr, topolow_result
         std::snprintf(res->message, sizeof res->message,
                       "Numerical instability at iteration %d. Reduce k0 or c_repulsion.", res->fail_iter);
     } else if (pr->mode == TOPOLOW_MODE_ROWBLOCK) {
-      struct Holder { RowPlan* p; ~Holder() { row_destroy(p); } } h{row_create(*pb, *pr, 0, 1)};
-      bool interrupted = false;
-      row_run(*h.p, pr->n_iter, nullptr, poll, user, &interrupted);
-      row_result(*h.p, *res, interrupted);
+      // host wall clock per phase under TOPOLOW_DEBUG (every phase ends synchronised)
+      const bool dbg = std::getenv("TOPOLOW_DEBUG") != nullptr;
+      auto t_last = std::chrono::steady_clock::now();
+      auto lap = [&](const char* what) {
+        if (!dbg) return;
+        const auto now = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[topolow] %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(now - t_last).count());
+        t_last = now;
+      };
+      {
+        struct Holder { RowPlan* p; ~Holder() { row_destroy(p); } } h{row_create(*pb, *pr, 0, 1)};
+        lap("fit: create");
+        bool interrupted = false;
+        row_run(*h.p, pr->n_iter, nullptr, poll, user, &interrupted);
+        lap("fit: iterations");
+        row_result(*h.p, *res, interrupted);
+        lap("fit: result");
+      }
+      lap("fit: destroy");
     } else {
       auto pl = make_plan(*pb, *pr);
       bool interrupted = false;

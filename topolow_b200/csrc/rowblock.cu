@@ -53,6 +53,7 @@ struct RowDev {
   int n, slots, D, Dp, G, rank, row0, rows, chunks;
   int rparts;                        // partial-sum entries per row in rpart: chunks (2 x chunks for the tensor-core pass)
   int adaptive;                      // 1: the repulsion form is chosen per iteration on the device (counters[6], set by image_tc_kernel)
+  int series;                        // tensor form: weights by the one-MUFU series where the probe allows it (adaptive) / always (not adaptive)
   int probe_k;                       // sampled partners per row of the near-pair probe
   unsigned probe_limit;              // tensor form while the probe finds at most this many near pairs
   int no_wait;                       // measurement only (TOPOLOW_IGNORE_PEERS): one rank of a sharded map timed without its peers
@@ -75,8 +76,9 @@ struct RowDev {
   const int* mwidth;
   FitState* state;
   double* trace;
-  unsigned* counters;                // [0..2] tickets of the "last CTA" of a launch / work items; [4] near pairs the probe found, [5] its
-                                     // ticket, [6] form of this iteration (1 = tensor cores), [7] iterations run in the tensor form
+  unsigned* counters;                // [0..2] tickets of the "last CTA" of a launch / work items; [3], [4] near pairs the probe found (series
+                                     // form / plain), [5] its ticket, [6] form of this iteration (0 FP32, 1 tensor, 2 tensor with the series
+                                     // weights), [7] iterations run in a tensor form
   volatile int* host_flag;           // mapped: [0] stop, [1] iterations done
   unsigned long long pairs_per_iter;
   unsigned long long seed;
@@ -1359,6 +1361,8 @@ void configure_repulse(RowPlan& rp, int sms) {
   // the host launches both kernels.  A form asked for by name (TOPOLOW_REP_VARIANT) runs unconditionally.
   rp.dv.adaptive = (rp.tc_form && !ev) ? 1 : 0;
   if (const char* ea = std::getenv("TOPOLOW_ADAPTIVE")) rp.dv.adaptive = (rp.tc_form && std::atoi(ea) != 0) ? 1 : 0;
+  rp.dv.series = rp.dv.adaptive;     // not adaptive: the series form only on request (it is exact only for pairs farther than 0.1 apart)
+  if (const char* es = std::getenv("TOPOLOW_TC_SERIES")) rp.dv.series = std::atoi(es) != 0 ? 1 : 0;
   rp.dv.probe_k = (int)std::min<long long>(64, std::max<long long>(4, (262144 + rp.dv.n - 1) / std::max(rp.dv.n, 1)));
   // Break-even, measured at cfg4 (ndim 16): the fix-ups cost about 4.7 s x (near fraction) per pass over 1e10 one-sided pairs,
   // the difference form 9 ms more than the tensor form: near fraction 2e-3; half of that is the limit, scaled with ndim

@@ -108,6 +108,8 @@ TL_D unsigned long long tc_desc(unsigned smem_addr, unsigned lbo_bytes, unsigned
 // (1 << 13), both K-major, N >> 3 in [17,23), M >> 4 in [24,29).
 constexpr unsigned kTcIdesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 13) | ((unsigned)(kTcSJ >> 3) << 17) | ((128u >> 4) << 24);
 
+constexpr float kSeriesNearS = 0.005f;   // = kT2SeriesS (rowblock_tc2.cuh): the series form of the weights takes pairs closer than 0.1 as near pairs
+
 TL_D float tf32_round(float x) { unsigned r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x)); return __uint_as_float(r); }
 
 // ---- the image: chunk planes of hi / lo, the norm columns, FP32 rows ---------------------------------
@@ -177,16 +179,21 @@ __global__ void __launch_bounds__(kBlockRows) image_tc_kernel(RowDev dv, TcImage
           d2 = fmaf(dx, dx, d2); d2 = fmaf(dy, dy, d2);
         }
         near += (0.5f * d2 < 3.01e-3f * h_hi) ? 1u : 0u;
+        near += (0.5f * d2 < fmaxf(3.01e-3f * h_hi, kSeriesNearS)) ? 0x10000u : 0u;   // near in the series form of the weights
       }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) near += __shfl_xor_sync(0xffffffffu, near, o);
-    if ((threadIdx.x & 31) == 0 && near) atomicAdd(&dv.counters[4], near);
+    for (int o = 16; o > 0; o >>= 1) near += __shfl_xor_sync(0xffffffffu, near, o);     // <= 64 x 32 per half: no carry
+    if ((threadIdx.x & 31) == 0 && near) {
+      if (near & 0xffffu) atomicAdd(&dv.counters[4], near & 0xffffu);
+      atomicAdd(&dv.counters[3], near >> 16);
+    }
     if (last_cta(&dv.counters[5]) && threadIdx.x == 0) {
-      const unsigned found = atomicExch(&dv.counters[4], 0u);
-      const unsigned tensor = found <= dv.probe_limit ? 1u : 0u;
-      dv.counters[6] = tensor;
-      dv.counters[7] += tensor;
+      const unsigned found = atomicExch(&dv.counters[4], 0u), found_series = atomicExch(&dv.counters[3], 0u);
+      // 2: tensor form, weights by the one-MUFU series; 1: tensor form, square root + reciprocal; 0: FP32 difference form
+      const unsigned form = (dv.series && found_series <= dv.probe_limit) ? 2u : (found <= dv.probe_limit ? 1u : 0u);
+      dv.counters[6] = form;
+      dv.counters[7] += form ? 1u : 0u;
       __threadfence();
     }
   }

@@ -24,6 +24,7 @@
 constexpr int kT2SJ = 32;            // partners per stage
 constexpr int kT2Stages = 4;
 constexpr int kT2Threads = 320;       // 8 consumer warps + the MMA warp + the copy warp
+constexpr float kT2SeriesS = 0.005f;   // series form of the weight: pairs closer than 0.1 (d^2 / 2 < 0.005) are near pairs
 constexpr bool kT2LoPass = false;     // second pass of GEMM 2 over the TF32 remainders of the partner coordinates (see below)
 
 struct T2Smem {
@@ -63,6 +64,7 @@ TL_D bool elect_one() {
   asm volatile("{ .reg .pred p; elect.sync _|p, 0xffffffff; selp.u32 %0, 1, 0, p; }" : "=r"(pred));
   return pred != 0;
 }
+TL_D float rsqrt_approx_ftz(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 TL_D float rcp_approx_ftz(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 
 constexpr unsigned kT2Idesc1 = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 13) | ((unsigned)(kT2SJ >> 3) << 17) | ((128u >> 4) << 24);   // -A B^T, N = 32
@@ -260,6 +262,7 @@ __global__ void __maxnreg__(80) repulse_tc2_kernel(RowDev dv, T2Image im, int cu
   } else {
     const int quad = warp & 3, half = warp >> 2;
     const unsigned lane_sel = (unsigned)(quad * 32) << 16;
+    const bool series = dv.adaptive ? (__ldcg(&dv.counters[6]) == 2u) : (dv.series != 0);   // warp-uniform, fixed for the launch
     unsigned g = 0, chunk_g = 0;
     for (long long item = blockIdx.x; item < items; item += gridDim.x) {
       const int tile = (int)(item / groups), grp = (int)(item % groups);
@@ -267,7 +270,10 @@ __global__ void __maxnreg__(80) repulse_tc2_kernel(RowDev dv, T2Image im, int cu
       const int lrow[2] = {tile * kTcRows + quad * 32 + lane, tile * kTcRows + 128 + quad * 32 + lane};
       float thr[2];
 #pragma unroll
-      for (int r = 0; r < 2; ++r) thr[r] = -3.01e-3f * __ldg(im.a.aug_a + (size_t)(dv.row0 + lrow[r]) * 4);
+      for (int r = 0; r < 2; ++r) {
+        thr[r] = -3.01e-3f * __ldg(im.a.aug_a + (size_t)(dv.row0 + lrow[r]) * 4);
+        if (series) thr[r] = fmaxf(thr[r], kT2SeriesS);
+      }
       for (int c = c_lo; c < c_hi; ++c, ++chunk_g) {
         float facc[32];
         bool fixed = false;
@@ -287,19 +293,52 @@ __global__ void __maxnreg__(80) repulse_tc2_kernel(RowDev dv, T2Image im, int cu
             tc_ld8(t_base + bt * 8, s0);
             tc_ld8(t_base + 32 + bt * 8, s1);
             tc_wait_ld();
-            bool flag = false;
+            // w = (d + 0.01)^-3 with d = sqrt(2 S); a near pair gets -0: it adds nothing in GEMM 2 and is told apart from a
+            // weight that underflowed to +0.  Near pairs are rare: one minimum per row and batch finds out whether there is
+            // any (a compare and a select per pair would cost a fifth of the loop), the marking itself is out of the way.
+            float m0 = __uint_as_float(s0[0]), m1 = __uint_as_float(s1[0]);
 #pragma unroll
-            for (int jj = 0; jj < 8; ++jj) {
+            for (int jj = 1; jj < 8; ++jj) { m0 = fminf(m0, __uint_as_float(s0[jj])); m1 = fminf(m1, __uint_as_float(s1[jj])); }
+            const bool flag = (m0 < thr[0]) | (m1 < thr[1]);
+            unsigned near_mask = 0u;
+            if (flag) {
 #pragma unroll
-              for (int r = 0; r < 2; ++r) {
-                const float S = __uint_as_float(r == 0 ? s0[jj] : s1[jj]);          // d^2 / 2
-                const bool nr = S < thr[r];
-                // (d + 0.01)^-3, d = sqrt(2 S):  (2^-0.5 / (sqrt(S) + 0.01 2^-0.5))^3
-                const float rc = 0.70710678f * rcp_approx_ftz(sqrt_approx(fabsf(S)) + 0.00707106781f);
-                float w = rc * rc * rc;
-                w = nr ? -0.0f : w;            // -0: adds nothing in GEMM 2 and is told apart from a weight that underflowed to +0
-                flag |= nr;
-                if (r == 0) s0[jj] = __float_as_uint(w); else s1[jj] = __float_as_uint(w);
+              for (int jj = 0; jj < 8; ++jj)
+                near_mask |= (__uint_as_float(s0[jj]) < thr[0] ? (1u << jj) : 0u) | (__uint_as_float(s1[jj]) < thr[1] ? (256u << jj) : 0u);
+            }
+            if (series) {
+              // one special-function instruction per pair: q = S^-1/2 = sqrt(2) / d, e = 0.01 / d <= 0.1 (closer pairs are
+              // near pairs in this form), w = d^-3 (1 + e)^-3 = q^3 2^-1.5 p(e), p the cubic that interpolates (1 + e)^-3 at
+              // the Chebyshev nodes of [0, 0.1]: 1.0e-5 relative (the weight is rounded to TF32, 4.9e-4, right after)
+#pragma unroll
+              for (int jj = 0; jj < 8; ++jj) {
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                  const float q = rsqrt_approx_ftz(fabsf(__uint_as_float(r == 0 ? s0[jj] : s1[jj])));
+                  const float q2 = q * q;
+                  float pl = fmaf(-9.3722616e-07f, q, 1.0345994e-4f);
+                  pl = fmaf(pl, q, -7.492801e-3f);
+                  pl = fmaf(pl, q, 0.35355023f);
+                  const float w = (q2 * q) * pl;
+                  if (r == 0) s0[jj] = __float_as_uint(w); else s1[jj] = __float_as_uint(w);
+                }
+              }
+            } else {
+#pragma unroll
+              for (int jj = 0; jj < 8; ++jj) {
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                  const float rc = rcp_approx_ftz(fmaf(sqrt_approx(fabsf(__uint_as_float(r == 0 ? s0[jj] : s1[jj]))), 1.41421356f, 0.01f));
+                  const float w = (rc * rc) * rc;
+                  if (r == 0) s0[jj] = __float_as_uint(w); else s1[jj] = __float_as_uint(w);
+                }
+              }
+            }
+            if (flag) {
+#pragma unroll
+              for (int jj = 0; jj < 8; ++jj) {
+                if (near_mask & (1u << jj)) s0[jj] = 0x80000000u;
+                if (near_mask & (256u << jj)) s1[jj] = 0x80000000u;
               }
             }
             tc_st8(t_base + bt * 8, s0);
