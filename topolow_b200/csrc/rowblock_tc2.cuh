@@ -19,7 +19,11 @@
 // divergent code) took 2 us per stage; hence two whole, converged warps - one issues the MMAs, one the copies - with
 // elect.sync around the single-lane instructions.
 //
-// TMEM (256 columns per CTA, two CTAs per SM): S / w  [2 buffers][2 tiles][32] = 128, D2 [2 buffers][2 tiles][32] = 128.
+// TMEM (256 columns per CTA, two CTAs per SM): S / w  [2 buffers][2 tiles][32] = 128, D2 [2 tiles][32] = 64 (one buffer: the
+// consumers read a chunk's sums before the first GEMM 2 of the next chunk, once per 64 stages), and the rows' TF32 image
+// -A_hi [2 tiles][24] = 48: five of the seven MMAs of a GEMM 1 take their A operand from tensor memory instead of reading
+// 4 KB of shared memory each (the tensor pipe's operand fetch was its busiest part: 57 % of the cycles, and the consumers
+// waited a fifth of their time for distances).
 
 constexpr int kT2SJ = 32;            // partners per stage
 constexpr int kT2Stages = 4;
@@ -38,7 +42,7 @@ struct T2Smem {
   static constexpr int kRows32 = kYLo + 8 * 16 * 16;               // 32 x 64 B (near pairs only)
   static constexpr int kStageBytes = kRows32 + kT2SJ * 64;
   static constexpr int kBars = kStage0 + kT2Stages * kStageBytes;
-  static constexpr int kNumBars = 1 + 2 * kT2Stages + 8 + 1;       // a_full | full, empty per stage | tfull, wfull, d2full, d2empty x 2 | a_free
+  static constexpr int kNumBars = 1 + 2 * kT2Stages + 8 + 1;       // a_full | full, empty per stage | tfull x 2, wfull x 2, d2full, d2empty, a_tmem, - | a_free
   static constexpr int kTmemPtr = kBars + kNumBars * 8;
   static constexpr int kTotal = kTmemPtr + 16;
   static constexpr int kStageTx = 4 * kT2SJ * 16 + kT2SJ * 16 + 4 * kT2SJ * 16 + 8 * 32 * 16 + (kT2LoPass ? 8 * 16 * 16 : 0) + kT2SJ * 64;
@@ -68,6 +72,7 @@ TL_D float rsqrt_approx_ftz(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1
 TL_D float rcp_approx_ftz(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 
 constexpr unsigned kT2Idesc1 = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 13) | ((unsigned)(kT2SJ >> 3) << 17) | ((128u >> 4) << 24);   // -A B^T, N = 32
+constexpr unsigned kT2Idesc1T = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(kT2SJ >> 3) << 17) | ((128u >> 4) << 24);                   // A (negated already) from TMEM, N = 32
 constexpr unsigned kT2Idesc2Hi = (1u << 4) | (2u << 7) | (2u << 10) | ((32u >> 3) << 17) | ((128u >> 4) << 24);                         // N = 32
 constexpr unsigned kT2Idesc2Lo = (1u << 4) | (2u << 7) | (2u << 10) | ((16u >> 3) << 17) | ((128u >> 4) << 24);                         // N = 16
 
@@ -103,7 +108,8 @@ __global__ void __maxnreg__(80) repulse_tc2_kernel(RowDev dv, T2Image im, int cu
   const unsigned bar_a_full = sm0 + T2Smem::kBars;
   auto bar_full = [&](int s) { return sm0 + T2Smem::kBars + 8u * (1 + s); };
   auto bar_empty = [&](int s) { return sm0 + T2Smem::kBars + 8u * (1 + kT2Stages + s); };
-  auto bar_x = [&](int kind, int b) { return sm0 + T2Smem::kBars + 8u * (1 + 2 * kT2Stages + 2 * kind + b); };   // 0 tfull 1 wfull 2 d2full 3 d2empty
+  auto bar_x = [&](int kind, int b) { return sm0 + T2Smem::kBars + 8u * (1 + 2 * kT2Stages + 2 * kind + b); };   // 0 tfull 1 wfull
+  const unsigned bar_d2full = bar_x(2, 0), bar_d2empty = bar_x(2, 1), bar_a_tmem = bar_x(3, 0);
   const unsigned bar_a_free = sm0 + T2Smem::kBars + 8u * (1 + 2 * kT2Stages + 8);
   unsigned* tmem_ptr_s = reinterpret_cast<unsigned*>(tc_smem + T2Smem::kTmemPtr);
 
@@ -115,7 +121,8 @@ __global__ void __maxnreg__(80) repulse_tc2_kernel(RowDev dv, T2Image im, int cu
     mbar_init(bar_a_full, 1);
     mbar_init(bar_a_free, 1);
     for (int s = 0; s < kT2Stages; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 9); }   // 8 consumer warps + the commit of GEMM 2
-    for (int b = 0; b < 2; ++b) { mbar_init(bar_x(0, b), 1); mbar_init(bar_x(1, b), 8); mbar_init(bar_x(2, b), 1); mbar_init(bar_x(3, b), 8); }
+    for (int b = 0; b < 2; ++b) { mbar_init(bar_x(0, b), 1); mbar_init(bar_x(1, b), 8); }
+    mbar_init(bar_d2full, 1); mbar_init(bar_d2empty, 8); mbar_init(bar_a_tmem, 8);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 8) {
@@ -128,7 +135,8 @@ __global__ void __maxnreg__(80) repulse_tc2_kernel(RowDev dv, T2Image im, int cu
   tc_fence_after();
   const unsigned tmem0 = *tmem_ptr_s;
   auto col_s = [&](int b, int m) { return (unsigned)(b * 64 + m * 32); };           // S / w of buffer b, tile m
-  auto col_d = [&](int e, int m) { return (unsigned)(128 + e * 64 + m * 32); };     // D2 of buffer e, tile m
+  auto col_d = [&](int m) { return (unsigned)(128 + m * 32); };                     // D2 of tile m
+  auto col_a = [&](int m) { return (unsigned)(192 + m * 24); };                     // -A_hi of tile m: 16 coordinates, (h_hi, h_lo, 1, 1), 4 zeros
 
   const int tiles = dv.rows / kTcRows;
   const int groups = (dv.chunks + cpi - 1) / cpi;
@@ -199,7 +207,7 @@ __global__ void __maxnreg__(80) repulse_tc2_kernel(RowDev dv, T2Image im, int cu
     open_item(g1); open_item(g2);
     unsigned g1_g = 0, g2_g = 0, a_uses = 0, chunk_g = 0;
     auto gemm1 = [&]() {
-      if (g1.s == 0 && g1.c % cpi == 0) { mbar_wait(bar_a_full, a_uses & 1); ++a_uses; }
+      if (g1.s == 0 && g1.c % cpi == 0) { mbar_wait(bar_a_full, a_uses & 1); mbar_wait(bar_a_tmem, a_uses & 1); ++a_uses; }
       const int s = g1_g % kT2Stages, b = g1_g & 1;
       mbar_wait(bar_full(s), (g1_g / kT2Stages) & 1);
       // buffer b: its last reader, GEMM 2 of stage g1_g - 2, was issued before this instruction (the tensor pipe runs in order)
@@ -209,15 +217,15 @@ __global__ void __maxnreg__(80) repulse_tc2_kernel(RowDev dv, T2Image im, int cu
 #pragma unroll
         for (int m = 0; m < 2; ++m) {
           const unsigned d = tmem0 + col_s(b, m);
-          const unsigned a_hi = sm0 + T2Smem::kAHi + m * 128 * 16, a_lo = sm0 + T2Smem::kALo + m * 128 * 16;
+          const unsigned a_t = tmem0 + col_a(m), a_lo = sm0 + T2Smem::kALo + m * 128 * 16;
           const unsigned b_hi = stg + T2Smem::kBHi, b_lo = stg + T2Smem::kBLo;
           constexpr unsigned kLboA = kTcRows * 16, kLboB = kT2SJ * 16;
 #pragma unroll
-          for (int k = 0; k < 3; ++k)
-            tc_mma_tf32(d, tc_desc(a_hi + k * 2 * kLboA, kLboA, 128), tc_desc(b_hi + k * 2 * kLboB, kLboB, 128), kT2Idesc1, k > 0);
+          for (int k = 0; k < 3; ++k)      // (-A_hi) B_hi^T, A from tensor memory (stored negated: no negate flag)
+            tc_mma_tf32_ts(d, a_t + k * 8, tc_desc(b_hi + k * 2 * kLboB, kLboB, 128), kT2Idesc1T, k > 0);
 #pragma unroll
           for (int k = 0; k < 2; ++k) {
-            tc_mma_tf32(d, tc_desc(a_hi + k * 2 * kLboA, kLboA, 128), tc_desc(b_lo + k * 2 * kLboB, kLboB, 128), kT2Idesc1, 1);
+            tc_mma_tf32_ts(d, a_t + k * 8, tc_desc(b_lo + k * 2 * kLboB, kLboB, 128), kT2Idesc1T, 1);
             tc_mma_tf32(d, tc_desc(a_lo + k * 2 * kLboA, kLboA, 128), tc_desc(b_hi + k * 2 * kLboB, kLboB, 128), kT2Idesc1, 1);
           }
         }
@@ -229,16 +237,16 @@ __global__ void __maxnreg__(80) repulse_tc2_kernel(RowDev dv, T2Image im, int cu
       advance(g1);
     };
     auto gemm2 = [&]() {
-      const int s = g2_g % kT2Stages, b = g2_g & 1, e = chunk_g & 1;
+      const int s = g2_g % kT2Stages, b = g2_g & 1;
       const bool first = g2.s == 0, last = g2.s + 1 == chunk_stages(g2.c);
       mbar_wait(bar_x(1, b), (g2_g >> 1) & 1);                       // the weights of the stage are in TMEM
-      if (first) mbar_wait(bar_x(3, e), ((chunk_g >> 1) & 1) ^ 1);   // the sums of chunk - 2 have been read
+      if (first) mbar_wait(bar_d2empty, (chunk_g & 1) ^ 1);          // the sums of the chunk before have been read
       tc_fence_after();
       if (elect_one()) {
         const unsigned stg = sm0 + T2Smem::kStage0 + s * T2Smem::kStageBytes;
 #pragma unroll
         for (int m = 0; m < 2; ++m) {
-          const unsigned d = tmem0 + col_d(e, m), a = tmem0 + col_s(b, m);
+          const unsigned d = tmem0 + col_d(m), a = tmem0 + col_s(b, m);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {                                // 8 partners (two quads) per MMA
             // Y planes: per partner quad [32 rows][16 B] (hi) / [16 rows][16 B] (lo): LBO = next quad, SBO = 8 rows
@@ -247,7 +255,7 @@ __global__ void __maxnreg__(80) repulse_tc2_kernel(RowDev dv, T2Image im, int cu
           }
         }
         tc_commit(bar_empty(s));                                       // the stage's shared memory (and w buffer b) are free
-        if (last) tc_commit(bar_x(2, e));
+        if (last) tc_commit(bar_d2full);
       }
       __syncwarp();
       if (last) ++chunk_g;
@@ -256,18 +264,47 @@ __global__ void __maxnreg__(80) repulse_tc2_kernel(RowDev dv, T2Image im, int cu
     };
     if (g1.valid) gemm1();
     while (g2.valid) {
-      if (g1.valid) gemm1();          // distances of the next stage while the consumers work on this one
+      // distances of the next stage while the consumers work on this one - except across an item boundary: the rows' image
+      // of the next item is written to tensor memory by the consumers, who first need this item's last GEMM 2
+      const bool boundary = g1.valid && g1.s == 0 && g1.c % cpi == 0;
+      if (g1.valid && !boundary) gemm1();
       gemm2();
+      if (boundary) gemm1();
     }
   } else {
     const int quad = warp & 3, half = warp >> 2;
     const unsigned lane_sel = (unsigned)(quad * 32) << 16;
     const bool series = dv.adaptive ? (__ldcg(&dv.counters[6]) == 2u) : (dv.series != 0);   // warp-uniform, fixed for the launch
-    unsigned g = 0, chunk_g = 0;
+    unsigned g = 0, chunk_g = 0, item_g = 0;
     for (long long item = blockIdx.x; item < items; item += gridDim.x) {
       const int tile = (int)(item / groups), grp = (int)(item % groups);
       const int c_lo = grp * cpi, c_hi = min(dv.chunks, c_lo + cpi);
       const int lrow[2] = {tile * kTcRows + quad * 32 + lane, tile * kTcRows + 128 + quad * 32 + lane};
+      {
+        // ---- the rows' image into tensor memory: warp (quad, half) writes rows quad * 32 .. + 31 of tile `half` ----
+        if (item_g > 0) mbar_wait(bar_a_free, (item_g - 1) & 1);      // the GEMM 1s of the item before have read theirs
+        ++item_g;
+        tc_fence_after();
+        const size_t grow = (size_t)dv.row0 + (size_t)(half ? lrow[1] : lrow[0]);
+        const float4* xh = reinterpret_cast<const float4*>(im.a.xhi);
+        const unsigned t_a = tmem0 + lane_sel + col_a(half);
+#pragma unroll
+        for (int cg = 0; cg < 2; ++cg) {
+          const float4 u0 = __ldg(xh + (size_t)(2 * cg) * dv.cap_rows + grow), u1 = __ldg(xh + (size_t)(2 * cg + 1) * dv.cap_rows + grow);
+          const unsigned v[8] = {__float_as_uint(-u0.x), __float_as_uint(-u0.y), __float_as_uint(-u0.z), __float_as_uint(-u0.w),
+                                 __float_as_uint(-u1.x), __float_as_uint(-u1.y), __float_as_uint(-u1.z), __float_as_uint(-u1.w)};
+          tc_st8(t_a + cg * 8, v);
+        }
+        {
+          const float4 ag = __ldg(reinterpret_cast<const float4*>(im.a.aug_a) + grow);      // (-h_hi, -h_lo, -1, -1)
+          const unsigned v[8] = {__float_as_uint(-ag.x), __float_as_uint(-ag.y), __float_as_uint(-ag.z), __float_as_uint(-ag.w), 0u, 0u, 0u, 0u};
+          tc_st8(t_a + 16, v);
+        }
+        tc_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_a_tmem);
+      }
       float thr[2];
 #pragma unroll
       for (int r = 0; r < 2; ++r) {
@@ -365,19 +402,18 @@ __global__ void __maxnreg__(80) repulse_tc2_kernel(RowDev dv, T2Image im, int cu
           if (lane == 0) { mbar_arrive(bar_x(1, b)); mbar_arrive(bar_empty(s)); }
         }
         // ---- the chunk's sums: warps of half h read tile h ----
-        const int e = chunk_g & 1;
-        mbar_wait(bar_x(2, e), (chunk_g >> 1) & 1);
+        mbar_wait(bar_d2full, chunk_g & 1);
         tc_fence_after();
         {
           unsigned dlo[8], dhi[8];
-          const unsigned d_base = tmem0 + lane_sel + col_d(e, half);
+          const unsigned d_base = tmem0 + lane_sel + col_d(half);
           tc_ld8(d_base, dlo);
           tc_ld8(d_base + 8, dhi);
           const float Wsum = __uint_as_float(tc_ld1(d_base + 16));
           tc_wait_ld();
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(bar_x(3, e));
+          if (lane == 0) mbar_arrive(bar_d2empty);
           // facc of the OTHER tile's rows lives in the other half's threads: exchange through shared memory would cost a
           // barrier; instead every thread adds its own near sums to the tile it writes... it only has them for its own
           // (half-specific) partners.  So near sums are written as their own partial entry (see below).
