@@ -21,7 +21,7 @@
 //
 // TMEM (256 columns per CTA, two CTAs per SM): S / w  [2 buffers][2 tiles][32] = 128, D2 [2 tiles][32] = 64 (one buffer: the
 // consumers read a chunk's sums before the first GEMM 2 of the next chunk, once per 64 stages), and the rows' TF32 image
-// -A_hi [2 tiles][24] = 48: five of the seven MMAs of a GEMM 1 take their A operand from tensor memory instead of reading
+// -A_hi [2 tiles][24] = 48 and -A_lo of tile 0 in the last 16: eleven of the fourteen MMAs of a GEMM 1 take their A operand from tensor memory instead of reading
 // 4 KB of shared memory each (the tensor pipe's operand fetch was its busiest part: 57 % of the cycles, and the consumers
 // waited a fifth of their time for distances).
 
@@ -72,6 +72,7 @@ TL_D float rsqrt_approx_ftz(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1
 TL_D float rcp_approx_ftz(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 
 constexpr unsigned kT2Idesc1 = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 13) | ((unsigned)(kT2SJ >> 3) << 17) | ((128u >> 4) << 24);   // -A B^T, N = 32
+constexpr unsigned kT2ColALo = 240;   // TMEM columns 240..255: -A_lo of tile 0
 constexpr unsigned kT2Idesc1T = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(kT2SJ >> 3) << 17) | ((128u >> 4) << 24);                   // A (negated already) from TMEM, N = 32
 constexpr unsigned kT2Idesc2Hi = (1u << 4) | (2u << 7) | (2u << 10) | ((32u >> 3) << 17) | ((128u >> 4) << 24);                         // N = 32
 constexpr unsigned kT2Idesc2Lo = (1u << 4) | (2u << 7) | (2u << 10) | ((16u >> 3) << 17) | ((128u >> 4) << 24);                         // N = 16
@@ -226,7 +227,8 @@ __global__ void __maxnreg__(80) repulse_tc2_kernel(RowDev dv, T2Image im, int cu
 #pragma unroll
           for (int k = 0; k < 2; ++k) {
             tc_mma_tf32_ts(d, a_t + k * 8, tc_desc(b_lo + k * 2 * kLboB, kLboB, 128), kT2Idesc1T, 1);
-            tc_mma_tf32(d, tc_desc(a_lo + k * 2 * kLboA, kLboA, 128), tc_desc(b_hi + k * 2 * kLboB, kLboB, 128), kT2Idesc1, 1);
+            if (m == 0) tc_mma_tf32_ts(d, tmem0 + kT2ColALo + k * 8, tc_desc(b_hi + k * 2 * kLboB, kLboB, 128), kT2Idesc1T, 1);   // the last 16 columns
+            else tc_mma_tf32(d, tc_desc(a_lo + k * 2 * kLboA, kLboA, 128), tc_desc(b_hi + k * 2 * kLboB, kLboB, 128), kT2Idesc1, 1);
           }
         }
         tc_commit(bar_x(0, b));
@@ -299,6 +301,16 @@ __global__ void __maxnreg__(80) repulse_tc2_kernel(RowDev dv, T2Image im, int cu
           const float4 ag = __ldg(reinterpret_cast<const float4*>(im.a.aug_a) + grow);      // (-h_hi, -h_lo, -1, -1)
           const unsigned v[8] = {__float_as_uint(-ag.x), __float_as_uint(-ag.y), __float_as_uint(-ag.z), __float_as_uint(-ag.w), 0u, 0u, 0u, 0u};
           tc_st8(t_a + 16, v);
+        }
+        if (half == 0) {          // the remainders of tile 0 fill the last 16 columns (tile 1's stay in shared memory)
+          const float4* xl = reinterpret_cast<const float4*>(im.a.xlo);
+#pragma unroll
+          for (int cg = 0; cg < 2; ++cg) {
+            const float4 u0 = __ldg(xl + (size_t)(2 * cg) * dv.cap_rows + grow), u1 = __ldg(xl + (size_t)(2 * cg + 1) * dv.cap_rows + grow);
+            const unsigned v[8] = {__float_as_uint(-u0.x), __float_as_uint(-u0.y), __float_as_uint(-u0.z), __float_as_uint(-u0.w),
+                                   __float_as_uint(-u1.x), __float_as_uint(-u1.y), __float_as_uint(-u1.z), __float_as_uint(-u1.w)};
+            tc_st8(tmem0 + lane_sel + kT2ColALo + cg * 8, v);
+          }
         }
         tc_wait_st();
         tc_fence_before();
