@@ -600,6 +600,15 @@ def main_map(args, n, d, missing):
         return
 
     # ---- roofline ---------------------------------------------------------------------------------
+    def tracked_ncu(kernel):
+        """Pipe utilisation of `kernel` from the tracked ncu capture (profiles/traffic.json), else None."""
+        try:
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                e = json.load(f).get("%s/%d/%s" % (args.workload, world, kernel))
+            return e.get("ncu") if e else None
+        except (OSError, ValueError, KeyError):
+            return None
+
     def tracked_traffic(kernel):
         """DRAM bytes per launch of `kernel` from a tracked ncu capture of this workload at this GPU count, else None."""
         try:
@@ -626,7 +635,7 @@ def main_map(args, n, d, missing):
         rep_kernel = {11: "repulse_tc2_kernel", 10: "repulse_tc_kernel"}.get(form, "repulse_kernel")
         one_sided = pairs * 2.0 / world                       # interactions one launch evaluates (every pair from both sides)
         mufu_peak = _lib.microbench(4, local) * 32.0          # MUFU lane-operations / s, measured now on this GPU
-        mufu_per = 2.0 if form == 11 else 3.0                 # form 11: sqrt + reciprocal; forms 5 / 10: sqrt, lg2, ex2
+        mufu_per = 1.0 if form == 11 else 3.0                 # form 11 in a spread-out map: one rsqrt (the weight's series form); forms 5 / 10: sqrt, lg2, ex2
         roofline = {"bound": "fp32", "kernel": rep_names.get(form, "repulse_kernel<ndim/2, 2 rows per thread>") + " (one launch per iteration and rank)",
                     "repulsion_form": form,
                     "achieved": rep_flop / rep_s / 1e12, "peak": ffma_peak / 1e12, "unit": "TFLOP/s",
@@ -636,8 +645,10 @@ def main_map(args, n, d, missing):
                     "note": "algorithmic = (7 ndim + 8) flop per unordered pair (SURVEY 8d) against the FP32 FFMA peak, the denominator the "
                             "north-star names; the kernel visits every pair from both sides (one-sided updates). In form 11 both "
                             "contractions (the 5 ndim flop of the distance and the accumulation) run on the tensor cores, so the fraction "
-                            "can exceed what the FP32 pipes alone could reach; what bounds the pass is the special-function unit "
-                            "(`special_function_unit`: sqrt + reciprocal per interaction). The FP32 difference form (ndim < 5) ran at 0.51",
+                            "exceeds what the FP32 pipes alone could reach. What is left on the FP32 side is one rsqrt + a cubic per "
+                            "interaction (7.6 instructions); ncu (`tracked_ncu`, profiles/r2_ncu_rowblock_cfg4.md): 75 % of the issue slots, "
+                            "FMA pipe 40 %, special-function unit 45 %, tensor-core unit 40 % - the pass is bound by instruction issue. The "
+                            "FP32 difference form (ndim < 5, and iterations 0-1 of the reference's start, chosen on the device) ran at 0.51",
                     "special_function_unit": {"ops_per_launch": mufu_per * one_sided, "achieved": mufu_per * one_sided / rep_s / 1e12,
                                               "peak": mufu_peak / 1e12, "unit": "T lane-ops/s",
                                               "frac": mufu_per * one_sided / rep_s / mufu_peak,
@@ -649,6 +660,7 @@ def main_map(args, n, d, missing):
                                        "GEMM 2 K = 32 partners x N = 32 columns (17 used); TF32 dense peak is half of the bf16 figure in "
                                        "MEASURED_PEAKS.json - the tensor pipe is not the bound"},
                     "traffic": tracked_traffic(rep_kernel),
+                    "tracked_ncu": tracked_ncu(rep_kernel),
                     "kernels_ms": kt,
                     "edge_pass": {"bound": "hbm", "kernel": "mae_kernel (edge MAE on check iterations)",
                                   "achieved": edge_b / (kt["mae"] * 1e-3) / 1e9 if kt["mae"] > 0 else None, "peak": peaks["hbm_gbs"],
