@@ -110,7 +110,7 @@ __global__ void __maxnreg__(80) repulse_tc2_kernel(RowDev dv, T2Image im, int cu
   auto bar_full = [&](int s) { return sm0 + T2Smem::kBars + 8u * (1 + s); };
   auto bar_empty = [&](int s) { return sm0 + T2Smem::kBars + 8u * (1 + kT2Stages + s); };
   auto bar_x = [&](int kind, int b) { return sm0 + T2Smem::kBars + 8u * (1 + 2 * kT2Stages + 2 * kind + b); };   // 0 tfull 1 wfull
-  const unsigned bar_d2full = bar_x(2, 0), bar_d2empty = bar_x(2, 1), bar_a_tmem = bar_x(3, 0);
+  const unsigned bar_d2full = bar_x(2, 0), bar_d2empty = bar_x(2, 1), bar_a_tmem = bar_x(3, 0), bar_item = bar_x(3, 1);
   const unsigned bar_a_free = sm0 + T2Smem::kBars + 8u * (1 + 2 * kT2Stages + 8);
   unsigned* tmem_ptr_s = reinterpret_cast<unsigned*>(tc_smem + T2Smem::kTmemPtr);
 
@@ -123,7 +123,7 @@ __global__ void __maxnreg__(80) repulse_tc2_kernel(RowDev dv, T2Image im, int cu
     mbar_init(bar_a_free, 1);
     for (int s = 0; s < kT2Stages; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 9); }   // 8 consumer warps + the commit of GEMM 2
     for (int b = 0; b < 2; ++b) { mbar_init(bar_x(0, b), 1); mbar_init(bar_x(1, b), 8); }
-    mbar_init(bar_d2full, 1); mbar_init(bar_d2empty, 8); mbar_init(bar_a_tmem, 8);
+    mbar_init(bar_d2full, 1); mbar_init(bar_d2empty, 8); mbar_init(bar_a_tmem, 8); mbar_init(bar_item, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 8) {
@@ -144,7 +144,12 @@ __global__ void __maxnreg__(80) repulse_tc2_kernel(RowDev dv, T2Image im, int cu
   const long long items = (long long)tiles * groups;
   auto chunk_stages = [&](int c) { return (min(kChunk, dv.n - c * kChunk) + kT2SJ - 1) / kT2SJ; };
 
-  struct Cursor { long long item; int c, c_hi, s; size_t r0; bool valid; };
+  // Work items are handed out by an atomic counter (the sums of an item do not depend on who computes it): CTAs that start
+  // late - the SMs the spring walk still occupies when the pass is launched under it - simply take fewer.  The copy warp
+  // draws the CTA's next item and publishes it in a two-entry ring in shared memory (bar_item, one phase per item); it
+  // publishes item k + 1 only after the consumers have started item k (bar_a_tmem), so no waiter can miss a phase.
+  volatile int* item_ring = reinterpret_cast<volatile int*>(tc_smem + T2Smem::kTmemPtr) + 2;
+  struct Cursor { long long item; int c, c_hi, s; size_t r0; bool valid; unsigned seq; };
   auto open_item = [&](Cursor& cu) {
     cu.valid = cu.item < items;
     if (!cu.valid) return;
@@ -156,15 +161,31 @@ __global__ void __maxnreg__(80) repulse_tc2_kernel(RowDev dv, T2Image im, int cu
     if (++cu.s < chunk_stages(cu.c)) return;
     cu.s = 0;
     if (++cu.c < cu.c_hi) return;
-    cu.item += gridDim.x;
+    cu.valid = false;                 // the caller draws / takes the next item
+  };
+  auto draw_item = [&](Cursor& cu) {  // copy warp (converged)
+    if (cu.seq > 0) mbar_wait(bar_a_tmem, (cu.seq - 1) & 1);
+    int id = 0;
+    if (lane == 0) id = (int)atomicAdd(&dv.counters[2], 1u);
+    id = __shfl_sync(0xffffffffu, id, 0);
+    if (lane == 0) { item_ring[cu.seq & 1] = id; mbar_arrive(bar_item); }
+    __syncwarp();
+    ++cu.seq;
+    cu.item = id;
+    open_item(cu);
+  };
+  auto take_item = [&](Cursor& cu) {  // MMA warp (its leading cursor), consumer warps
+    mbar_wait(bar_item, cu.seq & 1);
+    cu.item = item_ring[cu.seq & 1];
+    ++cu.seq;
     open_item(cu);
   };
 
   if (warp == 9) {
     // =========================== copy warp: shared-memory stages and the A tile of every item ===========================
     Cursor ld;
-    ld.item = blockIdx.x;
-    open_item(ld);
+    ld.seq = 0;
+    draw_item(ld);
     unsigned load_g = 0, item_g = 0;
     while (ld.valid) {
       if (ld.s == 0 && ld.c % cpi == 0) {
@@ -200,12 +221,17 @@ __global__ void __maxnreg__(80) repulse_tc2_kernel(RowDev dv, T2Image im, int cu
       __syncwarp();
       ++load_g;
       advance(ld);
+      if (!ld.valid) draw_item(ld);
     }
   } else if (warp == 8) {
     // =========================== MMA warp: GEMM 1 of stage g + 1, then GEMM 2 of stage g ===========================
     Cursor g1, g2;
-    g1.item = g2.item = blockIdx.x;
-    open_item(g1); open_item(g2);
+    g1.seq = g2.seq = 0;
+    int taken[2];                     // the leading cursor is at most one item ahead of the trailing one
+    take_item(g1);
+    taken[0] = (int)g1.item;
+    g2.item = g1.item; g2.seq = 1;
+    open_item(g2);
     unsigned g1_g = 0, g2_g = 0, a_uses = 0, chunk_g = 0;
     auto gemm1 = [&]() {
       if (g1.s == 0 && g1.c % cpi == 0) { mbar_wait(bar_a_full, a_uses & 1); mbar_wait(bar_a_tmem, a_uses & 1); ++a_uses; }
@@ -237,6 +263,7 @@ __global__ void __maxnreg__(80) repulse_tc2_kernel(RowDev dv, T2Image im, int cu
       __syncwarp();
       ++g1_g;
       advance(g1);
+      if (!g1.valid) { take_item(g1); taken[(g1.seq - 1) & 1] = (int)g1.item; }
     };
     auto gemm2 = [&]() {
       const int s = g2_g % kT2Stages, b = g2_g & 1;
@@ -263,6 +290,7 @@ __global__ void __maxnreg__(80) repulse_tc2_kernel(RowDev dv, T2Image im, int cu
       if (last) ++chunk_g;
       ++g2_g;
       advance(g2);
+      if (!g2.valid) { g2.item = taken[g2.seq & 1]; ++g2.seq; open_item(g2); }
     };
     if (g1.valid) gemm1();
     while (g2.valid) {
@@ -278,7 +306,12 @@ __global__ void __maxnreg__(80) repulse_tc2_kernel(RowDev dv, T2Image im, int cu
     const unsigned lane_sel = (unsigned)(quad * 32) << 16;
     const bool series = dv.adaptive ? (__ldcg(&dv.counters[6]) == 2u) : (dv.series != 0);   // warp-uniform, fixed for the launch
     unsigned g = 0, chunk_g = 0, item_g = 0;
-    for (long long item = blockIdx.x; item < items; item += gridDim.x) {
+    Cursor cs;
+    cs.seq = 0;
+    for (;;) {
+      take_item(cs);
+      if (!cs.valid) break;
+      const long long item = cs.item;
       const int tile = (int)(item / groups), grp = (int)(item % groups);
       const int c_lo = grp * cpi, c_hi = min(dv.chunks, c_lo + cpi);
       const int lrow[2] = {tile * kTcRows + quad * 32 + lane, tile * kTcRows + 128 + quad * 32 + lane};
