@@ -242,3 +242,41 @@ def test_rowblock_cfg3_size_against_the_reference_loop():
         cm.append(c["final_mae"]); ch.append(np.abs(ed[held] - cd[held]).mean())
     assert g["final_mae"] == pytest.approx(np.mean(cm), rel=0.03), (g["final_mae"], cm)
     assert np.abs(ed[held] - gd[held]).mean() == pytest.approx(np.mean(ch), rel=0.03), (ch,)
+
+
+# ------------------------------------------------------------------ the forms of the repulsion pass ----
+def test_rowblock_repulsion_forms_agree_and_the_device_picks_one_per_iteration(monkeypatch):
+    """The forms of the repulsion pass - FP32 difference form (TOPOLOW_REP_VARIANT=5), two-GEMM tcgen05 form with the
+    weights by square root + reciprocal (11, TOPOLOW_TC_SERIES=0) or by the one-MUFU series (11, TOPOLOW_TC_SERIES=1) -
+    compute the same sums: after 8 iterations each is where the FP32 form is, within the FP32 / TF32 noise the
+    restatement test allows twice over.  The policy's run (no variable set) chooses among them per iteration on the
+    device and reports how many iterations ran a tensor form.  (Kept last in the file on purpose.)"""
+    n, d, iters = 1500, 8, 8
+    args = small_problem(n, d, 0.05, 4242, thresholds=True)
+    runs = {}
+    for name, env in (("f32", {"TOPOLOW_REP_VARIANT": "5"}),
+                      ("tensor", {"TOPOLOW_REP_VARIANT": "11", "TOPOLOW_TC_SERIES": "0"}),
+                      ("series", {"TOPOLOW_REP_VARIANT": "11", "TOPOLOW_TC_SERIES": "1"}),
+                      ("policy", {})):
+        for k in ("TOPOLOW_REP_VARIANT", "TOPOLOW_TC_SERIES", "TOPOLOW_ADAPTIVE"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        sh = rowblock.Shard(*args, iters, *HP, seed=3)
+        try:
+            sh.run(iters)
+            runs[name] = (sh.result(), sh.info())
+        finally:
+            sh.close()
+    base = runs["f32"][0]
+    scale = max(np.abs(base["positions"]).max(), 1.0)
+    for name in ("tensor", "series", "policy"):
+        r = runs[name][0]
+        err = np.abs(r["positions"] - base["positions"])
+        assert np.quantile(err, 0.99) <= 4e-4 * scale and err.max() <= 4e-3 * scale, (name, np.quantile(err, 0.99), err.max(), scale)
+        assert r["final_mae"] == pytest.approx(base["final_mae"], rel=2e-3), name
+        assert r["iterations_run"] == iters
+    assert runs["f32"][1]["repulsion_form"] == 5 and runs["f32"][1]["tensor_form_iterations"] == -1
+    assert runs["series"][1]["repulsion_form"] == 11 and runs["series"][1]["tensor_form_iterations"] == -1
+    info = runs["policy"][1]
+    assert info["repulsion_form"] == 11 and 0 <= info["tensor_form_iterations"] <= iters, info
