@@ -5,8 +5,11 @@
 //   FP32     w = (d + 0.01)^-3 per pair, read from and written back to the same TMEM columns (weights of near pairs 0)
 //   GEMM 2   D2[128 x 32] += w[128 x 32] Y[32 partners x 32]            A operand from TMEM, Y = (x_0..x_15, 1, 0...): columns
 //                                                                       0..15 collect sum_j w x_j, column 16 collects sum_j w
-// and per chunk of 2048 partners the rows' sums come out as D2[0..15] - x_i D2[16].  The FP32 pipes are left with about nine
-// instructions per pair, two of them on the special-function unit (sqrt, reciprocal), which is what bounds the pass.
+// and per chunk of 2048 partners the rows' sums come out as D2[0..15] - x_i D2[16].  The FP32 pipes are left with 7.6
+// instructions per pair - one of them on the special-function unit when the weights can be computed by the series form
+// (all pairs of the batch farther apart than 0.1; image_tc_kernel's probe decides per iteration, rowblock_tc.cuh), two
+// (square root, reciprocal) otherwise.  Measured at cfg4 (ncu): 5.7 ms per pass, 75 % of the issue slots, FMA pipe 40 %,
+// special-function unit 45 %, tensor-core unit 40 %.
 //
 // Precision of GEMM 2: w is used as TF32 (truncated by the tensor core) consistently in the sums of w x_j and of w, so
 // the difference D2[0..15] - x_i D2[16] still telescopes.  The partner coordinates enter rounded to TF32 (2^-11 relative:
