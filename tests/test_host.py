@@ -580,3 +580,29 @@ def test_lhs_design_and_batched_chains():
     assert np.all(np.exp(grown["log_N"][60:]).round() >= 1)
     with pytest.raises(ValueError, match="Samples file missing required columns: NLL"):
         sampler.adaptive_mc_batch({k: v for k, v in t.items() if k != "NLL"}, None, 1, 2, 10, 1e-4, evaluate=evaluate)
+
+
+def test_series_weight_constants_of_the_tensor_repulsion_pass():
+    """rowblock_tc2.cuh computes the repulsion weight (d + 0.01)^-3 of a pair from S = d^2 / 2 with one rsqrt and a cubic
+    (src/optimization.cpp:257-267 is the formula it stands for).  The constants are read from the source: for every
+    pair the series form accepts (S >= kT2SeriesS, i.e. d >= 0.1) the result is within 1.2e-5 of the formula - far inside
+    the TF32 rounding (4.9e-4) the weight gets next -, the threshold is the one the probe in rowblock_tc.cuh counts
+    with, and the two-MUFU form's constants restate the same formula."""
+    import re
+    src = open(os.path.join(ROOT, "topolow_b200", "csrc", "rowblock_tc2.cuh")).read()
+    probe = open(os.path.join(ROOT, "topolow_b200", "csrc", "rowblock_tc.cuh")).read()
+    m = re.search(r"float pl = fmaf\(([-0-9.e+]+)f, q, ([-0-9.e+]+)f\);\s*pl = fmaf\(pl, q, ([-0-9.e+]+)f\);\s*pl = fmaf\(pl, q, ([-0-9.e+]+)f\);", src)
+    assert m, "series polynomial not found"
+    c3, c2, c1, c0 = (float(x) for x in m.groups())
+    s_min = float(re.search(r"constexpr float kT2SeriesS = ([0-9.e+-]+)f;", src).group(1))
+    assert s_min == float(re.search(r"constexpr float kSeriesNearS = ([0-9.e+-]+)f;", probe).group(1)) == 0.005
+    d = np.concatenate([np.geomspace(np.sqrt(2 * s_min), 1e4, 20001), np.linspace(0.1, 0.3, 5001)])
+    S = 0.5 * d * d
+    q = 1.0 / np.sqrt(S)
+    w = q ** 3 * (((c3 * q + c2) * q + c1) * q + c0)
+    want = (d + 0.01) ** -3
+    assert np.abs(w / want - 1).max() < 1.2e-5, np.abs(w / want - 1).max()
+    m2 = re.search(r"rcp_approx_ftz\(fmaf\(sqrt_approx\(fabsf\([^;]*\)\)\), ([0-9.]+)f, ([0-9.]+)f\)\)", src)
+    assert m2, "two-MUFU form not found"
+    a, b = float(m2.group(1)), float(m2.group(2))
+    assert np.abs((1.0 / (np.sqrt(S) * a + b)) ** 3 / want - 1).max() < 1e-7
