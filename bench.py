@@ -656,6 +656,10 @@ def main_map(args, n, d, missing):
                     "tensor": {"executed_flop_per_launch": (2.0 * 56 + 2.0 * 32) * one_sided if form == 11 else
                                                            (2.0 * 56 * one_sided if form == 10 else 0.0),
                                "achieved_tflops": ((2.0 * 56 + 2.0 * 32) if form == 11 else (2.0 * 56 if form == 10 else 0.0)) * one_sided / rep_s / 1e12,
+                               "peak_tflops": 0.5 * float(peaks.get("bf16_tflops", 0.0)),
+                               "frac": (((2.0 * 56 + 2.0 * 32) if form == 11 else (2.0 * 56 if form == 10 else 0.0)) * one_sided / rep_s / 1e12
+                                        / (0.5 * float(peaks["bf16_tflops"]))) if peaks.get("bf16_tflops") else None,
+                               "peak_source": "half of the dense bf16 figure of MEASURED_PEAKS.json (%s): TF32 runs at half the bf16 rate" % peak_src,
                                "note": "executed TF32 flop: GEMM 1 K = 24 + 16 + 16 (hi x hi, hi x lo, lo x hi with the half norms in K), "
                                        "GEMM 2 K = 32 partners x N = 32 columns (17 used); TF32 dense peak is half of the bf16 figure in "
                                        "MEASURED_PEAKS.json - the tensor pipe is not the bound"},
