@@ -168,6 +168,11 @@ __global__ void __maxnreg__(80) repulse_tc2_kernel(RowDev dv, T2Image im, int cu
   };
   auto draw_item = [&](Cursor& cu) {  // copy warp (converged)
     if (cu.seq > 0) mbar_wait(bar_a_tmem, (cu.seq - 1) & 1);
+    // The MMA warp takes item k + 1 before it issues the last GEMM 2 of item k, which the consumers need before they can
+    // start item k + 1 - so from item 2 on it cannot miss a phase of bar_item either.  Only its very first take has no
+    // such anchor (the consumers write the rows' image of item 0 without it, and an item of <= 4 stages is loaded without
+    // it): item 1 is published only after the GEMM 1s of item 0 (tests/tc2_protocol_model.py finds the hang without this).
+    if (cu.seq == 1) mbar_wait(bar_a_free, 0);
     int id = 0;
     if (lane == 0) id = (int)atomicAdd(&dv.counters[2], 1u);
     id = __shfl_sync(0xffffffffu, id, 0);
