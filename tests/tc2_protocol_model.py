@@ -60,6 +60,7 @@ class Model:
         self.pipe = []                               # tensor pipe, in order: callables
         self.gemm1_left = {}                         # item seq -> GEMM 1 ops issued and not yet executed
         self.stages_done = 0
+        self.speed = {}
 
     # ---- helpers -------------------------------------------------------------------------------
     def draw_id(self):
@@ -275,7 +276,9 @@ class Model:
             if not choices:
                 assert not roles, f"deadlock: {sorted(roles)} wait forever"
                 return
-            kind, x = self.rng.choice(choices)
+            # every actor has its own speed in a run (a warp that is rarely scheduled, a slow tensor pipe, ...)
+            kind, x = self.rng.choices(choices, weights=[self.speed.setdefault(c if c[0] == "role" else c[0], self.rng.choice([0.02, 1.0, 1.0, 10.0]))
+                                                         for c in choices])[0]
             if kind == "tma":
                 self.tma.pop(x)()
             elif kind == "pipe":
