@@ -523,6 +523,7 @@ def main_map(args, n, d, missing):
         launches = m.info()["launches"] - launches_before
         kt = m.time_kernels(probe_iters)                  # events around every launch (all ranks step together)
         res = m.result()
+        info0["tensor_form_iterations"] = m.info().get("tensor_form_iterations", -1)   # read back by result(): of all iterations run
         m.close()
     else:
         plan = _lib.Plan(*fa, total_iters, *hp, nw, freq, precision=prec, seed=0, device=local)
